@@ -1,0 +1,19 @@
+"""B200-native flow-based temporal-consistency path (warp + occlusion mask + masked temporal error).
+
+The directory name is not a Python identifier; import it with
+``importlib.import_module("gan-based-video-style-transfer_b200")`` or through the ``tcl_b200`` shim at
+the repository root.  ``dropin/`` holds modules named like the reference's (``flowtools``, ``fs_lib``,
+``sintel_eval``) for ``sys.path``-style drop-in use.
+"""
+from . import _cabi  # noqa: F401
+from .ops import (FusedResult, fbcCheckTorch, fbcCheckTorch_mob, fbcheck_with_near_count, fs_warp,  # noqa: F401
+                  fused_forward, gradient, temporal_error, temporal_error_per_pair, temporal_loss,
+                  temporal_rmse_per_sample, warp, warp_blend)
+from .sintel_eval import (aggregate_means, computeTCL, computeTCL_from_flows, save_dict_as_json)  # noqa: F401
+from .sharding import (ShardPlan, plan_shards, evaluate_sharded, allreduce_sums)  # noqa: F401
+from . import synth  # noqa: F401
+
+__all__ = ["gradient", "warp", "fbcCheckTorch", "fbcCheckTorch_mob", "fs_warp", "fused_forward",
+           "temporal_error", "temporal_error_per_pair", "temporal_loss", "temporal_rmse_per_sample",
+           "warp_blend", "computeTCL", "computeTCL_from_flows", "save_dict_as_json", "aggregate_means",
+           "plan_shards", "evaluate_sharded", "allreduce_sums", "synth"]

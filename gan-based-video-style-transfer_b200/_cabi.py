@@ -1,0 +1,103 @@
+"""ctypes binding of ``csrc/libtcl_b200.so`` (the C ABI declared in ``include/tcl_b200.h``).
+
+There is deliberately no fallback of any kind: if the shared library is missing, cannot be
+loaded, or reports a different ABI version, importing the compute wrappers raises.  Tensors are
+handed over as raw device pointers (``Tensor.data_ptr()``) plus the current CUDA stream handle.
+"""
+import ctypes
+import os
+import subprocess
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(_HERE, "csrc")
+LIB_PATH = os.path.join(CSRC, "libtcl_b200.so")
+HEADER = os.path.join(os.path.dirname(_HERE), "include", "tcl_b200.h")
+ABI_VERSION = 1
+
+# enums mirrored from include/tcl_b200.h
+F32, BF16 = 0, 1
+OCC, MOB, VALIDITY = 1, 2, 4
+L2, L1 = 0, 1
+FIN_MEAN, FIN_RMSE = 0, 1
+
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
+              "-Xcompiler", "-fPIC", "-shared"]
+SOURCES = ["tcl_kernels.cu"]
+
+
+class TclArgs(ctypes.Structure):
+    """``tclb200_tcl_args`` (include/tcl_b200.h)."""
+    _fields_ = [
+        ("ff", ctypes.c_void_p), ("bf", ctypes.c_void_p), ("mask_in", ctypes.c_void_p),
+        ("prev", ctypes.c_void_p), ("cur", ctypes.c_void_p),
+        ("warp_out", ctypes.c_void_p), ("mask_out", ctypes.c_void_p), ("blend_out", ctypes.c_void_p),
+        ("pair_sums", ctypes.c_void_p), ("total_sums", ctypes.c_void_p),
+        ("pair_vals", ctypes.c_void_p), ("total_val", ctypes.c_void_p),
+        ("near_threshold", ctypes.c_void_p),
+        ("scratch", ctypes.c_void_p), ("scratch_bytes", ctypes.c_size_t),
+        ("B", ctypes.c_int), ("C", ctypes.c_int), ("H", ctypes.c_int), ("W", ctypes.c_int),
+        ("dtype", ctypes.c_int), ("flags", ctypes.c_int), ("loss", ctypes.c_int), ("finalize", ctypes.c_int),
+    ]
+
+
+def build(force=False, verbose=False):
+    """nvcc the kernels for sm_100a, in-tree (cross-compiles without a GPU)."""
+    srcs = [os.path.join(CSRC, s) for s in SOURCES]
+    deps = srcs + [os.path.join(CSRC, "tcl_math.cuh"), HEADER]
+    if (not force and os.path.exists(LIB_PATH)
+            and all(os.path.getmtime(LIB_PATH) >= os.path.getmtime(d) for d in deps)):
+        return LIB_PATH
+    cmd = ["nvcc"] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_PATH] + srcs
+    subprocess.run(cmd, check=True, cwd=CSRC)
+    return LIB_PATH
+
+
+_c = ctypes
+_vp, _i = ctypes.c_void_p, ctypes.c_int
+_PROTOTYPES = {
+    "tclb200_abi_version": (_c.c_int, []),
+    "tclb200_last_error": (_c.c_char_p, []),
+    "tclb200_scratch_bytes": (_c.c_size_t, [_i, _i, _i]),
+    "tclb200_gradient": (_c.c_int, [_vp, _vp, _i, _i, _i, _vp]),
+    "tclb200_warp": (_c.c_int, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
+    "tclb200_warp_backward": (_c.c_int, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
+    "tclb200_fbcheck": (_c.c_int, [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp]),
+    "tclb200_tcl_forward": (_c.c_int, [_c.POINTER(TclArgs), _vp]),
+    "tclb200_tcl_backward": (_c.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
+}
+
+_lib = None
+
+
+class TclB200Error(RuntimeError):
+    pass
+
+
+def lib():
+    """Load (once) and return the C-ABI library; raises if it is not there."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise TclB200Error(
+            f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(nvcc, sm_100a). There is no CPU or PyTorch fallback for this path.")
+    handle = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in _PROTOTYPES.items():
+        fn = getattr(handle, name)  # AttributeError here = the library does not export the header's symbol
+        fn.restype, fn.argtypes = res, args
+    got = handle.tclb200_abi_version()
+    if got != ABI_VERSION:
+        raise TclB200Error(f"ABI mismatch: library reports {got}, wrappers expect {ABI_VERSION}")
+    _lib = handle
+    return _lib
+
+
+def exported_symbols():
+    return list(_PROTOTYPES)
+
+
+def check(status):
+    if status != 0:
+        msg = lib().tclb200_last_error().decode("utf-8", "replace")
+        raise TclB200Error(f"tcl_b200 call failed (status {status}): {msg}")

@@ -1,0 +1,316 @@
+"""Host-side mirror of the reference's flow-tools interface over the C-ABI CUDA library.
+
+Every function keeps the name, argument meaning and result convention of the reference function
+it replaces (upstream paths relative to the repository root):
+
+* ``gradient(x)``                         utils/flowtools.py:12-16
+* ``warp(x, f)``                          utils/flowtools.py:18-32 (+ the inline copies)
+* ``fbcCheckTorch(ff, bf, device)``       utils/flowtools.py:34-58
+* ``fbcCheckTorch_mob(ff, bf, device)``   methods/optimization-based/flowtools.py:34-58 (occlusion test off)
+* ``fs_warp(x, flo)``                     methods/learning-based/fs_lib.py:5-39
+* ``temporal_error(...)``                 utils/sintel_eval.py:104-110 minus RAFT and the generator (fused)
+* ``temporal_loss(...)``                  StarGANv2AdvCon/core/solver.py:427-446, fs_ruder.py:97, MoGAN ...:280-281
+* ``temporal_rmse_per_sample(...)``       utils/metrics/eval.py:137-138
+* ``warp_blend(...)``                     methods/optimization-based/obst_eval.py:500
+
+PyTorch is used for device memory, streams and autograd plumbing only; all arithmetic runs in
+``csrc/tcl_kernels.cu``.  There is no CPU path: CPU tensors raise, like the reference's hard-coded
+``.cuda()`` (flowtools.py:25) does on a box without a GPU.
+"""
+import ctypes
+
+import torch
+
+from . import _cabi
+from ._cabi import BF16, F32, FIN_MEAN, FIN_RMSE, L1, L2, MOB, OCC, VALIDITY, TclArgs, check
+
+_scratch_cache = {}
+
+
+def _stream_handle():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def _require_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("tcl_b200: expected CUDA tensors; this path has no CPU implementation "
+                               "(the reference moves its grid with .cuda(), utils/flowtools.py:25)")
+
+
+def _flow(f, name="flow"):
+    if f.dim() != 4 or f.shape[1] != 2:
+        raise RuntimeError(f"tcl_b200: {name} must be (B,2,H,W), got {tuple(f.shape)}")
+    if f.dtype != torch.float32:
+        f = f.float()
+    return f.contiguous()
+
+
+def _frame_dtype(t):
+    if t.dtype == torch.float32:
+        return F32
+    if t.dtype == torch.bfloat16:
+        return BF16
+    raise RuntimeError(f"tcl_b200: frames must be float32 or bfloat16, got {t.dtype}")
+
+
+def _scratch(B, H, W, device):
+    """Zero-filled ticket/partials scratch, cached per (device, stream); kernels leave it zeroed."""
+    need = _cabi.lib().tclb200_scratch_bytes(B, H, W)
+    key = (device.index, torch.cuda.current_stream(device).cuda_stream)
+    buf = _scratch_cache.get(key)
+    if buf is None or buf.numel() < need:
+        buf = torch.zeros(max(need, 1 << 16), dtype=torch.uint8, device=device)
+        _scratch_cache[key] = buf
+    return buf
+
+
+# ------------------------------------------------------------------------------------------------
+# reference-named functions
+# ------------------------------------------------------------------------------------------------
+def gradient(x):
+    """Zero-padded central differences of (B,H,W) -> (2,B,H,W) = stack([dx, dy])."""
+    _require_cuda(x)
+    if x.dim() != 3:
+        raise RuntimeError(f"tcl_b200: gradient expects (B,H,W), got {tuple(x.shape)}")
+    x = x.float().contiguous()
+    B, H, W = x.shape
+    out = torch.empty((2, B, H, W), dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        check(_cabi.lib().tclb200_gradient(_ptr(x), _ptr(out), B, H, W, _stream_handle()))
+    return out
+
+
+def _warp_forward(x, f, flags):
+    B, C, H, W = x.shape
+    out = torch.empty_like(x)
+    with torch.cuda.device(x.device):
+        check(_cabi.lib().tclb200_warp(_ptr(x), _ptr(f), _ptr(out), B, C, H, W, _frame_dtype(x), flags,
+                                       _stream_handle()))
+    return out
+
+
+class _WarpFn(torch.autograd.Function):
+    """warp with the gradients F.grid_sample + the grid normalisation give the reference."""
+
+    @staticmethod
+    def forward(ctx, x, f, flags):
+        ctx.flags = flags
+        ctx.save_for_backward(x, f)
+        return _warp_forward(x, f, flags)
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        x, f = ctx.saved_tensors
+        if x.dtype != torch.float32:
+            raise RuntimeError("tcl_b200: warp backward is implemented for float32 frames")
+        B, C, H, W = x.shape
+        need_x, need_f = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        gx = torch.empty_like(x) if need_x else None
+        gf = torch.empty_like(f) if need_f else None
+        go = grad_out.float().contiguous()
+        with torch.cuda.device(x.device):
+            check(_cabi.lib().tclb200_warp_backward(_ptr(go), _ptr(x), _ptr(f), _ptr(gx), _ptr(gf), B, C, H, W,
+                                                    ctx.flags, _stream_handle()))
+        return gx, gf, None
+
+
+def _warp(x, f, flags):
+    _require_cuda(x, f)
+    if x.dim() != 4:
+        raise RuntimeError(f"tcl_b200: warp expects x of shape (B,C,H,W), got {tuple(x.shape)}")
+    f = _flow(f, "f")
+    if f.shape[0] != x.shape[0] or f.shape[2:] != x.shape[2:]:
+        raise RuntimeError(f"tcl_b200: x {tuple(x.shape)} and flow {tuple(f.shape)} do not match")
+    _frame_dtype(x)
+    x = x.contiguous()
+    if torch.is_grad_enabled() and (x.requires_grad or f.requires_grad):
+        return _WarpFn.apply(x, f, flags)
+    return _warp_forward(x, f, flags)
+
+
+def warp(x, f):
+    """Bilinear zero-padded backward warp of ``x`` (B,C,H,W) by pixel flow ``f`` (B,2,H,W).
+
+    Keeps the reference's sampling convention exactly (normalise by size-1, sample with
+    align_corners=False), so zero flow is NOT the identity -- see SURVEY.md section 7 hard part 3.
+    """
+    return _warp(x, f, 0)
+
+
+def fs_warp(x, flo):
+    """fs_lib.warp: ``warp`` times the binarised (>= 0.9999) warp of an all-ones image."""
+    return _warp(x, flo, VALIDITY)
+
+
+def _fbcheck(ff, bf, flags, device, return_near=False):
+    _require_cuda(bf)
+    bf = _flow(bf, "bf")
+    if flags & OCC:
+        _require_cuda(ff)
+        ff = _flow(ff, "ff")
+        if ff.shape != bf.shape:
+            raise RuntimeError(f"tcl_b200: ff {tuple(ff.shape)} and bf {tuple(bf.shape)} do not match")
+    else:
+        ff = None
+    B, _, H, W = bf.shape
+    mask = torch.empty((B, 1, H, W), dtype=torch.float32, device=bf.device)
+    near = torch.zeros(1, dtype=torch.int64, device=bf.device) if return_near else None
+    with torch.cuda.device(bf.device):
+        check(_cabi.lib().tclb200_fbcheck(_ptr(ff), _ptr(bf), _ptr(mask), B, H, W, flags, _ptr(near),
+                                          _stream_handle()))
+    if device is not None and torch.device(device) != mask.device and torch.device(device).type != "cuda":
+        mask = mask.to(device)
+    return (mask, near) if return_near else mask
+
+
+def fbcCheckTorch(ff, bf, device="cuda"):
+    """Forward-backward consistency + motion-boundary mask (B,1,H,W) fp32 in {0,1}, no grad."""
+    return _fbcheck(ff, bf, OCC | MOB, device)
+
+
+def fbcCheckTorch_mob(ff, bf, device="cuda"):
+    """The optimisation-based variant: motion-boundary test only (``ff`` is ignored)."""
+    return _fbcheck(ff, bf, MOB, device)
+
+
+def fbcheck_with_near_count(ff, bf, flags=OCC | MOB):
+    """``fbcCheckTorch`` plus the count of pixels whose test margin is within 1e-6 of the threshold."""
+    return _fbcheck(ff, bf, flags, None, return_near=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# fused path
+# ------------------------------------------------------------------------------------------------
+class FusedResult:
+    """Device-resident results of one fused launch (nothing is synchronised)."""
+    __slots__ = ("pair_vals", "total_val", "pair_sums", "total_sums", "warp", "mask", "blend", "near_threshold")
+
+    def __init__(self):
+        for s in self.__slots__:
+            setattr(self, s, None)
+
+
+def fused_forward(bf, prev, cur, ff=None, mask=None, loss=L2, finalize=FIN_RMSE, flags=OCC | MOB,
+                  want_warp=False, want_mask=False, want_blend=False, want_near=False, want_sums=True):
+    """One launch: warp ``prev`` by ``bf``, build or read the mask, reduce the masked error against ``cur``.
+
+    ``ff`` given -> the mask is computed (fbcCheckTorch semantics, tests per ``flags``);
+    else ``mask`` given -> dataset mask (B,1,H,W); else no mask.  Returns a ``FusedResult``.
+    """
+    _require_cuda(bf, prev, cur, ff, mask)
+    bf = _flow(bf, "bf")
+    B, _, H, W = bf.shape
+    ff = _flow(ff, "ff") if ff is not None else None
+    if prev.dim() != 4 or prev.shape[0] != B or prev.shape[2:] != bf.shape[2:]:
+        raise RuntimeError(f"tcl_b200: prev {tuple(prev.shape)} does not match flow {tuple(bf.shape)}")
+    if cur.shape != prev.shape or cur.dtype != prev.dtype:
+        raise RuntimeError("tcl_b200: prev and cur must have the same shape and dtype")
+    dt = _frame_dtype(prev)
+    prev, cur = prev.contiguous(), cur.contiguous()
+    C = prev.shape[1]
+    dev = bf.device
+    if mask is not None and ff is None:
+        if mask.shape != (B, 1, H, W):
+            raise RuntimeError(f"tcl_b200: mask must be (B,1,H,W), got {tuple(mask.shape)}")
+        mask = mask.float().contiguous()
+    else:
+        mask = None
+    res = FusedResult()
+    if want_sums:
+        f32 = torch.empty(B + 1, dtype=torch.float32, device=dev)
+        f64 = torch.empty(B + 2, dtype=torch.float64, device=dev)
+        res.pair_vals, res.total_val = f32[:B], f32[B]
+        res.pair_sums, res.total_sums = f64[:B], f64[B:]
+    if want_warp:
+        res.warp = torch.empty_like(prev)
+    if want_mask:
+        res.mask = torch.empty((B, 1, H, W), dtype=torch.float32, device=dev)
+    if want_blend:
+        res.blend = torch.empty_like(prev)
+    if want_near:
+        res.near_threshold = torch.zeros(1, dtype=torch.int64, device=dev)
+    with torch.cuda.device(dev):
+        scratch = _scratch(B, H, W, dev) if want_sums else None
+        a = TclArgs()
+        a.ff, a.bf, a.mask_in, a.prev, a.cur = _ptr(ff), _ptr(bf), _ptr(mask), _ptr(prev), _ptr(cur)
+        a.warp_out, a.mask_out, a.blend_out = _ptr(res.warp), _ptr(res.mask), _ptr(res.blend)
+        if want_sums:
+            a.pair_sums, a.total_sums = _ptr(res.pair_sums), _ptr(res.total_sums)
+            a.pair_vals, a.total_val = _ptr(res.pair_vals), _ptr(res.total_val)
+            a.scratch, a.scratch_bytes = _ptr(scratch), scratch.numel()
+        a.near_threshold = _ptr(res.near_threshold)
+        a.B, a.C, a.H, a.W = B, C, H, W
+        a.dtype, a.flags, a.loss, a.finalize = dt, flags, loss, finalize
+        check(_cabi.lib().tclb200_tcl_forward(ctypes.byref(a), _stream_handle()))
+    return res
+
+
+def temporal_error(ff, bf, prev, cur):
+    """``computeTCL`` minus RAFT and the generator: sqrt(mean((mask*(cur - warp(prev,bf)))**2)), 0-dim tensor."""
+    return fused_forward(bf, prev, cur, ff=ff, finalize=FIN_RMSE).total_val
+
+
+def temporal_error_per_pair(ff, bf, prev, cur):
+    """Per-pair RMSE (B,) with the mask computed from (ff,bf) -- the batched form of ``computeTCL``."""
+    return fused_forward(bf, prev, cur, ff=ff, finalize=FIN_RMSE).pair_vals
+
+
+def temporal_rmse_per_sample(mask, cur, prev, flow):
+    """FC2 metric: ((mask*(cur - warp(prev,flow)))**2).mean(dim=(1,2,3))**0.5 -> (N,)."""
+    return fused_forward(flow, prev, cur, mask=mask, finalize=FIN_RMSE).pair_vals
+
+
+def warp_blend(mask, prev, flow, img):
+    """mask*warp(prev,flow) + (1-mask)*img in one pass (obst_eval.py:500)."""
+    return fused_forward(flow, prev, img, mask=mask, want_blend=True, want_sums=False).blend
+
+
+class _TemporalLossFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, prev, cur, flow, mask, loss, flags):
+        res = fused_forward(flow, prev, cur, mask=mask, loss=loss, finalize=FIN_MEAN, flags=flags)
+        ctx.save_for_backward(prev, cur, flow, mask)
+        ctx.loss, ctx.flags = loss, flags
+        return res.total_val.clone()
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        prev, cur, flow, mask = ctx.saved_tensors
+        if prev.dtype != torch.float32:
+            raise RuntimeError("tcl_b200: temporal_loss backward is implemented for float32 frames")
+        B, C, H, W = prev.shape
+        need_prev, need_cur = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        gp = torch.empty_like(prev) if need_prev else None
+        gc = torch.empty_like(cur) if need_cur else None
+        scale = (grad_out.float() / float(B * C * H * W)).reshape(1).contiguous()
+        with torch.cuda.device(prev.device):
+            check(_cabi.lib().tclb200_tcl_backward(_ptr(flow), _ptr(mask), _ptr(prev), _ptr(cur), _ptr(scale),
+                                                   _ptr(gp), _ptr(gc), B, C, H, W, ctx.flags, ctx.loss,
+                                                   _stream_handle()))
+        return gp, gc, None, None, None, None
+
+
+def temporal_loss(mask, cur, prev, flow, loss="l2", validity=False):
+    """Training temporal loss, differentiable w.r.t. ``cur`` and ``prev``.
+
+    ``loss='l2'``: ((mask*(cur - warp(prev,flow)))**2).mean()      (solver.py:444, fs_ruder.py:97)
+    ``loss='l1'``: (mask*abs(warp(prev,flow) - cur)).mean()         (MoGAN cycle_gan_model.py:280-281)
+    ``validity`` selects fs_lib.warp for the learning-based trainers.
+    """
+    _require_cuda(mask, cur, prev, flow)
+    code = {"l2": L2, "l1": L1}[loss]
+    flow = _flow(flow)
+    prev, cur = prev.contiguous(), cur.contiguous()
+    B, _, H, W = flow.shape
+    if mask is None:
+        mask = torch.ones((B, 1, H, W), dtype=torch.float32, device=flow.device)
+    mask = mask.float().contiguous()
+    flags = VALIDITY if validity else 0
+    if torch.is_grad_enabled() and (prev.requires_grad or cur.requires_grad):
+        return _TemporalLossFn.apply(prev, cur, flow, mask, code, flags)
+    return fused_forward(flow, prev, cur, mask=mask, loss=code, finalize=FIN_MEAN, flags=flags).total_val

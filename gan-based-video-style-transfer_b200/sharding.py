@@ -1,0 +1,104 @@
+"""Sharding of frame pairs over the GPUs of one box + the single sum all-reduce.
+
+Pairs are independent (each reads only its own two flows and two frames), so the path shards by
+pair with no data-path collective.  The only cross-GPU step is the final aggregation of the
+reference's evaluation loop (per-video mean of per-pair RMSE, then the mean over videos:
+StarGANv2AdvCon/core/solver.py:352-354, utils/sintel_eval.py:112-126): ONE ``all_reduce(SUM)`` of a
+packed float64 vector ``[sum_rmse per sequence | pair count per sequence | sum of squared error | element count]``.
+One process per GPU; ``torch.distributed`` (NCCL over NVLink on the GPU box, gloo in CPU tests).
+"""
+from dataclasses import dataclass
+from typing import List, Optional, Sequence
+
+import torch
+import torch.distributed as dist
+
+
+@dataclass
+class ShardPlan:
+    rank: int
+    world: int
+    start: int  # first global pair index owned by this rank
+    stop: int   # one past the last
+    seq_of_pair: List[int]  # sequence id of each LOCAL pair
+
+    @property
+    def n_local(self):
+        return self.stop - self.start
+
+
+def pairs_per_sequence(frames_per_sequence: Sequence[int], gap: int = 1) -> List[int]:
+    """Number of (t-gap, t) pairs each clip yields: short-term gap=1, long-term gap=5 (utils/sintel_eval.py:63)."""
+    return [max(0, n - gap) for n in frames_per_sequence]
+
+
+def plan_shards(pairs_in_sequence: Sequence[int], world: int, rank: int) -> ShardPlan:
+    """Contiguous, balanced blocks of pairs; a clip's pairs stay on one GPU where the split allows."""
+    if not (0 <= rank < world):
+        raise ValueError(f"rank {rank} outside world of {world}")
+    total = sum(pairs_in_sequence)
+    base, rem = divmod(total, world)
+    start = rank * base + min(rank, rem)
+    stop = start + base + (1 if rank < rem else 0)
+    seq_of_pair, g = [], 0
+    for s, n in enumerate(pairs_in_sequence):
+        lo, hi = max(g, start), min(g + n, stop)
+        seq_of_pair.extend([s] * max(0, hi - lo))
+        g += n
+    return ShardPlan(rank, world, start, stop, seq_of_pair)
+
+
+def pack_local(pair_vals: torch.Tensor, sum_sq: torch.Tensor, seq_of_pair: torch.Tensor, n_seq: int,
+               elems_per_pair: int) -> torch.Tensor:
+    """Local contribution to the packed vector (float64, on the tensors' device)."""
+    n = pair_vals.numel()
+    packed = torch.zeros(2 * n_seq + 2, dtype=torch.float64, device=pair_vals.device)
+    if n:
+        packed[:n_seq].index_add_(0, seq_of_pair, pair_vals.double())
+        packed[n_seq:2 * n_seq].index_add_(0, seq_of_pair, torch.ones(n, dtype=torch.float64, device=pair_vals.device))
+        packed[2 * n_seq] = sum_sq.double().reshape(())
+    packed[2 * n_seq + 1] = float(n) * float(elems_per_pair)
+    return packed
+
+
+def allreduce_sums(packed: torch.Tensor, group: Optional[dist.ProcessGroup] = None) -> torch.Tensor:
+    """The path's single collective; a no-op when not running distributed."""
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(packed, op=dist.ReduceOp.SUM, group=group)
+    return packed
+
+
+def unpack(packed: torch.Tensor, n_seq: int) -> dict:
+    """Per-sequence mean RMSE, the reference's mean over sequences, pooled RMSE. Device tensors, no sync."""
+    sums, cnt = packed[:n_seq], packed[n_seq:2 * n_seq]
+    per_seq = sums / cnt.clamp(min=1.0)
+    present = (cnt > 0).double()
+    return {
+        "per_sequence_mean": per_seq,
+        "mean_over_sequences": (per_seq * present).sum() / present.sum().clamp(min=1.0),
+        "mean_over_pairs": sums.sum() / cnt.sum().clamp(min=1.0),
+        "pooled_rmse": (packed[2 * n_seq] / packed[2 * n_seq + 1].clamp(min=1.0)).sqrt(),
+        "n_pairs": cnt.sum(),
+    }
+
+
+def evaluate_sharded(ff, bf, prev, cur, seq_of_pair: torch.Tensor, n_seq: int,
+                     group: Optional[dist.ProcessGroup] = None, chunk: Optional[int] = None) -> dict:
+    """Temporal error of this rank's shard of pairs (already resident on its GPU) + the one all-reduce.
+
+    ``chunk`` bounds the pairs per launch (None = one launch for the shard).  Returns ``unpack``'s dict.
+    """
+    from . import ops
+    n = bf.shape[0]
+    C, H, W = prev.shape[1:]
+    if n == 0:
+        packed = torch.zeros(2 * n_seq + 2, dtype=torch.float64, device=seq_of_pair.device)
+    else:
+        step = n if not chunk else chunk
+        packed = None
+        for s in range(0, n, step):
+            e = min(n, s + step)
+            res = ops.fused_forward(bf[s:e], prev[s:e], cur[s:e], ff=ff[s:e], finalize=ops.FIN_RMSE)
+            part = pack_local(res.pair_vals, res.total_sums[0], seq_of_pair[s:e], n_seq, C * H * W)
+            packed = part if packed is None else packed + part
+    return unpack(allreduce_sums(packed, group), n_seq)

@@ -1,0 +1,137 @@
+/*
+ * tcl_b200.h -- C ABI of the B200-native flow-based temporal-consistency path.
+ *
+ * Drop-in boundary.  The reference (tomstrident/GAN-based-Video-Style-Transfer) is
+ * pure Python; its "FFI" for this path is the module-function API
+ *     from flowtools import gradient, warp, fbcCheckTorch        (utils/flowtools.py)
+ *     from fs_lib import warp                                     (methods/learning-based/fs_lib.py)
+ *     from sintel_eval import computeTCL                          (utils/sintel_eval.py)
+ * The thin PyTorch wrappers in gan-based-video-style-transfer_b200/ keep those signatures and bind the
+ * entry points below with ctypes (INTEGRATION.md shows the stub).  No torch types cross this
+ * boundary: plain device pointers owned by the caller, explicit sizes, an explicit cudaStream_t.
+ *
+ * Conventions
+ *   - all tensors NCHW contiguous; flows are (B,2,H,W) fp32 in pixels, channel 0 = u (x), 1 = v (y);
+ *     frames are (B,C,H,W) fp32 or bf16 (TCLB200_F32 / TCLB200_BF16); masks are (B,1,H,W) fp32 in {0,1}
+ *   - every function returns 0 on success, a TCLB200_ERR_* code otherwise, never throws or aborts;
+ *     tclb200_last_error() returns a thread-local message for the last failing call
+ *   - no hidden global state: accumulators and scratch are passed in; calls are asynchronous on
+ *     `stream` and re-entrant across streams as long as each stream uses its own scratch
+ *   - there is NO CPU fallback: without a CUDA device every compute entry returns TCLB200_ERR_CUDA
+ */
+#ifndef TCL_B200_H_
+#define TCL_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TCLB200_ABI_VERSION 1
+
+#define TCLB200_OK 0
+#define TCLB200_ERR_INVALID 1     /* bad argument (null pointer, non-positive size, unknown enum) */
+#define TCLB200_ERR_CUDA 2        /* a CUDA runtime call failed; see tclb200_last_error() */
+#define TCLB200_ERR_UNSUPPORTED 3 /* valid request this build does not implement */
+
+/* frame dtype */
+#define TCLB200_F32 0
+#define TCLB200_BF16 1
+
+/* mask tests of fbcCheckTorch (utils/flowtools.py:45,53); the optimisation-based variant
+ * (methods/optimization-based/flowtools.py:34-58) is TCLB200_MOB alone */
+#define TCLB200_OCC 1
+#define TCLB200_MOB 2
+/* fs_lib.warp validity mask (methods/learning-based/fs_lib.py:29-39) */
+#define TCLB200_VALIDITY 4
+
+/* masked error */
+#define TCLB200_L2 0 /* sum (m*(cur-warp))^2   solver.py:444, sintel_eval.py:110, metrics/eval.py:138 */
+#define TCLB200_L1 1 /* sum  m*|warp-cur|      MoGAN/models/cycle_gan_model.py:280-281 */
+
+/* how pair_vals / total_val are derived from the sums (N = C*H*W) */
+#define TCLB200_FIN_MEAN 0 /* pair: S_b/N        total: sum_b S_b/(B*N)        (training loss)       */
+#define TCLB200_FIN_RMSE 1 /* pair: sqrt(S_b/N)  total: sqrt(sum_b S_b/(B*N))  (computeTCL, tcl_err) */
+
+typedef void* tclb200_stream_t; /* cudaStream_t */
+
+int tclb200_abi_version(void);
+const char* tclb200_last_error(void);
+
+/* bytes of device scratch tclb200_tcl_forward needs for a (B,H,W) problem.  The scratch must be
+ * zero-filled once when allocated; every call leaves it zeroed again. */
+size_t tclb200_scratch_bytes(int B, int H, int W);
+
+/* gradient(x)  utils/flowtools.py:12-16
+ * x (B,H,W) fp32 -> out (2,B,H,W) fp32 = [d/dx, d/dy], zero-padded central differences. */
+int tclb200_gradient(const float* x, float* out, int B, int H, int W, tclb200_stream_t stream);
+
+/* warp(x, f)  utils/flowtools.py:18-32 (copies: utils/metrics/eval.py:43-57, StarGAN/solver.py:42-56;
+ * inline: StarGANv2AdvCon/core/solver.py:427-443, CycleGANCon/models/cycle_gan_model.py:191-203)
+ * flags & TCLB200_VALIDITY selects fs_lib.warp (methods/learning-based/fs_lib.py:5-39).
+ * x, out (B,C,H,W) of `dtype`; f (B,2,H,W) fp32. */
+int tclb200_warp(const void* x, const float* f, void* out, int B, int C, int H, int W, int dtype, int flags,
+                 tclb200_stream_t stream);
+
+/* autograd of warp(): what F.grid_sample's backward + the grid normalisation give the reference
+ * (solver.py:181 g_loss.backward()).  grad_out, x as in tclb200_warp (fp32 only); grad_x (B,C,H,W) fp32 is
+ * OVERWRITTEN (zero-filled, then bilinear scatter-add); grad_f (B,2,H,W) fp32.  Either output may be NULL. */
+int tclb200_warp_backward(const float* grad_out, const float* x, const float* f, float* grad_x, float* grad_f, int B,
+                          int C, int H, int W, int flags, tclb200_stream_t stream);
+
+/* fbcCheckTorch(ff, bf)  utils/flowtools.py:34-58
+ * mask_out (B,1,H,W) fp32 in {0,1}.  near_threshold (device, optional) is incremented by the number of
+ * pixels whose occlusion or motion-boundary margin |lhs-rhs| is below 1e-6 (north_star's exemption band). */
+int tclb200_fbcheck(const float* ff, const float* bf, float* mask_out, int B, int H, int W, int flags,
+                    unsigned long long* near_threshold, tclb200_stream_t stream);
+
+/* Fused warp + occlusion mask + masked reduction: one pass that reads each pair's flows and frames once.
+ *   computeTCL            utils/sintel_eval.py:104-110   (ff,bf given, mask computed, FIN_RMSE)
+ *   FC2 tcl_err           utils/metrics/eval.py:137-138  (mask_in given, per-sample FIN_RMSE)
+ *   GAN training loss     StarGANv2AdvCon/core/solver.py:427-446 (mask_in given, FIN_MEAN)
+ *   MoGAN masked L1       MoGAN/models/cycle_gan_model.py:276-281 (TCLB200_L1)
+ *   warp+mask blend       methods/optimization-based/obst_eval.py:500 (blend_out)
+ */
+typedef struct tclb200_tcl_args {
+  /* inputs (device) */
+  const float* ff;      /* (B,2,H,W) forward flow, or NULL when mask_in is given / no mask wanted */
+  const float* bf;      /* (B,2,H,W) flow the warp samples with; required */
+  const float* mask_in; /* (B,1,H,W) dataset mask, or NULL; ignored when ff is given */
+  const void* prev;     /* (B,C,H,W) frame t-1 (stylised), `dtype` */
+  const void* cur;      /* (B,C,H,W) frame t, `dtype` */
+  /* optional per-pixel outputs (device), NULL to skip */
+  void* warp_out;       /* (B,C,H,W) `dtype` */
+  float* mask_out;      /* (B,1,H,W) */
+  void* blend_out;      /* (B,C,H,W) `dtype`: m*warp + (1-m)*cur */
+  /* reductions (device), NULL to skip */
+  double* pair_sums;    /* [B]  S_b                                   */
+  double* total_sums;   /* [2]  {sum_b S_b, sum_b pair_val_b}          */
+  float* pair_vals;     /* [B]  per `finalize`                         */
+  float* total_val;     /* [1]  per `finalize`                         */
+  unsigned long long* near_threshold; /* [1] += near-threshold pixel count, or NULL */
+  void* scratch;        /* >= tclb200_scratch_bytes(B,H,W), zero-filled at allocation */
+  size_t scratch_bytes;
+  int B, C, H, W;
+  int dtype;            /* TCLB200_F32 / TCLB200_BF16 (frames only; flows and masks are fp32) */
+  int flags;            /* TCLB200_OCC | TCLB200_MOB tests when ff is given; TCLB200_VALIDITY */
+  int loss;             /* TCLB200_L2 / TCLB200_L1 */
+  int finalize;         /* TCLB200_FIN_MEAN / TCLB200_FIN_RMSE */
+} tclb200_tcl_args;
+
+int tclb200_tcl_forward(const tclb200_tcl_args* args, tclb200_stream_t stream);
+
+/* Backward of the fused training loss  L = grad_scale * sum (m*(cur-warp(prev,bf)))^2   (L2)
+ *                                   or L = grad_scale * sum  m*|warp(prev,bf)-cur|      (L1)
+ * (solver.py:444-446 + :181; fs_ruder.py:97-106; MoGAN .. :281,285).  grad_scale is a device scalar
+ * (upstream gradient times 1/(B*C*H*W) times lambda).  grad_cur (B,C,H,W) fp32 is written; grad_prev
+ * (B,C,H,W) fp32 is OVERWRITTEN with the bilinear scatter-add.  Either may be NULL.  fp32 frames only. */
+int tclb200_tcl_backward(const float* bf, const float* mask, const float* prev, const float* cur,
+                         const float* grad_scale, float* grad_prev, float* grad_cur, int B, int C, int H, int W,
+                         int flags, int loss, tclb200_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TCL_B200_H_ */
