@@ -1,0 +1,431 @@
+#!/usr/bin/env python
+"""Benchmark of the flow-based temporal-consistency hot path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME]
+
+A step = one pass of the fused warp + occlusion-mask + masked-error kernel over this rank's shard
+of synthetic frame pairs (default workload: the full Sintel-shape evaluation, 23 sequences /
+1041 pairs of 1024x436 fp32 per GPU -- weak scaling, pairs sharded by rank, ONE all-reduce of the
+packed sums per step when N > 1).  Prints ONE JSON line (see README / DESIGN.md for the keys).
+
+`--impl reference` times the reference's own CPU implementation of the path: the op-for-op ATen
+restatement in oracle/torch_port.py (the Python reference itself cannot travel to the GPU box),
+on all host cores, on a bounded sample of the same workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+BYTES_PER_PX = {"fp32": 40, "bf16": 28}  # ff 8 + bf 8 + prev 4C|2C + cur 4C|2C, C = 3
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="sintel_full")
+    ap.add_argument("--pairs", type=int, default=None, help="pairs per GPU per step (default: the workload's)")
+    ap.add_argument("--frames", default="smooth", choices=["smooth", "white"])
+    ap.add_argument("--no-extras", action="store_true", help="skip e2e / cpu_baseline / other workloads")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
+        mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 2 + i and r[2 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def make_shard(tcl, cfg_name, n_pairs, seed, device, frames, chunk=32):
+    """Synthetic shard resident in HBM: dict of (n,2,H,W)/(n,3,H,W) tensors, generated chunk-wise."""
+    cfg = tcl.synth.CONFIGS[cfg_name]
+    H, W, C = cfg["H"], cfg["W"], cfg["C"]
+    dt = torch.bfloat16 if cfg["dtype"] == "bf16" else torch.float32
+    out = dict(ff=torch.empty(n_pairs, 2, H, W, device=device), bf=torch.empty(n_pairs, 2, H, W, device=device),
+               prev=torch.empty(n_pairs, C, H, W, device=device, dtype=dt),
+               cur=torch.empty(n_pairs, C, H, W, device=device, dtype=dt))
+    for s in range(0, n_pairs, chunk):
+        e = min(n_pairs, s + chunk)
+        ff, bf = tcl.synth.make_flows(e - s, H, W, seed=seed + s, max_shift=cfg["max_shift"],
+                                      max_rot_deg=cfg["max_rot_deg"], device=device)
+        prev, cur = tcl.synth.make_frames(e - s, C, H, W, seed=seed + s, kind=frames, device=device, dtype=dt)
+        out["ff"][s:e], out["bf"][s:e], out["prev"][s:e], out["cur"][s:e] = ff, bf, prev, cur
+    return out
+
+
+def time_kernel(fn, steps, warmup):
+    """CUDA-event timing on the current stream; returns (total_ms, per-step ms list)."""
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    for a, b in evs:
+        a.record()
+        fn()
+        b.record()
+    torch.cuda.synchronize()
+    per = [a.elapsed_time(b) for a, b in evs]
+    return evs[0][0].elapsed_time(evs[-1][1]), per
+
+
+# ------------------------------------------------------------------------------------------------
+def cpu_reference_rate(tcl, cfg_name, frames, budget_s, max_pairs=64):
+    """The reference's CPU path (ATen-op port, all host threads) on a bounded sample: pairs/s."""
+    from oracle import torch_port as tp
+    import oracle
+    cfg = tcl.synth.CONFIGS[cfg_name]
+    H, W, C = cfg["H"], cfg["W"], cfg["C"]
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    ff, bf = tcl.synth.make_flows(2, H, W, seed=4321, max_shift=cfg["max_shift"], max_rot_deg=cfg["max_rot_deg"])
+    prev, cur = tcl.synth.make_frames(2, C, H, W, seed=4321, kind=frames)
+    with torch.no_grad():
+        tp.temporal_error(ff[:1], bf[:1], prev[:1], cur[:1])  # warm-up
+        n, t0 = 0, time.perf_counter()
+        while True:
+            i = n % 2
+            tp.temporal_error(ff[i:i + 1], bf[i:i + 1], prev[i:i + 1], cur[i:i + 1])
+            n += 1
+            el = time.perf_counter() - t0
+            if el >= budget_s or n >= max_pairs:
+                break
+    rate = n / el
+    # the plain-C restatement (OpenMP) for context: a tighter CPU implementation than the ATen op chain
+    oracle.build()
+    a = [t.numpy() for t in (ff[:1], bf[:1], prev[:1], cur[:1])]
+    oracle.temporal_error_sums(*a)
+    m, t0 = 0, time.perf_counter()
+    while time.perf_counter() - t0 < min(3.0, budget_s / 3) and m < 200:
+        oracle.temporal_error_sums(*a)
+        m += 1
+    c_rate = m / (time.perf_counter() - t0)
+    return dict(value=rate, unit="pairs/s", cores=cores, kind="port",
+                sample=f"{n} {W}x{H} fp32 pairs of the same synthetic workload in {el:.1f} s; oracle/torch_port.py = the "
+                       f"reference's ATen op sequence (bit-identical to utils/flowtools.py on CPU), torch threads={cores}",
+                gpix_per_s=rate * H * W / 1e9, c_port_pairs_per_s=c_rate,
+                c_port_note="oracle/tcl_oracle.c fused restatement, OpenMP over rows, same sample")
+
+
+def run_reference(args, tcl):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cfg = tcl.synth.CONFIGS[args.workload]
+    H, W, C = cfg["H"], cfg["W"], cfg["C"]
+    from oracle import torch_port as tp
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    sample_pairs = 2
+    ff, bf = tcl.synth.make_flows(sample_pairs, H, W, seed=4321, max_shift=cfg["max_shift"], max_rot_deg=cfg["max_rot_deg"])
+    prev, cur = tcl.synth.make_frames(sample_pairs, C, H, W, seed=4321, kind=args.frames)
+    prev, cur = prev.float(), cur.float()
+
+    def step():
+        with torch.no_grad():
+            for i in range(sample_pairs):
+                tp.temporal_error(ff[i:i + 1], bf[i:i + 1], prev[i:i + 1], cur[i:i + 1])
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    el = time.perf_counter() - t0
+    rate = args.steps * sample_pairs / el
+    line = {"impl": "reference", "metric": "warped frame-pairs/sec", "value": rate, "unit": "pairs/s",
+            "gpix_per_s": rate * H * W / 1e9, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": el / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": args.workload, "shape": f"{W}x{H}", "pairs_per_step": sample_pairs,
+                       "note": "bounded sample of the workload; each step = fbcCheckTorch + warp + masked RMSE per pair"},
+            "cpu_baseline": {"value": rate, "unit": "pairs/s", "cores": cores, "kind": "port",
+                             "sample": f"{sample_pairs} pairs/step x {args.steps} steps, oracle/torch_port.py (ATen op sequence of "
+                                       f"utils/flowtools.py + sintel_eval.py:110), torch threads={cores}"},
+            "e2e": {"value": rate, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+def e2e_rate(tcl, shard, n_pairs, steps, warmup, device, host_pairs=96, chunk=32):
+    """Same metric through the public API with HOST buffers: every step copies each pair's inputs from pinned
+    host memory (3-deep ring of device chunks, copy stream overlapped with compute) and reads the per-pair
+    results back to the host."""
+    host_pairs = min(host_pairs, n_pairs)
+    host = {k: v[:host_pairs].cpu().pin_memory() for k, v in shard.items()}
+    ring = [{k: torch.empty((chunk,) + tuple(v.shape[1:]), dtype=v.dtype, device=device) for k, v in shard.items()} for _ in range(3)]
+    copy_s, comp_s = torch.cuda.Stream(device), torch.cuda.Stream(device)
+    out_host = torch.empty(n_pairs, dtype=torch.float32).pin_memory()
+    bytes_pair = sum(v[0].numel() * v.element_size() for v in shard.values())
+    launches = [0]
+
+    def step():
+        free_ev = [None, None, None]
+        results = []
+        for ci, s in enumerate(range(0, n_pairs, chunk)):
+            n = min(chunk, n_pairs - s)
+            slot = ring[ci % 3]
+            h0 = s % host_pairs
+            with torch.cuda.stream(copy_s):
+                if free_ev[ci % 3] is not None:
+                    copy_s.wait_event(free_ev[ci % 3])
+                for k in slot:
+                    # host pool is cycled; every pair is copied, so bytes/step are exact
+                    first = min(n, host_pairs - h0)
+                    slot[k][:first].copy_(host[k][h0:h0 + first], non_blocking=True)
+                    if first < n:
+                        slot[k][first:n].copy_(host[k][:n - first], non_blocking=True)
+                ready = torch.cuda.Event()
+                ready.record(copy_s)
+            with torch.cuda.stream(comp_s):
+                comp_s.wait_event(ready)
+                r = tcl.fused_forward(slot["bf"][:n], slot["prev"][:n], slot["cur"][:n], ff=slot["ff"][:n])
+                launches[0] += 1
+                out_host[s:s + n].copy_(r.pair_vals, non_blocking=True)
+                done = torch.cuda.Event()
+                done.record(comp_s)
+                free_ev[ci % 3] = done
+                results.append(r)
+        comp_s.synchronize()
+        return float(out_host.mean())
+
+    for _ in range(warmup):
+        step()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    torch.cuda.synchronize()
+    el = time.perf_counter() - t0
+    return dict(value=steps * n_pairs / el, unit="pairs/s", h2d_bytes_per_step=bytes_pair * n_pairs,
+                d2h_bytes_per_step=4 * n_pairs, ms_per_step=el / steps * 1e3,
+                h2d_gb_per_s=bytes_pair * n_pairs * steps / el / 1e9,
+                note=f"pinned host pool of {host_pairs} pairs cycled; {chunk}-pair chunks, 3-slot device ring, copy/compute streams")
+
+
+def other_workloads(tcl, device, frames, peak):
+    """Secondary configs of BASELINE.json (not bench lines; context for the roofline)."""
+    out = []
+    specs = [("train_b16_256", 16, 12, "mask_in"), ("hd1080_window", 6, 4, "ff"), ("uhd4k_stress", 1, 4, "ff"),
+             ("sintel_clip", 49, 1, "ff")]
+    for name, n, nbuf, mode in specs:
+        try:
+            cfg = tcl.synth.CONFIGS[name]
+            bufs = [make_shard(tcl, name, n, 9000 + 97 * i, device, frames, chunk=8) for i in range(nbuf)]
+            masks = [tcl.fbcCheckTorch(b["ff"], b["bf"]) for b in bufs] if mode == "mask_in" else None
+            def launch(i):
+                b = bufs[i % nbuf]
+                if mode == "mask_in":
+                    tcl.fused_forward(b["bf"], b["prev"], b["cur"], mask=masks[i % nbuf], finalize=tcl.ops.FIN_MEAN)
+                else:
+                    tcl.fused_forward(b["bf"], b["prev"], b["cur"], ff=b["ff"])
+            # launch-bound sizes: capture one launch per rotating buffer in a CUDA graph and time replays
+            side = torch.cuda.Stream(device)
+            with torch.cuda.stream(side):
+                for i in range(nbuf):
+                    launch(i)
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                for i in range(nbuf):
+                    launch(i)
+            total, per = time_kernel(graph.replay, 20, 5)
+            per.sort()
+            ms = per[len(per) // 2] / nbuf
+            px = n * cfg["H"] * cfg["W"]
+            bpp = (36 if mode == "mask_in" else 40) if cfg["dtype"] == "fp32" else 28
+            out.append(dict(workload=name, pairs=n, shape=f'{cfg["W"]}x{cfg["H"]}', dtype=cfg["dtype"], mask=mode,
+                            ms_per_launch_median=ms, timing="CUDA graph of one launch per rotating buffer, median of 20 replays", gpix_per_s=px / ms / 1e6, bytes_per_px=bpp,
+                            achieved_gbs=px * bpp / ms / 1e6, frac_of_measured_peak=px * bpp / ms / 1e6 / peak,
+                            rotating_buffers=nbuf, working_set_mb=px * bpp * nbuf / 1e6))
+            del bufs, masks
+            torch.cuda.empty_cache()
+        except Exception as ex:  # report, never hide
+            out.append(dict(workload=name, error=repr(ex)))
+    return out
+
+
+def main():
+    args = parse()
+    import tcl_b200 as tcl
+    if args.impl == "reference":
+        return run_reference(args, tcl)
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the product path has no CPU fallback (use --impl reference for the CPU arm)")
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    device = torch.device("cuda", local)
+    torch.cuda.set_device(device)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=device)
+    tcl._cabi.lib()  # fail loudly now if the CUDA extension is missing
+
+    cfg = tcl.synth.CONFIGS[args.workload]
+    H, W, C = cfg["H"], cfg["W"], cfg["C"]
+    dtype = cfg["dtype"]
+    # weak scaling: every rank owns one workload-sized shard of pairs (for sintel_full: all 23 sequences)
+    if args.workload == "sintel_full":
+        pairs_in_seq = tcl.sharding.pairs_per_sequence(tcl.synth.SINTEL_TRAIN_FRAMES)
+    else:
+        pairs_in_seq = [cfg["pairs"]]
+    n_local = args.pairs or sum(pairs_in_seq)
+    if args.pairs:
+        pairs_in_seq = [args.pairs]
+    n_seq = len(pairs_in_seq)
+    seq_of_pair = torch.tensor([s for s, n in enumerate(pairs_in_seq) for _ in range(n)], dtype=torch.long, device=device)
+    shard = make_shard(tcl, args.workload, n_local, 1234 + 2000 + 100000 * rank, device, args.frames)
+    torch.cuda.synchronize()
+
+    launches = [0]
+    last = {}
+
+    def step():
+        out = tcl.evaluate_sharded(shard["ff"], shard["bf"], shard["prev"], shard["cur"], seq_of_pair, n_seq)
+        launches[0] += 1
+        last["out"] = out
+
+    def kernel_only():
+        tcl.fused_forward(shard["bf"], shard["prev"], shard["cur"], ff=shard["ff"])
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    torch.cuda.synchronize()
+    if dist:
+        dist.barrier()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches[0] = 0
+    start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    start.record()
+    for _ in range(args.steps):
+        step()
+    end.record()
+    torch.cuda.synchronize()
+    if dist:
+        dist.barrier()
+    torch.cuda.synchronize()
+    elapsed_ms = start.elapsed_time(end)
+    # dominant kernel alone, same inputs, CUDA events per launch (the roofline numerator)
+    _, per = time_kernel(kernel_only, args.steps, 1)
+    clocks = sampler.stop() if rank == 0 else None
+    k_ms = sum(per) / len(per)
+    if dist:
+        t = torch.tensor([elapsed_ms, k_ms], device=device, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        elapsed_ms, k_ms = float(t[0]), float(t[1])
+    total_pairs = n_local * world * args.steps
+    pairs_per_s = total_pairs / (elapsed_ms / 1e3)
+    peak, peak_src = load_peaks()
+    bpp = BYTES_PER_PX[dtype]
+    alg_bytes = n_local * H * W * bpp
+    achieved = alg_bytes / (k_ms / 1e3) / 1e9
+    res = last["out"]
+    line = {
+        "metric": "warped frame-pairs/sec", "value": pairs_per_s, "unit": "pairs/s",
+        "gpix_per_s": pairs_per_s * H * W / 1e9,
+        "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": elapsed_ms / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32" if dtype == "fp32" else "bf16 frames / f32 flows+math", "data": "synthetic",
+        "config": {"workload": args.workload, "shape": f"{W}x{H}", "channels": C, "pairs_per_gpu_per_step": n_local,
+                   "sequences": n_seq, "frames": args.frames, "sharding": "by frame pair, one all-reduce of packed sums per step",
+                   "l2": "inputs (%.1f GB per GPU) are larger than L2, no flush needed" % (alg_bytes / 1e9)},
+        "gpu_launches": launches[0],
+        "result_check": {"mean_over_sequences_rmse": float(res["mean_over_sequences"]), "pooled_rmse": float(res["pooled_rmse"]),
+                         "n_pairs": int(res["n_pairs"])},
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": None, "peak_source": peak_src, "kernel": "tcl::fused_forward_kernel",
+                     "kernel_ms_per_launch": k_ms, "algorithmic_bytes_per_launch": alg_bytes, "bytes_per_px": bpp,
+                     "frac_of_nominal_8TBs": achieved / 8000.0},
+        "clocks": clocks,
+    }
+    if not args.no_extras:
+        try:
+            if dist:
+                dist.barrier()
+            e = e2e_rate(tcl, shard, n_local, max(3, args.steps // 2), 2, device)
+            if dist:  # whole-job rate = all ranks' pairs over the slowest rank's time
+                t = torch.tensor([e["ms_per_step"]], device=device, dtype=torch.float64)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                e["ms_per_step"] = float(t[0])
+                e["value"] = n_local * world / (e["ms_per_step"] / 1e3)
+                e["h2d_bytes_per_step"] *= world
+                e["d2h_bytes_per_step"] *= world
+            line["e2e"] = e
+        except Exception as ex:
+            line["e2e"] = {"error": repr(ex)}
+        del shard
+        torch.cuda.empty_cache()
+        if world == 1:
+            line["cpu_baseline"] = cpu_reference_rate(tcl, args.workload, args.frames, args.cpu_seconds)
+            line["other_workloads"] = other_workloads(tcl, device, args.frames, peak)
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if dist:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

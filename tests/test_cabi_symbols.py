@@ -1,0 +1,90 @@
+"""CPU suite: the C-ABI shared library builds, loads and exports every symbol include/*.h declares.
+No compute is attempted here (no GPU); argument validation that happens before any CUDA call is."""
+import ctypes
+import glob
+import os
+import re
+
+import pytest
+
+from conftest import ROOT
+
+
+def declared_symbols():
+    names = set()
+    for h in glob.glob(os.path.join(ROOT, "include", "*.h")):
+        text = re.sub(r"/\*.*?\*/", "", open(h).read(), flags=re.S)
+        names |= set(re.findall(r"\b(tclb200_[a-z0-9_]+)\s*\(", text))
+    return sorted(names)
+
+
+def test_header_declares_the_expected_entry_points():
+    syms = declared_symbols()
+    for s in ("tclb200_abi_version", "tclb200_last_error", "tclb200_scratch_bytes", "tclb200_gradient", "tclb200_warp",
+              "tclb200_warp_backward", "tclb200_fbcheck", "tclb200_tcl_forward", "tclb200_tcl_backward"):
+        assert s in syms
+
+
+def test_library_exports_every_declared_symbol(tcl):
+    handle = ctypes.CDLL(tcl._cabi.LIB_PATH)
+    for s in declared_symbols():
+        assert hasattr(handle, s), f"{s} declared in include/ but not exported"
+    assert set(tcl._cabi.exported_symbols()) <= set(declared_symbols())
+    assert tcl._cabi.lib().tclb200_abi_version() == tcl._cabi.ABI_VERSION
+
+
+def test_header_version_matches_wrappers(tcl):
+    text = open(os.path.join(ROOT, "include", "tcl_b200.h")).read()
+    assert int(re.search(r"#define TCLB200_ABI_VERSION (\d+)", text).group(1)) == tcl._cabi.ABI_VERSION
+    for name in ("F32", "BF16", "OCC", "MOB", "VALIDITY", "L2", "L1", "FIN_MEAN", "FIN_RMSE"):
+        assert int(re.search(rf"#define TCLB200_{name} (\d+)", text).group(1)) == getattr(tcl._cabi, name)
+
+
+def test_struct_layout_matches_header(tcl):
+    text = open(os.path.join(ROOT, "include", "tcl_b200.h")).read()
+    body = re.search(r"typedef struct tclb200_tcl_args \{(.*?)\} tclb200_tcl_args;", text, re.S).group(1)
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    fields = []
+    for decl in body.split(";"):
+        decl = decl.strip()
+        if not decl:
+            continue
+        names = decl.split(",")
+        first = re.findall(r"[A-Za-z_][A-Za-z0-9_]*", names[0])[-1]
+        fields.append(first)
+        fields += [n.strip().lstrip("*").strip() for n in names[1:]]
+    assert fields == [f[0] for f in tcl._cabi.TclArgs._fields_]
+
+
+def test_argument_validation_without_gpu(tcl):
+    lib = tcl._cabi.lib()
+    assert lib.tclb200_scratch_bytes(0, 10, 10) == 0
+    assert lib.tclb200_scratch_bytes(16, 256, 256) > 0
+    assert lib.tclb200_tcl_forward(None, None) == 1                      # TCLB200_ERR_INVALID
+    assert b"NULL" in lib.tclb200_last_error()
+    assert lib.tclb200_gradient(None, None, 1, 4, 4, None) == 1
+    assert lib.tclb200_warp(None, None, None, 1, 3, 4, 4, 0, 0, None) == 1
+    assert lib.tclb200_fbcheck(None, None, None, 1, 4, 4, 3, None, None) == 1
+    a = tcl._cabi.TclArgs()
+    a.B, a.C, a.H, a.W = 1, 3, 0, 4
+    assert lib.tclb200_tcl_forward(ctypes.byref(a), None) == 1
+    a.H = 4
+    assert lib.tclb200_tcl_forward(ctypes.byref(a), None) == 1           # bf missing
+    assert b"bf" in lib.tclb200_last_error()
+
+
+def test_missing_library_fails_loudly(tcl, monkeypatch):
+    monkeypatch.setattr(tcl._cabi, "_lib", None)
+    monkeypatch.setattr(tcl._cabi, "LIB_PATH", os.path.join(ROOT, "does", "not", "exist.so"))
+    with pytest.raises(tcl._cabi.TclB200Error):
+        tcl._cabi.lib()
+
+
+def test_product_package_never_touches_the_oracle():
+    pkg = os.path.join(ROOT, "gan-based-video-style-transfer_b200")
+    for path in glob.glob(os.path.join(pkg, "**", "*"), recursive=True):
+        if os.path.isfile(path) and path.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
+            src = open(path).read()
+            assert "import oracle" not in src and "from oracle" not in src and "tcl_oracle" not in src, path
+            if path.endswith(".py"):
+                assert "grid_sample(" not in src, f"{path}: the product path must not fall back to F.grid_sample"
