@@ -23,6 +23,7 @@ FIN_MEAN, FIN_RMSE = 0, 1
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
 SOURCES = ["tcl_kernels.cu"]
+HEADERS = ["tcl_math.cuh", "tcl_common.cuh"]
 
 
 class TclArgs(ctypes.Structure):
@@ -43,7 +44,7 @@ class TclArgs(ctypes.Structure):
 def build(force=False, verbose=False):
     """nvcc the kernels for sm_100a, in-tree (cross-compiles without a GPU)."""
     srcs = [os.path.join(CSRC, s) for s in SOURCES]
-    deps = srcs + [os.path.join(CSRC, "tcl_math.cuh"), HEADER]
+    deps = srcs + [os.path.join(CSRC, h) for h in HEADERS] + [HEADER]
     if (not force and os.path.exists(LIB_PATH)
             and all(os.path.getmtime(LIB_PATH) >= os.path.getmtime(d) for d in deps)):
         return LIB_PATH
@@ -64,6 +65,7 @@ _PROTOTYPES = {
     "tclb200_fbcheck": (_c.c_int, [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp]),
     "tclb200_tcl_forward": (_c.c_int, [_c.POINTER(TclArgs), _vp]),
     "tclb200_tcl_backward": (_c.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
+    "tclb200_debug_force_generic": (None, [_i]),
 }
 
 _lib = None

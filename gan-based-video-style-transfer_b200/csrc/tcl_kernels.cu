@@ -5,372 +5,357 @@
 // methods/learning-based/fs_lib.py:5-39, utils/sintel_eval.py:104-110, utils/metrics/eval.py:137-138,
 // methods/GAN-based/StarGANv2AdvCon/core/solver.py:427-446 of the upstream repository.
 //
-// Layout in HBM: planar NCHW, fp32 flows/masks, fp32 or bf16 frames.  A CTA owns a TW x TH tile of
-// one frame pair; a warp owns one tile row and each lane PX consecutive pixels, so every streaming
-// access (bf, cur, mask, outputs) is one 16-byte vector per lane and 512 contiguous bytes per warp.
-// The data-dependent bilinear taps of `ff` and `prev` go through the read-only L1/L2 path.
-// The masked error is reduced lane -> warp (shuffles) -> CTA (smem) -> pair -> batch with
-// self-resetting tickets, in a fixed order (deterministic), inside the same launch.
-// HBM-bound: no tensor cores, nothing here is a contraction.
+// Data layout in HBM: planar NCHW, fp32 flows/masks, fp32 or bf16 frames.
+//
+// fused_forward_tma_kernel (the hot kernel).  A CTA owns a TW x TH tile of one frame pair.
+//   phase A  one TMA box brings the tile of the backward flow `bf` (+1 px halo, zero-filled outside the
+//            image = the zero padding of flowtools.gradient) into shared memory; every lane derives its
+//            pixels' sampling positions and the motion-boundary test, and the CTA reduces the bounding box
+//            of all bilinear taps (warp redux + shared-memory atomics).
+//   phase B  two TMA boxes bring exactly that source region of `ff` (2 planes) and `prev` (C planes) into
+//            shared memory -- the box origin follows the flow, its size is fixed (BW x BH), out-of-image
+//            parts are zero-filled = grid_sample's padding_mode='zeros'.  The 4*(2+C) taps per pixel are then
+//            unit-stride, bank-conflict-free shared-memory reads.  Lanes own pixels x = lane + 32k, so every
+//            global access (cur, mask, outputs) is a fully coalesced 128-byte line per warp instruction.
+//   tiles whose taps do not fit the box (motion boundaries, extreme flows, non-finite values) take the
+//   exact predicated global-gather path for that tile only.
+//   reduction: lane -> warp shuffle -> CTA -> pair -> batch inside the same launch (tickets, fixed order).
+// fused_forward_generic_kernel covers shapes TMA cannot describe (W % 4 != 0, unaligned views, C != 3).
+// HBM-bound integer-free fp32 streaming + gather: no tensor cores, nothing here is a contraction.
+#include <cuda.h>
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
+#include <limits.h>
 #include <stdint.h>
 #include <stdio.h>
 #include <string.h>
 
 #include "../../include/tcl_b200.h"
+#include "tcl_common.cuh"
 #include "tcl_math.cuh"
 
 namespace tcl {
 
-constexpr int kV = V_ATEN_CUDA;  // arithmetic flavour of the product kernels (see tcl_math.cuh)
-constexpr int kWarps = 8;        // warps per CTA = tile rows
-constexpr int kThreads = 32 * kWarps;
-constexpr float kNearBand = 1e-6f;
-
 // ---------------------------------------------------------------------------------------------
-// vector I/O: N consecutive elements of T <-> fp32 registers, in the widest aligned chunks
+// per-pixel pieces shared by both forward kernels
 // ---------------------------------------------------------------------------------------------
-enum class Ld { Default, Stream };
-
-template <int BYTES> struct Chunk;
-template <> struct Chunk<16> { using type = uint4; };
-template <> struct Chunk<8> { using type = uint2; };
-template <> struct Chunk<4> { using type = uint32_t; };
-template <> struct Chunk<2> { using type = uint16_t; };
-
-template <typename T, int N>
-struct Raw {
-  static constexpr int kBytes = N * (int)sizeof(T);
-  static constexpr int kChunk = (kBytes % 16 == 0) ? 16 : (kBytes % 8 == 0) ? 8 : (kBytes % 4 == 0) ? 4 : 2;
-  using chunk_t = typename Chunk<kChunk>::type;
-  static constexpr int kCount = kBytes / kChunk;
-  union {
-    chunk_t c[kCount];
-    T e[N];
-  };
+struct PixTaps {   // four bilinear taps of one target pixel
+  int x0, y0;
+  float nw, ne, sw, se;
 };
 
-template <typename T, int N, Ld MODE = Ld::Default>
-__device__ __forceinline__ void load_vec(const T* __restrict__ p, float (&out)[N]) {
-  Raw<T, N> r;
-  using chunk_t = typename Raw<T, N>::chunk_t;
-  const chunk_t* q = reinterpret_cast<const chunk_t*>(p);
-#pragma unroll
-  for (int i = 0; i < Raw<T, N>::kCount; ++i) r.c[i] = (MODE == Ld::Stream) ? __ldcs(q + i) : __ldg(q + i);
-#pragma unroll
-  for (int i = 0; i < N; ++i) out[i] = to_f32(r.e[i]);
+__device__ __forceinline__ PixTaps pix_taps(float u, float v, int x, int y, const Geo& g) {
+  const float ix = source_coord(x, u, g.Wf, g.dxf, g.inv_dx, kV);
+  const float iy = source_coord(y, v, g.Hf, g.dyf, g.inv_dy, kV);
+  PixTaps t;
+  t.x0 = __float2int_rd(ix);  // = static_cast<int>(::floor(ix)): saturating, NaN -> 0
+  t.y0 = __float2int_rd(iy);
+  const float fx1 = __fsub_rn((float)(int)((unsigned)t.x0 + 1u), ix), fx0 = __fsub_rn(ix, (float)t.x0);
+  const float fy1 = __fsub_rn((float)(int)((unsigned)t.y0 + 1u), iy), fy0 = __fsub_rn(iy, (float)t.y0);
+  t.nw = __fmul_rn(fx1, fy1); t.ne = __fmul_rn(fx0, fy1);
+  t.sw = __fmul_rn(fx1, fy0); t.se = __fmul_rn(fx0, fy0);
+  return t;
 }
 
-__device__ __forceinline__ void from_f32(float v, float& o) { o = v; }
-__device__ __forceinline__ void from_f32(float v, __nv_bfloat16& o) { o = __float2bfloat16_rn(v); }
-
-template <typename T, int N>
-__device__ __forceinline__ void store_vec(T* __restrict__ p, const float (&v)[N]) {
-  Raw<T, N> r;
-  using chunk_t = typename Raw<T, N>::chunk_t;
-#pragma unroll
-  for (int i = 0; i < N; ++i) from_f32(v[i], r.e[i]);
-  chunk_t* q = reinterpret_cast<chunk_t*>(p);
-#pragma unroll
-  for (int i = 0; i < Raw<T, N>::kCount; ++i) __stcs(q + i, r.c[i]);
+__device__ __forceinline__ Taps full_taps(const PixTaps& s, const Geo& g) {
+  Taps t;
+  const int x1 = (int)((unsigned)s.x0 + 1u), y1 = (int)((unsigned)s.y0 + 1u);
+  const bool xin0 = (unsigned)s.x0 < (unsigned)g.W, xin1 = (unsigned)x1 < (unsigned)g.W;
+  const bool yin0 = (unsigned)s.y0 < (unsigned)g.H, yin1 = (unsigned)y1 < (unsigned)g.H;
+  t.p00 = xin0 && yin0; t.p10 = xin1 && yin0; t.p01 = xin0 && yin1; t.p11 = xin1 && yin1;
+  t.o00 = (int)((unsigned)s.y0 * (unsigned)g.W + (unsigned)s.x0);
+  t.nw = s.nw; t.ne = s.ne; t.sw = s.sw; t.se = s.se;
+  return t;
 }
 
-// ---------------------------------------------------------------------------------------------
-// reductions
-// ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ float warp_sum(float v) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-  return v;
-}
-__device__ __forceinline__ double warp_sum(double v) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-  return v;
-}
-__device__ __forceinline__ unsigned warp_sum(unsigned v) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-  return v;
-}
-
-// fixed-order CTA sum of per-thread doubles; result valid in thread 0
-__device__ __forceinline__ double block_sum(double v, double* smem /*[kWarps]*/) {
-  v = warp_sum(v);
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  __syncthreads();
-  if (lane == 0) smem[w] = v;
-  __syncthreads();
-  double s = 0.0;
-  if (threadIdx.x == 0) {
-#pragma unroll
-    for (int i = 0; i < kWarps; ++i) s += smem[i];
+// source planes in global memory: exact predicated gather (grid_sampler_2d skips out-of-image taps)
+template <typename T>
+struct GlobalSrc {
+  const T* base;   // plane 0 of this pair
+  size_t plane;
+  Geo g;
+  __device__ __forceinline__ float sample(int c, const PixTaps& s) const {
+    return sample_global(base + (size_t)c * plane, full_taps(s, g), g.W, kV);
   }
-  return s;
-}
-
-struct Scratch {
-  double* partials;        // [B * tiles_per_pair]
-  unsigned* pair_ticket;   // [B]
-  unsigned* batch_ticket;  // [1]
 };
 
-__host__ __device__ inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
-
-// ---------------------------------------------------------------------------------------------
-// fused forward
-// ---------------------------------------------------------------------------------------------
-struct FwdParams {
-  const float* ff;
-  const float* bf;
-  const float* mask_in;
-  const void* prev;
-  const void* cur;
-  void* warp_out;
-  float* mask_out;
-  void* blend_out;
-  double* pair_sums;
-  double* total_sums;
-  float* pair_vals;
-  float* total_val;
-  unsigned long long* near_threshold;
-  Scratch scratch;
-  Geo geo;
-  int B, C;
-  int tiles_x, tiles_per_pair;
-  int flags, loss, finalize;
-  double inv_count;  // 1/(C*H*W)
+// source box in shared memory, origin (ox,oy), zero-filled outside the image: all four taps are plain reads.
+// fma(0, w, acc) == acc for the finite weights of an in-box pixel, so this equals the predicated form.
+template <typename T, int PITCH, int CH_STRIDE>
+struct SmemSrc {
+  const T* base;
+  int ox, oy;
+  __device__ __forceinline__ float sample(int c, const PixTaps& s) const {
+    const T* q = base + c * CH_STRIDE + (s.y0 - oy) * PITCH + (s.x0 - ox);
+    float acc = __fmul_rn(to_f32(q[0]), s.nw);
+    acc = __fmaf_rn(to_f32(q[1]), s.ne, acc);
+    acc = __fmaf_rn(to_f32(q[PITCH]), s.sw, acc);
+    acc = __fmaf_rn(to_f32(q[PITCH + 1]), s.se, acc);
+    return acc;
+  }
 };
 
-enum : int { MASK_NONE = 0, MASK_GIVEN = 1, MASK_COMPUTED = 2 };
+template <typename FrameT>
+struct PairPtrs {
+  const FrameT* cur;
+  FrameT* wout;
+  FrameT* bout;
+};
 
-__device__ __forceinline__ float finalise_value(double mean, int finalize) {
-  return (float)(finalize == TCLB200_FIN_RMSE ? sqrt(mean) : mean);
+// everything that happens to one pixel once its taps and motion-boundary verdict are known
+template <typename FrameT, int MASK, bool REDUCE, int CT, typename FlowSrc, typename FrameSrc>
+__device__ __forceinline__ void finish_pixel(const FwdParams& p, const PixTaps& s, float u, float v, float keep, size_t o,
+                                             size_t plane, int pair, const FlowSrc& fsrc, const FrameSrc& psrc,
+                                             const PairPtrs<FrameT>& io, float& err, unsigned& near) {
+  if (MASK == MASK_COMPUTED && (p.flags & TCLB200_OCC)) {
+    const float wu = fsrc.sample(0, s), wv = fsrc.sample(1, s);
+    float margin;
+    if (occluded(wu, wv, u, v, sqnorm2(u, v, kV), kV, &margin)) keep = 0.0f;
+    near += fabsf(margin) < kNearBand;
+  }
+  if (p.mask_out) __stcs(p.mask_out + (size_t)pair * plane + o, keep);
+  if (p.prev == nullptr) return;
+  float valid = 1.0f;
+  if (p.flags & TCLB200_VALIDITY) valid = binarise_validity(ones_sample(full_taps(s, p.geo), kV));
+  const int C = CT > 0 ? CT : p.C;
+#pragma unroll
+  for (int c = 0; c < C; ++c) {
+    float w = psrc.sample(c, s);
+    if (p.flags & TCLB200_VALIDITY) w = __fmul_rn(w, valid);
+    if (io.wout) st_stream(io.wout + (size_t)c * plane + o, w);
+    if (io.cur) {
+      const float cv = ld_stream(io.cur + (size_t)c * plane + o);
+      if (REDUCE) {
+        if (p.loss == TCLB200_L2) {
+          const float md = __fmul_rn(keep, __fsub_rn(cv, w));   // mask*(cur - warp)   sintel_eval.py:110
+          err = __fmaf_rn(md, md, err);
+        } else {
+          err += __fmul_rn(keep, fabsf(__fsub_rn(w, cv)));      // mask*|warp - cur|   MoGAN cycle_gan_model.py:281
+        }
+      }
+      if (io.bout)                                              // m*warp + (1-m)*img   obst_eval.py:500
+        st_stream(io.bout + (size_t)c * plane + o, __fadd_rn(__fmul_rn(keep, w), __fmul_rn(__fsub_rn(1.0f, keep), cv)));
+    }
+  }
 }
 
-// FrameT: float / __nv_bfloat16.  PX: pixels per lane (vector width).  MASK: where the mask comes from.
-// REDUCE: accumulate the masked error.  CT: compile-time channel count (0 = runtime loop).
-template <typename FrameT, int PX, int MASK, bool REDUCE, int CT>
-__global__ void __launch_bounds__(kThreads) fused_forward_kernel(const FwdParams p) {
+template <typename FrameT>
+__device__ __forceinline__ PairPtrs<FrameT> pair_ptrs(const FwdParams& p, int pair, int C, size_t plane) {
+  PairPtrs<FrameT> io;
+  const size_t off = (size_t)pair * C * plane;
+  io.cur = p.cur ? reinterpret_cast<const FrameT*>(p.cur) + off : nullptr;
+  io.wout = p.warp_out ? reinterpret_cast<FrameT*>(p.warp_out) + off : nullptr;
+  io.bout = p.blend_out ? reinterpret_cast<FrameT*>(p.blend_out) + off : nullptr;
+  return io;
+}
+
+// ---------------------------------------------------------------------------------------------
+// generic forward kernel: one pixel per lane, everything straight from global memory
+// ---------------------------------------------------------------------------------------------
+template <typename FrameT, int MASK, bool REDUCE, int CT>
+__global__ void __launch_bounds__(kThreads) fused_forward_generic_kernel(const FwdParams p) {
   const Geo& g = p.geo;
   const int W = g.W, H = g.H;
   const size_t plane = (size_t)H * W;
   const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
-  const unsigned bid = blockIdx.x;
-  const int pair = bid / p.tiles_per_pair;
-  const int tile = bid - pair * p.tiles_per_pair;
+  const int pair = blockIdx.x / p.tiles_per_pair;
+  const int tile = blockIdx.x - pair * p.tiles_per_pair;
   const int ty = tile / p.tiles_x, tx = tile - ty * p.tiles_x;
-  const int x = (tx * 32 + lane) * PX;
-  const int y = ty * kWarps + wrp;
-  const bool active = (x < W) && (y < H);  // W % PX == 0 is guaranteed by the launcher
+  const int x = tx * 32 + lane, y = ty * kWarps + wrp;
   const int C = CT > 0 ? CT : p.C;
-
   float err = 0.0f;
   unsigned near = 0;
-
-  if (active) {
+  if (x < W && y < H) {
     const size_t o = (size_t)y * W + x;
     const float* bu = p.bf + (size_t)pair * 2 * plane;
     const float* bv = bu + plane;
-    float u[PX], v[PX], keep[PX];
-    load_vec<float, PX>(bu + o, u);
-    load_vec<float, PX>(bv + o, v);
-#pragma unroll
-    for (int i = 0; i < PX; ++i) keep[i] = 1.0f;
-
-    if (MASK == MASK_GIVEN) load_vec<float, PX, Ld::Stream>(p.mask_in + (size_t)pair * plane + o, keep);
-
+    const float u = __ldg(bu + o), v = __ldg(bv + o);
+    float keep = 1.0f;
+    if (MASK == MASK_GIVEN) keep = __ldcs(p.mask_in + (size_t)pair * plane + o);
     if (MASK == MASK_COMPUTED && (p.flags & TCLB200_MOB)) {
-      // zero-padded central differences of the backward flow (flowtools.py:12-16,47-53)
-      float uu[PX], ud[PX], vu[PX], vd[PX];
-      if (y > 0) { load_vec<float, PX>(bu + o - W, uu); load_vec<float, PX>(bv + o - W, vu); }
-      else {
-#pragma unroll
-        for (int i = 0; i < PX; ++i) uu[i] = vu[i] = 0.0f;
-      }
-      if (y + 1 < H) { load_vec<float, PX>(bu + o + W, ud); load_vec<float, PX>(bv + o + W, vd); }
-      else {
-#pragma unroll
-        for (int i = 0; i < PX; ++i) ud[i] = vd[i] = 0.0f;
-      }
-      const float ul_edge = x > 0 ? __ldg(bu + o - 1) : 0.0f, vl_edge = x > 0 ? __ldg(bv + o - 1) : 0.0f;
-      const float ur_edge = x + PX < W ? __ldg(bu + o + PX) : 0.0f, vr_edge = x + PX < W ? __ldg(bv + o + PX) : 0.0f;
-#pragma unroll
-      for (int i = 0; i < PX; ++i) {
-        const float ul = i > 0 ? u[i > 0 ? i - 1 : 0] : ul_edge, ur = i + 1 < PX ? u[i + 1 < PX ? i + 1 : 0] : ur_edge;
-        const float vl = i > 0 ? v[i > 0 ? i - 1 : 0] : vl_edge, vr = i + 1 < PX ? v[i + 1 < PX ? i + 1 : 0] : vr_edge;
-        const float nb = sqnorm2(u[i], v[i], kV);
-        float margin;
-        if (motion_boundary(ul, ur, uu[i], ud[i], vl, vr, vu[i], vd[i], nb, kV, &margin)) keep[i] = 0.0f;
-        near += fabsf(margin) < kNearBand;
-      }
+      const float ul = x > 0 ? __ldg(bu + o - 1) : 0.0f, ur = x + 1 < W ? __ldg(bu + o + 1) : 0.0f;
+      const float uu = y > 0 ? __ldg(bu + o - W) : 0.0f, ud = y + 1 < H ? __ldg(bu + o + W) : 0.0f;
+      const float vl = x > 0 ? __ldg(bv + o - 1) : 0.0f, vr = x + 1 < W ? __ldg(bv + o + 1) : 0.0f;
+      const float vu = y > 0 ? __ldg(bv + o - W) : 0.0f, vd = y + 1 < H ? __ldg(bv + o + W) : 0.0f;
+      float margin;
+      if (motion_boundary(ul, ur, uu, ud, vl, vr, vu, vd, sqnorm2(u, v, kV), kV, &margin)) keep = 0.0f;
+      near += fabsf(margin) < kNearBand;
     }
-
-    Taps t[PX];
-    const bool need_taps = (MASK == MASK_COMPUTED && (p.flags & TCLB200_OCC)) || p.prev != nullptr;
-    if (need_taps) {
-#pragma unroll
-      for (int i = 0; i < PX; ++i) t[i] = make_taps(u[i], v[i], x + i, y, g, kV);
-    }
-
-    if (MASK == MASK_COMPUTED && (p.flags & TCLB200_OCC)) {
-      const float* fu = p.ff + (size_t)pair * 2 * plane;
-      const float* fv = fu + plane;
-      float wu[PX], wv[PX];
-#pragma unroll
-      for (int i = 0; i < PX; ++i) { wu[i] = sample_global(fu, t[i], W, kV); wv[i] = sample_global(fv, t[i], W, kV); }
-#pragma unroll
-      for (int i = 0; i < PX; ++i) {
-        const float nb = sqnorm2(u[i], v[i], kV);
-        float margin;
-        if (occluded(wu[i], wv[i], u[i], v[i], nb, kV, &margin)) keep[i] = 0.0f;
-        near += fabsf(margin) < kNearBand;
-      }
-    }
-
-    if (p.mask_out) store_vec<float, PX>(p.mask_out + (size_t)pair * plane + o, keep);
-
-    if (p.prev != nullptr) {
-      float valid[PX];
-      if (p.flags & TCLB200_VALIDITY) {
-#pragma unroll
-        for (int i = 0; i < PX; ++i) valid[i] = binarise_validity(ones_sample(t[i], kV));
-      }
-      const FrameT* prev = reinterpret_cast<const FrameT*>(p.prev) + (size_t)pair * C * plane;
-      const FrameT* cur = p.cur ? reinterpret_cast<const FrameT*>(p.cur) + (size_t)pair * C * plane + o : nullptr;
-      FrameT* wout = p.warp_out ? reinterpret_cast<FrameT*>(p.warp_out) + (size_t)pair * C * plane + o : nullptr;
-      FrameT* bout = p.blend_out ? reinterpret_cast<FrameT*>(p.blend_out) + (size_t)pair * C * plane + o : nullptr;
-#pragma unroll
-      for (int c = 0; c < C; ++c) {
-        const FrameT* pl = prev + (size_t)c * plane;
-        float w[PX];
-#pragma unroll
-        for (int i = 0; i < PX; ++i) w[i] = sample_global(pl, t[i], W, kV);
-        if (p.flags & TCLB200_VALIDITY) {
-#pragma unroll
-          for (int i = 0; i < PX; ++i) w[i] = __fmul_rn(w[i], valid[i]);
-        }
-        if (wout) store_vec<FrameT, PX>(wout + (size_t)c * plane, w);
-        if (cur) {
-          float cv[PX];
-          load_vec<FrameT, PX, Ld::Stream>(cur + (size_t)c * plane, cv);
-          if (REDUCE) {
-#pragma unroll
-            for (int i = 0; i < PX; ++i) {
-              if (p.loss == TCLB200_L2) {
-                const float md = __fmul_rn(keep[i], __fsub_rn(cv[i], w[i]));  // mask*(cur - warp)
-                err = __fmaf_rn(md, md, err);
-              } else {
-                err += __fmul_rn(keep[i], fabsf(__fsub_rn(w[i], cv[i])));    // mask*|warp - cur|
-              }
-            }
-          }
-          if (bout) {
-            float bl[PX];
-#pragma unroll
-            for (int i = 0; i < PX; ++i)
-              bl[i] = __fadd_rn(__fmul_rn(keep[i], w[i]), __fmul_rn(__fsub_rn(1.0f, keep[i]), cv[i]));
-            store_vec<FrameT, PX>(bout + (size_t)c * plane, bl);
-          }
-        }
-      }
-    }
+    const PixTaps s = pix_taps(u, v, x, y, g);
+    GlobalSrc<float> fsrc{p.ff ? p.ff + (size_t)pair * 2 * plane : nullptr, plane, g};
+    GlobalSrc<FrameT> psrc{p.prev ? reinterpret_cast<const FrameT*>(p.prev) + (size_t)pair * C * plane : nullptr, plane, g};
+    finish_pixel<FrameT, MASK, REDUCE, CT>(p, s, u, v, keep, o, plane, pair, fsrc, psrc, pair_ptrs<FrameT>(p, pair, C, plane), err, near);
   }
-
-  if (p.near_threshold != nullptr) {
-    near = warp_sum(near);
-    if (lane == 0 && near) atomicAdd(p.near_threshold, (unsigned long long)near);
-  }
-
-  if (REDUCE) {
-    __shared__ double red[kWarps];
-    __shared__ int s_last;
-    const double bsum = block_sum((double)err, red);
-    const unsigned tpp = p.tiles_per_pair;
-    if (threadIdx.x == 0) {
-      __stcg(&p.scratch.partials[(size_t)pair * tpp + tile], bsum);
-      __threadfence();
-      const unsigned tk = atomicAdd(&p.scratch.pair_ticket[pair], 1u);
-      s_last = (tk == tpp - 1);
-    }
-    __syncthreads();
-    if (s_last) {
-      // last CTA of this pair: fold the pair's tile partials in a fixed order
-      __threadfence();
-      double s = 0.0;
-      const double* pp = p.scratch.partials + (size_t)pair * tpp;
-      for (unsigned i = threadIdx.x; i < tpp; i += kThreads) s += __ldcg(pp + i);
-      const double S = block_sum(s, red);
-      if (threadIdx.x == 0) {
-        const float val = finalise_value(S * p.inv_count, p.finalize);
-        if (p.pair_sums) p.pair_sums[pair] = S;
-        if (p.pair_vals) p.pair_vals[pair] = val;
-        // reuse partials[pair*tpp] / [pair*tpp+1] as this pair's (S, val) record for the batch fold
-        __stcg(&p.scratch.partials[(size_t)pair * tpp], S);
-        p.scratch.pair_ticket[pair] = 0;
-        __threadfence();
-        const unsigned tk = atomicAdd(p.scratch.batch_ticket, 1u);
-        s_last = (tk == (unsigned)p.B - 1) ? 2 : 1;
-      }
-      __syncthreads();
-      if (s_last == 2) {
-        __threadfence();
-        double a = 0.0, b = 0.0;
-        for (int i = threadIdx.x; i < p.B; i += kThreads) {
-          const double Si = __ldcg(p.scratch.partials + (size_t)i * tpp);
-          a += Si;
-          b += (double)finalise_value(Si * p.inv_count, p.finalize);
-        }
-        const double A = block_sum(a, red);
-        const double Bv = block_sum(b, red);
-        if (threadIdx.x == 0) {
-          if (p.total_sums) { p.total_sums[0] = A; p.total_sums[1] = Bv; }
-          if (p.total_val) *p.total_val = finalise_value(A * p.inv_count / (double)p.B, p.finalize);
-          *p.scratch.batch_ticket = 0;
-        }
-      }
-    }
-  }
+  count_near(near, p.near_threshold);
+  if (REDUCE) reduce_and_finalise(err, p, pair, tile);
 }
 
 // ---------------------------------------------------------------------------------------------
-// gradient(x): zero-padded central differences (flowtools.py:12-16)
+// TMA-staged forward kernel
 // ---------------------------------------------------------------------------------------------
-template <int PX>
-__global__ void __launch_bounds__(kThreads) gradient_kernel(const float* __restrict__ xin, float* __restrict__ out, int B,
-                                                            int H, int W, int tiles_x, int tiles_per_img) {
+template <typename FrameT, int CT, int TW_, int TH_, int BW_, int BH_>
+struct TileCfg {
+  static constexpr int TW = TW_, TH = TH_, BW = BW_, BH = BH_;
+  static constexpr int kBfW = TW + 4, kBfH = TH + 2;          // flow tile + 1 px halo (inner extent kept a 16-byte multiple)
+  static constexpr int kCols = TW / 32, kRows = TH / kWarps;  // pixels per lane: kCols x kRows
+  static constexpr unsigned kBfLoad = 2u * kBfH * kBfW * 4u;
+  static constexpr unsigned kFfLoad = 2u * BH * BW * 4u;
+  static constexpr unsigned kPrevLoad = (unsigned)(CT > 0 ? CT : 0) * BH * BW * (unsigned)sizeof(FrameT);
+  static constexpr size_t kBfOff = 0;
+  static constexpr size_t kFfOff = align_up(kBfLoad, 128);
+  static constexpr size_t kPrevOff = kFfOff + align_up(kFfLoad, 128);
+  static constexpr size_t kBarOff = kPrevOff + align_up(kPrevLoad, 128);
+  static constexpr size_t kSmemBytes = kBarOff + 64;
+  static_assert(TW % 32 == 0 && TH % kWarps == 0, "tile must be a multiple of 32 x 8");
+  static_assert((BW * sizeof(FrameT)) % 16 == 0 && (BW * 4) % 16 == 0, "TMA inner box extent must be a 16-byte multiple");
+  static_assert(BW > TW && BH > TH, "source box must exceed the tile");
+};
+
+template <typename FrameT, int MASK, bool REDUCE, int CT, typename Cfg>
+__global__ void __launch_bounds__(kThreads) fused_forward_tma_kernel(const FwdParams p, const __grid_constant__ CUtensorMap tm_bf,
+                                                                     const __grid_constant__ CUtensorMap tm_ff,
+                                                                     const __grid_constant__ CUtensorMap tm_prev) {
+  constexpr int TW = Cfg::TW, TH = Cfg::TH, BW = Cfg::BW, BH = Cfg::BH;
+  constexpr int NPX = Cfg::kCols * Cfg::kRows;
+  extern __shared__ __align__(128) unsigned char smem[];
+  float* s_bu = reinterpret_cast<float*>(smem + Cfg::kBfOff);  // [2][kBfH][kBfW]
+  float* s_bv = s_bu + Cfg::kBfH * Cfg::kBfW;
+  float* s_ff = reinterpret_cast<float*>(smem + Cfg::kFfOff);  // [2][BH][BW]
+  FrameT* s_prev = reinterpret_cast<FrameT*>(smem + Cfg::kPrevOff);  // [CT][BH][BW]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kBarOff);
+  __shared__ int s_box[4];  // xmin, ymin, xmax, ymax of the top-left taps
+
+  const Geo& g = p.geo;
+  const int W = g.W, H = g.H;
+  const size_t plane = (size_t)H * W;
+  const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
+  const int pair = blockIdx.x / p.tiles_per_pair;
+  const int tile = blockIdx.x - pair * p.tiles_per_pair;
+  const int ty = tile / p.tiles_x, tx = tile - ty * p.tiles_x;
+  const int tile_x0 = tx * TW, tile_y0 = ty * TH;
+  const bool want_occ = MASK == MASK_COMPUTED && (p.flags & TCLB200_OCC);
+  const bool want_frames = CT > 0 && p.prev != nullptr;
+
+  if (threadIdx.x == 0) {
+    mbar_init(&bars[0], 1);
+    mbar_init(&bars[1], 1);
+    fence_barrier_init();
+    s_box[0] = INT_MAX; s_box[1] = INT_MAX; s_box[2] = INT_MIN; s_box[3] = INT_MIN;
+    mbar_expect_tx(&bars[0], Cfg::kBfLoad);
+    tma_load_4d(s_bu, &tm_bf, &bars[0], tile_x0 - 1, tile_y0 - 1, 0, pair);
+  }
+  __syncthreads();
+  mbar_wait(&bars[0], 0);
+
+  // ---- phase A: sampling positions, motion-boundary test, bounding box of the taps
+  PixTaps taps[NPX];
+  float keep[NPX];
+  unsigned near = 0;
+  int bx0 = INT_MAX, by0 = INT_MAX, bx1 = INT_MIN, by1 = INT_MIN;
+#pragma unroll
+  for (int r = 0; r < Cfg::kRows; ++r) {
+#pragma unroll
+    for (int k = 0; k < Cfg::kCols; ++k) {
+      const int i = r * Cfg::kCols + k;
+      const int lx = lane + 32 * k, ly = wrp + kWarps * r;
+      const int x = tile_x0 + lx, y = tile_y0 + ly;
+      const int c = (ly + 1) * Cfg::kBfW + lx + 1;
+      const float u = s_bu[c], v = s_bv[c];
+      keep[i] = 1.0f;
+      if (MASK == MASK_COMPUTED && (p.flags & TCLB200_MOB)) {
+        float margin;
+        if (motion_boundary(s_bu[c - 1], s_bu[c + 1], s_bu[c - Cfg::kBfW], s_bu[c + Cfg::kBfW], s_bv[c - 1], s_bv[c + 1],
+                            s_bv[c - Cfg::kBfW], s_bv[c + Cfg::kBfW], sqnorm2(u, v, kV), kV, &margin))
+          keep[i] = 0.0f;
+        if (x < W && y < H) near += fabsf(margin) < kNearBand;
+      }
+      taps[i] = pix_taps(u, v, x, y, g);
+      if (x < W && y < H) {
+        bx0 = min(bx0, taps[i].x0); bx1 = max(bx1, taps[i].x0);
+        by0 = min(by0, taps[i].y0); by1 = max(by1, taps[i].y0);
+      }
+    }
+  }
+  if (want_occ || want_frames) {
+    bx0 = __reduce_min_sync(0xffffffffu, bx0); by0 = __reduce_min_sync(0xffffffffu, by0);
+    bx1 = __reduce_max_sync(0xffffffffu, bx1); by1 = __reduce_max_sync(0xffffffffu, by1);
+    if (lane == 0) {
+      atomicMin(&s_box[0], bx0); atomicMin(&s_box[1], by0);
+      atomicMax(&s_box[2], bx1); atomicMax(&s_box[3], by1);
+    }
+  }
+  __syncthreads();
+  const int ox = s_box[0], oy = s_box[1];
+  // taps span [x0, x0+1] x [y0, y0+1]; the widths are computed in 64 bits (saturated coordinates)
+  const bool fits = ((long long)s_box[2] + 1 - ox < BW) && ((long long)s_box[3] + 1 - oy < BH);
+  const bool staged = fits && (want_occ || want_frames);
+  if (staged && threadIdx.x == 0) {
+    mbar_expect_tx(&bars[1], (want_occ ? Cfg::kFfLoad : 0u) + (want_frames ? Cfg::kPrevLoad : 0u));
+    if (want_occ) tma_load_4d(s_ff, &tm_ff, &bars[1], ox, oy, 0, pair);
+    if (want_frames) tma_load_4d(s_prev, &tm_prev, &bars[1], ox, oy, 0, pair);
+  }
+
+  // ---- phase B: occlusion test, warp, masked error
+  const PairPtrs<FrameT> io = pair_ptrs<FrameT>(p, pair, CT, plane);
+  float mask_in[NPX];
+  if (MASK == MASK_GIVEN) {   // issued before the wait so the loads overlap the TMA
+#pragma unroll
+    for (int i = 0; i < NPX; ++i) {
+      const int x = tile_x0 + lane + 32 * (i % Cfg::kCols), y = tile_y0 + wrp + kWarps * (i / Cfg::kCols);
+      mask_in[i] = (x < W && y < H) ? __ldcs(p.mask_in + (size_t)pair * plane + (size_t)y * W + x) : 0.0f;
+    }
+  }
+  float err = 0.0f;
+  if (staged) {
+    mbar_wait(&bars[1], 0);
+    const SmemSrc<float, BW, BH * BW> fsrc{s_ff, ox, oy};
+    const SmemSrc<FrameT, BW, BH * BW> psrc{s_prev, ox, oy};
+#pragma unroll
+    for (int i = 0; i < NPX; ++i) {
+      const int lx = lane + 32 * (i % Cfg::kCols), ly = wrp + kWarps * (i / Cfg::kCols);
+      const int x = tile_x0 + lx, y = tile_y0 + ly;
+      if (x < W && y < H) {
+        const int c = (ly + 1) * Cfg::kBfW + lx + 1;
+        finish_pixel<FrameT, MASK, REDUCE, CT>(p, taps[i], s_bu[c], s_bv[c], MASK == MASK_GIVEN ? mask_in[i] : keep[i],
+                                               (size_t)y * W + x, plane, pair, fsrc, psrc, io, err, near);
+      }
+    }
+  } else {
+    const GlobalSrc<float> fsrc{p.ff ? p.ff + (size_t)pair * 2 * plane : nullptr, plane, g};
+    const GlobalSrc<FrameT> psrc{p.prev ? reinterpret_cast<const FrameT*>(p.prev) + (size_t)pair * CT * plane : nullptr, plane, g};
+#pragma unroll
+    for (int i = 0; i < NPX; ++i) {
+      const int lx = lane + 32 * (i % Cfg::kCols), ly = wrp + kWarps * (i / Cfg::kCols);
+      const int x = tile_x0 + lx, y = tile_y0 + ly;
+      if (x < W && y < H) {
+        const int c = (ly + 1) * Cfg::kBfW + lx + 1;
+        finish_pixel<FrameT, MASK, REDUCE, CT>(p, taps[i], s_bu[c], s_bv[c], MASK == MASK_GIVEN ? mask_in[i] : keep[i],
+                                               (size_t)y * W + x, plane, pair, fsrc, psrc, io, err, near);
+      }
+    }
+  }
+  count_near(near, p.near_threshold);
+  if (REDUCE) reduce_and_finalise(err, p, pair, tile);
+}
+
+// ---------------------------------------------------------------------------------------------
+// gradient(x): zero-padded central differences (flowtools.py:12-16); one pixel per lane, coalesced
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads) gradient_kernel(const float* __restrict__ xin, float* __restrict__ out, int B, int H,
+                                                            int W, int tiles_x, int tiles_per_img) {
   const size_t plane = (size_t)H * W;
   const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
   const int img = blockIdx.x / tiles_per_img;
   const int tile = blockIdx.x - img * tiles_per_img;
   const int ty = tile / tiles_x, tx = tile - ty * tiles_x;
-  const int x = (tx * 32 + lane) * PX, y = ty * kWarps + wrp;
+  const int x = tx * 32 + lane, y = ty * kWarps + wrp;
   if (x >= W || y >= H) return;
   const float* src = xin + (size_t)img * plane;
   const size_t o = (size_t)y * W + x;
-  float c[PX], up[PX], dn[PX], dx[PX], dy[PX];
-  load_vec<float, PX>(src + o, c);
-  if (y > 0) load_vec<float, PX>(src + o - W, up);
-  else {
-#pragma unroll
-    for (int i = 0; i < PX; ++i) up[i] = 0.0f;
-  }
-  if (y + 1 < H) load_vec<float, PX>(src + o + W, dn);
-  else {
-#pragma unroll
-    for (int i = 0; i < PX; ++i) dn[i] = 0.0f;
-  }
-  const float l_edge = x > 0 ? __ldg(src + o - 1) : 0.0f;
-  const float r_edge = x + PX < W ? __ldg(src + o + PX) : 0.0f;
-#pragma unroll
-  for (int i = 0; i < PX; ++i) {
-    const float l = i > 0 ? c[i > 0 ? i - 1 : 0] : l_edge, r = i + 1 < PX ? c[i + 1 < PX ? i + 1 : 0] : r_edge;
-    dx[i] = __fmul_rn(__fsub_rn(r, l), 0.5f);
-    dy[i] = __fmul_rn(__fsub_rn(dn[i], up[i]), 0.5f);
-  }
-  store_vec<float, PX>(out + (size_t)img * plane + o, dx);
-  store_vec<float, PX>(out + ((size_t)B + img) * plane + o, dy);
+  const float l = x > 0 ? __ldg(src + o - 1) : 0.0f, r = x + 1 < W ? __ldg(src + o + 1) : 0.0f;
+  const float up = y > 0 ? __ldg(src + o - W) : 0.0f, dn = y + 1 < H ? __ldg(src + o + W) : 0.0f;
+  __stcs(out + (size_t)img * plane + o, __fmul_rn(__fsub_rn(r, l), 0.5f));
+  __stcs(out + ((size_t)B + img) * plane + o, __fmul_rn(__fsub_rn(dn, up), 0.5f));
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -497,30 +482,90 @@ static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 
 extern "C" int tclb200_abi_version(void) { return TCLB200_ABI_VERSION; }
 extern "C" const char* tclb200_last_error(void) { return g_err; }
 
-static inline int tiles_x_for(int W, int px) { return (W + 32 * px - 1) / (32 * px); }
-static inline int tiles_y_for(int H) { return (H + kWarps - 1) / kWarps; }
-// scratch is sized for the narrowest tiling (PX = 1) so any vector width fits
+// tile shape of the TMA kernel: 64 x 16 pixels per CTA, 72 x 24 source box (taps may spread 7 px beyond the
+// tile's own extent in x and y before the tile falls back to global gathers)
+constexpr int kTW = 64, kTH = 16, kBW = 72, kBH = 24;
+
+static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
+// scratch is sized for the finest tiling any kernel uses (32 x 8 generic tiles)
 extern "C" size_t tclb200_scratch_bytes(int B, int H, int W) {
   if (B <= 0 || H <= 0 || W <= 0) return 0;
-  const size_t tpp = (size_t)tiles_x_for(W, 1) * tiles_y_for(H);
+  const size_t tpp = (size_t)cdiv(W, 32) * cdiv(H, kWarps);
   return align_up((size_t)B * tpp * sizeof(double), 256) + align_up(((size_t)B + 1) * sizeof(unsigned), 256);
 }
 
-template <typename FrameT, int PX, int MASK, bool REDUCE>
-static cudaError_t launch_fused(const FwdParams& p, cudaStream_t s) {
+// ---- tensor maps -------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = []() -> EncodeTiledFn {
+    void* sym = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &q) != cudaSuccess) return nullptr;
+    return q == cudaDriverEntryPointSuccess ? reinterpret_cast<EncodeTiledFn>(sym) : nullptr;
+  }();
+  return fn;
+}
+
+// (W, H, planes, B) view of an NCHW tensor with a (bw, bh, bp, 1) box
+static bool make_map(CUtensorMap* m, const void* base, int esize, int W, int H, int planes, int B, int bw, int bh, int bp) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn || !base) return false;
+  const cuuint64_t dims[4] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)planes, (cuuint64_t)B};
+  const cuuint64_t strides[3] = {(cuuint64_t)W * esize, (cuuint64_t)W * H * esize, (cuuint64_t)W * H * planes * esize};
+  const cuuint32_t box[4] = {(cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)bp, 1u};
+  const cuuint32_t estr[4] = {1u, 1u, 1u, 1u};
+  const CUtensorMapDataType dt = esize == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+  return fn(m, dt, 4, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+// ---- launches ----------------------------------------------------------------------------------
+template <typename FrameT, int MASK, bool REDUCE, int CT>
+static cudaError_t launch_tma(const FwdParams& p, const CUtensorMap& tb, const CUtensorMap& tf, const CUtensorMap& tp, cudaStream_t s) {
+  using Cfg = TileCfg<FrameT, CT, kTW, kTH, kBW, kBH>;
+  auto kern = fused_forward_tma_kernel<FrameT, MASK, REDUCE, CT, Cfg>;
+  static bool configured = false;  // per instantiation
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::kSmemBytes);
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
   const unsigned grid = (unsigned)((size_t)p.B * p.tiles_per_pair);
-  if (p.C == 3) fused_forward_kernel<FrameT, PX, MASK, REDUCE, 3><<<grid, kThreads, 0, s>>>(p);
-  else if (p.C == 2) fused_forward_kernel<FrameT, PX, MASK, REDUCE, 2><<<grid, kThreads, 0, s>>>(p);
-  else fused_forward_kernel<FrameT, PX, MASK, REDUCE, 0><<<grid, kThreads, 0, s>>>(p);
+  kern<<<grid, kThreads, Cfg::kSmemBytes, s>>>(p, tb, tf, tp);
   return cudaGetLastError();
 }
 
-template <typename FrameT, int PX>
-static cudaError_t dispatch_fused(const FwdParams& p, int mask_kind, bool reduce, cudaStream_t s) {
-  if (mask_kind == MASK_COMPUTED) return reduce ? launch_fused<FrameT, PX, MASK_COMPUTED, true>(p, s) : launch_fused<FrameT, PX, MASK_COMPUTED, false>(p, s);
-  if (mask_kind == MASK_GIVEN) return reduce ? launch_fused<FrameT, PX, MASK_GIVEN, true>(p, s) : launch_fused<FrameT, PX, MASK_GIVEN, false>(p, s);
-  return reduce ? launch_fused<FrameT, PX, MASK_NONE, true>(p, s) : launch_fused<FrameT, PX, MASK_NONE, false>(p, s);
+template <typename FrameT, int MASK, bool REDUCE>
+static cudaError_t launch_generic(const FwdParams& p, cudaStream_t s) {
+  const unsigned grid = (unsigned)((size_t)p.B * p.tiles_per_pair);
+  if (p.C == 3) fused_forward_generic_kernel<FrameT, MASK, REDUCE, 3><<<grid, kThreads, 0, s>>>(p);
+  else fused_forward_generic_kernel<FrameT, MASK, REDUCE, 0><<<grid, kThreads, 0, s>>>(p);
+  return cudaGetLastError();
 }
+
+template <typename FrameT>
+static cudaError_t dispatch(const FwdParams& p, int mask_kind, bool reduce, bool tma, const CUtensorMap& tb, const CUtensorMap& tf,
+                            const CUtensorMap& tp, cudaStream_t s) {
+#define TCL_CASE(MK, RD)                                                                       \
+  if (mask_kind == MK && reduce == RD) {                                                       \
+    if (!tma) return launch_generic<FrameT, MK, RD>(p, s);                                     \
+    return p.C == 3 ? launch_tma<FrameT, MK, RD, 3>(p, tb, tf, tp, s) : launch_tma<FrameT, MK, RD, 0>(p, tb, tf, tp, s); \
+  }
+  TCL_CASE(MASK_COMPUTED, true)
+  TCL_CASE(MASK_COMPUTED, false)
+  TCL_CASE(MASK_GIVEN, true)
+  TCL_CASE(MASK_GIVEN, false)
+  TCL_CASE(MASK_NONE, true)
+  TCL_CASE(MASK_NONE, false)
+#undef TCL_CASE
+  return cudaErrorInvalidValue;
+}
+
+static int g_force_generic = 0;  // test hook: exercise the generic kernel on TMA-capable shapes
+extern "C" void tclb200_debug_force_generic(int on) { g_force_generic = on; }
 
 static int run_fused(const tclb200_tcl_args* a, cudaStream_t s) {
   if (!a) return fail(TCLB200_ERR_INVALID, "args is NULL");
@@ -539,13 +584,17 @@ static int run_fused(const tclb200_tcl_args* a, cudaStream_t s) {
     return fail(TCLB200_ERR_INVALID, "ff given but neither TCLB200_OCC nor TCLB200_MOB requested");
   if (!a->prev && !a->mask_out) return fail(TCLB200_ERR_INVALID, "nothing to compute: no frames and no mask_out");
 
-  // vector width: 16-byte lanes need W % PX == 0 and 16-byte aligned bases
-  const int fsz = a->dtype == TCLB200_BF16 ? 2 : 4;
-  bool vec4 = (a->W % 4 == 0) && aligned16(a->bf) && aligned16(a->ff) && aligned16(a->mask_in) && aligned16(a->mask_out);
-  // frames: PX elements of fsz bytes each -> 8-byte (bf16) or 16-byte (fp32) accesses
-  auto frame_ok = [&](const void* q) { return (reinterpret_cast<uintptr_t>(q) & (uintptr_t)(4 * fsz - 1)) == 0; };
-  vec4 = vec4 && frame_ok(a->prev) && frame_ok(a->cur) && frame_ok(a->warp_out) && frame_ok(a->blend_out);
-  const int px = vec4 ? 4 : 1;
+  const int esz = a->dtype == TCLB200_BF16 ? 2 : 4;
+  // TMA needs 16-byte aligned bases and row strides; frames need C == 3 (the compiled box depth)
+  bool tma = !g_force_generic && (a->W % 4 == 0) && ((a->W * esz) % 16 == 0) && aligned16(a->bf) && aligned16(a->ff) &&
+             aligned16(a->prev) && (!a->prev || a->C == 3) && a->B <= 65535 * 16;
+  CUtensorMap tb, tf, tp;
+  memset(&tb, 0, sizeof(tb)); memset(&tf, 0, sizeof(tf)); memset(&tp, 0, sizeof(tp));
+  if (tma) {
+    tma = make_map(&tb, a->bf, 4, a->W, a->H, 2, a->B, kTW + 4, kTH + 2, 2);
+    if (tma && mask_kind == MASK_COMPUTED && (a->flags & TCLB200_OCC)) tma = make_map(&tf, a->ff, 4, a->W, a->H, 2, a->B, kBW, kBH, 2);
+    if (tma && a->prev) tma = make_map(&tp, a->prev, esz, a->W, a->H, 3, a->B, kBW, kBH, 3);
+  }
 
   FwdParams p;
   memset(&p, 0, sizeof(p));
@@ -555,8 +604,8 @@ static int run_fused(const tclb200_tcl_args* a, cudaStream_t s) {
   p.near_threshold = a->near_threshold;
   p.geo = make_geo(a->H, a->W);
   p.B = a->B; p.C = a->prev ? a->C : 0;
-  p.tiles_x = tiles_x_for(a->W, px);
-  p.tiles_per_pair = p.tiles_x * tiles_y_for(a->H);
+  p.tiles_x = tma ? cdiv(a->W, kTW) : cdiv(a->W, 32);
+  p.tiles_per_pair = p.tiles_x * (tma ? cdiv(a->H, kTH) : cdiv(a->H, kWarps));
   p.flags = a->flags; p.loss = a->loss; p.finalize = a->finalize;
   p.inv_count = a->prev ? 1.0 / ((double)a->C * a->H * a->W) : 0.0;
   if ((size_t)p.B * p.tiles_per_pair >= 0x7fffffffu) return fail(TCLB200_ERR_UNSUPPORTED, "too many tiles for one launch");
@@ -564,17 +613,14 @@ static int run_fused(const tclb200_tcl_args* a, cudaStream_t s) {
     if (!a->scratch || a->scratch_bytes < tclb200_scratch_bytes(a->B, a->H, a->W))
       return fail(TCLB200_ERR_INVALID, "scratch missing or smaller than tclb200_scratch_bytes(B,H,W)");
     char* base = reinterpret_cast<char*>(a->scratch);
-    const size_t tpp1 = (size_t)tiles_x_for(a->W, 1) * tiles_y_for(a->H);
+    const size_t tpp_max = (size_t)cdiv(a->W, 32) * cdiv(a->H, kWarps);
     p.scratch.partials = reinterpret_cast<double*>(base);
-    p.scratch.pair_ticket = reinterpret_cast<unsigned*>(base + align_up((size_t)a->B * tpp1 * sizeof(double), 256));
+    p.scratch.pair_ticket = reinterpret_cast<unsigned*>(base + align_up((size_t)a->B * tpp_max * sizeof(double), 256));
     p.scratch.batch_ticket = p.scratch.pair_ticket + a->B;
   }
-  cudaError_t e;
-  if (a->dtype == TCLB200_BF16)
-    e = px == 4 ? dispatch_fused<__nv_bfloat16, 4>(p, mask_kind, reduce, s) : dispatch_fused<__nv_bfloat16, 1>(p, mask_kind, reduce, s);
-  else
-    e = px == 4 ? dispatch_fused<float, 4>(p, mask_kind, reduce, s) : dispatch_fused<float, 1>(p, mask_kind, reduce, s);
-  if (e != cudaSuccess) return fail(TCLB200_ERR_CUDA, "fused_forward_kernel launch: %s", cudaGetErrorString(e));
+  const cudaError_t e = a->dtype == TCLB200_BF16 ? dispatch<__nv_bfloat16>(p, mask_kind, reduce, tma, tb, tf, tp, s)
+                                                 : dispatch<float>(p, mask_kind, reduce, tma, tb, tf, tp, s);
+  if (e != cudaSuccess) return fail(TCLB200_ERR_CUDA, "fused forward launch: %s", cudaGetErrorString(e));
   return TCLB200_OK;
 }
 
@@ -609,13 +655,9 @@ extern "C" int tclb200_gradient(const float* x, float* out, int B, int H, int W,
   if (!x || !out) return fail(TCLB200_ERR_INVALID, "x and out are required");
   if (B <= 0 || H <= 0 || W <= 0) return fail(TCLB200_ERR_INVALID, "B, H, W must be positive");
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-  const bool vec4 = (W % 4 == 0) && aligned16(x) && aligned16(out);
-  const int px = vec4 ? 4 : 1;
-  const int tx = tiles_x_for(W, px), tpi = tx * tiles_y_for(H);
+  const int tx = cdiv(W, 32), tpi = tx * cdiv(H, kWarps);
   if ((size_t)B * tpi >= 0x7fffffffu) return fail(TCLB200_ERR_UNSUPPORTED, "too many tiles for one launch");
-  const unsigned grid = (unsigned)((size_t)B * tpi);
-  if (vec4) gradient_kernel<4><<<grid, kThreads, 0, s>>>(x, out, B, H, W, tx, tpi);
-  else gradient_kernel<1><<<grid, kThreads, 0, s>>>(x, out, B, H, W, tx, tpi);
+  gradient_kernel<<<(unsigned)((size_t)B * tpi), kThreads, 0, s>>>(x, out, B, H, W, tx, tpi);
   CUDA_TRY(cudaGetLastError());
   return TCLB200_OK;
 }

@@ -131,6 +131,10 @@ int tclb200_tcl_backward(const float* bf, const float* mask, const float* prev, 
                          const float* grad_scale, float* grad_prev, float* grad_cur, int B, int C, int H, int W,
                          int flags, int loss, tclb200_stream_t stream);
 
+/* Test hook (process-global, not for production use): route TMA-capable shapes through the generic
+ * global-memory kernel so that both kernels are exercised on the same inputs.  0 = off (default). */
+void tclb200_debug_force_generic(int on);
+
 #ifdef __cplusplus
 }
 #endif

@@ -265,3 +265,68 @@ def test_blend_and_computeTCL_dropins(tcl):
     got2 = tcl.computeTCL(Net2(), raft, cur, img1, img2)
     want2 = tp.temporal_error(ff, bf, prev, cur)
     assert abs(float(got2) - float(want2)) <= LOSS_RTOL * float(want2)
+
+
+# ------------------------------------------------------------------ both forward kernels, every tile path
+@pytest.fixture
+def force_generic(tcl):
+    def _set(on):
+        tcl._cabi.lib().tclb200_debug_force_generic(int(on))
+    yield _set
+    _set(0)
+
+
+@pytest.mark.parametrize("B,H,W,shift,rot,rects", [(2, 96, 256, 8.0, 2.0, 8), (1, 436, 1024, 32.0, 3.0, 8), (2, 64, 128, 40.0, 25.0, 12),
+                                                   (1, 270, 480, 200.0, 1.0, 4)])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_tma_and_generic_kernels_agree_bitwise(tcl, force_generic, B, H, W, shift, rot, rects, dtype):
+    """The TMA-staged kernel (incl. its per-tile fallback for tiles whose taps exceed the source box) and the
+    generic global-memory kernel must produce identical bits: same arithmetic, different data movement."""
+    d = dev()
+    ff, bf = tcl.synth.make_flows(B, H, W, seed=W + 3, max_shift=shift, max_rot_deg=rot, n_rects=rects, rect_shift=30.0, device=d)
+    prev, cur = tcl.synth.make_frames(B, 3, H, W, seed=W + 3, kind="white", device=d, dtype=dtype)
+    outs = []
+    for generic in (False, True):
+        force_generic(generic)
+        r = tcl.fused_forward(bf, prev, cur, ff=ff, want_warp=True, want_mask=True, want_near=True)
+        w = tcl.warp(prev, bf)
+        m = tcl.fbcCheckTorch(ff, bf)
+        mob = tcl.fbcCheckTorch_mob(None, bf)
+        fsw = tcl.fs_warp(prev, bf)
+        given = tcl.fused_forward(bf, prev, cur, mask=m, loss=tcl.ops.L1, finalize=tcl.ops.FIN_MEAN, want_blend=True)
+        outs.append((r.warp, r.mask, r.near_threshold, w, m, mob, fsw, given.blend))
+        sums = (r.pair_sums, given.pair_sums)
+        outs[-1] += sums
+    force_generic(False)
+    for a, b in zip(outs[0][:8], outs[1][:8]):
+        assert torch.equal(a, b)
+    for a, b in zip(outs[0][8:], outs[1][8:]):   # different tile shapes -> different (fixed) summation trees
+        assert torch.allclose(a, b, rtol=1e-6, atol=0)
+
+
+def test_random_flow_exercises_the_per_tile_fallback(tcl, oracle_mod):
+    """White-noise flows of +-20 px: no tile fits the source box, every tile takes the exact gather path."""
+    g = torch.Generator().manual_seed(12)
+    B, H, W = 1, 48, 128
+    bf = (torch.rand(B, 2, H, W, generator=g) - 0.5) * 40
+    ff = (torch.rand(B, 2, H, W, generator=g) - 0.5) * 40
+    prev, cur = torch.randn(B, 3, H, W, generator=g), torch.randn(B, 3, H, W, generator=g)
+    d = dev()
+    v = oracle_mod.ATEN_CUDA
+    r = tcl.fused_forward(bf.to(d), prev.to(d), cur.to(d), ff=ff.to(d), want_warp=True, want_mask=True)
+    assert np.array_equal(r.warp.cpu().numpy(), oracle_mod.warp(prev.numpy(), bf.numpy(), v))
+    assert np.array_equal(r.mask.cpu().numpy(), oracle_mod.fbcheck(ff.numpy(), bf.numpy(), variant=v))
+    o = oracle_mod.temporal_error_sums(ff.numpy(), bf.numpy(), prev.numpy(), cur.numpy(), variant=v)
+    assert np.allclose(r.pair_sums.cpu().numpy(), o, rtol=LOSS_RTOL, atol=1e-30)
+
+
+def test_nonfinite_flow_matches_torch_cuda(tcl):
+    d = dev()
+    B, H, W = 1, 32, 64
+    ff, bf = tcl.synth.make_flows(B, H, W, seed=8, max_shift=4.0, device=d)
+    prev, _ = tcl.synth.make_frames(B, 3, H, W, seed=8, kind="white", device=d)
+    bf[0, 0, 5, 7] = float("inf"); bf[0, 1, 9, 40] = float("-inf"); bf[0, 0, 20, 20] = float("nan")
+    k = tcl.warp(prev, bf)
+    t = tp.backward_warp(prev, bf)
+    assert torch.equal(torch.isnan(k), torch.isnan(t))
+    assert torch.equal(torch.nan_to_num(k), torch.nan_to_num(t))
