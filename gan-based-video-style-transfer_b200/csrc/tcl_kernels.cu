@@ -196,7 +196,11 @@ __global__ void __launch_bounds__(kThreads) fused_forward_generic_kernel(const F
 template <typename FrameT, int CT, int TW_, int TH_, int BW_, int BH_>
 struct TileCfg {
   static constexpr int TW = TW_, TH = TH_, BW = BW_, BH = BH_;
-  static constexpr int kBfW = TW + 4, kBfH = TH + 2;          // flow tile + 1 px halo (inner extent kept a 16-byte multiple)
+  // flow tile + 1 px halo.  TMA needs the box's innermost start coordinate on a 16-byte boundary (measured on
+  // B200: an unaligned x raises 'illegal instruction'), so the halo is 4 columns wide on each side.
+  static constexpr int kHaloX = 4;
+  static constexpr int kBfW = TW + 2 * kHaloX, kBfH = TH + 2;
+  static constexpr int kXAlign = 16 / (int)sizeof(FrameT);   // source-box origin is rounded down to this many pixels
   static constexpr int kCols = TW / 32, kRows = TH / kWarps;  // pixels per lane: kCols x kRows
   static constexpr unsigned kBfLoad = 2u * kBfH * kBfW * 4u;
   static constexpr unsigned kFfLoad = 2u * BH * BW * 4u;
@@ -205,7 +209,7 @@ struct TileCfg {
   static constexpr size_t kFfOff = align_up(kBfLoad, 128);
   static constexpr size_t kPrevOff = kFfOff + align_up(kFfLoad, 128);
   static constexpr size_t kBarOff = kPrevOff + align_up(kPrevLoad, 128);
-  static constexpr size_t kSmemBytes = kBarOff + 64;
+  static constexpr size_t kSmemBytes = kBarOff + 64 + 128;  // + slack for the manual 128-byte alignment
   static_assert(TW % 32 == 0 && TH % kWarps == 0, "tile must be a multiple of 32 x 8");
   static_assert((BW * sizeof(FrameT)) % 16 == 0 && (BW * 4) % 16 == 0, "TMA inner box extent must be a 16-byte multiple");
   static_assert(BW > TW && BH > TH, "source box must exceed the tile");
@@ -217,7 +221,9 @@ __global__ void __launch_bounds__(kThreads) fused_forward_tma_kernel(const FwdPa
                                                                      const __grid_constant__ CUtensorMap tm_prev) {
   constexpr int TW = Cfg::TW, TH = Cfg::TH, BW = Cfg::BW, BH = Cfg::BH;
   constexpr int NPX = Cfg::kCols * Cfg::kRows;
-  extern __shared__ __align__(128) unsigned char smem[];
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  // TMA destinations must be 128-byte aligned: do not rely on where the dynamic window starts
+  unsigned char* smem = smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u);
   float* s_bu = reinterpret_cast<float*>(smem + Cfg::kBfOff);  // [2][kBfH][kBfW]
   float* s_bv = s_bu + Cfg::kBfH * Cfg::kBfW;
   float* s_ff = reinterpret_cast<float*>(smem + Cfg::kFfOff);  // [2][BH][BW]
@@ -242,7 +248,7 @@ __global__ void __launch_bounds__(kThreads) fused_forward_tma_kernel(const FwdPa
     fence_barrier_init();
     s_box[0] = INT_MAX; s_box[1] = INT_MAX; s_box[2] = INT_MIN; s_box[3] = INT_MIN;
     mbar_expect_tx(&bars[0], Cfg::kBfLoad);
-    tma_load_4d(s_bu, &tm_bf, &bars[0], tile_x0 - 1, tile_y0 - 1, 0, pair);
+    tma_load_4d(s_bu, &tm_bf, &bars[0], tile_x0 - Cfg::kHaloX, tile_y0 - 1, 0, pair);
   }
   __syncthreads();
   mbar_wait(&bars[0], 0);
@@ -259,7 +265,7 @@ __global__ void __launch_bounds__(kThreads) fused_forward_tma_kernel(const FwdPa
       const int i = r * Cfg::kCols + k;
       const int lx = lane + 32 * k, ly = wrp + kWarps * r;
       const int x = tile_x0 + lx, y = tile_y0 + ly;
-      const int c = (ly + 1) * Cfg::kBfW + lx + 1;
+      const int c = (ly + 1) * Cfg::kBfW + lx + Cfg::kHaloX;
       const float u = s_bu[c], v = s_bv[c];
       keep[i] = 1.0f;
       if (MASK == MASK_COMPUTED && (p.flags & TCLB200_MOB)) {
@@ -285,7 +291,7 @@ __global__ void __launch_bounds__(kThreads) fused_forward_tma_kernel(const FwdPa
     }
   }
   __syncthreads();
-  const int ox = s_box[0], oy = s_box[1];
+  const int ox = s_box[0] & ~(Cfg::kXAlign - 1), oy = s_box[1];  // 16-byte aligned box start (floor, also for negatives)
   // taps span [x0, x0+1] x [y0, y0+1]; the widths are computed in 64 bits (saturated coordinates)
   const bool fits = ((long long)s_box[2] + 1 - ox < BW) && ((long long)s_box[3] + 1 - oy < BH);
   const bool staged = fits && (want_occ || want_frames);
@@ -315,7 +321,7 @@ __global__ void __launch_bounds__(kThreads) fused_forward_tma_kernel(const FwdPa
       const int lx = lane + 32 * (i % Cfg::kCols), ly = wrp + kWarps * (i / Cfg::kCols);
       const int x = tile_x0 + lx, y = tile_y0 + ly;
       if (x < W && y < H) {
-        const int c = (ly + 1) * Cfg::kBfW + lx + 1;
+        const int c = (ly + 1) * Cfg::kBfW + lx + Cfg::kHaloX;
         finish_pixel<FrameT, MASK, REDUCE, CT>(p, taps[i], s_bu[c], s_bv[c], MASK == MASK_GIVEN ? mask_in[i] : keep[i],
                                                (size_t)y * W + x, plane, pair, fsrc, psrc, io, err, near);
       }
@@ -328,7 +334,7 @@ __global__ void __launch_bounds__(kThreads) fused_forward_tma_kernel(const FwdPa
       const int lx = lane + 32 * (i % Cfg::kCols), ly = wrp + kWarps * (i / Cfg::kCols);
       const int x = tile_x0 + lx, y = tile_y0 + ly;
       if (x < W && y < H) {
-        const int c = (ly + 1) * Cfg::kBfW + lx + 1;
+        const int c = (ly + 1) * Cfg::kBfW + lx + Cfg::kHaloX;
         finish_pixel<FrameT, MASK, REDUCE, CT>(p, taps[i], s_bu[c], s_bv[c], MASK == MASK_GIVEN ? mask_in[i] : keep[i],
                                                (size_t)y * W + x, plane, pair, fsrc, psrc, io, err, near);
       }
@@ -482,9 +488,11 @@ static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 
 extern "C" int tclb200_abi_version(void) { return TCLB200_ABI_VERSION; }
 extern "C" const char* tclb200_last_error(void) { return g_err; }
 
-// tile shape of the TMA kernel: 64 x 16 pixels per CTA, 72 x 24 source box (taps may spread 7 px beyond the
-// tile's own extent in x and y before the tile falls back to global gathers)
-constexpr int kTW = 64, kTH = 16, kBW = 72, kBH = 24;
+// tile shape of the TMA kernel: 64 x 16 pixels per CTA, 76(80 for bf16) x 24 source box: after rounding the box
+// origin down to a 16-byte boundary the taps may still spread >= 8 px in x and 7 px in y beyond the tile's own
+// extent before the tile falls back to global gathers
+constexpr int kTW = 64, kTH = 16, kBH = 24;
+template <typename FrameT> constexpr int box_w() { return sizeof(FrameT) == 2 ? 80 : 76; }  // 16-byte multiple per dtype
 
 static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 // scratch is sized for the finest tiling any kernel uses (32 x 8 generic tiles)
@@ -525,7 +533,7 @@ static bool make_map(CUtensorMap* m, const void* base, int esize, int W, int H, 
 // ---- launches ----------------------------------------------------------------------------------
 template <typename FrameT, int MASK, bool REDUCE, int CT>
 static cudaError_t launch_tma(const FwdParams& p, const CUtensorMap& tb, const CUtensorMap& tf, const CUtensorMap& tp, cudaStream_t s) {
-  using Cfg = TileCfg<FrameT, CT, kTW, kTH, kBW, kBH>;
+  using Cfg = TileCfg<FrameT, CT, kTW, kTH, box_w<FrameT>(), kBH>;
   auto kern = fused_forward_tma_kernel<FrameT, MASK, REDUCE, CT, Cfg>;
   static bool configured = false;  // per instantiation
   if (!configured) {
@@ -591,7 +599,8 @@ static int run_fused(const tclb200_tcl_args* a, cudaStream_t s) {
   CUtensorMap tb, tf, tp;
   memset(&tb, 0, sizeof(tb)); memset(&tf, 0, sizeof(tf)); memset(&tp, 0, sizeof(tp));
   if (tma) {
-    tma = make_map(&tb, a->bf, 4, a->W, a->H, 2, a->B, kTW + 4, kTH + 2, 2);
+    const int kBW = esz == 2 ? box_w<__nv_bfloat16>() : box_w<float>();
+    tma = make_map(&tb, a->bf, 4, a->W, a->H, 2, a->B, kTW + 8, kTH + 2, 2);
     if (tma && mask_kind == MASK_COMPUTED && (a->flags & TCLB200_OCC)) tma = make_map(&tf, a->ff, 4, a->W, a->H, 2, a->B, kBW, kBH, 2);
     if (tma && a->prev) tma = make_map(&tp, a->prev, esz, a->W, a->H, 3, a->B, kBW, kBH, 3);
   }
