@@ -102,39 +102,43 @@ struct PairPtrs {
   FrameT* bout;
 };
 
-// everything that happens to one pixel once its taps and motion-boundary verdict are known
-template <typename FrameT, int MASK, bool REDUCE, int CT, typename FlowSrc, typename FrameSrc>
-__device__ __forceinline__ void finish_pixel(const FwdParams& p, const PixTaps& s, float u, float v, float keep, size_t o,
-                                             size_t plane, int pair, const FlowSrc& fsrc, const FrameSrc& psrc,
-                                             const PairPtrs<FrameT>& io, float& err, unsigned& near) {
-  if (MASK == MASK_COMPUTED && (p.flags & TCLB200_OCC)) {
+// everything that happens to one pixel once its taps and motion-boundary verdict are known.
+// LEAN fixes the hot configuration at compile time (both mask tests, L2 error, no optional outputs, no
+// near-threshold count) so the per-pixel code carries no runtime feature checks.
+// `cv` = this pixel's prefetched `cur` values (CT of them) or nullptr to load them here.
+template <typename FrameT, int MASK, bool REDUCE, int CT, bool LEAN, typename FlowSrc, typename FrameSrc>
+__device__ __forceinline__ void finish_pixel(const FwdParams& p, const PixTaps& s, float u, float v, float nb, float keep,
+                                             size_t o, size_t plane, int pair, const FlowSrc& fsrc, const FrameSrc& psrc,
+                                             const PairPtrs<FrameT>& io, const float* cv, float& err, unsigned& near) {
+  if (MASK == MASK_COMPUTED && (LEAN || (p.flags & TCLB200_OCC))) {
     const float wu = fsrc.sample(0, s), wv = fsrc.sample(1, s);
     float margin;
-    if (occluded(wu, wv, u, v, sqnorm2(u, v, kV), kV, &margin)) keep = 0.0f;
-    near += fabsf(margin) < kNearBand;
+    if (occluded(wu, wv, u, v, nb, kV, &margin)) keep = 0.0f;
+    if (!LEAN) near += fabsf(margin) < kNearBand;
   }
-  if (p.mask_out) __stcs(p.mask_out + (size_t)pair * plane + o, keep);
+  if (!LEAN && p.mask_out) __stcs(p.mask_out + (size_t)pair * plane + o, keep);
   if (p.prev == nullptr) return;
+  const bool validity = !LEAN && (p.flags & TCLB200_VALIDITY);
   float valid = 1.0f;
-  if (p.flags & TCLB200_VALIDITY) valid = binarise_validity(ones_sample(full_taps(s, p.geo), kV));
+  if (validity) valid = binarise_validity(ones_sample(full_taps(s, p.geo), kV));
   const int C = CT > 0 ? CT : p.C;
 #pragma unroll
   for (int c = 0; c < C; ++c) {
     float w = psrc.sample(c, s);
-    if (p.flags & TCLB200_VALIDITY) w = __fmul_rn(w, valid);
-    if (io.wout) st_stream(io.wout + (size_t)c * plane + o, w);
-    if (io.cur) {
-      const float cv = ld_stream(io.cur + (size_t)c * plane + o);
+    if (validity) w = __fmul_rn(w, valid);
+    if (!LEAN && io.wout) st_stream(io.wout + (size_t)c * plane + o, w);
+    if (LEAN || io.cur) {
+      const float x = cv ? cv[c] : ld_stream(io.cur + (size_t)c * plane + o);
       if (REDUCE) {
-        if (p.loss == TCLB200_L2) {
-          const float md = __fmul_rn(keep, __fsub_rn(cv, w));   // mask*(cur - warp)   sintel_eval.py:110
+        if (LEAN || p.loss == TCLB200_L2) {
+          const float md = __fmul_rn(keep, __fsub_rn(x, w));     // mask*(cur - warp)   sintel_eval.py:110
           err = __fmaf_rn(md, md, err);
         } else {
-          err += __fmul_rn(keep, fabsf(__fsub_rn(w, cv)));      // mask*|warp - cur|   MoGAN cycle_gan_model.py:281
+          err += __fmul_rn(keep, fabsf(__fsub_rn(w, x)));        // mask*|warp - cur|   MoGAN cycle_gan_model.py:281
         }
       }
-      if (io.bout)                                              // m*warp + (1-m)*img   obst_eval.py:500
-        st_stream(io.bout + (size_t)c * plane + o, __fadd_rn(__fmul_rn(keep, w), __fmul_rn(__fsub_rn(1.0f, keep), cv)));
+      if (!LEAN && io.bout)                                      // m*warp + (1-m)*img   obst_eval.py:500
+        st_stream(io.bout + (size_t)c * plane + o, __fadd_rn(__fmul_rn(keep, w), __fmul_rn(__fsub_rn(1.0f, keep), x)));
     }
   }
 }
@@ -170,6 +174,7 @@ __global__ void __launch_bounds__(kThreads) fused_forward_generic_kernel(const F
     const float* bu = p.bf + (size_t)pair * 2 * plane;
     const float* bv = bu + plane;
     const float u = __ldg(bu + o), v = __ldg(bv + o);
+    const float nb = sqnorm2(u, v, kV);
     float keep = 1.0f;
     if (MASK == MASK_GIVEN) keep = __ldcs(p.mask_in + (size_t)pair * plane + o);
     if (MASK == MASK_COMPUTED && (p.flags & TCLB200_MOB)) {
@@ -178,13 +183,14 @@ __global__ void __launch_bounds__(kThreads) fused_forward_generic_kernel(const F
       const float vl = x > 0 ? __ldg(bv + o - 1) : 0.0f, vr = x + 1 < W ? __ldg(bv + o + 1) : 0.0f;
       const float vu = y > 0 ? __ldg(bv + o - W) : 0.0f, vd = y + 1 < H ? __ldg(bv + o + W) : 0.0f;
       float margin;
-      if (motion_boundary(ul, ur, uu, ud, vl, vr, vu, vd, sqnorm2(u, v, kV), kV, &margin)) keep = 0.0f;
+      if (motion_boundary(ul, ur, uu, ud, vl, vr, vu, vd, nb, kV, &margin)) keep = 0.0f;
       near += fabsf(margin) < kNearBand;
     }
     const PixTaps s = pix_taps(u, v, x, y, g);
     GlobalSrc<float> fsrc{p.ff ? p.ff + (size_t)pair * 2 * plane : nullptr, plane, g};
     GlobalSrc<FrameT> psrc{p.prev ? reinterpret_cast<const FrameT*>(p.prev) + (size_t)pair * C * plane : nullptr, plane, g};
-    finish_pixel<FrameT, MASK, REDUCE, CT>(p, s, u, v, keep, o, plane, pair, fsrc, psrc, pair_ptrs<FrameT>(p, pair, C, plane), err, near);
+    finish_pixel<FrameT, MASK, REDUCE, CT, false>(p, s, u, v, nb, keep, o, plane, pair, fsrc, psrc,
+                                                  pair_ptrs<FrameT>(p, pair, C, plane), nullptr, err, near);
   }
   count_near(near, p.near_threshold);
   if (REDUCE) reduce_and_finalise(err, p, pair, tile);
@@ -215,32 +221,150 @@ struct TileCfg {
   static_assert(BW > TW && BH > TH, "source box must exceed the tile");
 };
 
-template <typename FrameT, int MASK, bool REDUCE, int CT, typename Cfg>
-__global__ void __launch_bounds__(kThreads) fused_forward_tma_kernel(const FwdParams p, const __grid_constant__ CUtensorMap tm_bf,
+struct TileCtx {
+  const float* s_bu;
+  const float* s_bv;
+  int* s_box;
+  uint64_t* bars;
+  int pair, tile_x0, tile_y0, lane, wrp;
+};
+
+// The body of one tile.  EDGE = the tile crosses the right/bottom image border (bounds checks compiled in).
+template <typename FrameT, int MASK, bool REDUCE, int CT, bool LEAN, typename Cfg, bool EDGE>
+__device__ __forceinline__ void tile_body(const FwdParams& p, const TileCtx& t, const float* s_ff, const FrameT* s_prev,
+                                          const CUtensorMap* tm_ff, const CUtensorMap* tm_prev, float& err, unsigned& near) {
+  constexpr int BW = Cfg::BW, BH = Cfg::BH;
+  constexpr int NPX = Cfg::kCols * Cfg::kRows;
+  const Geo& g = p.geo;
+  const int W = g.W, H = g.H;
+  const size_t plane = (size_t)H * W;
+  const bool want_mob = MASK == MASK_COMPUTED && (LEAN || (p.flags & TCLB200_MOB));
+  const bool want_occ = MASK == MASK_COMPUTED && (LEAN || (p.flags & TCLB200_OCC));
+  const bool want_frames = CT > 0 && (LEAN || p.prev != nullptr);
+  const float* s_bu = t.s_bu;
+  const float* s_bv = t.s_bv;
+
+  // ---- phase A: sampling positions, motion-boundary test, bounding box of the taps
+  PixTaps taps[NPX];
+  float keep[NPX], nbs[NPX];
+  int bx0 = INT_MAX, by0 = INT_MAX, bx1 = INT_MIN, by1 = INT_MIN;
+#pragma unroll
+  for (int i = 0; i < NPX; ++i) {
+    const int lx = t.lane + 32 * (i % Cfg::kCols), ly = t.wrp + kWarps * (i / Cfg::kCols);
+    const int x = t.tile_x0 + lx, y = t.tile_y0 + ly;
+    const bool inside = !EDGE || (x < W && y < H);
+    const int c = (ly + 1) * Cfg::kBfW + lx + Cfg::kHaloX;
+    const float u = s_bu[c], v = s_bv[c];
+    nbs[i] = sqnorm2(u, v, kV);
+    keep[i] = 1.0f;
+    if (want_mob) {
+      float margin;
+      if (motion_boundary(s_bu[c - 1], s_bu[c + 1], s_bu[c - Cfg::kBfW], s_bu[c + Cfg::kBfW], s_bv[c - 1], s_bv[c + 1],
+                          s_bv[c - Cfg::kBfW], s_bv[c + Cfg::kBfW], nbs[i], kV, &margin))
+        keep[i] = 0.0f;
+      if (!LEAN && inside) near += fabsf(margin) < kNearBand;
+    }
+    taps[i] = pix_taps(u, v, x, y, g);
+    if (inside) {
+      bx0 = min(bx0, taps[i].x0); bx1 = max(bx1, taps[i].x0);
+      by0 = min(by0, taps[i].y0); by1 = max(by1, taps[i].y0);
+    }
+  }
+  if (want_occ || want_frames) {
+    bx0 = __reduce_min_sync(0xffffffffu, bx0); by0 = __reduce_min_sync(0xffffffffu, by0);
+    bx1 = __reduce_max_sync(0xffffffffu, bx1); by1 = __reduce_max_sync(0xffffffffu, by1);
+    if (t.lane == 0) {
+      atomicMin(&t.s_box[0], bx0); atomicMin(&t.s_box[1], by0);
+      atomicMax(&t.s_box[2], bx1); atomicMax(&t.s_box[3], by1);
+    }
+  }
+  __syncthreads();
+  const int ox = t.s_box[0] & ~(Cfg::kXAlign - 1), oy = t.s_box[1];  // 16-byte aligned box start (floor, also for negatives)
+  // taps span [x0, x0+1] x [y0, y0+1]; the widths are computed in 64 bits (saturated coordinates)
+  const bool fits = ((long long)t.s_box[2] + 1 - ox < BW) && ((long long)t.s_box[3] + 1 - oy < BH);
+  const bool staged = fits && (want_occ || want_frames);
+  if (staged && threadIdx.x == 0) {
+    mbar_expect_tx(&t.bars[1], (want_occ ? Cfg::kFfLoad : 0u) + (want_frames ? Cfg::kPrevLoad : 0u));
+    if (want_occ) tma_load_4d(const_cast<float*>(s_ff), tm_ff, &t.bars[1], ox, oy, 0, t.pair);
+    if (want_frames) tma_load_4d(const_cast<FrameT*>(s_prev), tm_prev, &t.bars[1], ox, oy, 0, t.pair);
+  }
+
+  // ---- phase B: occlusion test, warp, masked error
+  const PairPtrs<FrameT> io = pair_ptrs<FrameT>(p, t.pair, CT, plane);
+  if (MASK == MASK_GIVEN) {  // the dataset mask replaces `keep`; loads overlap the TMA
+#pragma unroll
+    for (int i = 0; i < NPX; ++i) {
+      const int x = t.tile_x0 + t.lane + 32 * (i % Cfg::kCols), y = t.tile_y0 + t.wrp + kWarps * (i / Cfg::kCols);
+      keep[i] = (!EDGE || (x < W && y < H)) ? __ldcs(p.mask_in + (size_t)t.pair * plane + (size_t)y * W + x) : 0.0f;
+    }
+  }
+  const bool have_cur = CT > 0 && (LEAN || io.cur != nullptr);
+  auto load_cur = [&](int i, float (&dst)[CT > 0 ? CT : 1]) {
+    const int x = t.tile_x0 + t.lane + 32 * (i % Cfg::kCols), y = t.tile_y0 + t.wrp + kWarps * (i / Cfg::kCols);
+    const bool inside = !EDGE || (x < W && y < H);
+#pragma unroll
+    for (int c = 0; c < CT; ++c) dst[c] = (have_cur && inside) ? ld_stream(io.cur + (size_t)c * plane + (size_t)y * W + x) : 0.0f;
+  };
+  float cnext[CT > 0 ? CT : 1];
+  load_cur(0, cnext);  // one pixel ahead: the global-load latency hides behind the previous pixel's taps
+  if (staged) {
+    mbar_wait(&t.bars[1], 0);
+    const SmemSrc<float, BW, BH * BW> fsrc{s_ff, ox, oy};
+    const SmemSrc<FrameT, BW, BH * BW> psrc{s_prev, ox, oy};
+#pragma unroll
+    for (int i = 0; i < NPX; ++i) {
+      float cv[CT > 0 ? CT : 1];
+#pragma unroll
+      for (int c = 0; c < (CT > 0 ? CT : 1); ++c) cv[c] = cnext[c];
+      if (i + 1 < NPX) load_cur(i + 1, cnext);
+      const int lx = t.lane + 32 * (i % Cfg::kCols), ly = t.wrp + kWarps * (i / Cfg::kCols);
+      const int x = t.tile_x0 + lx, y = t.tile_y0 + ly;
+      if (!EDGE || (x < W && y < H)) {
+        const int c = (ly + 1) * Cfg::kBfW + lx + Cfg::kHaloX;
+        finish_pixel<FrameT, MASK, REDUCE, CT, LEAN>(p, taps[i], s_bu[c], s_bv[c], nbs[i], keep[i], (size_t)y * W + x, plane,
+                                                     t.pair, fsrc, psrc, io, have_cur ? cv : nullptr, err, near);
+      }
+    }
+  } else {
+    const GlobalSrc<float> fsrc{p.ff ? p.ff + (size_t)t.pair * 2 * plane : nullptr, plane, g};
+    const GlobalSrc<FrameT> psrc{p.prev ? reinterpret_cast<const FrameT*>(p.prev) + (size_t)t.pair * CT * plane : nullptr, plane, g};
+#pragma unroll
+    for (int i = 0; i < NPX; ++i) {
+      float cv[CT > 0 ? CT : 1];
+#pragma unroll
+      for (int c = 0; c < (CT > 0 ? CT : 1); ++c) cv[c] = cnext[c];
+      if (i + 1 < NPX) load_cur(i + 1, cnext);
+      const int lx = t.lane + 32 * (i % Cfg::kCols), ly = t.wrp + kWarps * (i / Cfg::kCols);
+      const int x = t.tile_x0 + lx, y = t.tile_y0 + ly;
+      if (!EDGE || (x < W && y < H)) {
+        const int c = (ly + 1) * Cfg::kBfW + lx + Cfg::kHaloX;
+        finish_pixel<FrameT, MASK, REDUCE, CT, LEAN>(p, taps[i], s_bu[c], s_bv[c], nbs[i], keep[i], (size_t)y * W + x, plane,
+                                                     t.pair, fsrc, psrc, io, have_cur ? cv : nullptr, err, near);
+      }
+    }
+  }
+}
+
+template <typename FrameT, int MASK, bool REDUCE, int CT, bool LEAN, typename Cfg>
+__global__ void __launch_bounds__(kThreads, 4) fused_forward_tma_kernel(const FwdParams p, const __grid_constant__ CUtensorMap tm_bf,
                                                                      const __grid_constant__ CUtensorMap tm_ff,
                                                                      const __grid_constant__ CUtensorMap tm_prev) {
-  constexpr int TW = Cfg::TW, TH = Cfg::TH, BW = Cfg::BW, BH = Cfg::BH;
-  constexpr int NPX = Cfg::kCols * Cfg::kRows;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   // TMA destinations must be 128-byte aligned: do not rely on where the dynamic window starts
   unsigned char* smem = smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u);
   float* s_bu = reinterpret_cast<float*>(smem + Cfg::kBfOff);  // [2][kBfH][kBfW]
-  float* s_bv = s_bu + Cfg::kBfH * Cfg::kBfW;
   float* s_ff = reinterpret_cast<float*>(smem + Cfg::kFfOff);  // [2][BH][BW]
   FrameT* s_prev = reinterpret_cast<FrameT*>(smem + Cfg::kPrevOff);  // [CT][BH][BW]
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kBarOff);
   __shared__ int s_box[4];  // xmin, ymin, xmax, ymax of the top-left taps
 
-  const Geo& g = p.geo;
-  const int W = g.W, H = g.H;
-  const size_t plane = (size_t)H * W;
-  const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
-  const int pair = blockIdx.x / p.tiles_per_pair;
-  const int tile = blockIdx.x - pair * p.tiles_per_pair;
+  TileCtx t;
+  t.lane = threadIdx.x & 31; t.wrp = threadIdx.x >> 5;
+  t.pair = blockIdx.x / p.tiles_per_pair;
+  const int tile = blockIdx.x - t.pair * p.tiles_per_pair;
   const int ty = tile / p.tiles_x, tx = tile - ty * p.tiles_x;
-  const int tile_x0 = tx * TW, tile_y0 = ty * TH;
-  const bool want_occ = MASK == MASK_COMPUTED && (p.flags & TCLB200_OCC);
-  const bool want_frames = CT > 0 && p.prev != nullptr;
+  t.tile_x0 = tx * Cfg::TW; t.tile_y0 = ty * Cfg::TH;
+  t.s_bu = s_bu; t.s_bv = s_bu + Cfg::kBfH * Cfg::kBfW; t.s_box = s_box; t.bars = bars;
 
   if (threadIdx.x == 0) {
     mbar_init(&bars[0], 1);
@@ -248,100 +372,18 @@ __global__ void __launch_bounds__(kThreads) fused_forward_tma_kernel(const FwdPa
     fence_barrier_init();
     s_box[0] = INT_MAX; s_box[1] = INT_MAX; s_box[2] = INT_MIN; s_box[3] = INT_MIN;
     mbar_expect_tx(&bars[0], Cfg::kBfLoad);
-    tma_load_4d(s_bu, &tm_bf, &bars[0], tile_x0 - Cfg::kHaloX, tile_y0 - 1, 0, pair);
+    tma_load_4d(s_bu, &tm_bf, &bars[0], t.tile_x0 - Cfg::kHaloX, t.tile_y0 - 1, 0, t.pair);
   }
   __syncthreads();
   mbar_wait(&bars[0], 0);
 
-  // ---- phase A: sampling positions, motion-boundary test, bounding box of the taps
-  PixTaps taps[NPX];
-  float keep[NPX];
-  unsigned near = 0;
-  int bx0 = INT_MAX, by0 = INT_MAX, bx1 = INT_MIN, by1 = INT_MIN;
-#pragma unroll
-  for (int r = 0; r < Cfg::kRows; ++r) {
-#pragma unroll
-    for (int k = 0; k < Cfg::kCols; ++k) {
-      const int i = r * Cfg::kCols + k;
-      const int lx = lane + 32 * k, ly = wrp + kWarps * r;
-      const int x = tile_x0 + lx, y = tile_y0 + ly;
-      const int c = (ly + 1) * Cfg::kBfW + lx + Cfg::kHaloX;
-      const float u = s_bu[c], v = s_bv[c];
-      keep[i] = 1.0f;
-      if (MASK == MASK_COMPUTED && (p.flags & TCLB200_MOB)) {
-        float margin;
-        if (motion_boundary(s_bu[c - 1], s_bu[c + 1], s_bu[c - Cfg::kBfW], s_bu[c + Cfg::kBfW], s_bv[c - 1], s_bv[c + 1],
-                            s_bv[c - Cfg::kBfW], s_bv[c + Cfg::kBfW], sqnorm2(u, v, kV), kV, &margin))
-          keep[i] = 0.0f;
-        if (x < W && y < H) near += fabsf(margin) < kNearBand;
-      }
-      taps[i] = pix_taps(u, v, x, y, g);
-      if (x < W && y < H) {
-        bx0 = min(bx0, taps[i].x0); bx1 = max(bx1, taps[i].x0);
-        by0 = min(by0, taps[i].y0); by1 = max(by1, taps[i].y0);
-      }
-    }
-  }
-  if (want_occ || want_frames) {
-    bx0 = __reduce_min_sync(0xffffffffu, bx0); by0 = __reduce_min_sync(0xffffffffu, by0);
-    bx1 = __reduce_max_sync(0xffffffffu, bx1); by1 = __reduce_max_sync(0xffffffffu, by1);
-    if (lane == 0) {
-      atomicMin(&s_box[0], bx0); atomicMin(&s_box[1], by0);
-      atomicMax(&s_box[2], bx1); atomicMax(&s_box[3], by1);
-    }
-  }
-  __syncthreads();
-  const int ox = s_box[0] & ~(Cfg::kXAlign - 1), oy = s_box[1];  // 16-byte aligned box start (floor, also for negatives)
-  // taps span [x0, x0+1] x [y0, y0+1]; the widths are computed in 64 bits (saturated coordinates)
-  const bool fits = ((long long)s_box[2] + 1 - ox < BW) && ((long long)s_box[3] + 1 - oy < BH);
-  const bool staged = fits && (want_occ || want_frames);
-  if (staged && threadIdx.x == 0) {
-    mbar_expect_tx(&bars[1], (want_occ ? Cfg::kFfLoad : 0u) + (want_frames ? Cfg::kPrevLoad : 0u));
-    if (want_occ) tma_load_4d(s_ff, &tm_ff, &bars[1], ox, oy, 0, pair);
-    if (want_frames) tma_load_4d(s_prev, &tm_prev, &bars[1], ox, oy, 0, pair);
-  }
-
-  // ---- phase B: occlusion test, warp, masked error
-  const PairPtrs<FrameT> io = pair_ptrs<FrameT>(p, pair, CT, plane);
-  float mask_in[NPX];
-  if (MASK == MASK_GIVEN) {   // issued before the wait so the loads overlap the TMA
-#pragma unroll
-    for (int i = 0; i < NPX; ++i) {
-      const int x = tile_x0 + lane + 32 * (i % Cfg::kCols), y = tile_y0 + wrp + kWarps * (i / Cfg::kCols);
-      mask_in[i] = (x < W && y < H) ? __ldcs(p.mask_in + (size_t)pair * plane + (size_t)y * W + x) : 0.0f;
-    }
-  }
   float err = 0.0f;
-  if (staged) {
-    mbar_wait(&bars[1], 0);
-    const SmemSrc<float, BW, BH * BW> fsrc{s_ff, ox, oy};
-    const SmemSrc<FrameT, BW, BH * BW> psrc{s_prev, ox, oy};
-#pragma unroll
-    for (int i = 0; i < NPX; ++i) {
-      const int lx = lane + 32 * (i % Cfg::kCols), ly = wrp + kWarps * (i / Cfg::kCols);
-      const int x = tile_x0 + lx, y = tile_y0 + ly;
-      if (x < W && y < H) {
-        const int c = (ly + 1) * Cfg::kBfW + lx + Cfg::kHaloX;
-        finish_pixel<FrameT, MASK, REDUCE, CT>(p, taps[i], s_bu[c], s_bv[c], MASK == MASK_GIVEN ? mask_in[i] : keep[i],
-                                               (size_t)y * W + x, plane, pair, fsrc, psrc, io, err, near);
-      }
-    }
-  } else {
-    const GlobalSrc<float> fsrc{p.ff ? p.ff + (size_t)pair * 2 * plane : nullptr, plane, g};
-    const GlobalSrc<FrameT> psrc{p.prev ? reinterpret_cast<const FrameT*>(p.prev) + (size_t)pair * CT * plane : nullptr, plane, g};
-#pragma unroll
-    for (int i = 0; i < NPX; ++i) {
-      const int lx = lane + 32 * (i % Cfg::kCols), ly = wrp + kWarps * (i / Cfg::kCols);
-      const int x = tile_x0 + lx, y = tile_y0 + ly;
-      if (x < W && y < H) {
-        const int c = (ly + 1) * Cfg::kBfW + lx + Cfg::kHaloX;
-        finish_pixel<FrameT, MASK, REDUCE, CT>(p, taps[i], s_bu[c], s_bv[c], MASK == MASK_GIVEN ? mask_in[i] : keep[i],
-                                               (size_t)y * W + x, plane, pair, fsrc, psrc, io, err, near);
-      }
-    }
-  }
-  count_near(near, p.near_threshold);
-  if (REDUCE) reduce_and_finalise(err, p, pair, tile);
+  unsigned near = 0;
+  const bool edge = (t.tile_x0 + Cfg::TW > p.geo.W) || (t.tile_y0 + Cfg::TH > p.geo.H);
+  if (edge) tile_body<FrameT, MASK, REDUCE, CT, LEAN, Cfg, true>(p, t, s_ff, s_prev, &tm_ff, &tm_prev, err, near);
+  else tile_body<FrameT, MASK, REDUCE, CT, LEAN, Cfg, false>(p, t, s_ff, s_prev, &tm_ff, &tm_prev, err, near);
+  if (!LEAN) count_near(near, p.near_threshold);
+  if (REDUCE) reduce_and_finalise(err, p, t.pair, tile);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -531,10 +573,10 @@ static bool make_map(CUtensorMap* m, const void* base, int esize, int W, int H, 
 }
 
 // ---- launches ----------------------------------------------------------------------------------
-template <typename FrameT, int MASK, bool REDUCE, int CT>
+template <typename FrameT, int MASK, bool REDUCE, int CT, bool LEAN>
 static cudaError_t launch_tma(const FwdParams& p, const CUtensorMap& tb, const CUtensorMap& tf, const CUtensorMap& tp, cudaStream_t s) {
   using Cfg = TileCfg<FrameT, CT, kTW, kTH, box_w<FrameT>(), kBH>;
-  auto kern = fused_forward_tma_kernel<FrameT, MASK, REDUCE, CT, Cfg>;
+  auto kern = fused_forward_tma_kernel<FrameT, MASK, REDUCE, CT, LEAN, Cfg>;
   static bool configured = false;  // per instantiation
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::kSmemBytes);
@@ -560,8 +602,13 @@ static cudaError_t dispatch(const FwdParams& p, int mask_kind, bool reduce, bool
 #define TCL_CASE(MK, RD)                                                                       \
   if (mask_kind == MK && reduce == RD) {                                                       \
     if (!tma) return launch_generic<FrameT, MK, RD>(p, s);                                     \
-    return p.C == 3 ? launch_tma<FrameT, MK, RD, 3>(p, tb, tf, tp, s) : launch_tma<FrameT, MK, RD, 0>(p, tb, tf, tp, s); \
+    if (p.C == 3 && lean) return launch_tma<FrameT, MK, RD, 3, true>(p, tb, tf, tp, s);        \
+    return p.C == 3 ? launch_tma<FrameT, MK, RD, 3, false>(p, tb, tf, tp, s) : launch_tma<FrameT, MK, RD, 0, false>(p, tb, tf, tp, s); \
   }
+  // LEAN = the measured hot configurations, fixed at compile time: computeTCL / training loss with C == 3
+  const bool lean = reduce && p.prev && p.cur && !p.warp_out && !p.mask_out && !p.blend_out && !p.near_threshold &&
+                    p.loss == TCLB200_L2 && !(p.flags & TCLB200_VALIDITY) && mask_kind != MASK_NONE &&
+                    (mask_kind != MASK_COMPUTED || (p.flags & (TCLB200_OCC | TCLB200_MOB)) == (TCLB200_OCC | TCLB200_MOB));
   TCL_CASE(MASK_COMPUTED, true)
   TCL_CASE(MASK_COMPUTED, false)
   TCL_CASE(MASK_GIVEN, true)
