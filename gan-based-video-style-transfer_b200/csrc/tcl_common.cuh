@@ -10,7 +10,10 @@
 namespace tcl {
 
 constexpr int kV = V_ATEN_CUDA;  // arithmetic flavour of the product kernels (see tcl_math.cuh)
-constexpr int kWarps = 8;        // warps per CTA
+#ifndef TCL_WARPS
+#define TCL_WARPS 8
+#endif
+constexpr int kWarps = TCL_WARPS;  // warps per CTA
 constexpr int kThreads = 32 * kWarps;
 constexpr float kNearBand = 1e-6f;  // north_star's near-threshold exemption band
 

@@ -34,6 +34,23 @@
 #include "tcl_common.cuh"
 #include "tcl_math.cuh"
 
+// tile geometry of the TMA kernel (overridable at build time for tuning sweeps, see tools/sweep_build.py)
+#ifndef TCL_TW
+#define TCL_TW 64
+#endif
+#ifndef TCL_TH
+#define TCL_TH 16
+#endif
+#ifndef TCL_BH
+#define TCL_BH 24
+#endif
+#ifndef TCL_BW_F32
+#define TCL_BW_F32 76
+#endif
+#ifndef TCL_BW_BF16
+#define TCL_BW_BF16 80
+#endif
+
 namespace tcl {
 
 // ---------------------------------------------------------------------------------------------
@@ -174,7 +191,7 @@ __global__ void __launch_bounds__(kThreads) fused_forward_generic_kernel(const F
     const float* bu = p.bf + (size_t)pair * 2 * plane;
     const float* bv = bu + plane;
     const float u = __ldg(bu + o), v = __ldg(bv + o);
-    const float nb = sqnorm2(u, v, kV);
+    float nb = sqnorm2(u, v, kV);
     float keep = 1.0f;
     if (MASK == MASK_GIVEN) keep = __ldcs(p.mask_in + (size_t)pair * plane + o);
     if (MASK == MASK_COMPUTED && (p.flags & TCLB200_MOB)) {
@@ -183,7 +200,7 @@ __global__ void __launch_bounds__(kThreads) fused_forward_generic_kernel(const F
       const float vl = x > 0 ? __ldg(bv + o - 1) : 0.0f, vr = x + 1 < W ? __ldg(bv + o + 1) : 0.0f;
       const float vu = y > 0 ? __ldg(bv + o - W) : 0.0f, vd = y + 1 < H ? __ldg(bv + o + W) : 0.0f;
       float margin;
-      if (motion_boundary(ul, ur, uu, ud, vl, vr, vu, vd, nb, kV, &margin)) keep = 0.0f;
+      if (motion_boundary(u, v, ul, ur, uu, ud, vl, vr, vu, vd, kV, &nb, &margin)) keep = 0.0f;
       near += fabsf(margin) < kNearBand;
     }
     const PixTaps s = pix_taps(u, v, x, y, g);
@@ -197,8 +214,22 @@ __global__ void __launch_bounds__(kThreads) fused_forward_generic_kernel(const F
 }
 
 // ---------------------------------------------------------------------------------------------
-// TMA-staged forward kernel
+// TMA-staged, persistent, software-pipelined forward kernel
 // ---------------------------------------------------------------------------------------------
+// Two 512-thread CTAs per SM, each walking tiles  t = blockIdx.x + k * gridDim.x.  A tile has two phases whose
+// loads depend on each other (flow tile -> where the source boxes lie), so every CTA keeps two tiles in flight:
+//
+//     iteration k:   A(k+1)  flow tile k+1 (prefetched two tiles ahead) -> sampling positions, |bf|^2,
+//                            motion-boundary verdict (kept in registers), tap bounding box -> TMA of the
+//                            `ff`/`prev` source boxes of tile k+1
+//                    B(k)    source boxes of tile k (requested one iteration ago): bilinear taps from shared
+//                            memory, occlusion test, masked error, per-tile partial sum
+//
+// so both TMA latencies of a tile hide behind a full tile of arithmetic, with double-buffered flow tiles and
+// source boxes (2 x 10 KB + 2 x 36 KB per CTA).
+constexpr int kPpWarps = 16;
+constexpr int kPpThreads = 32 * kPpWarps;
+
 template <typename FrameT, int CT, int TW_, int TH_, int BW_, int BH_>
 struct TileCfg {
   static constexpr int TW = TW_, TH = TH_, BW = BW_, BH = BH_;
@@ -207,183 +238,323 @@ struct TileCfg {
   static constexpr int kHaloX = 4;
   static constexpr int kBfW = TW + 2 * kHaloX, kBfH = TH + 2;
   static constexpr int kXAlign = 16 / (int)sizeof(FrameT);   // source-box origin is rounded down to this many pixels
-  static constexpr int kCols = TW / 32, kRows = TH / kWarps;  // pixels per lane: kCols x kRows
+  static constexpr int kPx = TW * TH;
+  static constexpr int kNPX = kPx / kPpThreads;              // pixels per lane
   static constexpr unsigned kBfLoad = 2u * kBfH * kBfW * 4u;
   static constexpr unsigned kFfLoad = 2u * BH * BW * 4u;
   static constexpr unsigned kPrevLoad = (unsigned)(CT > 0 ? CT : 0) * BH * BW * (unsigned)sizeof(FrameT);
+  static constexpr size_t kBfStage = align_up(kBfLoad, 128);
+  static constexpr size_t kFfStage = align_up(kFfLoad, 128);
+  static constexpr size_t kPrevStage = align_up(kPrevLoad, 128);
   static constexpr size_t kBfOff = 0;
-  static constexpr size_t kFfOff = align_up(kBfLoad, 128);
-  static constexpr size_t kPrevOff = kFfOff + align_up(kFfLoad, 128);
-  static constexpr size_t kBarOff = kPrevOff + align_up(kPrevLoad, 128);
-  static constexpr size_t kSmemBytes = kBarOff + 64 + 128;  // + slack for the manual 128-byte alignment
-  static_assert(TW % 32 == 0 && TH % kWarps == 0, "tile must be a multiple of 32 x 8");
+  static constexpr size_t kFfOff = kBfOff + 2 * kBfStage;
+  static constexpr size_t kPrevOff = kFfOff + 2 * kFfStage;
+  static constexpr size_t kCtlOff = kPrevOff + 2 * kPrevStage;
+  static constexpr size_t kSmemBytes = kCtlOff + 512 + 128;  // control block + slack for manual 128-byte alignment
+  static_assert(TW % 32 == 0 && kPx % kPpThreads == 0, "tile must split evenly over the lanes");
   static_assert((BW * sizeof(FrameT)) % 16 == 0 && (BW * 4) % 16 == 0, "TMA inner box extent must be a 16-byte multiple");
   static_assert(BW > TW && BH > TH, "source box must exceed the tile");
 };
 
-struct TileCtx {
-  const float* s_bu;
-  const float* s_bv;
-  int* s_box;
-  uint64_t* bars;
-  int pair, tile_x0, tile_y0, lane, wrp;
-};
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void named_barrier_sync(int id, int threads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
+}
 
-// The body of one tile.  EDGE = the tile crosses the right/bottom image border (bounds checks compiled in).
-template <typename FrameT, int MASK, bool REDUCE, int CT, bool LEAN, typename Cfg, bool EDGE>
-__device__ __forceinline__ void tile_body(const FwdParams& p, const TileCtx& t, const float* s_ff, const FrameT* s_prev,
-                                          const CUtensorMap* tm_ff, const CUtensorMap* tm_prev, float& err, unsigned& near) {
-  constexpr int BW = Cfg::BW, BH = Cfg::BH;
-  constexpr int NPX = Cfg::kCols * Cfg::kRows;
-  const Geo& g = p.geo;
-  const int W = g.W, H = g.H;
-  const size_t plane = (size_t)H * W;
-  const bool want_mob = MASK == MASK_COMPUTED && (LEAN || (p.flags & TCLB200_MOB));
-  const bool want_occ = MASK == MASK_COMPUTED && (LEAN || (p.flags & TCLB200_OCC));
-  const bool want_frames = CT > 0 && (LEAN || p.prev != nullptr);
-  const float* s_bu = t.s_bu;
-  const float* s_bv = t.s_bv;
-
-  // ---- phase A: sampling positions, motion-boundary test, bounding box of the taps
-  PixTaps taps[NPX];
-  float keep[NPX], nbs[NPX];
-  int bx0 = INT_MAX, by0 = INT_MAX, bx1 = INT_MIN, by1 = INT_MIN;
-#pragma unroll
-  for (int i = 0; i < NPX; ++i) {
-    const int lx = t.lane + 32 * (i % Cfg::kCols), ly = t.wrp + kWarps * (i / Cfg::kCols);
-    const int x = t.tile_x0 + lx, y = t.tile_y0 + ly;
-    const bool inside = !EDGE || (x < W && y < H);
-    const int c = (ly + 1) * Cfg::kBfW + lx + Cfg::kHaloX;
-    const float u = s_bu[c], v = s_bv[c];
-    nbs[i] = sqnorm2(u, v, kV);
-    keep[i] = 1.0f;
-    if (want_mob) {
-      float margin;
-      if (motion_boundary(s_bu[c - 1], s_bu[c + 1], s_bu[c - Cfg::kBfW], s_bu[c + Cfg::kBfW], s_bv[c - 1], s_bv[c + 1],
-                          s_bv[c - Cfg::kBfW], s_bv[c + Cfg::kBfW], nbs[i], kV, &margin))
-        keep[i] = 0.0f;
-      if (!LEAN && inside) near += fabsf(margin) < kNearBand;
-    }
-    taps[i] = pix_taps(u, v, x, y, g);
-    if (inside) {
-      bx0 = min(bx0, taps[i].x0); bx1 = max(bx1, taps[i].x0);
-      by0 = min(by0, taps[i].y0); by1 = max(by1, taps[i].y0);
-    }
+// warp-level version of the pair/batch finalisation (see reduce_and_finalise): called by ONE warp per tile
+__device__ __forceinline__ void warp_finalise_tile(double tile_sum, const FwdParams& p, int pair, int tile, int lane) {
+  const unsigned tpp = p.tiles_per_pair;
+  int last = 0;
+  if (lane == 0) {
+    __stcg(&p.scratch.partials[(size_t)pair * tpp + tile], tile_sum);
+    __threadfence();
+    last = atomicAdd(&p.scratch.pair_ticket[pair], 1u) == tpp - 1;
   }
-  if (want_occ || want_frames) {
-    bx0 = __reduce_min_sync(0xffffffffu, bx0); by0 = __reduce_min_sync(0xffffffffu, by0);
-    bx1 = __reduce_max_sync(0xffffffffu, bx1); by1 = __reduce_max_sync(0xffffffffu, by1);
-    if (t.lane == 0) {
-      atomicMin(&t.s_box[0], bx0); atomicMin(&t.s_box[1], by0);
-      atomicMax(&t.s_box[2], bx1); atomicMax(&t.s_box[3], by1);
-    }
+  last = __shfl_sync(0xffffffffu, last, 0);
+  if (!last) return;
+  __threadfence();
+  double* pp = p.scratch.partials + (size_t)pair * tpp;
+  double s = 0.0;
+  for (unsigned i = lane; i < tpp; i += 32) { s += __ldcg(pp + i); __stcg(pp + i, 0.0); }
+  // fixed order: lane-strided partial sums, then a fixed butterfly
+  const double S = warp_sum(s);
+  __syncwarp();
+  if (lane == 0) {
+    if (p.pair_sums) p.pair_sums[pair] = S;
+    if (p.pair_vals) p.pair_vals[pair] = finalise_value(S * p.inv_count, p.finalize);
+    __stcg(pp, S);
+    p.scratch.pair_ticket[pair] = 0;
+    __threadfence();
+    last = atomicAdd(p.scratch.batch_ticket, 1u) == (unsigned)p.B - 1;
   }
-  __syncthreads();
-  const int ox = t.s_box[0] & ~(Cfg::kXAlign - 1), oy = t.s_box[1];  // 16-byte aligned box start (floor, also for negatives)
-  // taps span [x0, x0+1] x [y0, y0+1]; the widths are computed in 64 bits (saturated coordinates)
-  const bool fits = ((long long)t.s_box[2] + 1 - ox < BW) && ((long long)t.s_box[3] + 1 - oy < BH);
-  const bool staged = fits && (want_occ || want_frames);
-  if (staged && threadIdx.x == 0) {
-    mbar_expect_tx(&t.bars[1], (want_occ ? Cfg::kFfLoad : 0u) + (want_frames ? Cfg::kPrevLoad : 0u));
-    if (want_occ) tma_load_4d(const_cast<float*>(s_ff), tm_ff, &t.bars[1], ox, oy, 0, t.pair);
-    if (want_frames) tma_load_4d(const_cast<FrameT*>(s_prev), tm_prev, &t.bars[1], ox, oy, 0, t.pair);
+  last = __shfl_sync(0xffffffffu, last, 0);
+  if (!last) return;
+  __threadfence();
+  double a = 0.0, b = 0.0;
+  for (int i = lane; i < p.B; i += 32) {
+    double* rec = p.scratch.partials + (size_t)i * tpp;
+    const double Si = __ldcg(rec);
+    __stcg(rec, 0.0);
+    a += Si;
+    b += (double)finalise_value(Si * p.inv_count, p.finalize);
   }
-
-  // ---- phase B: occlusion test, warp, masked error
-  const PairPtrs<FrameT> io = pair_ptrs<FrameT>(p, t.pair, CT, plane);
-  if (MASK == MASK_GIVEN) {  // the dataset mask replaces `keep`; loads overlap the TMA
-#pragma unroll
-    for (int i = 0; i < NPX; ++i) {
-      const int x = t.tile_x0 + t.lane + 32 * (i % Cfg::kCols), y = t.tile_y0 + t.wrp + kWarps * (i / Cfg::kCols);
-      keep[i] = (!EDGE || (x < W && y < H)) ? __ldcs(p.mask_in + (size_t)t.pair * plane + (size_t)y * W + x) : 0.0f;
-    }
-  }
-  const bool have_cur = CT > 0 && (LEAN || io.cur != nullptr);
-  auto load_cur = [&](int i, float (&dst)[CT > 0 ? CT : 1]) {
-    const int x = t.tile_x0 + t.lane + 32 * (i % Cfg::kCols), y = t.tile_y0 + t.wrp + kWarps * (i / Cfg::kCols);
-    const bool inside = !EDGE || (x < W && y < H);
-#pragma unroll
-    for (int c = 0; c < CT; ++c) dst[c] = (have_cur && inside) ? ld_stream(io.cur + (size_t)c * plane + (size_t)y * W + x) : 0.0f;
-  };
-  float cnext[CT > 0 ? CT : 1];
-  load_cur(0, cnext);  // one pixel ahead: the global-load latency hides behind the previous pixel's taps
-  if (staged) {
-    mbar_wait(&t.bars[1], 0);
-    const SmemSrc<float, BW, BH * BW> fsrc{s_ff, ox, oy};
-    const SmemSrc<FrameT, BW, BH * BW> psrc{s_prev, ox, oy};
-#pragma unroll
-    for (int i = 0; i < NPX; ++i) {
-      float cv[CT > 0 ? CT : 1];
-#pragma unroll
-      for (int c = 0; c < (CT > 0 ? CT : 1); ++c) cv[c] = cnext[c];
-      if (i + 1 < NPX) load_cur(i + 1, cnext);
-      const int lx = t.lane + 32 * (i % Cfg::kCols), ly = t.wrp + kWarps * (i / Cfg::kCols);
-      const int x = t.tile_x0 + lx, y = t.tile_y0 + ly;
-      if (!EDGE || (x < W && y < H)) {
-        const int c = (ly + 1) * Cfg::kBfW + lx + Cfg::kHaloX;
-        finish_pixel<FrameT, MASK, REDUCE, CT, LEAN>(p, taps[i], s_bu[c], s_bv[c], nbs[i], keep[i], (size_t)y * W + x, plane,
-                                                     t.pair, fsrc, psrc, io, have_cur ? cv : nullptr, err, near);
-      }
-    }
-  } else {
-    const GlobalSrc<float> fsrc{p.ff ? p.ff + (size_t)t.pair * 2 * plane : nullptr, plane, g};
-    const GlobalSrc<FrameT> psrc{p.prev ? reinterpret_cast<const FrameT*>(p.prev) + (size_t)t.pair * CT * plane : nullptr, plane, g};
-#pragma unroll
-    for (int i = 0; i < NPX; ++i) {
-      float cv[CT > 0 ? CT : 1];
-#pragma unroll
-      for (int c = 0; c < (CT > 0 ? CT : 1); ++c) cv[c] = cnext[c];
-      if (i + 1 < NPX) load_cur(i + 1, cnext);
-      const int lx = t.lane + 32 * (i % Cfg::kCols), ly = t.wrp + kWarps * (i / Cfg::kCols);
-      const int x = t.tile_x0 + lx, y = t.tile_y0 + ly;
-      if (!EDGE || (x < W && y < H)) {
-        const int c = (ly + 1) * Cfg::kBfW + lx + Cfg::kHaloX;
-        finish_pixel<FrameT, MASK, REDUCE, CT, LEAN>(p, taps[i], s_bu[c], s_bv[c], nbs[i], keep[i], (size_t)y * W + x, plane,
-                                                     t.pair, fsrc, psrc, io, have_cur ? cv : nullptr, err, near);
-      }
-    }
+  a = warp_sum(a);
+  b = warp_sum(b);
+  if (lane == 0) {
+    if (p.total_sums) { p.total_sums[0] = a; p.total_sums[1] = b; }
+    if (p.total_val) *p.total_val = finalise_value(a * p.inv_count / (double)p.B, p.finalize);
+    *p.scratch.batch_ticket = 0;
   }
 }
 
-template <typename FrameT, int MASK, bool REDUCE, int CT, bool LEAN, typename Cfg>
-__global__ void __launch_bounds__(kThreads, 4) fused_forward_tma_kernel(const FwdParams p, const __grid_constant__ CUtensorMap tm_bf,
-                                                                     const __grid_constant__ CUtensorMap tm_ff,
-                                                                     const __grid_constant__ CUtensorMap tm_prev) {
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  // TMA destinations must be 128-byte aligned: do not rely on where the dynamic window starts
-  unsigned char* smem = smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u);
-  float* s_bu = reinterpret_cast<float*>(smem + Cfg::kBfOff);  // [2][kBfH][kBfW]
-  float* s_ff = reinterpret_cast<float*>(smem + Cfg::kFfOff);  // [2][BH][BW]
-  FrameT* s_prev = reinterpret_cast<FrameT*>(smem + Cfg::kPrevOff);  // [CT][BH][BW]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kBarOff);
-  __shared__ int s_box[4];  // xmin, ymin, xmax, ymax of the top-left taps
+struct TileId { int pair, tile, x0, y0, edge; };
 
-  TileCtx t;
-  t.lane = threadIdx.x & 31; t.wrp = threadIdx.x >> 5;
-  t.pair = blockIdx.x / p.tiles_per_pair;
-  const int tile = blockIdx.x - t.pair * p.tiles_per_pair;
-  const int ty = tile / p.tiles_x, tx = tile - ty * p.tiles_x;
-  t.tile_x0 = tx * Cfg::TW; t.tile_y0 = ty * Cfg::TH;
-  t.s_bu = s_bu; t.s_bv = s_bu + Cfg::kBfH * Cfg::kBfW; t.s_box = s_box; t.bars = bars;
+struct PpCtl {              // control block in shared memory
+  uint64_t bf_full[2], src_full[2];
+  TileId tinfo[4];          // descriptors of local tiles k..k+3 (ring), written by thread 0 with the flow-tile request
+  int box[4];               // xmin, ymin, xmax, ymax of the tile's top-left taps (phase A accumulates, thread 0 resets)
+  int meta[2][4];           // per source stage: ox, oy, staged?
+  double red[kPpWarps];
+  int last;
+};
+
+template <int N>
+struct PxState {            // what phase A hands to phase B, per lane
+  float ix[N], iy[N], nbk[N], u[N], v[N];
+};
+
+__device__ __forceinline__ TileId tile_id(const FwdParams& p, int tg, int TW, int TH) {
+  TileId t;
+  t.pair = tg / p.tiles_per_pair;
+  t.tile = tg - t.pair * p.tiles_per_pair;
+  const int ty = t.tile / p.tiles_x, tx = t.tile - ty * p.tiles_x;
+  t.x0 = tx * TW; t.y0 = ty * TH;
+  t.edge = ((t.x0 + TW > p.geo.W) || (t.y0 + TH > p.geo.H)) ? 1 : 0;
+  return t;
+}
+
+// rebuild the four taps from a sampling position (same operations as pix_taps from ix, iy on)
+__device__ __forceinline__ PixTaps taps_from_coords(float ix, float iy) {
+  PixTaps t;
+  t.x0 = __float2int_rd(ix);
+  t.y0 = __float2int_rd(iy);
+  const float fx1 = __fsub_rn((float)(int)((unsigned)t.x0 + 1u), ix), fx0 = __fsub_rn(ix, (float)t.x0);
+  const float fy1 = __fsub_rn((float)(int)((unsigned)t.y0 + 1u), iy), fy0 = __fsub_rn(iy, (float)t.y0);
+  t.nw = __fmul_rn(fx1, fy1); t.ne = __fmul_rn(fx0, fy1);
+  t.sw = __fmul_rn(fx1, fy0); t.se = __fmul_rn(fx0, fy0);
+  return t;
+}
+
+// ---- phase A of one tile ----------------------------------------------------------------------
+template <int MASK, bool LEAN, typename Cfg, bool EDGE>
+__device__ __forceinline__ void phase_a(const FwdParams& p, const float* s_bu, int* box, const TileId& t, PxState<Cfg::kNPX>& st,
+                                        unsigned& near) {
+  const Geo& g = p.geo;
+  const bool want_mob = MASK == MASK_COMPUTED && (LEAN || (p.flags & TCLB200_MOB));
+  const float* s_bv = s_bu + Cfg::kBfH * Cfg::kBfW;
+  int bx0 = INT_MAX, by0 = INT_MAX, bx1 = INT_MIN, by1 = INT_MIN;
+#pragma unroll
+  for (int i = 0; i < Cfg::kNPX; ++i) {
+    const int q = threadIdx.x + i * kPpThreads;   // pixel index in the tile, row-major: unit stride in x across a warp
+    const int lx = q % Cfg::TW, ly = q / Cfg::TW;
+    const int x = t.x0 + lx, y = t.y0 + ly;
+    const bool inside = !EDGE || (x < g.W && y < g.H);
+    const int c = (ly + 1) * Cfg::kBfW + lx + Cfg::kHaloX;
+    const float u = s_bu[c], v = s_bv[c];
+    float nb, keep = 1.0f;
+    if (want_mob) {
+      float margin;
+      if (motion_boundary(u, v, s_bu[c - 1], s_bu[c + 1], s_bu[c - Cfg::kBfW], s_bu[c + Cfg::kBfW], s_bv[c - 1], s_bv[c + 1],
+                          s_bv[c - Cfg::kBfW], s_bv[c + Cfg::kBfW], kV, &nb, &margin))
+        keep = 0.0f;
+      if (!LEAN && inside) near += fabsf(margin) < kNearBand;
+    } else {
+      nb = sqnorm2(u, v, kV);
+    }
+    st.u[i] = u; st.v[i] = v;
+    st.ix[i] = source_coord(x, u, g.Wf, g.dxf, g.inv_dx, kV);
+    st.iy[i] = source_coord(y, v, g.Hf, g.dyf, g.inv_dy, kV);
+    // |bf|^2 >= +0, so its sign bit is free to carry the motion-boundary verdict (set = masked out)
+    st.nbk[i] = keep == 0.0f ? __uint_as_float(__float_as_uint(nb) | 0x80000000u) : nb;
+    if (inside) {
+      const int x0 = __float2int_rd(st.ix[i]), y0 = __float2int_rd(st.iy[i]);
+      bx0 = min(bx0, x0); bx1 = max(bx1, x0);
+      by0 = min(by0, y0); by1 = max(by1, y0);
+    }
+  }
+  bx0 = __reduce_min_sync(0xffffffffu, bx0); by0 = __reduce_min_sync(0xffffffffu, by0);
+  bx1 = __reduce_max_sync(0xffffffffu, bx1); by1 = __reduce_max_sync(0xffffffffu, by1);
+  if ((threadIdx.x & 31) == 0) {
+    atomicMin(&box[0], bx0); atomicMin(&box[1], by0);
+    atomicMax(&box[2], bx1); atomicMax(&box[3], by1);
+  }
+}
+
+// ---- phase B of one tile ----------------------------------------------------------------------
+template <typename FrameT, int MASK, bool REDUCE, int CT, bool LEAN, typename Cfg, bool EDGE>
+__device__ __forceinline__ float phase_b(const FwdParams& p, const float* s_ff, const FrameT* s_prev, const int* meta, const TileId& t,
+                                         const PxState<Cfg::kNPX>& st, const float (&cur)[Cfg::kNPX][CT > 0 ? CT : 1], unsigned& near) {
+  constexpr int BW = Cfg::BW, BH = Cfg::BH;
+  const Geo& g = p.geo;
+  const int W = g.W, H = g.H;
+  const size_t plane = (size_t)H * W;
+  const PairPtrs<FrameT> io = pair_ptrs<FrameT>(p, t.pair, CT, plane);
+  const bool have_cur = CT > 0 && (LEAN || io.cur != nullptr);
+  const int ox = meta[0], oy = meta[1];
+  const bool staged = meta[2] != 0;
+  const SmemSrc<float, BW, BH * BW> fs{s_ff, ox, oy};
+  const SmemSrc<FrameT, BW, BH * BW> ps{s_prev, ox, oy};
+  float err = 0.0f;
+#pragma unroll
+  for (int i = 0; i < Cfg::kNPX; ++i) {
+    const int q = threadIdx.x + i * kPpThreads;
+    const int lx = q % Cfg::TW, ly = q / Cfg::TW;
+    const int x = t.x0 + lx, y = t.y0 + ly;
+    if (!EDGE || (x < W && y < H)) {
+      const PixTaps taps = taps_from_coords(st.ix[i], st.iy[i]);
+      float keep = (__float_as_uint(st.nbk[i]) & 0x80000000u) ? 0.0f : 1.0f;
+      const size_t o = (size_t)y * W + x;
+      if (MASK == MASK_GIVEN) keep = __ldcs(p.mask_in + (size_t)t.pair * plane + o);
+      if (staged)
+        finish_pixel<FrameT, MASK, REDUCE, CT, LEAN>(p, taps, st.u[i], st.v[i], fabsf(st.nbk[i]), keep, o, plane, t.pair, fs, ps, io,
+                                                     have_cur ? cur[i] : nullptr, err, near);
+      else {  // rare: taps of this tile do not fit the box -> exact predicated gathers from global memory
+        const GlobalSrc<float> fg{p.ff ? p.ff + (size_t)t.pair * 2 * plane : nullptr, plane, g};
+        const GlobalSrc<FrameT> pg{p.prev ? reinterpret_cast<const FrameT*>(p.prev) + (size_t)t.pair * CT * plane : nullptr, plane, g};
+        finish_pixel<FrameT, MASK, REDUCE, CT, LEAN>(p, taps, st.u[i], st.v[i], fabsf(st.nbk[i]), keep, o, plane, t.pair, fg, pg, io,
+                                                     have_cur ? cur[i] : nullptr, err, near);
+      }
+    }
+  }
+  return err;
+}
+
+template <typename FrameT, int MASK, bool REDUCE, int CT, bool LEAN, typename Cfg>
+__global__ void __launch_bounds__(kPpThreads, 2) fused_forward_pp_kernel(const FwdParams p, const __grid_constant__ CUtensorMap tm_bf,
+                                                                         const __grid_constant__ CUtensorMap tm_ff,
+                                                                         const __grid_constant__ CUtensorMap tm_prev) {
+  constexpr int NPX = Cfg::kNPX;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  unsigned char* smem = smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u);  // TMA destinations: 128-byte aligned
+  PpCtl* ctl = reinterpret_cast<PpCtl*>(smem + Cfg::kCtlOff);
+  static_assert(sizeof(PpCtl) <= 512, "control block too large");
+  auto bf_stage = [&](int s) { return reinterpret_cast<float*>(smem + Cfg::kBfOff + (size_t)s * Cfg::kBfStage); };
+  auto ff_stage = [&](int s) { return reinterpret_cast<float*>(smem + Cfg::kFfOff + (size_t)s * Cfg::kFfStage); };
+  auto prev_stage = [&](int s) { return reinterpret_cast<FrameT*>(smem + Cfg::kPrevOff + (size_t)s * Cfg::kPrevStage); };
+
+  const int total_tiles = p.B * p.tiles_per_pair;
+  const int n = (total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;  // tiles of this CTA (>= 1)
+  const bool want_occ = MASK == MASK_COMPUTED && (LEAN || (p.flags & TCLB200_OCC));
+  const bool want_frames = CT > 0 && (LEAN || p.prev != nullptr);
+  // the tile decomposition costs two integer divisions: thread 0 does it once per tile and publishes it
+  auto tile_of = [&](int k) { return ctl->tinfo[k & 3]; };
+
+  // thread 0 only: describe local tile k and request its flow tile into flow stage k & 1
+  auto issue_bf = [&](int k) {
+    const TileId t = tile_id(p, (int)blockIdx.x + k * (int)gridDim.x, Cfg::TW, Cfg::TH);
+    ctl->tinfo[k & 3] = t;
+    mbar_expect_tx(&ctl->bf_full[k & 1], Cfg::kBfLoad);
+    tma_load_4d(bf_stage(k & 1), &tm_bf, &ctl->bf_full[k & 1], t.x0 - Cfg::kHaloX, t.y0 - 1, 0, t.pair);
+  };
+  // thread 0 only, after the CTA barrier that follows phase A of local tile k: place and request its source boxes
+  auto issue_src = [&](int k, int pair) {
+    const int s = k & 1;
+    const int ox = ctl->box[0] & ~(Cfg::kXAlign - 1), oy = ctl->box[1];  // 16-byte aligned box start (floor, also for negatives)
+    // taps span [x0, x0+1] x [y0, y0+1]; widths in 64 bits (saturated coordinates)
+    const bool fits = ((long long)ctl->box[2] + 1 - ox < Cfg::BW) && ((long long)ctl->box[3] + 1 - oy < Cfg::BH);
+    const bool staged = fits && (want_occ || want_frames);
+    ctl->meta[s][0] = ox; ctl->meta[s][1] = oy; ctl->meta[s][2] = staged;
+    ctl->box[0] = INT_MAX; ctl->box[1] = INT_MAX; ctl->box[2] = INT_MIN; ctl->box[3] = INT_MIN;
+    if (staged) {
+      fence_proxy_async();  // the stage was last read through the generic proxy (previous tile's phase B)
+      mbar_expect_tx(&ctl->src_full[s], (want_occ ? Cfg::kFfLoad : 0u) + (want_frames ? Cfg::kPrevLoad : 0u));
+      if (want_occ) tma_load_4d(ff_stage(s), &tm_ff, &ctl->src_full[s], ox, oy, 0, pair);
+      if (want_frames) tma_load_4d(prev_stage(s), &tm_prev, &ctl->src_full[s], ox, oy, 0, pair);
+    } else {
+      mbar_arrive(&ctl->src_full[s]);
+    }
+  };
 
   if (threadIdx.x == 0) {
-    mbar_init(&bars[0], 1);
-    mbar_init(&bars[1], 1);
+    mbar_init(&ctl->bf_full[0], 1); mbar_init(&ctl->bf_full[1], 1);
+    mbar_init(&ctl->src_full[0], 1); mbar_init(&ctl->src_full[1], 1);
+    ctl->box[0] = INT_MAX; ctl->box[1] = INT_MAX; ctl->box[2] = INT_MIN; ctl->box[3] = INT_MIN;
     fence_barrier_init();
-    s_box[0] = INT_MAX; s_box[1] = INT_MAX; s_box[2] = INT_MIN; s_box[3] = INT_MIN;
-    mbar_expect_tx(&bars[0], Cfg::kBfLoad);
-    tma_load_4d(s_bu, &tm_bf, &bars[0], t.tile_x0 - Cfg::kHaloX, t.tile_y0 - 1, 0, t.pair);
+    issue_bf(0);
+    if (n > 1) issue_bf(1);
   }
   __syncthreads();
-  mbar_wait(&bars[0], 0);
 
-  float err = 0.0f;
+  PxState<NPX> st[2];
   unsigned near = 0;
-  const bool edge = (t.tile_x0 + Cfg::TW > p.geo.W) || (t.tile_y0 + Cfg::TH > p.geo.H);
-  if (edge) tile_body<FrameT, MASK, REDUCE, CT, LEAN, Cfg, true>(p, t, s_ff, s_prev, &tm_ff, &tm_prev, err, near);
-  else tile_body<FrameT, MASK, REDUCE, CT, LEAN, Cfg, false>(p, t, s_ff, s_prev, &tm_ff, &tm_prev, err, near);
+  const size_t plane = (size_t)p.geo.H * p.geo.W;
+  int pix_off[NPX];  // offset of this lane's pixels from the tile origin: the same for every tile
+#pragma unroll
+  for (int i = 0; i < NPX; ++i) {
+    const int q = threadIdx.x + i * kPpThreads;
+    pix_off[i] = (q / Cfg::TW) * p.geo.W + q % Cfg::TW;
+  }
+
+  // phase A of local tile k into register set st[k & 1] (k & 1 must be a compile-time constant at the call site)
+  auto run_a = [&](int k, PxState<NPX>& dst) {
+    mbar_wait(&ctl->bf_full[k & 1], (k >> 1) & 1);
+    const TileId t = tile_of(k);
+    if (t.edge) phase_a<MASK, LEAN, Cfg, true>(p, bf_stage(k & 1), ctl->box, t, dst, near);
+    else phase_a<MASK, LEAN, Cfg, false>(p, bf_stage(k & 1), ctl->box, t, dst, near);
+    __syncthreads();  // bounding box complete; everyone is done reading flow stage k & 1
+    if (threadIdx.x == 0) {
+      issue_src(k, t.pair);
+      if (k + 2 < n) { fence_proxy_async(); issue_bf(k + 2); }
+    }
+  };
+  // phase B of local tile k from register set st[k & 1]
+  auto run_b = [&](int k, const PxState<NPX>& src) {
+    const TileId t = tile_of(k);
+    // this tile's `cur` values: requested before the wait, they arrive while the source boxes do
+    float cur[NPX][CT > 0 ? CT : 1];
+    {
+      const bool have_cur = CT > 0 && (LEAN || p.cur != nullptr);
+      const FrameT* cbase = reinterpret_cast<const FrameT*>(p.cur) + (size_t)t.pair * (CT > 0 ? CT : 1) * plane + ((size_t)t.y0 * p.geo.W + t.x0);
+#pragma unroll
+      for (int i = 0; i < NPX; ++i) {
+        const int q = threadIdx.x + i * kPpThreads;
+        const bool inside = !t.edge || (t.x0 + q % Cfg::TW < p.geo.W && t.y0 + q / Cfg::TW < p.geo.H);
+#pragma unroll
+        for (int c = 0; c < (CT > 0 ? CT : 1); ++c) cur[i][c] = (have_cur && inside) ? ld_stream(cbase + pix_off[i] + (size_t)c * plane) : 0.0f;
+      }
+    }
+    mbar_wait(&ctl->src_full[k & 1], (k >> 1) & 1);
+    float err;
+    if (t.edge) err = phase_b<FrameT, MASK, REDUCE, CT, LEAN, Cfg, true>(p, ff_stage(k & 1), prev_stage(k & 1), ctl->meta[k & 1], t, src, cur, near);
+    else err = phase_b<FrameT, MASK, REDUCE, CT, LEAN, Cfg, false>(p, ff_stage(k & 1), prev_stage(k & 1), ctl->meta[k & 1], t, src, cur, near);
+    // per-tile partial in a fixed order (lanes: butterfly; warps: index order), then the pair/batch tickets
+    if (REDUCE) {
+      const float ws = warp_sum(err);   // <= 192 fp32 terms per warp, then fp64 across warps/tiles/pairs
+      if ((threadIdx.x & 31) == 0) ctl->red[threadIdx.x >> 5] = (double)ws;
+    }
+    __syncthreads();  // source stage k & 1 may be refilled after this point
+    if (REDUCE) {
+      if (threadIdx.x < 32) {
+        double ts = 0.0;
+#pragma unroll
+        for (int i = 0; i < kPpWarps; ++i) ts += ctl->red[i];
+        warp_finalise_tile(ts, p, t.pair, t.tile, threadIdx.x);
+      }
+    }
+  };
+
+  run_a(0, st[0]);
+  for (int k = 0; k < n; k += 2) {
+    if (k + 1 < n) run_a(k + 1, st[1]);
+    run_b(k, st[0]);
+    if (k + 1 < n) {
+      if (k + 2 < n) run_a(k + 2, st[0]);
+      run_b(k + 1, st[1]);
+    }
+  }
   if (!LEAN) count_near(near, p.near_threshold);
-  if (REDUCE) reduce_and_finalise(err, p, t.pair, tile);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -533,8 +704,8 @@ extern "C" const char* tclb200_last_error(void) { return g_err; }
 // tile shape of the TMA kernel: 64 x 16 pixels per CTA, 76(80 for bf16) x 24 source box: after rounding the box
 // origin down to a 16-byte boundary the taps may still spread >= 8 px in x and 7 px in y beyond the tile's own
 // extent before the tile falls back to global gathers
-constexpr int kTW = 64, kTH = 16, kBH = 24;
-template <typename FrameT> constexpr int box_w() { return sizeof(FrameT) == 2 ? 80 : 76; }  // 16-byte multiple per dtype
+constexpr int kTW = TCL_TW, kTH = TCL_TH, kBH = TCL_BH;
+template <typename FrameT> constexpr int box_w() { return sizeof(FrameT) == 2 ? TCL_BW_BF16 : TCL_BW_F32; }  // 16-byte multiple per dtype
 
 static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 // scratch is sized for the finest tiling any kernel uses (32 x 8 generic tiles)
@@ -573,18 +744,30 @@ static bool make_map(CUtensorMap* m, const void* base, int esize, int W, int H, 
 }
 
 // ---- launches ----------------------------------------------------------------------------------
+static int sm_count() {
+  static int n = []() {
+    int dev = 0, v = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return 148;
+    return v > 0 ? v : 148;
+  }();
+  return n;
+}
+
 template <typename FrameT, int MASK, bool REDUCE, int CT, bool LEAN>
 static cudaError_t launch_tma(const FwdParams& p, const CUtensorMap& tb, const CUtensorMap& tf, const CUtensorMap& tp, cudaStream_t s) {
   using Cfg = TileCfg<FrameT, CT, kTW, kTH, box_w<FrameT>(), kBH>;
-  auto kern = fused_forward_tma_kernel<FrameT, MASK, REDUCE, CT, LEAN, Cfg>;
+  auto kern = fused_forward_pp_kernel<FrameT, MASK, REDUCE, CT, LEAN, Cfg>;
   static bool configured = false;  // per instantiation
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::kSmemBytes);
     if (e != cudaSuccess) return e;
     configured = true;
   }
-  const unsigned grid = (unsigned)((size_t)p.B * p.tiles_per_pair);
-  kern<<<grid, kThreads, Cfg::kSmemBytes, s>>>(p, tb, tf, tp);
+  // persistent: two CTAs per SM (or fewer when there are fewer tiles)
+  const size_t tiles = (size_t)p.B * p.tiles_per_pair;
+  const size_t slots = 2 * (size_t)sm_count();
+  const unsigned grid = (unsigned)(tiles < slots ? tiles : slots);
+  kern<<<grid, kPpThreads, Cfg::kSmemBytes, s>>>(p, tb, tf, tp);
   return cudaGetLastError();
 }
 
