@@ -35,20 +35,17 @@
 #include "tcl_math.cuh"
 
 // tile geometry of the TMA kernel (overridable at build time for tuning sweeps, see tools/sweep_build.py)
-#ifndef TCL_TW
-#define TCL_TW 64
-#endif
 #ifndef TCL_TH
-#define TCL_TH 16
+#define TCL_TH 16     // tile height (the width is 64)
 #endif
 #ifndef TCL_BH
-#define TCL_BH 24
+#define TCL_BH 24     // source-box height (the width is 80)
 #endif
-#ifndef TCL_BW_F32
-#define TCL_BW_F32 76
+#ifndef TCL_NS
+#define TCL_NS 3      // source-box stages in flight
 #endif
-#ifndef TCL_BW_BF16
-#define TCL_BW_BF16 80
+#ifndef TCL_NB
+#define TCL_NB (TCL_NS + 1)   // flow-tile stages in flight
 #endif
 
 namespace tcl {
@@ -214,116 +211,108 @@ __global__ void __launch_bounds__(kThreads) fused_forward_generic_kernel(const F
 }
 
 // ---------------------------------------------------------------------------------------------
-// TMA-staged, persistent, software-pipelined forward kernel
+// TMA-staged, persistent, warp-specialised forward kernel (the hot kernel)
 // ---------------------------------------------------------------------------------------------
-// Two 512-thread CTAs per SM, each walking tiles  t = blockIdx.x + k * gridDim.x.  A tile has two phases whose
-// loads depend on each other (flow tile -> where the source boxes lie), so every CTA keeps two tiles in flight:
+// One 544-thread CTA per SM walks tiles  t = blockIdx.x + k * gridDim.x  of TW x TH pixels.
 //
-//     iteration k:   A(k+1)  flow tile k+1 (prefetched two tiles ahead) -> sampling positions, |bf|^2,
-//                            motion-boundary verdict (kept in registers), tap bounding box -> TMA of the
-//                            `ff`/`prev` source boxes of tile k+1
-//                    B(k)    source boxes of tile k (requested one iteration ago): bilinear taps from shared
-//                            memory, occlusion test, masked error, per-tile partial sum
+//   producer warp (warp 16)   keeps NB flow tiles and NS source-box sets in flight with TMA:
+//       bf tile k   (TW+16) x (TH+2) x 2, 1 px halo (8 columns for the 16-byte TMA alignment), zero-filled
+//                   outside the image = the zero padding of flowtools.gradient
+//       when it lands: scan it (LDS.128) for the extent of x+u, y+v -> bounding box of all bilinear taps
+//       ff / prev   BW x BH boxes at that origin, zero-filled outside the image = grid_sample's
+//                   padding_mode='zeros'; tiles whose taps do not fit the box (or hold non-finite flow) are
+//                   flagged and take the exact predicated global-gather path
+//       when the consumers release a tile: fold its 16 warp partials, pair / batch tickets (fixed order)
+//   consumer warps (0..15)    one pass per pixel: flow + 4 neighbours from the flow tile, motion-boundary test,
+//                   sampling position, 4 x (2 + C) taps from the source boxes, occlusion test, masked error
+//                   against `cur` (coalesced global loads issued before the wait for the boxes).
 //
-// so both TMA latencies of a tile hide behind a full tile of arithmetic, with double-buffered flow tiles and
-// source boxes (2 x 10 KB + 2 x 36 KB per CTA).
-constexpr int kPpWarps = 16;
-constexpr int kPpThreads = 32 * kPpWarps;
+// A warp instruction covers 16 x 2 pixels (lane = 16 * row + column) and both the flow tile and the source boxes
+// have a pitch of 80 words = 16 (mod 32): the two rows fall into disjoint halves of the 32 banks, also when the
+// flow shifts some lanes to the next source row, so the taps are (nearly) conflict-free shared-memory reads.
+constexpr int kCWarps = 16;                      // consumer warps
+constexpr int kWsThreads = 32 * (kCWarps + 1);   // + 1 producer warp
 
-template <typename FrameT, int CT, int TW_, int TH_, int BW_, int BH_>
-struct TileCfg {
-  static constexpr int TW = TW_, TH = TH_, BW = BW_, BH = BH_;
-  // flow tile + 1 px halo.  TMA needs the box's innermost start coordinate on a 16-byte boundary (measured on
-  // B200: an unaligned x raises 'illegal instruction'), so the halo is 4 columns wide on each side.
-  static constexpr int kHaloX = 4;
+template <typename FrameT, int CT, int TW_, int TH_, int BH_, int NB_, int NS_>
+struct WsCfg {
+  static constexpr int TW = TW_, TH = TH_, BW = TW_ + 16, BH = BH_, NB = NB_, NS = NS_;
+  static constexpr int kHaloX = 8;               // TMA needs the box's innermost start on a 16-byte boundary
   static constexpr int kBfW = TW + 2 * kHaloX, kBfH = TH + 2;
   static constexpr int kXAlign = 16 / (int)sizeof(FrameT);   // source-box origin is rounded down to this many pixels
-  static constexpr int kPx = TW * TH;
-  static constexpr int kNPX = kPx / kPpThreads;              // pixels per lane
+  static constexpr int kPPL = TW * TH / (32 * kCWarps);      // pixels per lane per tile
+  static constexpr int kC = CT > 0 ? CT : 1;
   static constexpr unsigned kBfLoad = 2u * kBfH * kBfW * 4u;
   static constexpr unsigned kFfLoad = 2u * BH * BW * 4u;
   static constexpr unsigned kPrevLoad = (unsigned)(CT > 0 ? CT : 0) * BH * BW * (unsigned)sizeof(FrameT);
   static constexpr size_t kBfStage = align_up(kBfLoad, 128);
   static constexpr size_t kFfStage = align_up(kFfLoad, 128);
-  static constexpr size_t kPrevStage = align_up(kPrevLoad, 128);
+  static constexpr size_t kSrcStage = kFfStage + align_up(kPrevLoad, 128);
   static constexpr size_t kBfOff = 0;
-  static constexpr size_t kFfOff = kBfOff + 2 * kBfStage;
-  static constexpr size_t kPrevOff = kFfOff + 2 * kFfStage;
-  static constexpr size_t kCtlOff = kPrevOff + 2 * kPrevStage;
-  static constexpr size_t kSmemBytes = kCtlOff + 512 + 128;  // control block + slack for manual 128-byte alignment
-  static_assert(TW % 32 == 0 && kPx % kPpThreads == 0, "tile must split evenly over the lanes");
-  static_assert((BW * sizeof(FrameT)) % 16 == 0 && (BW * 4) % 16 == 0, "TMA inner box extent must be a 16-byte multiple");
-  static_assert(BW > TW && BH > TH, "source box must exceed the tile");
+  static constexpr size_t kSrcOff = kBfOff + NB * kBfStage;
+  static constexpr size_t kCtlOff = kSrcOff + NS * kSrcStage;
+  static constexpr size_t kSmemBytes = kCtlOff + 1024 + 128;  // control block + slack for manual 128-byte alignment
+  static_assert(TW == 64 && TH % 16 == 0 && kPPL % 2 == 0, "lane mapping assumes 64-wide tiles, 16 consumer warps");
+  static_assert(BW % 32 == 16 && kBfW % 32 == 16, "pitch must be 16 (mod 32) words for the 16 x 2 lane footprint");
+  static_assert(NB > NS, "the flow tile of a tile must be requested before its source boxes");
+};
+
+struct TileId { int pair, tile, x0, y0, edge, pad[3]; };
+
+template <int NB, int NS>
+struct WsCtl {              // control block in shared memory
+  uint64_t bf_full[NB], src_full[NS], done[NS];
+  TileId tinfo[NB];         // written by the producer with the flow-tile request
+  int meta[NS][4];          // per source stage: ox, oy, staged?
+  double red[NS][kCWarps];
 };
 
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-__device__ __forceinline__ void named_barrier_sync(int id, int threads) {
-  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
-}
 
-// warp-level version of the pair/batch finalisation (see reduce_and_finalise): called by ONE warp per tile
-__device__ __forceinline__ void warp_finalise_tile(double tile_sum, const FwdParams& p, int pair, int tile, int lane) {
+// Fold kernel of the warp-specialised path: the hot kernel only stores one fp64 partial per tile (no fences, no
+// atomics on its critical path); this kernel, launched behind it with programmatic dependent launch so that its
+// launch latency overlaps the hot kernel, sums each pair's partials in index order and the pairs in index order
+// (deterministic), finalises (mean / RMSE) and leaves the scratch zeroed as the protocol of tcl_common.cuh wants.
+__global__ void __launch_bounds__(kThreads) fold_partials_kernel(const FwdParams p) {
+  __shared__ double red[kWarps];
+  __shared__ int s_last;
+  asm volatile("griddepcontrol.wait;" ::: "memory");   // all of the hot kernel's stores are visible after this
+  const int pair = blockIdx.x;
   const unsigned tpp = p.tiles_per_pair;
-  int last = 0;
-  if (lane == 0) {
-    __stcg(&p.scratch.partials[(size_t)pair * tpp + tile], tile_sum);
-    __threadfence();
-    last = atomicAdd(&p.scratch.pair_ticket[pair], 1u) == tpp - 1;
-  }
-  last = __shfl_sync(0xffffffffu, last, 0);
-  if (!last) return;
-  __threadfence();
   double* pp = p.scratch.partials + (size_t)pair * tpp;
   double s = 0.0;
-  for (unsigned i = lane; i < tpp; i += 32) { s += __ldcg(pp + i); __stcg(pp + i, 0.0); }
-  // fixed order: lane-strided partial sums, then a fixed butterfly
-  const double S = warp_sum(s);
-  __syncwarp();
-  if (lane == 0) {
+  for (unsigned i = threadIdx.x; i < tpp; i += kThreads) {
+    s += __ldcg(pp + i);
+    __stcg(pp + i, 0.0);
+  }
+  const double S = block_sum(s, red);
+  if (threadIdx.x == 0) {
     if (p.pair_sums) p.pair_sums[pair] = S;
     if (p.pair_vals) p.pair_vals[pair] = finalise_value(S * p.inv_count, p.finalize);
-    __stcg(pp, S);
-    p.scratch.pair_ticket[pair] = 0;
+    __stcg(pp, S);  // this pair's record for the batch fold
     __threadfence();
-    last = atomicAdd(p.scratch.batch_ticket, 1u) == (unsigned)p.B - 1;
+    s_last = atomicAdd(p.scratch.batch_ticket, 1u) == (unsigned)p.B - 1;
   }
-  last = __shfl_sync(0xffffffffu, last, 0);
-  if (!last) return;
+  __syncthreads();
+  if (!s_last) return;
   __threadfence();
   double a = 0.0, b = 0.0;
-  for (int i = lane; i < p.B; i += 32) {
+  for (int i = threadIdx.x; i < p.B; i += kThreads) {
     double* rec = p.scratch.partials + (size_t)i * tpp;
     const double Si = __ldcg(rec);
     __stcg(rec, 0.0);
     a += Si;
     b += (double)finalise_value(Si * p.inv_count, p.finalize);
   }
-  a = warp_sum(a);
-  b = warp_sum(b);
-  if (lane == 0) {
-    if (p.total_sums) { p.total_sums[0] = a; p.total_sums[1] = b; }
-    if (p.total_val) *p.total_val = finalise_value(a * p.inv_count / (double)p.B, p.finalize);
+  const double A = block_sum(a, red);
+  const double Bv = block_sum(b, red);
+  if (threadIdx.x == 0) {
+    if (p.total_sums) { p.total_sums[0] = A; p.total_sums[1] = Bv; }
+    if (p.total_val) *p.total_val = finalise_value(A * p.inv_count / (double)p.B, p.finalize);
     *p.scratch.batch_ticket = 0;
   }
 }
-
-struct TileId { int pair, tile, x0, y0, edge; };
-
-struct PpCtl {              // control block in shared memory
-  uint64_t bf_full[2], src_full[2];
-  TileId tinfo[4];          // descriptors of local tiles k..k+3 (ring), written by thread 0 with the flow-tile request
-  int box[4];               // xmin, ymin, xmax, ymax of the tile's top-left taps (phase A accumulates, thread 0 resets)
-  int meta[2][4];           // per source stage: ox, oy, staged?
-  double red[kPpWarps];
-  int last;
-};
-
-template <int N>
-struct PxState {            // what phase A hands to phase B, per lane
-  float ix[N], iy[N], nbk[N], u[N], v[N];
-};
 
 __device__ __forceinline__ TileId tile_id(const FwdParams& p, int tg, int TW, int TH) {
   TileId t;
@@ -335,32 +324,34 @@ __device__ __forceinline__ TileId tile_id(const FwdParams& p, int tg, int TW, in
   return t;
 }
 
-// rebuild the four taps from a sampling position (same operations as pix_taps from ix, iy on)
-__device__ __forceinline__ PixTaps taps_from_coords(float ix, float iy) {
-  PixTaps t;
-  t.x0 = __float2int_rd(ix);
-  t.y0 = __float2int_rd(iy);
-  const float fx1 = __fsub_rn((float)(int)((unsigned)t.x0 + 1u), ix), fx0 = __fsub_rn(ix, (float)t.x0);
-  const float fy1 = __fsub_rn((float)(int)((unsigned)t.y0 + 1u), iy), fy0 = __fsub_rn(iy, (float)t.y0);
-  t.nw = __fmul_rn(fx1, fy1); t.ne = __fmul_rn(fx0, fy1);
-  t.sw = __fmul_rn(fx1, fy0); t.se = __fmul_rn(fx0, fy0);
-  return t;
+// lane -> pixel k of the tile: a warp instruction covers 16 columns x 2 rows
+__device__ __forceinline__ void lane_pixel(int warp, int lane, int k, int& lx, int& ly) {
+  const int task = warp + kCWarps * (k >> 1);   // 32 x 2 pixel strip of the tile
+  lx = 32 * (task & 1) + 16 * (k & 1) + (lane & 15);
+  ly = 2 * (task >> 1) + (lane >> 4);
 }
 
-// ---- phase A of one tile ----------------------------------------------------------------------
-template <int MASK, bool LEAN, typename Cfg, bool EDGE>
-__device__ __forceinline__ void phase_a(const FwdParams& p, const float* s_bu, int* box, const TileId& t, PxState<Cfg::kNPX>& st,
-                                        unsigned& near) {
+// ---- consumer: exact per-pixel path (all features; staged boxes or global gathers) -------------------
+template <typename FrameT, int MASK, bool REDUCE, int CT, bool LEAN, typename Cfg, bool EDGE>
+__device__ __forceinline__ float full_tile(const FwdParams& p, const float* s_bu, const float* s_ff, const FrameT* s_prev,
+                                           const int* meta, const TileId& t, int warp, int lane, unsigned& near) {
   const Geo& g = p.geo;
+  const int W = g.W, H = g.H;
+  const size_t plane = (size_t)H * W;
   const bool want_mob = MASK == MASK_COMPUTED && (LEAN || (p.flags & TCLB200_MOB));
   const float* s_bv = s_bu + Cfg::kBfH * Cfg::kBfW;
-  int bx0 = INT_MAX, by0 = INT_MAX, bx1 = INT_MIN, by1 = INT_MIN;
-#pragma unroll
-  for (int i = 0; i < Cfg::kNPX; ++i) {
-    const int q = threadIdx.x + i * kPpThreads;   // pixel index in the tile, row-major: unit stride in x across a warp
-    const int lx = q % Cfg::TW, ly = q / Cfg::TW;
+  const PairPtrs<FrameT> io = pair_ptrs<FrameT>(p, t.pair, CT > 0 ? CT : p.C, plane);
+  const int ox = meta[0], oy = meta[1];
+  const bool staged = meta[2] != 0;
+  const SmemSrc<float, Cfg::BW, Cfg::BH * Cfg::BW> fs{s_ff, ox, oy};
+  const SmemSrc<FrameT, Cfg::BW, Cfg::BH * Cfg::BW> ps{s_prev, ox, oy};
+  float err = 0.0f;
+#pragma unroll 1
+  for (int k = 0; k < Cfg::kPPL; ++k) {
+    int lx, ly;
+    lane_pixel(warp, lane, k, lx, ly);
     const int x = t.x0 + lx, y = t.y0 + ly;
-    const bool inside = !EDGE || (x < g.W && y < g.H);
+    if (EDGE && (x >= W || y >= H)) continue;
     const int c = (ly + 1) * Cfg::kBfW + lx + Cfg::kHaloX;
     const float u = s_bu[c], v = s_bv[c];
     float nb, keep = 1.0f;
@@ -369,190 +360,294 @@ __device__ __forceinline__ void phase_a(const FwdParams& p, const float* s_bu, i
       if (motion_boundary(u, v, s_bu[c - 1], s_bu[c + 1], s_bu[c - Cfg::kBfW], s_bu[c + Cfg::kBfW], s_bv[c - 1], s_bv[c + 1],
                           s_bv[c - Cfg::kBfW], s_bv[c + Cfg::kBfW], kV, &nb, &margin))
         keep = 0.0f;
-      if (!LEAN && inside) near += fabsf(margin) < kNearBand;
+      if (!LEAN) near += fabsf(margin) < kNearBand;
     } else {
       nb = sqnorm2(u, v, kV);
     }
-    st.u[i] = u; st.v[i] = v;
-    st.ix[i] = source_coord(x, u, g.Wf, g.dxf, g.inv_dx, kV);
-    st.iy[i] = source_coord(y, v, g.Hf, g.dyf, g.inv_dy, kV);
-    // |bf|^2 >= +0, so its sign bit is free to carry the motion-boundary verdict (set = masked out)
-    st.nbk[i] = keep == 0.0f ? __uint_as_float(__float_as_uint(nb) | 0x80000000u) : nb;
-    if (inside) {
-      const int x0 = __float2int_rd(st.ix[i]), y0 = __float2int_rd(st.iy[i]);
-      bx0 = min(bx0, x0); bx1 = max(bx1, x0);
-      by0 = min(by0, y0); by1 = max(by1, y0);
-    }
-  }
-  bx0 = __reduce_min_sync(0xffffffffu, bx0); by0 = __reduce_min_sync(0xffffffffu, by0);
-  bx1 = __reduce_max_sync(0xffffffffu, bx1); by1 = __reduce_max_sync(0xffffffffu, by1);
-  if ((threadIdx.x & 31) == 0) {
-    atomicMin(&box[0], bx0); atomicMin(&box[1], by0);
-    atomicMax(&box[2], bx1); atomicMax(&box[3], by1);
-  }
-}
-
-// ---- phase B of one tile ----------------------------------------------------------------------
-template <typename FrameT, int MASK, bool REDUCE, int CT, bool LEAN, typename Cfg, bool EDGE>
-__device__ __forceinline__ float phase_b(const FwdParams& p, const float* s_ff, const FrameT* s_prev, const int* meta, const TileId& t,
-                                         const PxState<Cfg::kNPX>& st, const float (&cur)[Cfg::kNPX][CT > 0 ? CT : 1], unsigned& near) {
-  constexpr int BW = Cfg::BW, BH = Cfg::BH;
-  const Geo& g = p.geo;
-  const int W = g.W, H = g.H;
-  const size_t plane = (size_t)H * W;
-  const PairPtrs<FrameT> io = pair_ptrs<FrameT>(p, t.pair, CT, plane);
-  const bool have_cur = CT > 0 && (LEAN || io.cur != nullptr);
-  const int ox = meta[0], oy = meta[1];
-  const bool staged = meta[2] != 0;
-  const SmemSrc<float, BW, BH * BW> fs{s_ff, ox, oy};
-  const SmemSrc<FrameT, BW, BH * BW> ps{s_prev, ox, oy};
-  float err = 0.0f;
-#pragma unroll
-  for (int i = 0; i < Cfg::kNPX; ++i) {
-    const int q = threadIdx.x + i * kPpThreads;
-    const int lx = q % Cfg::TW, ly = q / Cfg::TW;
-    const int x = t.x0 + lx, y = t.y0 + ly;
-    if (!EDGE || (x < W && y < H)) {
-      const PixTaps taps = taps_from_coords(st.ix[i], st.iy[i]);
-      float keep = (__float_as_uint(st.nbk[i]) & 0x80000000u) ? 0.0f : 1.0f;
-      const size_t o = (size_t)y * W + x;
-      if (MASK == MASK_GIVEN) keep = __ldcs(p.mask_in + (size_t)t.pair * plane + o);
-      if (staged)
-        finish_pixel<FrameT, MASK, REDUCE, CT, LEAN>(p, taps, st.u[i], st.v[i], fabsf(st.nbk[i]), keep, o, plane, t.pair, fs, ps, io,
-                                                     have_cur ? cur[i] : nullptr, err, near);
-      else {  // rare: taps of this tile do not fit the box -> exact predicated gathers from global memory
-        const GlobalSrc<float> fg{p.ff ? p.ff + (size_t)t.pair * 2 * plane : nullptr, plane, g};
-        const GlobalSrc<FrameT> pg{p.prev ? reinterpret_cast<const FrameT*>(p.prev) + (size_t)t.pair * CT * plane : nullptr, plane, g};
-        finish_pixel<FrameT, MASK, REDUCE, CT, LEAN>(p, taps, st.u[i], st.v[i], fabsf(st.nbk[i]), keep, o, plane, t.pair, fg, pg, io,
-                                                     have_cur ? cur[i] : nullptr, err, near);
-      }
+    const PixTaps taps = pix_taps(u, v, x, y, g);
+    const size_t o = (size_t)y * W + x;
+    if (MASK == MASK_GIVEN) keep = __ldcs(p.mask_in + (size_t)t.pair * plane + o);
+    if (staged) {
+      finish_pixel<FrameT, MASK, REDUCE, CT, LEAN>(p, taps, u, v, nb, keep, o, plane, t.pair, fs, ps, io, nullptr, err, near);
+    } else {  // taps of this tile do not fit the box -> exact predicated gathers from global memory
+      const GlobalSrc<float> fg{p.ff ? p.ff + (size_t)t.pair * 2 * plane : nullptr, plane, g};
+      const GlobalSrc<FrameT> pg{p.prev ? reinterpret_cast<const FrameT*>(p.prev) + (size_t)t.pair * (CT > 0 ? CT : p.C) * plane : nullptr, plane, g};
+      finish_pixel<FrameT, MASK, REDUCE, CT, LEAN>(p, taps, u, v, nb, keep, o, plane, t.pair, fg, pg, io, nullptr, err, near);
     }
   }
   return err;
 }
 
+// ---- consumer: the hot configuration (LEAN: C == 3, L2 error, no optional outputs), staged tiles only ----------
+// The mask tests compare  lhs > rhs  where both sides are sums of torch.norm(.)**2 terms, i.e. sqrt-then-square
+// of a sum of squares (flowtools.py:41-53).  Each such term differs from the plain sum of squares by at most a few
+// ulp, so the plain (sqrt-free) evaluation decides the test whenever |lhs - rhs| > kFilterEps * (lhs + rhs); only the
+// remaining pixels (a few per million) replay the exact sequence.  Results are identical to the exact path.
+constexpr float kFilterEps = 4e-6f;   // >= 8x the worst-case relative deviation (< 16 * 2^-24 per side)
+
+template <typename FrameT, int MASK, typename Cfg, bool EDGE>
+__device__ __forceinline__ float lean_tile(const FwdParams& p, const float* s_bu, const float* s_ff, const FrameT* s_prev,
+                                           const int* meta, const TileId& t, int warp, int lane,
+                                           const float (&cur)[Cfg::kPPL][3], const float (&mk)[Cfg::kPPL]) {
+  constexpr int P = Cfg::kPPL, BW = Cfg::BW, BFW = Cfg::kBfW, PL = Cfg::BH * Cfg::BW;
+  const Geo& g = p.geo;
+  const float* s_bv = s_bu + Cfg::kBfH * BFW;
+  const int box0 = meta[1] * BW + meta[0];   // box-relative index of source pixel (0,0)
+  const float x0f = (float)t.x0, y0f = (float)t.y0;
+  const float i2x = __fmul_rn(2.0f, g.inv_dx), i2y = __fmul_rn(2.0f, g.inv_dy);   // exact doubling: (2a)*r == a*(2r)
+  float e[P], wu[P], wv[P], fu[P], fv[P];
+  bool keep[P];
+  bool amb = false;
+#pragma unroll
+  for (int k = 0; k < P; ++k) {
+    int lx, ly;
+    lane_pixel(warp, lane, k, lx, ly);
+    const bool inside = !EDGE || (t.x0 + lx < g.W && t.y0 + ly < g.H);
+    const int c = (ly + 1) * BFW + lx + Cfg::kHaloX;
+    const float u = s_bu[c], v = s_bv[c];
+    fu[k] = u; fv[k] = v;
+    const float s0 = __fmaf_rn(u, u, __fmul_rn(v, v));
+    keep[k] = inside;
+    if (MASK == MASK_COMPUTED) {
+      // motion boundary: 4*(|grad u|^2 + |grad v|^2)  vs  4*(0.01*|bf|^2 + 0.002)
+      const float dux = __fsub_rn(s_bu[c + 1], s_bu[c - 1]), duy = __fsub_rn(s_bu[c + BFW], s_bu[c - BFW]);
+      const float dvx = __fsub_rn(s_bv[c + 1], s_bv[c - 1]), dvy = __fsub_rn(s_bv[c + BFW], s_bv[c - BFW]);
+      const float G = __fmaf_rn(dux, dux, __fmaf_rn(duy, duy, __fmaf_rn(dvx, dvx, __fmul_rn(dvy, dvy))));
+      const float R = __fmaf_rn(0.04f, s0, 0.008f);
+      keep[k] = keep[k] && !(G > R);
+      amb = amb || (inside && !(fabsf(__fsub_rn(G, R)) > __fmul_rn(kFilterEps, __fadd_rn(G, R))));
+    }
+    // sampling position: the reference's [-1,1] round trip (flowtools.py:28-29 + grid_sampler's unnormalise).  Inside a
+    // staged tile every coordinate is finite and far inside the int range: no safe_downgrade guard needed.
+    const float ax = __fadd_rn(__fadd_rn(x0f, (float)lx), u), ay = __fadd_rn(__fadd_rn(y0f, (float)ly), v);
+    const float tx = __fadd_rn(__fsub_rn(__fmul_rn(ax, i2x), 1.0f), 1.0f), ty = __fadd_rn(__fsub_rn(__fmul_rn(ay, i2y), 1.0f), 1.0f);
+    const float ix = __fmul_rn(__fmaf_rn(tx, g.Wf, -1.0f), 0.5f), iy = __fmul_rn(__fmaf_rn(ty, g.Hf, -1.0f), 0.5f);
+    const float fxf = floorf(ix), fyf = floorf(iy);
+    const float fx1 = __fsub_rn(__fadd_rn(fxf, 1.0f), ix), fx0 = __fsub_rn(ix, fxf);
+    const float fy1 = __fsub_rn(__fadd_rn(fyf, 1.0f), iy), fy0 = __fsub_rn(iy, fyf);
+    const float nw = __fmul_rn(fx1, fy1), ne = __fmul_rn(fx0, fy1), sw = __fmul_rn(fx1, fy0), se = __fmul_rn(fx0, fy0);
+    int q = (int)fyf * BW + (int)fxf - box0;
+    if (EDGE && !inside) q = 0;   // pixels beyond the image edge: any in-box address, result discarded
+    if (MASK == MASK_COMPUTED) {
+      const float* f0 = s_ff + q;
+      float a = __fmul_rn(f0[0], nw);
+      a = __fmaf_rn(f0[1], ne, a); a = __fmaf_rn(f0[BW], sw, a); a = __fmaf_rn(f0[BW + 1], se, a);
+      float b = __fmul_rn(f0[PL], nw);
+      b = __fmaf_rn(f0[PL + 1], ne, b); b = __fmaf_rn(f0[PL + BW], sw, b); b = __fmaf_rn(f0[PL + BW + 1], se, b);
+      wu[k] = a; wv[k] = b;
+      // occlusion: |wf+bf|^2  vs  0.01*(|wf|^2+|bf|^2) + 0.5
+      const float su = __fadd_rn(a, u), sv = __fadd_rn(b, v);
+      const float L = __fmaf_rn(su, su, __fmul_rn(sv, sv));
+      const float R = __fmaf_rn(0.01f, __fadd_rn(__fmaf_rn(a, a, __fmul_rn(b, b)), s0), 0.5f);
+      keep[k] = keep[k] && !(L > R);
+      amb = amb || (inside && !(fabsf(__fsub_rn(L, R)) > __fmul_rn(kFilterEps, __fadd_rn(L, R))));
+    }
+    const FrameT* q0 = s_prev + q;
+    float acc = 0.0f;
+#pragma unroll
+    for (int ch = 0; ch < 3; ++ch) {
+      float w = __fmul_rn(to_f32(q0[ch * PL]), nw);
+      w = __fmaf_rn(to_f32(q0[ch * PL + 1]), ne, w);
+      w = __fmaf_rn(to_f32(q0[ch * PL + BW]), sw, w);
+      w = __fmaf_rn(to_f32(q0[ch * PL + BW + 1]), se, w);
+      const float d = __fsub_rn(cur[k][ch], w);
+      acc = __fmaf_rn(d, d, acc);
+    }
+    e[k] = acc;
+  }
+  if (MASK == MASK_COMPUTED && __any_sync(0xffffffffu, amb)) {
+    // a test of some pixel in this warp is too close to call: replay the exact sequences (rare)
+#pragma unroll
+    for (int k = 0; k < P; ++k) {
+      int lx, ly;
+      lane_pixel(warp, lane, k, lx, ly);
+      const bool inside = !EDGE || (t.x0 + lx < g.W && t.y0 + ly < g.H);
+      const int c = (ly + 1) * BFW + lx + Cfg::kHaloX;
+      float nb, m1, m2;
+      const bool mob = motion_boundary(fu[k], fv[k], s_bu[c - 1], s_bu[c + 1], s_bu[c - BFW], s_bu[c + BFW], s_bv[c - 1], s_bv[c + 1],
+                                       s_bv[c - BFW], s_bv[c + BFW], kV, &nb, &m1);
+      const bool occ = occluded(wu[k], wv[k], fu[k], fv[k], nb, kV, &m2);
+      keep[k] = inside && !mob && !occ;
+    }
+  }
+  float err = 0.0f;
+#pragma unroll
+  for (int k = 0; k < P; ++k) {
+    if (MASK == MASK_GIVEN) err = __fmaf_rn(__fmul_rn(mk[k], mk[k]), e[k], err);   // (m*d)^2 summed over channels
+    else err = keep[k] ? __fadd_rn(err, e[k]) : err;
+  }
+  return err;
+}
+
 template <typename FrameT, int MASK, bool REDUCE, int CT, bool LEAN, typename Cfg>
-__global__ void __launch_bounds__(kPpThreads, 2) fused_forward_pp_kernel(const FwdParams p, const __grid_constant__ CUtensorMap tm_bf,
+__global__ void __launch_bounds__(kWsThreads, 1) fused_forward_ws_kernel(const FwdParams p, const __grid_constant__ CUtensorMap tm_bf,
                                                                          const __grid_constant__ CUtensorMap tm_ff,
                                                                          const __grid_constant__ CUtensorMap tm_prev) {
-  constexpr int NPX = Cfg::kNPX;
+  constexpr int NB = Cfg::NB, NS = Cfg::NS, P = Cfg::kPPL;
+  using Ctl = WsCtl<NB, NS>;
+  static_assert(sizeof(Ctl) <= 1024, "control block too large");
   extern __shared__ __align__(128) unsigned char smem_raw[];
   unsigned char* smem = smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u);  // TMA destinations: 128-byte aligned
-  PpCtl* ctl = reinterpret_cast<PpCtl*>(smem + Cfg::kCtlOff);
-  static_assert(sizeof(PpCtl) <= 512, "control block too large");
+  Ctl* ctl = reinterpret_cast<Ctl*>(smem + Cfg::kCtlOff);
   auto bf_stage = [&](int s) { return reinterpret_cast<float*>(smem + Cfg::kBfOff + (size_t)s * Cfg::kBfStage); };
-  auto ff_stage = [&](int s) { return reinterpret_cast<float*>(smem + Cfg::kFfOff + (size_t)s * Cfg::kFfStage); };
-  auto prev_stage = [&](int s) { return reinterpret_cast<FrameT*>(smem + Cfg::kPrevOff + (size_t)s * Cfg::kPrevStage); };
+  auto ff_stage = [&](int s) { return reinterpret_cast<float*>(smem + Cfg::kSrcOff + (size_t)s * Cfg::kSrcStage); };
+  auto prev_stage = [&](int s) { return reinterpret_cast<FrameT*>(smem + Cfg::kSrcOff + (size_t)s * Cfg::kSrcStage + Cfg::kFfStage); };
 
   const int total_tiles = p.B * p.tiles_per_pair;
   const int n = (total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;  // tiles of this CTA (>= 1)
   const bool want_occ = MASK == MASK_COMPUTED && (LEAN || (p.flags & TCLB200_OCC));
   const bool want_frames = CT > 0 && (LEAN || p.prev != nullptr);
-  // the tile decomposition costs two integer divisions: thread 0 does it once per tile and publishes it
-  auto tile_of = [&](int k) { return ctl->tinfo[k & 3]; };
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const Geo& g = p.geo;
 
-  // thread 0 only: describe local tile k and request its flow tile into flow stage k & 1
-  auto issue_bf = [&](int k) {
-    const TileId t = tile_id(p, (int)blockIdx.x + k * (int)gridDim.x, Cfg::TW, Cfg::TH);
-    ctl->tinfo[k & 3] = t;
-    mbar_expect_tx(&ctl->bf_full[k & 1], Cfg::kBfLoad);
-    tma_load_4d(bf_stage(k & 1), &tm_bf, &ctl->bf_full[k & 1], t.x0 - Cfg::kHaloX, t.y0 - 1, 0, t.pair);
-  };
-  // thread 0 only, after the CTA barrier that follows phase A of local tile k: place and request its source boxes
-  auto issue_src = [&](int k, int pair) {
-    const int s = k & 1;
-    const int ox = ctl->box[0] & ~(Cfg::kXAlign - 1), oy = ctl->box[1];  // 16-byte aligned box start (floor, also for negatives)
-    // taps span [x0, x0+1] x [y0, y0+1]; widths in 64 bits (saturated coordinates)
-    const bool fits = ((long long)ctl->box[2] + 1 - ox < Cfg::BW) && ((long long)ctl->box[3] + 1 - oy < Cfg::BH);
-    const bool staged = fits && (want_occ || want_frames);
-    ctl->meta[s][0] = ox; ctl->meta[s][1] = oy; ctl->meta[s][2] = staged;
-    ctl->box[0] = INT_MAX; ctl->box[1] = INT_MAX; ctl->box[2] = INT_MIN; ctl->box[3] = INT_MIN;
-    if (staged) {
-      fence_proxy_async();  // the stage was last read through the generic proxy (previous tile's phase B)
-      mbar_expect_tx(&ctl->src_full[s], (want_occ ? Cfg::kFfLoad : 0u) + (want_frames ? Cfg::kPrevLoad : 0u));
-      if (want_occ) tma_load_4d(ff_stage(s), &tm_ff, &ctl->src_full[s], ox, oy, 0, pair);
-      if (want_frames) tma_load_4d(prev_stage(s), &tm_prev, &ctl->src_full[s], ox, oy, 0, pair);
-    } else {
-      mbar_arrive(&ctl->src_full[s]);
-    }
-  };
-
+  if (REDUCE) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // let the fold kernel get resident early
   if (threadIdx.x == 0) {
-    mbar_init(&ctl->bf_full[0], 1); mbar_init(&ctl->bf_full[1], 1);
-    mbar_init(&ctl->src_full[0], 1); mbar_init(&ctl->src_full[1], 1);
-    ctl->box[0] = INT_MAX; ctl->box[1] = INT_MAX; ctl->box[2] = INT_MIN; ctl->box[3] = INT_MIN;
+    for (int i = 0; i < NB; ++i) mbar_init(&ctl->bf_full[i], 1);
+    for (int i = 0; i < NS; ++i) { mbar_init(&ctl->src_full[i], 1); mbar_init(&ctl->done[i], kCWarps); }
     fence_barrier_init();
-    issue_bf(0);
-    if (n > 1) issue_bf(1);
   }
   __syncthreads();
 
-  PxState<NPX> st[2];
-  unsigned near = 0;
-  const size_t plane = (size_t)p.geo.H * p.geo.W;
-  int pix_off[NPX];  // offset of this lane's pixels from the tile origin: the same for every tile
+  if (warp == kCWarps) {
+    // ===================================== producer warp =====================================
+    auto issue_bf = [&](int k) {   // lane 0: describe local tile k, request its flow tile
+      const int s = k % NB;
+      const TileId t = tile_id(p, (int)blockIdx.x + k * (int)gridDim.x, Cfg::TW, Cfg::TH);
+      ctl->tinfo[s] = t;
+      mbar_expect_tx(&ctl->bf_full[s], Cfg::kBfLoad);
+      tma_load_4d(bf_stage(s), &tm_bf, &ctl->bf_full[s], t.x0 - Cfg::kHaloX, t.y0 - 1, 0, t.pair);
+    };
+    // whole warp: extent of x+u, y+v over the tile's pixels -> origin of the source boxes -> request them
+    auto issue_src = [&](int k) {
+      const int sb = k % NB, ss = k % NS;
+      mbar_wait(&ctl->bf_full[sb], (k / NB) & 1);
+      const TileId t = ctl->tinfo[sb];
+      bool staged = want_occ || want_frames;
+      int ox = 0, oy = 0;
+      if (staged) {
+        const float* s_bu = bf_stage(sb);
+        const float* s_bv = s_bu + Cfg::kBfH * Cfg::kBfW;
+        const int c4 = 4 * (lane & 15);
+        const int rows = min(Cfg::TH, g.H - t.y0);
+        const bool col_ok = t.x0 + c4 < g.W;      // W % 4 == 0: a lane's four columns are all inside or all outside
+        const float xf = (float)(t.x0 + c4);
+        float xmin = 3e38f, xmax = -3e38f, ymin = 3e38f, ymax = -3e38f, z = 0.0f;
+        if (col_ok) {
+          for (int r = lane >> 4; r < rows; r += 2) {
+            const float4 u4 = *reinterpret_cast<const float4*>(s_bu + (r + 1) * Cfg::kBfW + Cfg::kHaloX + c4);
+            const float4 v4 = *reinterpret_cast<const float4*>(s_bv + (r + 1) * Cfg::kBfW + Cfg::kHaloX + c4);
+            const float a0 = __fadd_rn(xf, u4.x), a1 = __fadd_rn(xf + 1.0f, u4.y), a2 = __fadd_rn(xf + 2.0f, u4.z), a3 = __fadd_rn(xf + 3.0f, u4.w);
+            xmin = fminf(fminf(xmin, a0), fminf(a1, fminf(a2, a3)));
+            xmax = fmaxf(fmaxf(xmax, a0), fmaxf(a1, fmaxf(a2, a3)));
+            const float yf = (float)(t.y0 + r);
+            const float vmin = fminf(fminf(v4.x, v4.y), fminf(v4.z, v4.w)), vmax = fmaxf(fmaxf(v4.x, v4.y), fmaxf(v4.z, v4.w));
+            ymin = fminf(ymin, __fadd_rn(yf, vmin));
+            ymax = fmaxf(ymax, __fadd_rn(yf, vmax));
+            // 0 * finite == 0; an Inf or NaN anywhere makes z NaN (fminf / fmaxf would silently drop a NaN)
+            z = __fmaf_rn(u4.x, 0.0f, z); z = __fmaf_rn(u4.y, 0.0f, z); z = __fmaf_rn(u4.z, 0.0f, z); z = __fmaf_rn(u4.w, 0.0f, z);
+            z = __fmaf_rn(v4.x, 0.0f, z); z = __fmaf_rn(v4.y, 0.0f, z); z = __fmaf_rn(v4.z, 0.0f, z); z = __fmaf_rn(v4.w, 0.0f, z);
+          }
+        }
+        // the coordinate map is monotone in x+u (every step is a correctly rounded monotone operation), so the
+        // extreme taps come from the extreme sums; clamp first so the conversions stay in range
+        const float lim = 1048576.0f;
+        const float i2x = __fmul_rn(2.0f, g.inv_dx), i2y = __fmul_rn(2.0f, g.inv_dy);
+        auto coord = [](float a, float i2, float sz) {
+          const float tt = __fadd_rn(__fsub_rn(__fmul_rn(a, i2), 1.0f), 1.0f);
+          return __fmul_rn(__fmaf_rn(tt, sz, -1.0f), 0.5f);
+        };
+        int bx0 = __float2int_rd(coord(fminf(fmaxf(xmin, -lim), lim), i2x, g.Wf));
+        int bx1 = __float2int_rd(coord(fminf(fmaxf(xmax, -lim), lim), i2x, g.Wf));
+        int by0 = __float2int_rd(coord(fminf(fmaxf(ymin, -lim), lim), i2y, g.Hf));
+        int by1 = __float2int_rd(coord(fminf(fmaxf(ymax, -lim), lim), i2y, g.Hf));
+        bx0 = __reduce_min_sync(0xffffffffu, bx0); by0 = __reduce_min_sync(0xffffffffu, by0);
+        bx1 = __reduce_max_sync(0xffffffffu, bx1); by1 = __reduce_max_sync(0xffffffffu, by1);
+        const bool bad = __any_sync(0xffffffffu, !(z == 0.0f));
+        ox = bx0 & ~(Cfg::kXAlign - 1);   // 16-byte aligned box start (floor, also for negatives)
+        oy = by0;
+        // taps span [x0, x0+1] x [y0, y0+1]
+        staged = !bad && bx0 <= bx1 && by0 <= by1 && (bx1 + 1 - ox < Cfg::BW) && (by1 + 1 - oy < Cfg::BH);
+      }
+      if (lane == 0) {
+        ctl->meta[ss][0] = ox; ctl->meta[ss][1] = oy; ctl->meta[ss][2] = staged;
+        if (staged) {
+          mbar_expect_tx(&ctl->src_full[ss], (want_occ ? Cfg::kFfLoad : 0u) + (want_frames ? Cfg::kPrevLoad : 0u));
+          if (want_occ) tma_load_4d(ff_stage(ss), &tm_ff, &ctl->src_full[ss], ox, oy, 0, t.pair);
+          if (want_frames) tma_load_4d(prev_stage(ss), &tm_prev, &ctl->src_full[ss], ox, oy, 0, t.pair);
+        } else {
+          mbar_arrive(&ctl->src_full[ss]);
+        }
+      }
+      __syncwarp();
+    };
+
+    if (lane == 0) {
+      prefetch_tmap(&tm_bf);
+      if (want_occ) prefetch_tmap(&tm_ff);
+      if (want_frames) prefetch_tmap(&tm_prev);
+      for (int j = 0; j < NB && j < n; ++j) issue_bf(j);
+    }
+    __syncwarp();
+    for (int j = 0; j < NS && j < n; ++j) issue_src(j);
+    for (int j = 0; j < n; ++j) {
+      mbar_wait(&ctl->done[j % NS], (j / NS) & 1);   // consumers are finished with tile j: its stages are free
+      const TileId t = ctl->tinfo[j % NB];
+      double ts = 0.0;
+      if (REDUCE && lane == 0) {
 #pragma unroll
-  for (int i = 0; i < NPX; ++i) {
-    const int q = threadIdx.x + i * kPpThreads;
-    pix_off[i] = (q / Cfg::TW) * p.geo.W + q % Cfg::TW;
+        for (int i = 0; i < kCWarps; ++i) ts += ctl->red[j % NS][i];   // fixed order
+      }
+      __syncwarp();
+      if (lane == 0 && j + NB < n) issue_bf(j + NB);
+      __syncwarp();
+      if (j + NS < n) issue_src(j + NS);
+      if (REDUCE && lane == 0) __stcg(&p.scratch.partials[(size_t)t.pair * p.tiles_per_pair + t.tile], ts);
+    }
+    return;
   }
 
-  // phase A of local tile k into register set st[k & 1] (k & 1 must be a compile-time constant at the call site)
-  auto run_a = [&](int k, PxState<NPX>& dst) {
-    mbar_wait(&ctl->bf_full[k & 1], (k >> 1) & 1);
-    const TileId t = tile_of(k);
-    if (t.edge) phase_a<MASK, LEAN, Cfg, true>(p, bf_stage(k & 1), ctl->box, t, dst, near);
-    else phase_a<MASK, LEAN, Cfg, false>(p, bf_stage(k & 1), ctl->box, t, dst, near);
-    __syncthreads();  // bounding box complete; everyone is done reading flow stage k & 1
-    if (threadIdx.x == 0) {
-      issue_src(k, t.pair);
-      if (k + 2 < n) { fence_proxy_async(); issue_bf(k + 2); }
-    }
-  };
-  // phase B of local tile k from register set st[k & 1]
-  auto run_b = [&](int k, const PxState<NPX>& src) {
-    const TileId t = tile_of(k);
-    // this tile's `cur` values: requested before the wait, they arrive while the source boxes do
-    float cur[NPX][CT > 0 ? CT : 1];
-    {
-      const bool have_cur = CT > 0 && (LEAN || p.cur != nullptr);
-      const FrameT* cbase = reinterpret_cast<const FrameT*>(p.cur) + (size_t)t.pair * (CT > 0 ? CT : 1) * plane + ((size_t)t.y0 * p.geo.W + t.x0);
+  // ======================================= consumer warps =======================================
+  unsigned near = 0;
+  const size_t plane = (size_t)g.H * g.W;
+  for (int k = 0; k < n; ++k) {
+    const int sb = k % NB, ss = k % NS;
+    mbar_wait(&ctl->bf_full[sb], (k / NB) & 1);
+    const TileId t = ctl->tinfo[sb];
+    float err = 0.0f;
+    if (LEAN) {
+      // this tile's `cur` (and dataset mask) values: requested before the wait, they arrive while the source boxes do
+      float cur[P][3], mk[P];
+      const FrameT* cbase = reinterpret_cast<const FrameT*>(p.cur) + (size_t)t.pair * 3 * plane + ((size_t)t.y0 * g.W + t.x0);
+      const float* mbase = MASK == MASK_GIVEN ? p.mask_in + (size_t)t.pair * plane + ((size_t)t.y0 * g.W + t.x0) : nullptr;
 #pragma unroll
-      for (int i = 0; i < NPX; ++i) {
-        const int q = threadIdx.x + i * kPpThreads;
-        const bool inside = !t.edge || (t.x0 + q % Cfg::TW < p.geo.W && t.y0 + q / Cfg::TW < p.geo.H);
+      for (int i = 0; i < P; ++i) {
+        int lx, ly;
+        lane_pixel(warp, lane, i, lx, ly);
+        const bool inside = !t.edge || (t.x0 + lx < g.W && t.y0 + ly < g.H);
+        const int off = ly * g.W + lx;
 #pragma unroll
-        for (int c = 0; c < (CT > 0 ? CT : 1); ++c) cur[i][c] = (have_cur && inside) ? ld_stream(cbase + pix_off[i] + (size_t)c * plane) : 0.0f;
+        for (int c = 0; c < 3; ++c) cur[i][c] = inside ? ld_stream(cbase + off + (size_t)c * plane) : 0.0f;
+        mk[i] = (MASK == MASK_GIVEN && inside) ? __ldcs(mbase + off) : 0.0f;
       }
-    }
-    mbar_wait(&ctl->src_full[k & 1], (k >> 1) & 1);
-    float err;
-    if (t.edge) err = phase_b<FrameT, MASK, REDUCE, CT, LEAN, Cfg, true>(p, ff_stage(k & 1), prev_stage(k & 1), ctl->meta[k & 1], t, src, cur, near);
-    else err = phase_b<FrameT, MASK, REDUCE, CT, LEAN, Cfg, false>(p, ff_stage(k & 1), prev_stage(k & 1), ctl->meta[k & 1], t, src, cur, near);
-    // per-tile partial in a fixed order (lanes: butterfly; warps: index order), then the pair/batch tickets
-    if (REDUCE) {
-      const float ws = warp_sum(err);   // <= 192 fp32 terms per warp, then fp64 across warps/tiles/pairs
-      if ((threadIdx.x & 31) == 0) ctl->red[threadIdx.x >> 5] = (double)ws;
-    }
-    __syncthreads();  // source stage k & 1 may be refilled after this point
-    if (REDUCE) {
-      if (threadIdx.x < 32) {
-        double ts = 0.0;
-#pragma unroll
-        for (int i = 0; i < kPpWarps; ++i) ts += ctl->red[i];
-        warp_finalise_tile(ts, p, t.pair, t.tile, threadIdx.x);
+      mbar_wait(&ctl->src_full[ss], (k / NS) & 1);
+      if (ctl->meta[ss][2]) {
+        if (t.edge) err = lean_tile<FrameT, MASK, Cfg, true>(p, bf_stage(sb), ff_stage(ss), prev_stage(ss), ctl->meta[ss], t, warp, lane, cur, mk);
+        else err = lean_tile<FrameT, MASK, Cfg, false>(p, bf_stage(sb), ff_stage(ss), prev_stage(ss), ctl->meta[ss], t, warp, lane, cur, mk);
+      } else {
+        err = full_tile<FrameT, MASK, REDUCE, CT, true, Cfg, true>(p, bf_stage(sb), ff_stage(ss), prev_stage(ss), ctl->meta[ss], t, warp, lane, near);
       }
+    } else {
+      mbar_wait(&ctl->src_full[ss], (k / NS) & 1);
+      if (t.edge) err = full_tile<FrameT, MASK, REDUCE, CT, false, Cfg, true>(p, bf_stage(sb), ff_stage(ss), prev_stage(ss), ctl->meta[ss], t, warp, lane, near);
+      else err = full_tile<FrameT, MASK, REDUCE, CT, false, Cfg, false>(p, bf_stage(sb), ff_stage(ss), prev_stage(ss), ctl->meta[ss], t, warp, lane, near);
     }
-  };
-
-  run_a(0, st[0]);
-  for (int k = 0; k < n; k += 2) {
-    if (k + 1 < n) run_a(k + 1, st[1]);
-    run_b(k, st[0]);
-    if (k + 1 < n) {
-      if (k + 2 < n) run_a(k + 2, st[0]);
-      run_b(k + 1, st[1]);
+    // per-tile partial in a fixed order (lanes: butterfly; warps: index order in the producer), fp64 from here on
+    if (REDUCE) {
+      const float ws = warp_sum(err);
+      if (lane == 0) ctl->red[ss][warp] = (double)ws;
     }
+    __syncwarp();   // every lane is done reading the stages of tile k
+    if (lane == 0) mbar_arrive(&ctl->done[ss]);
   }
   if (!LEAN) count_near(near, p.near_threshold);
 }
@@ -701,11 +796,10 @@ static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 
 extern "C" int tclb200_abi_version(void) { return TCLB200_ABI_VERSION; }
 extern "C" const char* tclb200_last_error(void) { return g_err; }
 
-// tile shape of the TMA kernel: 64 x 16 pixels per CTA, 76(80 for bf16) x 24 source box: after rounding the box
-// origin down to a 16-byte boundary the taps may still spread >= 8 px in x and 7 px in y beyond the tile's own
-// extent before the tile falls back to global gathers
-constexpr int kTW = TCL_TW, kTH = TCL_TH, kBH = TCL_BH;
-template <typename FrameT> constexpr int box_w() { return sizeof(FrameT) == 2 ? TCL_BW_BF16 : TCL_BW_F32; }  // 16-byte multiple per dtype
+// tile shape of the TMA kernel: 64 x TH pixels per tile, 80 x BH source boxes: after rounding the box origin down
+// to a 16-byte boundary the taps may still spread >= 8 px in x and BH-TH-1 px in y beyond the tile's own extent
+// before the tile falls back to global gathers
+constexpr int kTW = 64, kTH = TCL_TH, kBH = TCL_BH, kBW = kTW + 16;
 
 static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 // scratch is sized for the finest tiling any kernel uses (32 x 8 generic tiles)
@@ -755,20 +849,29 @@ static int sm_count() {
 
 template <typename FrameT, int MASK, bool REDUCE, int CT, bool LEAN>
 static cudaError_t launch_tma(const FwdParams& p, const CUtensorMap& tb, const CUtensorMap& tf, const CUtensorMap& tp, cudaStream_t s) {
-  using Cfg = TileCfg<FrameT, CT, kTW, kTH, box_w<FrameT>(), kBH>;
-  auto kern = fused_forward_pp_kernel<FrameT, MASK, REDUCE, CT, LEAN, Cfg>;
+  using Cfg = WsCfg<FrameT, CT, kTW, kTH, kBH, TCL_NB, TCL_NS>;
+  auto kern = fused_forward_ws_kernel<FrameT, MASK, REDUCE, CT, LEAN, Cfg>;
   static bool configured = false;  // per instantiation
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::kSmemBytes);
     if (e != cudaSuccess) return e;
     configured = true;
   }
-  // persistent: two CTAs per SM (or fewer when there are fewer tiles)
+  // persistent: one CTA per SM (or fewer when there are fewer tiles)
   const size_t tiles = (size_t)p.B * p.tiles_per_pair;
-  const size_t slots = 2 * (size_t)sm_count();
+  const size_t slots = (size_t)sm_count();
   const unsigned grid = (unsigned)(tiles < slots ? tiles : slots);
-  kern<<<grid, kPpThreads, Cfg::kSmemBytes, s>>>(p, tb, tf, tp);
-  return cudaGetLastError();
+  kern<<<grid, kWsThreads, Cfg::kSmemBytes, s>>>(p, tb, tf, tp);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess || !REDUCE) return e;
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3((unsigned)p.B); cfg.blockDim = dim3(kThreads); cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, fold_partials_kernel, p);
 }
 
 template <typename FrameT, int MASK, bool REDUCE>
@@ -829,8 +932,7 @@ static int run_fused(const tclb200_tcl_args* a, cudaStream_t s) {
   CUtensorMap tb, tf, tp;
   memset(&tb, 0, sizeof(tb)); memset(&tf, 0, sizeof(tf)); memset(&tp, 0, sizeof(tp));
   if (tma) {
-    const int kBW = esz == 2 ? box_w<__nv_bfloat16>() : box_w<float>();
-    tma = make_map(&tb, a->bf, 4, a->W, a->H, 2, a->B, kTW + 8, kTH + 2, 2);
+    tma = make_map(&tb, a->bf, 4, a->W, a->H, 2, a->B, kTW + 16, kTH + 2, 2);
     if (tma && mask_kind == MASK_COMPUTED && (a->flags & TCLB200_OCC)) tma = make_map(&tf, a->ff, 4, a->W, a->H, 2, a->B, kBW, kBH, 2);
     if (tma && a->prev) tma = make_map(&tp, a->prev, esz, a->W, a->H, 3, a->B, kBW, kBH, 3);
   }
