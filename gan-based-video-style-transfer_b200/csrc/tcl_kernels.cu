@@ -36,16 +36,16 @@
 
 // tile geometry of the TMA kernel (overridable at build time for tuning sweeps, see tools/sweep_build.py)
 #ifndef TCL_TH
-#define TCL_TH 16     // tile height (the width is 64)
+#define TCL_TH 32     // tile height (the width is 64)
 #endif
 #ifndef TCL_BH
-#define TCL_BH 24     // source-box height (the width is 80)
+#define TCL_BH 40     // source-box height (the width is 80)
 #endif
 #ifndef TCL_NS
-#define TCL_NS 3      // source-box stages in flight
+#define TCL_NS 2      // source-box stages in flight
 #endif
 #ifndef TCL_NB
-#define TCL_NB (TCL_NS + 1)   // flow-tile stages in flight
+#define TCL_NB (TCL_NS + 2)   // flow-tile stages in flight
 #endif
 
 namespace tcl {
@@ -230,6 +230,7 @@ __global__ void __launch_bounds__(kThreads) fused_forward_generic_kernel(const F
 // A warp instruction covers 16 x 2 pixels (lane = 16 * row + column) and both the flow tile and the source boxes
 // have a pitch of 80 words = 16 (mod 32): the two rows fall into disjoint halves of the 32 banks, also when the
 // flow shifts some lanes to the next source row, so the taps are (nearly) conflict-free shared-memory reads.
+__device__ unsigned long long g_tile_stats[2];   // debug statistics: tiles taken from global memory entirely / mixed tiles
 constexpr int kCWarps = 16;                      // consumer warps
 constexpr int kWsThreads = 32 * (kCWarps + 1);   // + 1 producer warp
 
@@ -381,100 +382,189 @@ __device__ __forceinline__ float full_tile(const FwdParams& p, const float* s_bu
 // ---- consumer: the hot configuration (LEAN: C == 3, L2 error, no optional outputs), staged tiles only ----------
 // The mask tests compare  lhs > rhs  where both sides are sums of torch.norm(.)**2 terms, i.e. sqrt-then-square
 // of a sum of squares (flowtools.py:41-53).  Each such term differs from the plain sum of squares by at most a few
-// ulp, so the plain (sqrt-free) evaluation decides the test whenever |lhs - rhs| > kFilterEps * (lhs + rhs); only the
-// remaining pixels (a few per million) replay the exact sequence.  Results are identical to the exact path.
-constexpr float kFilterEps = 4e-6f;   // >= 8x the worst-case relative deviation (< 16 * 2^-24 per side)
+// ulp (< 12 * 2^-24 relative per side), so the plain (sqrt-free) evaluation decides the test whenever lhs lies outside
+// [rhs * (1 - kFilterEps), rhs * (1 + kFilterEps)]; only the remaining pixels (a few per million) replay the exact
+// sequence after the branch-free pixel loop.  Results are identical to the exact path.
+constexpr float kFilterEps = 4e-6f;
 
-template <typename FrameT, int MASK, typename Cfg, bool EDGE>
-__device__ __forceinline__ float lean_tile(const FwdParams& p, const float* s_bu, const float* s_ff, const FrameT* s_prev,
-                                           const int* meta, const TileId& t, int warp, int lane,
-                                           const float (&cur)[Cfg::kPPL][3], const float (&mk)[Cfg::kPPL]) {
+struct LeanGeo {   // per-thread constants of lean_tile
+  float i2x, i2y, Wf, Hf;
+};
+
+// sampling position of one pixel of a staged tile, relative to the box origin (floor parts) + the four weights
+struct LeanTaps {
+  float rx, ry;   // floor(ix) - box_x, floor(iy) - box_y as floats (small exact integers inside the box)
+  float nw, ne, sw, se;
+};
+__device__ __forceinline__ LeanTaps lean_taps(float xf, float yf, float u, float v, const LeanGeo& lg, float box_xf, float box_yf) {
+  // the reference's [-1,1] round trip (flowtools.py:28-29 + grid_sampler's unnormalise).  Inside a staged tile every
+  // coordinate is finite and far inside the int range: no safe_downgrade guard needed.
+  const float ax = __fadd_rn(xf, u), ay = __fadd_rn(yf, v);
+  const float tx = __fadd_rn(__fsub_rn(__fmul_rn(ax, lg.i2x), 1.0f), 1.0f), ty = __fadd_rn(__fsub_rn(__fmul_rn(ay, lg.i2y), 1.0f), 1.0f);
+  const float ix = __fmul_rn(__fmaf_rn(tx, lg.Wf, -1.0f), 0.5f), iy = __fmul_rn(__fmaf_rn(ty, lg.Hf, -1.0f), 0.5f);
+  const float fxf = floorf(ix), fyf = floorf(iy);
+  const float fx1 = __fsub_rn(__fadd_rn(fxf, 1.0f), ix), fx0 = __fsub_rn(ix, fxf);
+  const float fy1 = __fsub_rn(__fadd_rn(fyf, 1.0f), iy), fy0 = __fsub_rn(iy, fyf);
+  LeanTaps t;
+  t.nw = __fmul_rn(fx1, fy1); t.ne = __fmul_rn(fx0, fy1); t.sw = __fmul_rn(fx1, fy0); t.se = __fmul_rn(fx0, fy0);
+  t.rx = __fsub_rn(fxf, box_xf); t.ry = __fsub_rn(fyf, box_yf);
+  return t;
+}
+
+// exact mask verdict of one pixel of a staged tile (the rare replay of lean_tile)
+template <typename Cfg>
+__device__ __noinline__ bool exact_keep(const float* s_bu, const float* s_ff, int c, float xf, float yf, LeanGeo lg, float box_xf, float box_yf) {
+  constexpr int BW = Cfg::BW, BFW = Cfg::kBfW, PL = Cfg::BH * Cfg::BW;
+  const float* s_bv = s_bu + Cfg::kBfH * BFW;
+  const float u = s_bu[c], v = s_bv[c];
+  float nb, m1, m2;
+  const bool mob = motion_boundary(u, v, s_bu[c - 1], s_bu[c + 1], s_bu[c - BFW], s_bu[c + BFW], s_bv[c - 1], s_bv[c + 1],
+                                   s_bv[c - BFW], s_bv[c + BFW], kV, &nb, &m1);
+  const LeanTaps t = lean_taps(xf, yf, u, v, lg, box_xf, box_yf);
+  const float* f0 = s_ff + (int)__fmaf_rn(t.ry, (float)BW, t.rx);
+  float a = __fmul_rn(f0[0], t.nw);
+  a = __fmaf_rn(f0[1], t.ne, a); a = __fmaf_rn(f0[BW], t.sw, a); a = __fmaf_rn(f0[BW + 1], t.se, a);
+  float b = __fmul_rn(f0[PL], t.nw);
+  b = __fmaf_rn(f0[PL + 1], t.ne, b); b = __fmaf_rn(f0[PL + BW], t.sw, b); b = __fmaf_rn(f0[PL + BW + 1], t.se, b);
+  const bool occ = occluded(a, b, u, v, nb, kV, &m2);
+  return !mob && !occ;
+}
+
+// one pixel of the hot configuration entirely from global memory with the exact sequences: the pixels of a "mixed" tile
+// (a motion boundary runs through it) whose taps lie outside the staged source boxes.  Returns the masked squared error.
+template <typename FrameT, int MASK>
+__device__ __noinline__ float pixel_global(const float* bf_pair, const float* ff_pair, const FrameT* prev_pair, Geo g, int x, int y,
+                                           float c0, float c1, float c2, float mkv) {
+  const int W = g.W, H = g.H;
+  const size_t plane = (size_t)H * W;
+  const size_t o = (size_t)y * W + x;
+  const float* bu = bf_pair;
+  const float* bv = bf_pair + plane;
+  const float u = __ldg(bu + o), v = __ldg(bv + o);
+  bool keep = true;
+  float nb = 0.0f;
+  if (MASK == MASK_COMPUTED) {
+    const float ul = x > 0 ? __ldg(bu + o - 1) : 0.0f, ur = x + 1 < W ? __ldg(bu + o + 1) : 0.0f;
+    const float uu = y > 0 ? __ldg(bu + o - W) : 0.0f, ud = y + 1 < H ? __ldg(bu + o + W) : 0.0f;
+    const float vl = x > 0 ? __ldg(bv + o - 1) : 0.0f, vr = x + 1 < W ? __ldg(bv + o + 1) : 0.0f;
+    const float vu = y > 0 ? __ldg(bv + o - W) : 0.0f, vd = y + 1 < H ? __ldg(bv + o + W) : 0.0f;
+    float margin;
+    keep = !motion_boundary(u, v, ul, ur, uu, ud, vl, vr, vu, vd, kV, &nb, &margin);
+  }
+  const PixTaps s = pix_taps(u, v, x, y, g);
+  if (MASK == MASK_COMPUTED) {
+    const GlobalSrc<float> fsrc{ff_pair, plane, g};
+    const float wu = fsrc.sample(0, s), wv = fsrc.sample(1, s);
+    float margin;
+    if (occluded(wu, wv, u, v, nb, kV, &margin)) keep = false;
+  }
+  const GlobalSrc<FrameT> psrc{prev_pair, plane, g};
+  const float d0 = __fsub_rn(c0, psrc.sample(0, s)), d1 = __fsub_rn(c1, psrc.sample(1, s)), d2 = __fsub_rn(c2, psrc.sample(2, s));
+  const float acc = __fmaf_rn(d2, d2, __fmaf_rn(d1, d1, __fmul_rn(d0, d0)));
+  if (MASK == MASK_GIVEN) return __fmul_rn(__fmul_rn(mkv, mkv), acc);
+  return keep ? acc : 0.0f;
+}
+
+template <typename FrameT, int MASK, typename Cfg, bool EDGE, bool MIXED>
+__device__ __forceinline__ float lean_tile(const FwdParams& p, const float* s_bu, const float* s_ff, const int* meta, const TileId& t,
+                                           int warp, int lane, const float (&cur)[Cfg::kPPL][3], const float (&mk)[Cfg::kPPL]) {
   constexpr int P = Cfg::kPPL, BW = Cfg::BW, BFW = Cfg::kBfW, PL = Cfg::BH * Cfg::BW;
+  constexpr float kHi = 1.0f + kFilterEps, kLo = 1.0f - kFilterEps;
   const Geo& g = p.geo;
   const float* s_bv = s_bu + Cfg::kBfH * BFW;
-  const int box0 = meta[1] * BW + meta[0];   // box-relative index of source pixel (0,0)
-  const float x0f = (float)t.x0, y0f = (float)t.y0;
-  const float i2x = __fmul_rn(2.0f, g.inv_dx), i2y = __fmul_rn(2.0f, g.inv_dy);   // exact doubling: (2a)*r == a*(2r)
-  float e[P], wu[P], wv[P], fu[P], fv[P];
-  bool keep[P];
-  bool amb = false;
+  // the prev boxes follow the ff boxes in the stage: one address register serves both (fp32 frames)
+  const FrameT* s_prev = reinterpret_cast<const FrameT*>(reinterpret_cast<const unsigned char*>(s_ff) + Cfg::kFfStage);
+  const float box_xf = (float)meta[0], box_yf = (float)meta[1];
+  LeanGeo lg;
+  lg.i2x = __fmul_rn(2.0f, g.inv_dx); lg.i2y = __fmul_rn(2.0f, g.inv_dy);   // exact doubling: (2a)*r == a*(2r)
+  lg.Wf = g.Wf; lg.Hf = g.Hf;
+  int lx0, ly0;
+  lane_pixel(warp, lane, 0, lx0, ly0);
+  // pixel k of this lane: 16 columns right of pixel k-1 (k odd) / 16 rows below pixel k-2
+  const float xs[2] = {(float)(t.x0 + lx0), (float)(t.x0 + lx0 + 16)}, ys[2] = {(float)(t.y0 + ly0), (float)(t.y0 + ly0 + 16)};
+  const int c0 = (ly0 + 1) * BFW + lx0 + Cfg::kHaloX;
+  float e[P];
+  unsigned keepbits = 0, ambbits = 0, outbits = 0;
 #pragma unroll
   for (int k = 0; k < P; ++k) {
-    int lx, ly;
-    lane_pixel(warp, lane, k, lx, ly);
-    const bool inside = !EDGE || (t.x0 + lx < g.W && t.y0 + ly < g.H);
-    const int c = (ly + 1) * BFW + lx + Cfg::kHaloX;
+    const int dxk = 16 * (k & 1), dyk = 16 * (k >> 1);
+    const bool inside = !EDGE || (t.x0 + lx0 + dxk < g.W && t.y0 + ly0 + dyk < g.H);
+    const int c = c0 + dyk * BFW + dxk;
     const float u = s_bu[c], v = s_bv[c];
-    fu[k] = u; fv[k] = v;
     const float s0 = __fmaf_rn(u, u, __fmul_rn(v, v));
-    keep[k] = inside;
+    bool keep = inside, amb = false;
     if (MASK == MASK_COMPUTED) {
       // motion boundary: 4*(|grad u|^2 + |grad v|^2)  vs  4*(0.01*|bf|^2 + 0.002)
       const float dux = __fsub_rn(s_bu[c + 1], s_bu[c - 1]), duy = __fsub_rn(s_bu[c + BFW], s_bu[c - BFW]);
       const float dvx = __fsub_rn(s_bv[c + 1], s_bv[c - 1]), dvy = __fsub_rn(s_bv[c + BFW], s_bv[c - BFW]);
       const float G = __fmaf_rn(dux, dux, __fmaf_rn(duy, duy, __fmaf_rn(dvx, dvx, __fmul_rn(dvy, dvy))));
-      const float R = __fmaf_rn(0.04f, s0, 0.008f);
-      keep[k] = keep[k] && !(G > R);
-      amb = amb || (inside && !(fabsf(__fsub_rn(G, R)) > __fmul_rn(kFilterEps, __fadd_rn(G, R))));
+      const float Rhi = __fmaf_rn(4.0f * 0.01f * kHi, s0, 4.0f * 0.002f * kHi), Rlo = __fmaf_rn(4.0f * 0.01f * kLo, s0, 4.0f * 0.002f * kLo);
+      const bool mob = G > Rhi;
+      keep = keep && !mob;
+      amb = !(mob || G < Rlo);
     }
-    // sampling position: the reference's [-1,1] round trip (flowtools.py:28-29 + grid_sampler's unnormalise).  Inside a
-    // staged tile every coordinate is finite and far inside the int range: no safe_downgrade guard needed.
-    const float ax = __fadd_rn(__fadd_rn(x0f, (float)lx), u), ay = __fadd_rn(__fadd_rn(y0f, (float)ly), v);
-    const float tx = __fadd_rn(__fsub_rn(__fmul_rn(ax, i2x), 1.0f), 1.0f), ty = __fadd_rn(__fsub_rn(__fmul_rn(ay, i2y), 1.0f), 1.0f);
-    const float ix = __fmul_rn(__fmaf_rn(tx, g.Wf, -1.0f), 0.5f), iy = __fmul_rn(__fmaf_rn(ty, g.Hf, -1.0f), 0.5f);
-    const float fxf = floorf(ix), fyf = floorf(iy);
-    const float fx1 = __fsub_rn(__fadd_rn(fxf, 1.0f), ix), fx0 = __fsub_rn(ix, fxf);
-    const float fy1 = __fsub_rn(__fadd_rn(fyf, 1.0f), iy), fy0 = __fsub_rn(iy, fyf);
-    const float nw = __fmul_rn(fx1, fy1), ne = __fmul_rn(fx0, fy1), sw = __fmul_rn(fx1, fy0), se = __fmul_rn(fx0, fy0);
-    int q = (int)fyf * BW + (int)fxf - box0;
-    if (EDGE && !inside) q = 0;   // pixels beyond the image edge: any in-box address, result discarded
+    LeanTaps tp = lean_taps(xs[k & 1], ys[k >> 1], u, v, lg, box_xf, box_yf);
+    bool usable = inside;
+    if (MIXED) usable = inside && tp.rx >= 0.0f && tp.rx < (float)(BW - 1) && tp.ry >= 0.0f && tp.ry < (float)(Cfg::BH - 1);
+    // pixels beyond the image edge / taps outside the box: read any in-box address, the result is discarded
+    const int q = (EDGE || MIXED) && !usable ? 0 : (int)__fmaf_rn(tp.ry, (float)BW, tp.rx);
     if (MASK == MASK_COMPUTED) {
       const float* f0 = s_ff + q;
-      float a = __fmul_rn(f0[0], nw);
-      a = __fmaf_rn(f0[1], ne, a); a = __fmaf_rn(f0[BW], sw, a); a = __fmaf_rn(f0[BW + 1], se, a);
-      float b = __fmul_rn(f0[PL], nw);
-      b = __fmaf_rn(f0[PL + 1], ne, b); b = __fmaf_rn(f0[PL + BW], sw, b); b = __fmaf_rn(f0[PL + BW + 1], se, b);
-      wu[k] = a; wv[k] = b;
+      float a = __fmul_rn(f0[0], tp.nw);
+      a = __fmaf_rn(f0[1], tp.ne, a); a = __fmaf_rn(f0[BW], tp.sw, a); a = __fmaf_rn(f0[BW + 1], tp.se, a);
+      float b = __fmul_rn(f0[PL], tp.nw);
+      b = __fmaf_rn(f0[PL + 1], tp.ne, b); b = __fmaf_rn(f0[PL + BW], tp.sw, b); b = __fmaf_rn(f0[PL + BW + 1], tp.se, b);
       // occlusion: |wf+bf|^2  vs  0.01*(|wf|^2+|bf|^2) + 0.5
       const float su = __fadd_rn(a, u), sv = __fadd_rn(b, v);
       const float L = __fmaf_rn(su, su, __fmul_rn(sv, sv));
-      const float R = __fmaf_rn(0.01f, __fadd_rn(__fmaf_rn(a, a, __fmul_rn(b, b)), s0), 0.5f);
-      keep[k] = keep[k] && !(L > R);
-      amb = amb || (inside && !(fabsf(__fsub_rn(L, R)) > __fmul_rn(kFilterEps, __fadd_rn(L, R))));
+      const float nn = __fadd_rn(__fmaf_rn(a, a, __fmul_rn(b, b)), s0);
+      const float Rhi = __fmaf_rn(0.01f * kHi, nn, 0.5f * kHi), Rlo = __fmaf_rn(0.01f * kLo, nn, 0.5f * kLo);
+      const bool occ = L > Rhi;
+      keep = keep && !occ;
+      amb = amb || !(occ || L < Rlo);
     }
     const FrameT* q0 = s_prev + q;
     float acc = 0.0f;
 #pragma unroll
     for (int ch = 0; ch < 3; ++ch) {
-      float w = __fmul_rn(to_f32(q0[ch * PL]), nw);
-      w = __fmaf_rn(to_f32(q0[ch * PL + 1]), ne, w);
-      w = __fmaf_rn(to_f32(q0[ch * PL + BW]), sw, w);
-      w = __fmaf_rn(to_f32(q0[ch * PL + BW + 1]), se, w);
+      float w = __fmul_rn(to_f32(q0[ch * PL]), tp.nw);
+      w = __fmaf_rn(to_f32(q0[ch * PL + 1]), tp.ne, w);
+      w = __fmaf_rn(to_f32(q0[ch * PL + BW]), tp.sw, w);
+      w = __fmaf_rn(to_f32(q0[ch * PL + BW + 1]), tp.se, w);
       const float d = __fsub_rn(cur[k][ch], w);
       acc = __fmaf_rn(d, d, acc);
     }
-    e[k] = acc;
+    e[k] = MASK == MASK_GIVEN ? __fmul_rn(__fmul_rn(mk[k], mk[k]), acc) : acc;   // (m*d)^2 summed over channels (mk = 0 outside)
+    keepbits |= (keep ? 1u : 0u) << k;
+    ambbits |= (amb && usable ? 1u : 0u) << k;
+    if (MIXED) outbits |= (inside && !usable ? 1u : 0u) << k;
   }
-  if (MASK == MASK_COMPUTED && __any_sync(0xffffffffu, amb)) {
-    // a test of some pixel in this warp is too close to call: replay the exact sequences (rare)
+  // rare, divergent: tests too close to call replay the exact sequences (a few pixels per million) ...
+  if (MASK == MASK_COMPUTED && __builtin_expect(ambbits != 0, 0)) {
 #pragma unroll
-    for (int k = 0; k < P; ++k) {
-      int lx, ly;
-      lane_pixel(warp, lane, k, lx, ly);
-      const bool inside = !EDGE || (t.x0 + lx < g.W && t.y0 + ly < g.H);
-      const int c = (ly + 1) * BFW + lx + Cfg::kHaloX;
-      float nb, m1, m2;
-      const bool mob = motion_boundary(fu[k], fv[k], s_bu[c - 1], s_bu[c + 1], s_bu[c - BFW], s_bu[c + BFW], s_bv[c - 1], s_bv[c + 1],
-                                       s_bv[c - BFW], s_bv[c + BFW], kV, &nb, &m1);
-      const bool occ = occluded(wu[k], wv[k], fu[k], fv[k], nb, kV, &m2);
-      keep[k] = inside && !mob && !occ;
-    }
+    for (int k = 0; k < P; ++k)
+      if ((ambbits >> k) & 1u) {
+        const bool kp = exact_keep<Cfg>(s_bu, s_ff, c0 + 16 * (k >> 1) * BFW + 16 * (k & 1), xs[k & 1], ys[k >> 1], lg, box_xf, box_yf);
+        keepbits = (keepbits & ~(1u << k)) | ((kp ? 1u : 0u) << k);
+      }
+  }
+  // ... and pixels of a mixed tile whose taps left the boxes are redone from global memory
+  if (MIXED && outbits != 0) {
+    const size_t plane = (size_t)g.H * g.W;
+#pragma unroll
+    for (int k = 0; k < P; ++k)
+      if ((outbits >> k) & 1u) {
+        e[k] = pixel_global<FrameT, MASK>(p.bf + (size_t)t.pair * 2 * plane, MASK == MASK_COMPUTED ? p.ff + (size_t)t.pair * 2 * plane : nullptr,
+                                          reinterpret_cast<const FrameT*>(p.prev) + (size_t)t.pair * 3 * plane, g, t.x0 + lx0 + 16 * (k & 1),
+                                          t.y0 + ly0 + 16 * (k >> 1), cur[k][0], cur[k][1], cur[k][2], mk[k]);
+        keepbits |= 1u << k;   // the verdict is already applied
+      }
   }
   float err = 0.0f;
 #pragma unroll
   for (int k = 0; k < P; ++k) {
-    if (MASK == MASK_GIVEN) err = __fmaf_rn(__fmul_rn(mk[k], mk[k]), e[k], err);   // (m*d)^2 summed over channels
-    else err = keep[k] ? __fadd_rn(err, e[k]) : err;
+    if (MASK == MASK_GIVEN) err = __fadd_rn(err, e[k]);
+    else err = ((keepbits >> k) & 1u) ? __fadd_rn(err, e[k]) : err;
   }
   return err;
 }
@@ -499,6 +589,8 @@ __global__ void __launch_bounds__(kWsThreads, 1) fused_forward_ws_kernel(const F
   const bool want_frames = CT > 0 && (LEAN || p.prev != nullptr);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const Geo& g = p.geo;
+  // a CTA's partial sums are carried across its consecutive tiles of one pair and handed over with the pair's last one
+  auto flushes = [&](const TileId& t, int k) { return t.tile + (int)gridDim.x >= p.tiles_per_pair || k == n - 1; };
 
   if (REDUCE) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // let the fold kernel get resident early
   if (threadIdx.x == 0) {
@@ -517,13 +609,15 @@ __global__ void __launch_bounds__(kWsThreads, 1) fused_forward_ws_kernel(const F
       mbar_expect_tx(&ctl->bf_full[s], Cfg::kBfLoad);
       tma_load_4d(bf_stage(s), &tm_bf, &ctl->bf_full[s], t.x0 - Cfg::kHaloX, t.y0 - 1, 0, t.pair);
     };
-    // whole warp: extent of x+u, y+v over the tile's pixels -> origin of the source boxes -> request them
-    auto issue_src = [&](int k) {
-      const int sb = k % NB, ss = k % NS;
+    // whole warp: extent of x+u, y+v over the tile's pixels -> origin of the source boxes (needs only the flow tile,
+    // so it runs while the consumers are still busy with earlier tiles) ...
+    struct Placement { int ox, oy, mode, pair; };
+    auto place_src = [&](int k) -> Placement {
+      const int sb = k % NB;
       mbar_wait(&ctl->bf_full[sb], (k / NB) & 1);
       const TileId t = ctl->tinfo[sb];
       bool staged = want_occ || want_frames;
-      int ox = 0, oy = 0;
+      int ox = 0, oy = 0, mode = 0;   // mode: 0 = nothing staged, 1 = every tap inside the boxes, 2 = mixed (LEAN only)
       if (staged) {
         const float* s_bu = bf_stage(sb);
         const float* s_bv = s_bu + Cfg::kBfH * Cfg::kBfW;
@@ -531,8 +625,9 @@ __global__ void __launch_bounds__(kWsThreads, 1) fused_forward_ws_kernel(const F
         const int rows = min(Cfg::TH, g.H - t.y0);
         const bool col_ok = t.x0 + c4 < g.W;      // W % 4 == 0: a lane's four columns are all inside or all outside
         const float xf = (float)(t.x0 + c4);
-        float xmin = 3e38f, xmax = -3e38f, ymin = 3e38f, ymax = -3e38f, z = 0.0f;
+        float xmin = 3e38f, xmax = -3e38f, ymin = 3e38f, ymax = -3e38f, z = 0.0f, xsum = 0.0f, ysum = 0.0f;
         if (col_ok) {
+#pragma unroll 2
           for (int r = lane >> 4; r < rows; r += 2) {
             const float4 u4 = *reinterpret_cast<const float4*>(s_bu + (r + 1) * Cfg::kBfW + Cfg::kHaloX + c4);
             const float4 v4 = *reinterpret_cast<const float4*>(s_bv + (r + 1) * Cfg::kBfW + Cfg::kHaloX + c4);
@@ -543,6 +638,8 @@ __global__ void __launch_bounds__(kWsThreads, 1) fused_forward_ws_kernel(const F
             const float vmin = fminf(fminf(v4.x, v4.y), fminf(v4.z, v4.w)), vmax = fmaxf(fmaxf(v4.x, v4.y), fmaxf(v4.z, v4.w));
             ymin = fminf(ymin, __fadd_rn(yf, vmin));
             ymax = fmaxf(ymax, __fadd_rn(yf, vmax));
+            xsum += (a0 + a1) + (a2 + a3);
+            ysum += 4.0f * yf + ((v4.x + v4.y) + (v4.z + v4.w));
             // 0 * finite == 0; an Inf or NaN anywhere makes z NaN (fminf / fmaxf would silently drop a NaN)
             z = __fmaf_rn(u4.x, 0.0f, z); z = __fmaf_rn(u4.y, 0.0f, z); z = __fmaf_rn(u4.z, 0.0f, z); z = __fmaf_rn(u4.w, 0.0f, z);
             z = __fmaf_rn(v4.x, 0.0f, z); z = __fmaf_rn(v4.y, 0.0f, z); z = __fmaf_rn(v4.z, 0.0f, z); z = __fmaf_rn(v4.w, 0.0f, z);
@@ -566,14 +663,37 @@ __global__ void __launch_bounds__(kWsThreads, 1) fused_forward_ws_kernel(const F
         ox = bx0 & ~(Cfg::kXAlign - 1);   // 16-byte aligned box start (floor, also for negatives)
         oy = by0;
         // taps span [x0, x0+1] x [y0, y0+1]
-        staged = !bad && bx0 <= bx1 && by0 <= by1 && (bx1 + 1 - ox < Cfg::BW) && (by1 + 1 - oy < Cfg::BH);
+        const bool sane = !bad && bx0 <= bx1 && by0 <= by1 && bx0 > -1000000 && bx1 < 1000000 && by0 > -1000000 && by1 < 1000000;
+        const bool fitx = bx1 + 1 - ox < Cfg::BW, fity = by1 + 1 - oy < Cfg::BH;
+        staged = sane;
+        mode = (fitx && fity) ? 1 : 2;
+        if (sane && LEAN && mode == 2) {
+          // a motion boundary runs through the tile: centre the box on the mean sampling position (per axis, where the
+          // extent does not fit); pixels whose taps fall outside take the global path one by one
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) { xsum += __shfl_xor_sync(0xffffffffu, xsum, o); ysum += __shfl_xor_sync(0xffffffffu, ysum, o); }
+          const float inv_n = 1.0f / (float)(rows * min(Cfg::TW, g.W - t.x0));
+          if (!fitx) ox = (__float2int_rd(coord(xsum * inv_n, i2x, g.Wf)) - Cfg::BW / 2) & ~(Cfg::kXAlign - 1);
+          if (!fity) oy = __float2int_rd(coord(ysum * inv_n, i2y, g.Hf)) - Cfg::BH / 2;
+        } else if (mode == 2) {
+          staged = false;   // the feature-complete path has no per-pixel fallback: whole tile from global memory
+        }
+        if (!staged) mode = 0;
+      } else {
+        mode = 0;
       }
+      if (lane == 0 && mode != 1 && (want_occ || want_frames)) atomicAdd(&g_tile_stats[mode == 2 ? 1 : 0], 1ull);
+      return Placement{ox, oy, mode, t.pair};
+    };
+    // ... and, once the source stage is free, the request itself (lane 0)
+    auto issue_src = [&](int k, const Placement& pl) {
+      const int ss = k % NS;
       if (lane == 0) {
-        ctl->meta[ss][0] = ox; ctl->meta[ss][1] = oy; ctl->meta[ss][2] = staged;
-        if (staged) {
+        ctl->meta[ss][0] = pl.ox; ctl->meta[ss][1] = pl.oy; ctl->meta[ss][2] = pl.mode;
+        if (pl.mode != 0) {
           mbar_expect_tx(&ctl->src_full[ss], (want_occ ? Cfg::kFfLoad : 0u) + (want_frames ? Cfg::kPrevLoad : 0u));
-          if (want_occ) tma_load_4d(ff_stage(ss), &tm_ff, &ctl->src_full[ss], ox, oy, 0, t.pair);
-          if (want_frames) tma_load_4d(prev_stage(ss), &tm_prev, &ctl->src_full[ss], ox, oy, 0, t.pair);
+          if (want_occ) tma_load_4d(ff_stage(ss), &tm_ff, &ctl->src_full[ss], pl.ox, pl.oy, 0, pl.pair);
+          if (want_frames) tma_load_4d(prev_stage(ss), &tm_prev, &ctl->src_full[ss], pl.ox, pl.oy, 0, pl.pair);
         } else {
           mbar_arrive(&ctl->src_full[ss]);
         }
@@ -588,66 +708,96 @@ __global__ void __launch_bounds__(kWsThreads, 1) fused_forward_ws_kernel(const F
       for (int j = 0; j < NB && j < n; ++j) issue_bf(j);
     }
     __syncwarp();
-    for (int j = 0; j < NS && j < n; ++j) issue_src(j);
+    for (int j = 0; j < NS && j < n; ++j) issue_src(j, place_src(j));
     for (int j = 0; j < n; ++j) {
+      Placement pl{0, 0, 0, 0};
+      if (j + NS < n) pl = place_src(j + NS);        // off the critical path: tile j is still being computed
       mbar_wait(&ctl->done[j % NS], (j / NS) & 1);   // consumers are finished with tile j: its stages are free
       const TileId t = ctl->tinfo[j % NB];
+      // the 16 consumer warps' sums for this CTA's share of the pair, folded in index order (lanes 0..15, fixed tree)
       double ts = 0.0;
-      if (REDUCE && lane == 0) {
-#pragma unroll
-        for (int i = 0; i < kCWarps; ++i) ts += ctl->red[j % NS][i];   // fixed order
-      }
+      const bool fl = REDUCE && flushes(t, j);
+      if (fl && lane < kCWarps) ts = ctl->red[j % NS][lane];
       __syncwarp();
+      if (j + NS < n) issue_src(j + NS, pl);
       if (lane == 0 && j + NB < n) issue_bf(j + NB);
       __syncwarp();
-      if (j + NS < n) issue_src(j + NS);
-      if (REDUCE && lane == 0) __stcg(&p.scratch.partials[(size_t)t.pair * p.tiles_per_pair + t.tile], ts);
+      if (fl) {
+        ts = warp_sum(ts);
+        if (lane == 0) __stcg(&p.scratch.partials[(size_t)t.pair * p.tiles_per_pair + t.tile], ts);
+      }
     }
     return;
   }
 
   // ======================================= consumer warps =======================================
   unsigned near = 0;
+  double acc = 0.0;   // this lane's share of the CTA's partial sum of the current pair
   const size_t plane = (size_t)g.H * g.W;
+  int lx0, ly0;
+  lane_pixel(warp, lane, 0, lx0, ly0);
+  const int lane_off = ly0 * g.W + lx0;
+  const ptrdiff_t row16 = (ptrdiff_t)16 * g.W;
+  int sb = 0, ss = 0;
+  unsigned pb = 0, ps = 0;   // stage indices and phase parities of the current tile
   for (int k = 0; k < n; ++k) {
-    const int sb = k % NB, ss = k % NS;
-    mbar_wait(&ctl->bf_full[sb], (k / NB) & 1);
-    const TileId t = ctl->tinfo[sb];
     float err = 0.0f;
+    mbar_wait(&ctl->bf_full[sb], pb);
+    const TileId t = ctl->tinfo[sb];
     if (LEAN) {
-      // this tile's `cur` (and dataset mask) values: requested before the wait, they arrive while the source boxes do
+      // this tile's `cur` (and dataset mask) values: coalesced 64-byte row segments, streaming; requested before the wait
+      // for the source boxes and first used at the very end of the per-pixel work
       float cur[P][3], mk[P];
-      const FrameT* cbase = reinterpret_cast<const FrameT*>(p.cur) + (size_t)t.pair * 3 * plane + ((size_t)t.y0 * g.W + t.x0);
-      const float* mbase = MASK == MASK_GIVEN ? p.mask_in + (size_t)t.pair * plane + ((size_t)t.y0 * g.W + t.x0) : nullptr;
+      const size_t pix = (size_t)(t.y0 * g.W + t.x0) + lane_off;
+      const FrameT* cb = reinterpret_cast<const FrameT*>(p.cur) + (size_t)t.pair * 3 * plane + pix;
+      const float* mb = MASK == MASK_GIVEN ? p.mask_in + (size_t)t.pair * plane + pix : nullptr;
+      if (!t.edge) {
 #pragma unroll
-      for (int i = 0; i < P; ++i) {
-        int lx, ly;
-        lane_pixel(warp, lane, i, lx, ly);
-        const bool inside = !t.edge || (t.x0 + lx < g.W && t.y0 + ly < g.H);
-        const int off = ly * g.W + lx;
+        for (int c = 0; c < 3; ++c) {
+          const FrameT* pc = cb + (size_t)c * plane;
 #pragma unroll
-        for (int c = 0; c < 3; ++c) cur[i][c] = inside ? ld_stream(cbase + off + (size_t)c * plane) : 0.0f;
-        mk[i] = (MASK == MASK_GIVEN && inside) ? __ldcs(mbase + off) : 0.0f;
+          for (int i = 0; i < P; ++i) cur[i][c] = ld_stream(pc + (i >> 1) * row16 + 16 * (i & 1));
+        }
+#pragma unroll
+        for (int i = 0; i < P; ++i) mk[i] = MASK == MASK_GIVEN ? __ldcs(mb + (i >> 1) * row16 + 16 * (i & 1)) : 0.0f;
+      } else {
+#pragma unroll
+        for (int i = 0; i < P; ++i) {
+          const bool inside = t.x0 + lx0 + 16 * (i & 1) < g.W && t.y0 + ly0 + 16 * (i >> 1) < g.H;
+          const ptrdiff_t off = (i >> 1) * row16 + 16 * (i & 1);
+#pragma unroll
+          for (int c = 0; c < 3; ++c) cur[i][c] = inside ? ld_stream(cb + off + (size_t)c * plane) : 0.0f;
+          mk[i] = (MASK == MASK_GIVEN && inside) ? __ldcs(mb + off) : 0.0f;
+        }
       }
-      mbar_wait(&ctl->src_full[ss], (k / NS) & 1);
-      if (ctl->meta[ss][2]) {
-        if (t.edge) err = lean_tile<FrameT, MASK, Cfg, true>(p, bf_stage(sb), ff_stage(ss), prev_stage(ss), ctl->meta[ss], t, warp, lane, cur, mk);
-        else err = lean_tile<FrameT, MASK, Cfg, false>(p, bf_stage(sb), ff_stage(ss), prev_stage(ss), ctl->meta[ss], t, warp, lane, cur, mk);
+      mbar_wait(&ctl->src_full[ss], ps);
+      const int mode = ctl->meta[ss][2];
+      if (mode == 1) {
+        if (t.edge) err = lean_tile<FrameT, MASK, Cfg, true, false>(p, bf_stage(sb), ff_stage(ss), ctl->meta[ss], t, warp, lane, cur, mk);
+        else err = lean_tile<FrameT, MASK, Cfg, false, false>(p, bf_stage(sb), ff_stage(ss), ctl->meta[ss], t, warp, lane, cur, mk);
+      } else if (mode == 2) {
+        err = lean_tile<FrameT, MASK, Cfg, true, true>(p, bf_stage(sb), ff_stage(ss), ctl->meta[ss], t, warp, lane, cur, mk);
       } else {
         err = full_tile<FrameT, MASK, REDUCE, CT, true, Cfg, true>(p, bf_stage(sb), ff_stage(ss), prev_stage(ss), ctl->meta[ss], t, warp, lane, near);
       }
     } else {
-      mbar_wait(&ctl->src_full[ss], (k / NS) & 1);
+      mbar_wait(&ctl->src_full[ss], ps);
       if (t.edge) err = full_tile<FrameT, MASK, REDUCE, CT, false, Cfg, true>(p, bf_stage(sb), ff_stage(ss), prev_stage(ss), ctl->meta[ss], t, warp, lane, near);
       else err = full_tile<FrameT, MASK, REDUCE, CT, false, Cfg, false>(p, bf_stage(sb), ff_stage(ss), prev_stage(ss), ctl->meta[ss], t, warp, lane, near);
     }
-    // per-tile partial in a fixed order (lanes: butterfly; warps: index order in the producer), fp64 from here on
+    // <= 3 * P fp32 terms per lane and tile, fp64 from here on; lanes: fixed butterfly; warps: index order in the producer
     if (REDUCE) {
-      const float ws = warp_sum(err);
-      if (lane == 0) ctl->red[ss][warp] = (double)ws;
+      acc += (double)err;
+      if (flushes(t, k)) {
+        const double ws = warp_sum(acc);
+        if (lane == 0) ctl->red[ss][warp] = ws;
+        acc = 0.0;
+      }
     }
     __syncwarp();   // every lane is done reading the stages of tile k
     if (lane == 0) mbar_arrive(&ctl->done[ss]);
+    if (++sb == NB) { sb = 0; pb ^= 1u; }
+    if (++ss == NS) { ss = 0; ps ^= 1u; }
   }
   if (!LEAN) count_near(near, p.near_threshold);
 }
@@ -903,6 +1053,13 @@ static cudaError_t dispatch(const FwdParams& p, int mask_kind, bool reduce, bool
   TCL_CASE(MASK_NONE, false)
 #undef TCL_CASE
   return cudaErrorInvalidValue;
+}
+
+extern "C" int tclb200_debug_tile_stats(unsigned long long* out2, int reset) {
+  unsigned long long zero[2] = {0, 0};
+  if (out2) CUDA_TRY(cudaMemcpyFromSymbol(out2, tcl::g_tile_stats, sizeof(zero)));
+  if (reset) CUDA_TRY(cudaMemcpyToSymbol(tcl::g_tile_stats, zero, sizeof(zero)));
+  return TCLB200_OK;
 }
 
 static int g_force_generic = 0;  // test hook: exercise the generic kernel on TMA-capable shapes

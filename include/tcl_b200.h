@@ -135,6 +135,12 @@ int tclb200_tcl_backward(const float* bf, const float* mask, const float* prev, 
  * global-memory kernel so that both kernels are exercised on the same inputs.  0 = off (default). */
 void tclb200_debug_force_generic(int on);
 
+/* Diagnostics (process-global device counters, not for production use): out2[0] = tiles of the TMA kernel that
+ * could not stage their source boxes (non-finite or extreme flow) and were gathered from global memory,
+ * out2[1] = "mixed" tiles (a motion boundary runs through them: some pixels gathered from global memory).
+ * Synchronises the device.  reset != 0 clears the counters afterwards. */
+int tclb200_debug_tile_stats(unsigned long long* out2, int reset);
+
 #ifdef __cplusplus
 }
 #endif

@@ -42,10 +42,16 @@ def run(name, pairs, mode="ff", kind="smooth"):
     else:
         fn = lambda: tcl.fused_forward(bf, prev, cur, ff=ff)
         bpp = 40 if dt == torch.float32 else 28
+    import ctypes
+    lib = tcl._cabi.lib()
+    lib.tclb200_debug_tile_stats(None, 1)
+    fn()
+    st = (ctypes.c_ulonglong * 2)()
+    lib.tclb200_debug_tile_stats(st, 1)
     ms = timeit(fn)
     px = pairs * H * W
     print(f"{name:14s} pairs={pairs:4d} mode={mode:4s} {ms*1e3:9.1f} us  {px/ms/1e6:7.1f} Gpix/s  {px*bpp/ms/1e6:7.0f} GB/s  "
-          f"{px*bpp/ms/1e6/6548.2*100:5.1f}% of measured peak", flush=True)
+          f"{px*bpp/ms/1e6/6548.2*100:5.1f}% of measured peak  global/mixed tiles {st[0]}/{st[1]}", flush=True)
 
 
 if __name__ == "__main__":

@@ -7,12 +7,10 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 CSRC = os.path.join(ROOT, "gan-based-video-style-transfer_b200", "csrc")
 OUT = os.path.join(ROOT, "tools", "_sweep")
 VARIANTS = {
-    "base_64x16_b4": {},
-    "64x16_b3": {"TCL_MINB": 3},
-    "64x8_w4": {"TCL_WARPS": 4, "TCL_TH": 8, "TCL_BH": 16, "TCL_MINB": 7},
-    "64x16_bw96": {"TCL_BW_F32": 96, "TCL_BW_BF16": 96, "TCL_MINB": 3},
-    "64x16_bh20": {"TCL_BH": 20, "TCL_MINB": 4},
-    "32x16_w4": {"TCL_WARPS": 4, "TCL_TW": 32, "TCL_TH": 16, "TCL_BW_F32": 44, "TCL_BW_BF16": 48, "TCL_BH": 24, "TCL_MINB": 7},
+    "th32_ns2_nb4": {},
+    "th32_ns2_nb3": {"TCL_NB": 3},
+    "th16_ns4_nb5": {"TCL_TH": 16, "TCL_BH": 24, "TCL_NS": 4, "TCL_NB": 5},
+    "th16_ns3_nb5": {"TCL_TH": 16, "TCL_BH": 24, "TCL_NS": 3, "TCL_NB": 5},
 }
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
@@ -26,6 +24,6 @@ if __name__ == "__main__":
     for n, pr in procs:
         out = pr.communicate()[0]
         lines = out.splitlines()
-        hot = [i for i, l in enumerate(lines) if "tma_kernelIfLi2ELb1ELi3ELb1" in l and "Compiling" in l]
+        hot = [i for i, l in enumerate(lines) if "ws_kernelIfLi2ELb1ELi3ELb1" in l and "Compiling" in l]
         info = " | ".join(l.strip() for l in lines[hot[0] + 1:hot[0] + 4]) if hot else "?"
         print(n, "rc", pr.returncode, info[:230])
