@@ -180,6 +180,30 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
       "r"(parity)
       : "memory");
 }
+// same, for a warp that has nothing else to do while it waits: sleeps between polls so that its polling does not
+// take issue slots from the warps that share its scheduler
+__device__ __forceinline__ void mbar_wait_idle(uint64_t* bar, unsigned parity) {
+  for (;;) {
+    unsigned done;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(done)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    if (done) return;
+    __nanosleep(40);
+  }
+}
+// TMA prefetch of a 4-D tile into L2 (no shared-memory destination, nothing to wait for)
+__device__ __forceinline__ void tma_prefetch_l2_4d(const void* tmap, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global.tile [%0, {%1, %2, %3, %4}];"
+               ::"l"(tmap), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
 // 4-D tiled TMA load global -> shared, completion on an mbarrier; out-of-range elements are zero-filled
 __device__ __forceinline__ void tma_load_4d(void* dst, const void* tmap, uint64_t* bar, int c0, int c1, int c2, int c3) {
   asm volatile(

@@ -231,6 +231,15 @@ __global__ void __launch_bounds__(kThreads) fused_forward_generic_kernel(const F
 // have a pitch of 80 words = 16 (mod 32): the two rows fall into disjoint halves of the 32 banks, also when the
 // flow shifts some lanes to the next source row, so the taps are (nearly) conflict-free shared-memory reads.
 __device__ unsigned long long g_tile_stats[2];   // debug statistics: tiles taken from global memory entirely / mixed tiles
+#ifdef TCL_TRACE
+// tuning aid (tools/trace_pipeline.py): per CTA and local tile, globaltimer stamps of the pipeline events
+constexpr int kTraceTiles = 64;
+__device__ unsigned long long g_trace[160][kTraceTiles][4];   // src requested, src observed ready (before / after the wait), tile done
+__device__ __forceinline__ unsigned long long gtime() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
+#define TCL_STAMP(k, slot) do { if ((k) < kTraceTiles && blockIdx.x < 160) g_trace[blockIdx.x][(k)][(slot)] = gtime(); } while (0)
+#else
+#define TCL_STAMP(k, slot) do { } while (0)
+#endif
 constexpr int kCWarps = 16;                      // consumer warps
 constexpr int kWsThreads = 32 * (kCWarps + 1);   // + 1 producer warp
 
@@ -261,11 +270,48 @@ struct TileId { int pair, tile, x0, y0, edge, pad[3]; };
 
 template <int NB, int NS>
 struct WsCtl {              // control block in shared memory
-  uint64_t bf_full[NB], src_full[NS], done[NS];
+  uint64_t bf_full[NB], src_full[NS], done[NS], scan0;
   TileId tinfo[NB];         // written by the producer with the flow-tile request
   int meta[NS][4];          // per source stage: ox, oy, staged?
+  int box[NB][4];           // per flow stage: extent of x+u, y+v over the tile (ordered-int encoding): xmin, ymin, xmax, ymax
   double red[NS][kCWarps];
 };
+
+// order-preserving float <-> int (total order of IEEE bit patterns; NaNs land beyond +-Inf): lets redux.sync and
+// shared-memory atomicMin / atomicMax work on float extents
+__device__ __forceinline__ int f2ord(float f) { const int i = __float_as_int(f); return i ^ ((i >> 31) & 0x7fffffff); }
+__device__ __forceinline__ float ord2f(int i) { return __int_as_float(i ^ ((i >> 31) & 0x7fffffff)); }
+__device__ __forceinline__ float fmin_nan(float a, float b) { float r; asm("min.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b)); return r; }
+__device__ __forceinline__ float fmax_nan(float a, float b) { float r; asm("max.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b)); return r; }
+
+// consumer warp `warp`: its TH/16 rows of the flow tile `t` -> extent of x+u, y+v (the same sums the sampling positions
+// start from) folded into box[4].  Non-finite flow propagates (min/max.NaN) and is rejected by the placement.
+template <typename Cfg>
+__device__ __forceinline__ void scan_flow_rows(const float* s_bu, const TileId& t, const Geo& g, int* box, int warp, int lane) {
+  constexpr int RPW = Cfg::TH / kCWarps;   // rows per warp: 1 or 2
+  const float* s_bv = s_bu + Cfg::kBfH * Cfg::kBfW;
+  const int c4 = 4 * (lane & 15);
+  const int r = warp * RPW + (lane >> 4);
+  // W % 4 == 0: a lane's four columns are all inside the image or all outside
+  const bool ok = (RPW == 2 || lane < 16) && t.x0 + c4 < g.W && t.y0 + r < g.H;
+  int ixmin = INT_MAX, iymin = INT_MAX, ixmax = INT_MIN, iymax = INT_MIN;
+  if (ok) {
+    const float4 u4 = *reinterpret_cast<const float4*>(s_bu + (r + 1) * Cfg::kBfW + Cfg::kHaloX + c4);
+    const float4 v4 = *reinterpret_cast<const float4*>(s_bv + (r + 1) * Cfg::kBfW + Cfg::kHaloX + c4);
+    const float xf = (float)(t.x0 + c4), yf = (float)(t.y0 + r);
+    const float a0 = __fadd_rn(xf, u4.x), a1 = __fadd_rn(xf + 1.0f, u4.y), a2 = __fadd_rn(xf + 2.0f, u4.z), a3 = __fadd_rn(xf + 3.0f, u4.w);
+    ixmin = f2ord(fmin_nan(fmin_nan(a0, a1), fmin_nan(a2, a3)));
+    ixmax = f2ord(fmax_nan(fmax_nan(a0, a1), fmax_nan(a2, a3)));
+    iymin = f2ord(__fadd_rn(yf, fmin_nan(fmin_nan(v4.x, v4.y), fmin_nan(v4.z, v4.w))));
+    iymax = f2ord(__fadd_rn(yf, fmax_nan(fmax_nan(v4.x, v4.y), fmax_nan(v4.z, v4.w))));
+  }
+  ixmin = __reduce_min_sync(0xffffffffu, ixmin); iymin = __reduce_min_sync(0xffffffffu, iymin);
+  ixmax = __reduce_max_sync(0xffffffffu, ixmax); iymax = __reduce_max_sync(0xffffffffu, iymax);
+  if (lane == 0) {
+    atomicMin(&box[0], ixmin); atomicMin(&box[1], iymin);
+    atomicMax(&box[2], ixmax); atomicMax(&box[3], iymax);
+  }
+}
 
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -572,7 +618,8 @@ __device__ __forceinline__ float lean_tile(const FwdParams& p, const float* s_bu
 template <typename FrameT, int MASK, bool REDUCE, int CT, bool LEAN, typename Cfg>
 __global__ void __launch_bounds__(kWsThreads, 1) fused_forward_ws_kernel(const FwdParams p, const __grid_constant__ CUtensorMap tm_bf,
                                                                          const __grid_constant__ CUtensorMap tm_ff,
-                                                                         const __grid_constant__ CUtensorMap tm_prev) {
+                                                                         const __grid_constant__ CUtensorMap tm_prev,
+                                                                         const __grid_constant__ CUtensorMap tm_cur) {
   constexpr int NB = Cfg::NB, NS = Cfg::NS, P = Cfg::kPPL;
   using Ctl = WsCtl<NB, NS>;
   static_assert(sizeof(Ctl) <= 1024, "control block too large");
@@ -596,6 +643,8 @@ __global__ void __launch_bounds__(kWsThreads, 1) fused_forward_ws_kernel(const F
   if (threadIdx.x == 0) {
     for (int i = 0; i < NB; ++i) mbar_init(&ctl->bf_full[i], 1);
     for (int i = 0; i < NS; ++i) { mbar_init(&ctl->src_full[i], 1); mbar_init(&ctl->done[i], kCWarps); }
+    mbar_init(&ctl->scan0, kCWarps);
+    for (int i = 0; i < NB; ++i) { ctl->box[i][0] = INT_MAX; ctl->box[i][1] = INT_MAX; ctl->box[i][2] = INT_MIN; ctl->box[i][3] = INT_MIN; }
     fence_barrier_init();
   }
   __syncthreads();
@@ -608,97 +657,59 @@ __global__ void __launch_bounds__(kWsThreads, 1) fused_forward_ws_kernel(const F
       ctl->tinfo[s] = t;
       mbar_expect_tx(&ctl->bf_full[s], Cfg::kBfLoad);
       tma_load_4d(bf_stage(s), &tm_bf, &ctl->bf_full[s], t.x0 - Cfg::kHaloX, t.y0 - 1, 0, t.pair);
+      // the consumers read this tile's `cur` values straight from global memory NB tiles from now: have them in L2 by then
+      if (LEAN) tma_prefetch_l2_4d(&tm_cur, t.x0, t.y0, 0, t.pair);
     };
-    // whole warp: extent of x+u, y+v over the tile's pixels -> origin of the source boxes (needs only the flow tile,
-    // so it runs while the consumers are still busy with earlier tiles) ...
+    // lane 0: the consumers have folded the extent of x+u, y+v over local tile k into box[k % NB] -> origin of the source
+    // boxes.  The coordinate map is monotone in x+u (every step is a correctly rounded monotone operation), so the
+    // extreme taps come from the extreme sums.
     struct Placement { int ox, oy, mode, pair; };
     auto place_src = [&](int k) -> Placement {
       const int sb = k % NB;
-      mbar_wait(&ctl->bf_full[sb], (k / NB) & 1);
       const TileId t = ctl->tinfo[sb];
-      bool staged = want_occ || want_frames;
       int ox = 0, oy = 0, mode = 0;   // mode: 0 = nothing staged, 1 = every tap inside the boxes, 2 = mixed (LEAN only)
-      if (staged) {
-        const float* s_bu = bf_stage(sb);
-        const float* s_bv = s_bu + Cfg::kBfH * Cfg::kBfW;
-        const int c4 = 4 * (lane & 15);
-        const int rows = min(Cfg::TH, g.H - t.y0);
-        const bool col_ok = t.x0 + c4 < g.W;      // W % 4 == 0: a lane's four columns are all inside or all outside
-        const float xf = (float)(t.x0 + c4);
-        float xmin = 3e38f, xmax = -3e38f, ymin = 3e38f, ymax = -3e38f, z = 0.0f, xsum = 0.0f, ysum = 0.0f;
-        if (col_ok) {
-#pragma unroll 2
-          for (int r = lane >> 4; r < rows; r += 2) {
-            const float4 u4 = *reinterpret_cast<const float4*>(s_bu + (r + 1) * Cfg::kBfW + Cfg::kHaloX + c4);
-            const float4 v4 = *reinterpret_cast<const float4*>(s_bv + (r + 1) * Cfg::kBfW + Cfg::kHaloX + c4);
-            const float a0 = __fadd_rn(xf, u4.x), a1 = __fadd_rn(xf + 1.0f, u4.y), a2 = __fadd_rn(xf + 2.0f, u4.z), a3 = __fadd_rn(xf + 3.0f, u4.w);
-            xmin = fminf(fminf(xmin, a0), fminf(a1, fminf(a2, a3)));
-            xmax = fmaxf(fmaxf(xmax, a0), fmaxf(a1, fmaxf(a2, a3)));
-            const float yf = (float)(t.y0 + r);
-            const float vmin = fminf(fminf(v4.x, v4.y), fminf(v4.z, v4.w)), vmax = fmaxf(fmaxf(v4.x, v4.y), fmaxf(v4.z, v4.w));
-            ymin = fminf(ymin, __fadd_rn(yf, vmin));
-            ymax = fmaxf(ymax, __fadd_rn(yf, vmax));
-            xsum += (a0 + a1) + (a2 + a3);
-            ysum += 4.0f * yf + ((v4.x + v4.y) + (v4.z + v4.w));
-            // 0 * finite == 0; an Inf or NaN anywhere makes z NaN (fminf / fmaxf would silently drop a NaN)
-            z = __fmaf_rn(u4.x, 0.0f, z); z = __fmaf_rn(u4.y, 0.0f, z); z = __fmaf_rn(u4.z, 0.0f, z); z = __fmaf_rn(u4.w, 0.0f, z);
-            z = __fmaf_rn(v4.x, 0.0f, z); z = __fmaf_rn(v4.y, 0.0f, z); z = __fmaf_rn(v4.z, 0.0f, z); z = __fmaf_rn(v4.w, 0.0f, z);
+      if (want_occ || want_frames) {
+        const float xmin = ord2f(ctl->box[sb][0]), ymin = ord2f(ctl->box[sb][1]), xmax = ord2f(ctl->box[sb][2]), ymax = ord2f(ctl->box[sb][3]);
+        const float lim = 1048576.0f;
+        const bool sane = xmin > -lim && xmax < lim && ymin > -lim && ymax < lim && xmin <= xmax && ymin <= ymax;   // false for NaN / Inf
+        if (sane) {
+          const float i2x = __fmul_rn(2.0f, g.inv_dx), i2y = __fmul_rn(2.0f, g.inv_dy);
+          auto coord = [](float a, float i2, float sz) {
+            const float tt = __fadd_rn(__fsub_rn(__fmul_rn(a, i2), 1.0f), 1.0f);
+            return __fmul_rn(__fmaf_rn(tt, sz, -1.0f), 0.5f);
+          };
+          const int bx0 = __float2int_rd(coord(xmin, i2x, g.Wf)), bx1 = __float2int_rd(coord(xmax, i2x, g.Wf));
+          const int by0 = __float2int_rd(coord(ymin, i2y, g.Hf)), by1 = __float2int_rd(coord(ymax, i2y, g.Hf));
+          ox = bx0 & ~(Cfg::kXAlign - 1);   // 16-byte aligned box start (floor, also for negatives)
+          oy = by0;
+          // taps span [x0, x0+1] x [y0, y0+1]
+          const bool fitx = bx1 + 1 - ox < Cfg::BW, fity = by1 + 1 - oy < Cfg::BH;
+          mode = (fitx && fity) ? 1 : (LEAN ? 2 : 0);
+          if (mode == 2) {
+            // a motion boundary runs through the tile: centre the box on the extent (per axis, where it does not fit);
+            // pixels whose taps fall outside take the global path one by one.  The feature-complete path has no
+            // per-pixel fallback: there the whole tile is gathered from global memory (mode 0).
+            if (!fitx) ox = ((bx0 + bx1 + 1 - Cfg::BW) / 2) & ~(Cfg::kXAlign - 1);
+            if (!fity) oy = (by0 + by1 + 1 - Cfg::BH) / 2;
           }
         }
-        // the coordinate map is monotone in x+u (every step is a correctly rounded monotone operation), so the
-        // extreme taps come from the extreme sums; clamp first so the conversions stay in range
-        const float lim = 1048576.0f;
-        const float i2x = __fmul_rn(2.0f, g.inv_dx), i2y = __fmul_rn(2.0f, g.inv_dy);
-        auto coord = [](float a, float i2, float sz) {
-          const float tt = __fadd_rn(__fsub_rn(__fmul_rn(a, i2), 1.0f), 1.0f);
-          return __fmul_rn(__fmaf_rn(tt, sz, -1.0f), 0.5f);
-        };
-        int bx0 = __float2int_rd(coord(fminf(fmaxf(xmin, -lim), lim), i2x, g.Wf));
-        int bx1 = __float2int_rd(coord(fminf(fmaxf(xmax, -lim), lim), i2x, g.Wf));
-        int by0 = __float2int_rd(coord(fminf(fmaxf(ymin, -lim), lim), i2y, g.Hf));
-        int by1 = __float2int_rd(coord(fminf(fmaxf(ymax, -lim), lim), i2y, g.Hf));
-        bx0 = __reduce_min_sync(0xffffffffu, bx0); by0 = __reduce_min_sync(0xffffffffu, by0);
-        bx1 = __reduce_max_sync(0xffffffffu, bx1); by1 = __reduce_max_sync(0xffffffffu, by1);
-        const bool bad = __any_sync(0xffffffffu, !(z == 0.0f));
-        ox = bx0 & ~(Cfg::kXAlign - 1);   // 16-byte aligned box start (floor, also for negatives)
-        oy = by0;
-        // taps span [x0, x0+1] x [y0, y0+1]
-        const bool sane = !bad && bx0 <= bx1 && by0 <= by1 && bx0 > -1000000 && bx1 < 1000000 && by0 > -1000000 && by1 < 1000000;
-        const bool fitx = bx1 + 1 - ox < Cfg::BW, fity = by1 + 1 - oy < Cfg::BH;
-        staged = sane;
-        mode = (fitx && fity) ? 1 : 2;
-        if (sane && LEAN && mode == 2) {
-          // a motion boundary runs through the tile: centre the box on the mean sampling position (per axis, where the
-          // extent does not fit); pixels whose taps fall outside take the global path one by one
-#pragma unroll
-          for (int o = 16; o > 0; o >>= 1) { xsum += __shfl_xor_sync(0xffffffffu, xsum, o); ysum += __shfl_xor_sync(0xffffffffu, ysum, o); }
-          const float inv_n = 1.0f / (float)(rows * min(Cfg::TW, g.W - t.x0));
-          if (!fitx) ox = (__float2int_rd(coord(xsum * inv_n, i2x, g.Wf)) - Cfg::BW / 2) & ~(Cfg::kXAlign - 1);
-          if (!fity) oy = __float2int_rd(coord(ysum * inv_n, i2y, g.Hf)) - Cfg::BH / 2;
-        } else if (mode == 2) {
-          staged = false;   // the feature-complete path has no per-pixel fallback: whole tile from global memory
-        }
-        if (!staged) mode = 0;
-      } else {
-        mode = 0;
+        if (mode != 1) atomicAdd(&g_tile_stats[mode == 2 ? 1 : 0], 1ull);
       }
-      if (lane == 0 && mode != 1 && (want_occ || want_frames)) atomicAdd(&g_tile_stats[mode == 2 ? 1 : 0], 1ull);
+      ctl->box[sb][0] = INT_MAX; ctl->box[sb][1] = INT_MAX; ctl->box[sb][2] = INT_MIN; ctl->box[sb][3] = INT_MIN;
       return Placement{ox, oy, mode, t.pair};
     };
     // ... and, once the source stage is free, the request itself (lane 0)
     auto issue_src = [&](int k, const Placement& pl) {
       const int ss = k % NS;
-      if (lane == 0) {
-        ctl->meta[ss][0] = pl.ox; ctl->meta[ss][1] = pl.oy; ctl->meta[ss][2] = pl.mode;
-        if (pl.mode != 0) {
-          mbar_expect_tx(&ctl->src_full[ss], (want_occ ? Cfg::kFfLoad : 0u) + (want_frames ? Cfg::kPrevLoad : 0u));
-          if (want_occ) tma_load_4d(ff_stage(ss), &tm_ff, &ctl->src_full[ss], pl.ox, pl.oy, 0, pl.pair);
-          if (want_frames) tma_load_4d(prev_stage(ss), &tm_prev, &ctl->src_full[ss], pl.ox, pl.oy, 0, pl.pair);
-        } else {
-          mbar_arrive(&ctl->src_full[ss]);
-        }
+      ctl->meta[ss][0] = pl.ox; ctl->meta[ss][1] = pl.oy; ctl->meta[ss][2] = pl.mode;
+      if (pl.mode != 0) {
+        TCL_STAMP(k, 0);
+        mbar_expect_tx(&ctl->src_full[ss], (want_occ ? Cfg::kFfLoad : 0u) + (want_frames ? Cfg::kPrevLoad : 0u));
+        if (want_occ) tma_load_4d(ff_stage(ss), &tm_ff, &ctl->src_full[ss], pl.ox, pl.oy, 0, pl.pair);
+        if (want_frames) tma_load_4d(prev_stage(ss), &tm_prev, &ctl->src_full[ss], pl.ox, pl.oy, 0, pl.pair);
+      } else {
+        mbar_arrive(&ctl->src_full[ss]);
       }
-      __syncwarp();
     };
 
     if (lane == 0) {
@@ -708,19 +719,23 @@ __global__ void __launch_bounds__(kWsThreads, 1) fused_forward_ws_kernel(const F
       for (int j = 0; j < NB && j < n; ++j) issue_bf(j);
     }
     __syncwarp();
-    for (int j = 0; j < NS && j < n; ++j) issue_src(j, place_src(j));
+    mbar_wait_idle(&ctl->scan0, 0);   // the consumers have scanned the first NS flow tiles
+    if (lane == 0)
+      for (int j = 0; j < NS && j < n; ++j) issue_src(j, place_src(j));
+    __syncwarp();
     for (int j = 0; j < n; ++j) {
-      Placement pl{0, 0, 0, 0};
-      if (j + NS < n) pl = place_src(j + NS);        // off the critical path: tile j is still being computed
-      mbar_wait(&ctl->done[j % NS], (j / NS) & 1);   // consumers are finished with tile j: its stages are free
+      // consumers are finished with tile j (its stages are free) and have scanned the flow tile of tile j + NS
+      mbar_wait_idle(&ctl->done[j % NS], (j / NS) & 1);
       const TileId t = ctl->tinfo[j % NB];
       // the 16 consumer warps' sums for this CTA's share of the pair, folded in index order (lanes 0..15, fixed tree)
       double ts = 0.0;
       const bool fl = REDUCE && flushes(t, j);
       if (fl && lane < kCWarps) ts = ctl->red[j % NS][lane];
       __syncwarp();
-      if (j + NS < n) issue_src(j + NS, pl);
-      if (lane == 0 && j + NB < n) issue_bf(j + NB);
+      if (lane == 0) {
+        if (j + NS < n) issue_src(j + NS, place_src(j + NS));
+        if (j + NB < n) issue_bf(j + NB);
+      }
       __syncwarp();
       if (fl) {
         ts = warp_sum(ts);
@@ -738,6 +753,18 @@ __global__ void __launch_bounds__(kWsThreads, 1) fused_forward_ws_kernel(const F
   lane_pixel(warp, lane, 0, lx0, ly0);
   const int lane_off = ly0 * g.W + lx0;
   const ptrdiff_t row16 = (ptrdiff_t)16 * g.W;
+  // the source boxes of a tile are placed from the extent of its sampling positions: every consumer warp scans its rows
+  // of the flow tile NS tiles ahead (the first NS ones here, tile k + NS at the end of tile k)
+  const bool want_scan = want_occ || want_frames;
+  auto scan_tile = [&](int k2) {
+    const int s2 = k2 % NB;
+    mbar_wait(&ctl->bf_full[s2], (k2 / NB) & 1);
+    scan_flow_rows<Cfg>(bf_stage(s2), ctl->tinfo[s2], g, ctl->box[s2], warp, lane);
+  };
+  if (want_scan)
+    for (int j = 0; j < NS && j < n; ++j) scan_tile(j);
+  __syncwarp();
+  if (lane == 0) mbar_arrive(&ctl->scan0);
   int sb = 0, ss = 0;
   unsigned pb = 0, ps = 0;   // stage indices and phase parities of the current tile
   for (int k = 0; k < n; ++k) {
@@ -770,7 +797,9 @@ __global__ void __launch_bounds__(kWsThreads, 1) fused_forward_ws_kernel(const F
           mk[i] = (MASK == MASK_GIVEN && inside) ? __ldcs(mb + off) : 0.0f;
         }
       }
+      if (threadIdx.x == 0) TCL_STAMP(k, 1);
       mbar_wait(&ctl->src_full[ss], ps);
+      if (threadIdx.x == 0) TCL_STAMP(k, 2);
       const int mode = ctl->meta[ss][2];
       if (mode == 1) {
         if (t.edge) err = lean_tile<FrameT, MASK, Cfg, true, false>(p, bf_stage(sb), ff_stage(ss), ctl->meta[ss], t, warp, lane, cur, mk);
@@ -794,8 +823,10 @@ __global__ void __launch_bounds__(kWsThreads, 1) fused_forward_ws_kernel(const F
         acc = 0.0;
       }
     }
+    if (want_scan && k + NS < n) scan_tile(k + NS);
     __syncwarp();   // every lane is done reading the stages of tile k
     if (lane == 0) mbar_arrive(&ctl->done[ss]);
+    if (threadIdx.x == 0) TCL_STAMP(k, 3);
     if (++sb == NB) { sb = 0; pb ^= 1u; }
     if (++ss == NS) { ss = 0; ps ^= 1u; }
   }
@@ -998,7 +1029,8 @@ static int sm_count() {
 }
 
 template <typename FrameT, int MASK, bool REDUCE, int CT, bool LEAN>
-static cudaError_t launch_tma(const FwdParams& p, const CUtensorMap& tb, const CUtensorMap& tf, const CUtensorMap& tp, cudaStream_t s) {
+static cudaError_t launch_tma(const FwdParams& p, const CUtensorMap& tb, const CUtensorMap& tf, const CUtensorMap& tp, const CUtensorMap& tc,
+                              cudaStream_t s) {
   using Cfg = WsCfg<FrameT, CT, kTW, kTH, kBH, TCL_NB, TCL_NS>;
   auto kern = fused_forward_ws_kernel<FrameT, MASK, REDUCE, CT, LEAN, Cfg>;
   static bool configured = false;  // per instantiation
@@ -1011,7 +1043,7 @@ static cudaError_t launch_tma(const FwdParams& p, const CUtensorMap& tb, const C
   const size_t tiles = (size_t)p.B * p.tiles_per_pair;
   const size_t slots = (size_t)sm_count();
   const unsigned grid = (unsigned)(tiles < slots ? tiles : slots);
-  kern<<<grid, kWsThreads, Cfg::kSmemBytes, s>>>(p, tb, tf, tp);
+  kern<<<grid, kWsThreads, Cfg::kSmemBytes, s>>>(p, tb, tf, tp, tc);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess || !REDUCE) return e;
   cudaLaunchConfig_t cfg;
@@ -1034,12 +1066,12 @@ static cudaError_t launch_generic(const FwdParams& p, cudaStream_t s) {
 
 template <typename FrameT>
 static cudaError_t dispatch(const FwdParams& p, int mask_kind, bool reduce, bool tma, const CUtensorMap& tb, const CUtensorMap& tf,
-                            const CUtensorMap& tp, cudaStream_t s) {
+                            const CUtensorMap& tp, const CUtensorMap& tc, cudaStream_t s) {
 #define TCL_CASE(MK, RD)                                                                       \
   if (mask_kind == MK && reduce == RD) {                                                       \
     if (!tma) return launch_generic<FrameT, MK, RD>(p, s);                                     \
-    if (p.C == 3 && lean) return launch_tma<FrameT, MK, RD, 3, true>(p, tb, tf, tp, s);        \
-    return p.C == 3 ? launch_tma<FrameT, MK, RD, 3, false>(p, tb, tf, tp, s) : launch_tma<FrameT, MK, RD, 0, false>(p, tb, tf, tp, s); \
+    if (p.C == 3 && lean) return launch_tma<FrameT, MK, RD, 3, true>(p, tb, tf, tp, tc, s);    \
+    return p.C == 3 ? launch_tma<FrameT, MK, RD, 3, false>(p, tb, tf, tp, tc, s) : launch_tma<FrameT, MK, RD, 0, false>(p, tb, tf, tp, tc, s); \
   }
   // LEAN = the measured hot configurations, fixed at compile time: computeTCL / training loss with C == 3
   const bool lean = reduce && p.prev && p.cur && !p.warp_out && !p.mask_out && !p.blend_out && !p.near_threshold &&
@@ -1061,6 +1093,14 @@ extern "C" int tclb200_debug_tile_stats(unsigned long long* out2, int reset) {
   if (reset) CUDA_TRY(cudaMemcpyToSymbol(tcl::g_tile_stats, zero, sizeof(zero)));
   return TCLB200_OK;
 }
+
+#ifdef TCL_TRACE
+extern "C" int tclb200_debug_trace(unsigned long long* out, size_t bytes) {
+  if (bytes > sizeof(tcl::g_trace)) bytes = sizeof(tcl::g_trace);
+  CUDA_TRY(cudaMemcpyFromSymbol(out, tcl::g_trace, bytes));
+  return TCLB200_OK;
+}
+#endif
 
 static int g_force_generic = 0;  // test hook: exercise the generic kernel on TMA-capable shapes
 extern "C" void tclb200_debug_force_generic(int on) { g_force_generic = on; }
@@ -1085,13 +1125,14 @@ static int run_fused(const tclb200_tcl_args* a, cudaStream_t s) {
   const int esz = a->dtype == TCLB200_BF16 ? 2 : 4;
   // TMA needs 16-byte aligned bases and row strides; frames need C == 3 (the compiled box depth)
   bool tma = !g_force_generic && (a->W % 4 == 0) && ((a->W * esz) % 16 == 0) && aligned16(a->bf) && aligned16(a->ff) &&
-             aligned16(a->prev) && (!a->prev || a->C == 3) && a->B <= 65535 * 16;
-  CUtensorMap tb, tf, tp;
-  memset(&tb, 0, sizeof(tb)); memset(&tf, 0, sizeof(tf)); memset(&tp, 0, sizeof(tp));
+             aligned16(a->prev) && aligned16(a->cur) && (!a->prev || a->C == 3) && a->B <= 65535 * 16;
+  CUtensorMap tb, tf, tp, tc;
+  memset(&tb, 0, sizeof(tb)); memset(&tf, 0, sizeof(tf)); memset(&tp, 0, sizeof(tp)); memset(&tc, 0, sizeof(tc));
   if (tma) {
     tma = make_map(&tb, a->bf, 4, a->W, a->H, 2, a->B, kTW + 16, kTH + 2, 2);
     if (tma && mask_kind == MASK_COMPUTED && (a->flags & TCLB200_OCC)) tma = make_map(&tf, a->ff, 4, a->W, a->H, 2, a->B, kBW, kBH, 2);
     if (tma && a->prev) tma = make_map(&tp, a->prev, esz, a->W, a->H, 3, a->B, kBW, kBH, 3);
+    if (tma && a->prev && a->cur) tma = make_map(&tc, a->cur, esz, a->W, a->H, 3, a->B, kTW, kTH, 3);
   }
 
   FwdParams p;
@@ -1116,8 +1157,8 @@ static int run_fused(const tclb200_tcl_args* a, cudaStream_t s) {
     p.scratch.pair_ticket = reinterpret_cast<unsigned*>(base + align_up((size_t)a->B * tpp_max * sizeof(double), 256));
     p.scratch.batch_ticket = p.scratch.pair_ticket + a->B;
   }
-  const cudaError_t e = a->dtype == TCLB200_BF16 ? dispatch<__nv_bfloat16>(p, mask_kind, reduce, tma, tb, tf, tp, s)
-                                                 : dispatch<float>(p, mask_kind, reduce, tma, tb, tf, tp, s);
+  const cudaError_t e = a->dtype == TCLB200_BF16 ? dispatch<__nv_bfloat16>(p, mask_kind, reduce, tma, tb, tf, tp, tc, s)
+                                                 : dispatch<float>(p, mask_kind, reduce, tma, tb, tf, tp, tc, s);
   if (e != cudaSuccess) return fail(TCLB200_ERR_CUDA, "fused forward launch: %s", cudaGetErrorString(e));
   return TCLB200_OK;
 }

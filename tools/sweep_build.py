@@ -8,6 +8,8 @@ CSRC = os.path.join(ROOT, "gan-based-video-style-transfer_b200", "csrc")
 OUT = os.path.join(ROOT, "tools", "_sweep")
 VARIANTS = {
     "th32_ns2_nb4": {},
+    "trace": {"TCL_TRACE": 1},
+    "th16_ns4_nb6": {"TCL_TH": 16, "TCL_BH": 24, "TCL_NS": 4, "TCL_NB": 6},
     "th32_ns2_nb3": {"TCL_NB": 3},
     "th16_ns4_nb5": {"TCL_TH": 16, "TCL_BH": 24, "TCL_NS": 4, "TCL_NB": 5},
     "th16_ns3_nb5": {"TCL_TH": 16, "TCL_BH": 24, "TCL_NS": 3, "TCL_NB": 5},
