@@ -520,7 +520,11 @@ __device__ __forceinline__ float lean_tile(const FwdParams& p, const float* s_bu
   const float* s_bv = s_bu + Cfg::kBfH * BFW;
   // the prev boxes follow the ff boxes in the stage: one address register serves both (fp32 frames)
   const FrameT* s_prev = reinterpret_cast<const FrameT*>(reinterpret_cast<const unsigned char*>(s_ff) + Cfg::kFfStage);
-  const float box_xf = (float)meta[0], box_yf = (float)meta[1];
+  const int box_x = meta[0], box_y = meta[1];
+  const float box_xf = (float)box_x, box_yf = (float)box_y;
+  const ptrdiff_t gplane = (ptrdiff_t)g.H * g.W;
+  const float* gff = (MIXED && MASK == MASK_COMPUTED) ? p.ff + (size_t)t.pair * 2 * gplane : nullptr;
+  const FrameT* gprev = MIXED ? reinterpret_cast<const FrameT*>(p.prev) + (size_t)t.pair * 3 * gplane : nullptr;
   LeanGeo lg;
   lg.i2x = __fmul_rn(2.0f, g.inv_dx); lg.i2y = __fmul_rn(2.0f, g.inv_dy);   // exact doubling: (2a)*r == a*(2r)
   lg.Wf = g.Wf; lg.Hf = g.Hf;
@@ -550,16 +554,44 @@ __device__ __forceinline__ float lean_tile(const FwdParams& p, const float* s_bu
       amb = !(mob || G < Rlo);
     }
     LeanTaps tp = lean_taps(xs[k & 1], ys[k >> 1], u, v, lg, box_xf, box_yf);
-    bool usable = inside;
-    if (MIXED) usable = inside && tp.rx >= 0.0f && tp.rx < (float)(BW - 1) && tp.ry >= 0.0f && tp.ry < (float)(Cfg::BH - 1);
-    // pixels beyond the image edge / taps outside the box: read any in-box address, the result is discarded
-    const int q = (EDGE || MIXED) && !usable ? 0 : (int)__fmaf_rn(tp.ry, (float)BW, tp.rx);
+    // pixels beyond the image edge read any in-box address, their result is discarded
+    bool inbox = true;
+    if (MIXED) inbox = !inside || (tp.rx >= 0.0f && tp.rx < (float)(BW - 1) && tp.ry >= 0.0f && tp.ry < (float)(Cfg::BH - 1));
+    const int q = ((EDGE || MIXED) && !(inside && inbox)) ? 0 : (int)__fmaf_rn(tp.ry, (float)BW, tp.rx);
+    // where the four taps of each plane come from: the staged boxes (zero-filled outside the image), or -- pixels of a
+    // mixed tile whose taps left the boxes -- global memory with grid_sample's zero padding as per-tap predicates
+    const float* pf = s_ff + q;
+    const FrameT* pp = s_prev + q;
+    int rs = BW;
+    ptrdiff_t ps = PL;
+    bool p00 = true, p10 = true, p01 = true, p11 = true;
+    if (MIXED && !inbox) {
+      const int gx = (int)tp.rx + box_x, gy = (int)tp.ry + box_y;   // top-left tap in the image (sane: the placement checked)
+      const ptrdiff_t off = (ptrdiff_t)gy * g.W + gx;
+      if (MASK == MASK_COMPUTED) pf = gff + off;
+      pp = gprev + off;
+      rs = g.W; ps = gplane;
+      const bool xin0 = (unsigned)gx < (unsigned)g.W, xin1 = (unsigned)(gx + 1) < (unsigned)g.W;
+      const bool yin0 = (unsigned)gy < (unsigned)g.H, yin1 = (unsigned)(gy + 1) < (unsigned)g.H;
+      p00 = xin0 && yin0; p10 = xin1 && yin0; p01 = xin0 && yin1; p11 = xin1 && yin1;
+    }
+    auto tap4 = [&](auto* b) {   // one plane, grid_sampler_2d's accumulation order
+      float w;
+      if (MIXED) {
+        w = __fmul_rn(p00 ? to_f32(b[0]) : 0.0f, tp.nw);
+        w = __fmaf_rn(p10 ? to_f32(b[1]) : 0.0f, tp.ne, w);
+        w = __fmaf_rn(p01 ? to_f32(b[rs]) : 0.0f, tp.sw, w);
+        w = __fmaf_rn(p11 ? to_f32(b[rs + 1]) : 0.0f, tp.se, w);
+      } else {
+        w = __fmul_rn(to_f32(b[0]), tp.nw);
+        w = __fmaf_rn(to_f32(b[1]), tp.ne, w);
+        w = __fmaf_rn(to_f32(b[BW]), tp.sw, w);
+        w = __fmaf_rn(to_f32(b[BW + 1]), tp.se, w);
+      }
+      return w;
+    };
     if (MASK == MASK_COMPUTED) {
-      const float* f0 = s_ff + q;
-      float a = __fmul_rn(f0[0], tp.nw);
-      a = __fmaf_rn(f0[1], tp.ne, a); a = __fmaf_rn(f0[BW], tp.sw, a); a = __fmaf_rn(f0[BW + 1], tp.se, a);
-      float b = __fmul_rn(f0[PL], tp.nw);
-      b = __fmaf_rn(f0[PL + 1], tp.ne, b); b = __fmaf_rn(f0[PL + BW], tp.sw, b); b = __fmaf_rn(f0[PL + BW + 1], tp.se, b);
+      const float a = tap4(pf), b = tap4(MIXED ? pf + ps : pf + PL);
       // occlusion: |wf+bf|^2  vs  0.01*(|wf|^2+|bf|^2) + 0.5
       const float su = __fadd_rn(a, u), sv = __fadd_rn(b, v);
       const float L = __fmaf_rn(su, su, __fmul_rn(sv, sv));
@@ -569,21 +601,17 @@ __device__ __forceinline__ float lean_tile(const FwdParams& p, const float* s_bu
       keep = keep && !occ;
       amb = amb || !(occ || L < Rlo);
     }
-    const FrameT* q0 = s_prev + q;
     float acc = 0.0f;
 #pragma unroll
     for (int ch = 0; ch < 3; ++ch) {
-      float w = __fmul_rn(to_f32(q0[ch * PL]), tp.nw);
-      w = __fmaf_rn(to_f32(q0[ch * PL + 1]), tp.ne, w);
-      w = __fmaf_rn(to_f32(q0[ch * PL + BW]), tp.sw, w);
-      w = __fmaf_rn(to_f32(q0[ch * PL + BW + 1]), tp.se, w);
+      const float w = tap4(MIXED ? pp + ch * ps : pp + ch * PL);
       const float d = __fsub_rn(cur[k][ch], w);
       acc = __fmaf_rn(d, d, acc);
     }
     e[k] = MASK == MASK_GIVEN ? __fmul_rn(__fmul_rn(mk[k], mk[k]), acc) : acc;   // (m*d)^2 summed over channels (mk = 0 outside)
     keepbits |= (keep ? 1u : 0u) << k;
-    ambbits |= (amb && usable ? 1u : 0u) << k;
-    if (MIXED) outbits |= (inside && !usable ? 1u : 0u) << k;
+    ambbits |= (amb && inside && inbox ? 1u : 0u) << k;
+    if (MIXED) outbits |= (amb && inside && !inbox ? 1u : 0u) << k;
   }
   // rare, divergent: tests too close to call replay the exact sequences (a few pixels per million) ...
   if (MASK == MASK_COMPUTED && __builtin_expect(ambbits != 0, 0)) {
@@ -594,8 +622,8 @@ __device__ __forceinline__ float lean_tile(const FwdParams& p, const float* s_bu
         keepbits = (keepbits & ~(1u << k)) | ((kp ? 1u : 0u) << k);
       }
   }
-  // ... and pixels of a mixed tile whose taps left the boxes are redone from global memory
-  if (MIXED && outbits != 0) {
+  // ... the same for pixels of a mixed tile whose taps left the boxes: redone from global memory
+  if (MIXED && MASK == MASK_COMPUTED && __builtin_expect(outbits != 0, 0)) {
     const size_t plane = (size_t)g.H * g.W;
 #pragma unroll
     for (int k = 0; k < P; ++k)
