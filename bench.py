@@ -43,6 +43,19 @@ def parse():
 
 
 # ------------------------------------------------------------------------------------------------
+def load_traffic(workload, n_pairs):
+    """dram__bytes_read+write of the dominant kernel per launch, from the committed ncu capture of this very
+    command (profiles/r01_bench_traffic.json, written by tools/ncu_traffic.py); None when there is no capture."""
+    p = os.path.join(ROOT, "profiles", "r01_bench_traffic.json")
+    try:
+        rec = json.load(open(p))
+        if rec.get("workload") == workload and int(rec.get("pairs_per_launch", -1)) == int(n_pairs):
+            return float(rec["dram_bytes_per_launch"])
+    except Exception:
+        pass
+    return None
+
+
 def load_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -336,12 +349,11 @@ def main():
     shard = make_shard(tcl, args.workload, n_local, 1234 + 2000 + 100000 * rank, device, args.frames)
     torch.cuda.synchronize()
 
-    launches = [0]
     last = {}
+    lib = tcl._cabi.lib()
 
     def step():
         out = tcl.evaluate_sharded(shard["ff"], shard["bf"], shard["prev"], shard["cur"], seq_of_pair, n_seq)
-        launches[0] += 1
         last["out"] = out
 
     def kernel_only():
@@ -356,13 +368,20 @@ def main():
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    launches[0] = 0
+    lib.tclb200_debug_launch_count(1)
+    lib.tclb200_debug_tile_stats(None, 1)
     start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.cudart().cudaProfilerStart()   # no-op unless run under `ncu --profile-from-start off` (profiles/ launch lists)
     start.record()
     for _ in range(args.steps):
         step()
     end.record()
     torch.cuda.synchronize()
+    torch.cuda.cudart().cudaProfilerStop()
+    n_launches = int(lib.tclb200_debug_launch_count(0))   # kernels of libtcl_b200.so launched inside the timed region
+    import ctypes
+    tile_stats = (ctypes.c_ulonglong * 2)()
+    lib.tclb200_debug_tile_stats(tile_stats, 1)
     if dist:
         dist.barrier()
     torch.cuda.synchronize()
@@ -391,11 +410,17 @@ def main():
         "config": {"workload": args.workload, "shape": f"{W}x{H}", "channels": C, "pairs_per_gpu_per_step": n_local,
                    "sequences": n_seq, "frames": args.frames, "sharding": "by frame pair, one all-reduce of packed sums per step",
                    "l2": "inputs (%.1f GB per GPU) are larger than L2, no flush needed" % (alg_bytes / 1e9)},
-        "gpu_launches": launches[0],
+        "gpu_launches": n_launches,
+        "gpu_launches_note": "kernels of libtcl_b200.so inside the timed region: per step one fused_forward_ws_kernel + one "
+                             "fold_partials_kernel (programmatic dependent launch)",
+        "tiles": {"per_step": n_local * ((W + 63) // 64) * ((H + 31) // 32),
+                  "mixed_per_step": int(tile_stats[1]) // max(args.steps, 1), "global_per_step": int(tile_stats[0]) // max(args.steps, 1),
+                  "note": "mixed = a motion boundary runs through the 64x32 tile, some pixels gather from global memory"},
         "result_check": {"mean_over_sequences_rmse": float(res["mean_over_sequences"]), "pooled_rmse": float(res["pooled_rmse"]),
                          "n_pairs": int(res["n_pairs"])},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": None, "peak_source": peak_src, "kernel": "tcl::fused_forward_kernel",
+                     "traffic": load_traffic(args.workload, n_local), "peak_source": peak_src,
+                     "kernel": "tcl::fused_forward_ws_kernel<float, MASK_COMPUTED, reduce, C=3, lean> (+ fold_partials_kernel, <0.1 % of the time)",
                      "kernel_ms_per_launch": k_ms, "algorithmic_bytes_per_launch": alg_bytes, "bytes_per_px": bpp,
                      "frac_of_nominal_8TBs": achieved / 8000.0},
         "clocks": clocks,

@@ -66,6 +66,7 @@ struct Scratch {
   double* partials;        // [B * tiles_per_pair]; all zero between launches
   unsigned* pair_ticket;   // [B]; all zero between launches
   unsigned* batch_ticket;  // [1]
+  unsigned* tile_ctr;      // [2] tile counter / finished-CTA counter of the dynamic tile schedule (nullptr: static); zero between launches
 };
 
 struct FwdParams {

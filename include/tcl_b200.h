@@ -141,6 +141,10 @@ void tclb200_debug_force_generic(int on);
  * Synchronises the device.  reset != 0 clears the counters afterwards. */
 int tclb200_debug_tile_stats(unsigned long long* out2, int reset);
 
+/* Diagnostics: number of kernels this library has launched in this process (the fused TMA path launches two per
+ * reducing call: the fused kernel and the fold kernel behind it).  reset != 0 clears the counter. */
+unsigned long long tclb200_debug_launch_count(int reset);
+
 #ifdef __cplusplus
 }
 #endif
