@@ -378,23 +378,26 @@ __device__ __forceinline__ void lane_pixel(int warp, int lane, int k, int& lx, i
   ly = 2 * (task >> 1) + (lane >> 4);
 }
 
-// ---- consumer: exact per-pixel path (all features; staged boxes or global gathers) -------------------
+// ---- consumer: exact per-pixel path (all features; staged boxes, global gathers, or both in a mixed tile) -------
 template <typename FrameT, int MASK, bool REDUCE, int CT, bool LEAN, typename Cfg, bool EDGE>
 __device__ __forceinline__ float full_tile(const FwdParams& p, const float* s_bu, const float* s_ff, const FrameT* s_prev,
-                                           const int* meta, const TileId& t, int warp, int lane, unsigned& near) {
+                                           const int* meta, const TileId& t, int warp, int lane,
+                                           const float (&cur)[Cfg::kPPL][Cfg::kC], const float (&mk)[Cfg::kPPL], bool have_cur,
+                                           unsigned& near) {
   const Geo& g = p.geo;
   const int W = g.W, H = g.H;
   const size_t plane = (size_t)H * W;
   const bool want_mob = MASK == MASK_COMPUTED && (LEAN || (p.flags & TCLB200_MOB));
   const float* s_bv = s_bu + Cfg::kBfH * Cfg::kBfW;
   const PairPtrs<FrameT> io = pair_ptrs<FrameT>(p, t.pair, CT > 0 ? CT : p.C, plane);
-  const int ox = meta[0], oy = meta[1];
-  const bool staged = meta[2] != 0;
+  const int ox = meta[0], oy = meta[1], mode = meta[2];   // mode 0: nothing staged, 1: every tap in the boxes, 2: mixed
   const SmemSrc<float, Cfg::BW, Cfg::BH * Cfg::BW> fs{s_ff, ox, oy};
   const SmemSrc<FrameT, Cfg::BW, Cfg::BH * Cfg::BW> ps{s_prev, ox, oy};
+  const GlobalSrc<float> fg{p.ff ? p.ff + (size_t)t.pair * 2 * plane : nullptr, plane, g};
+  const GlobalSrc<FrameT> pg{p.prev ? reinterpret_cast<const FrameT*>(p.prev) + (size_t)t.pair * (CT > 0 ? CT : p.C) * plane : nullptr, plane, g};
   float err = 0.0f;
-#pragma unroll 1
-  for (int k = 0; k < Cfg::kPPL; ++k) {
+#pragma unroll
+  for (int k = 0; k < Cfg::kPPL; ++k) {   // fully unrolled: cur[k] / mk[k] must stay in registers
     int lx, ly;
     lane_pixel(warp, lane, k, lx, ly);
     const int x = t.x0 + lx, y = t.y0 + ly;
@@ -413,14 +416,13 @@ __device__ __forceinline__ float full_tile(const FwdParams& p, const float* s_bu
     }
     const PixTaps taps = pix_taps(u, v, x, y, g);
     const size_t o = (size_t)y * W + x;
-    if (MASK == MASK_GIVEN) keep = __ldcs(p.mask_in + (size_t)t.pair * plane + o);
-    if (staged) {
-      finish_pixel<FrameT, MASK, REDUCE, CT, LEAN>(p, taps, u, v, nb, keep, o, plane, t.pair, fs, ps, io, nullptr, err, near);
-    } else {  // taps of this tile do not fit the box -> exact predicated gathers from global memory
-      const GlobalSrc<float> fg{p.ff ? p.ff + (size_t)t.pair * 2 * plane : nullptr, plane, g};
-      const GlobalSrc<FrameT> pg{p.prev ? reinterpret_cast<const FrameT*>(p.prev) + (size_t)t.pair * (CT > 0 ? CT : p.C) * plane : nullptr, plane, g};
-      finish_pixel<FrameT, MASK, REDUCE, CT, LEAN>(p, taps, u, v, nb, keep, o, plane, t.pair, fg, pg, io, nullptr, err, near);
-    }
+    if (MASK == MASK_GIVEN) keep = mk[k];
+    const float* cv = have_cur ? cur[k] : nullptr;
+    // taps [x0, x0+1] x [y0, y0+1] inside the staged boxes?  (unsigned compare: also catches negatives / saturation)
+    const bool inbox = mode == 1 || (mode == 2 && (unsigned)(taps.x0 - ox) < (unsigned)(Cfg::BW - 1) &&
+                                     (unsigned)(taps.y0 - oy) < (unsigned)(Cfg::BH - 1));
+    if (inbox) finish_pixel<FrameT, MASK, REDUCE, CT, LEAN>(p, taps, u, v, nb, keep, o, plane, t.pair, fs, ps, io, cv, err, near);
+    else finish_pixel<FrameT, MASK, REDUCE, CT, LEAN>(p, taps, u, v, nb, keep, o, plane, t.pair, fg, pg, io, cv, err, near);   // exact predicated gathers
   }
   return err;
 }
@@ -513,7 +515,7 @@ __device__ __noinline__ float pixel_global(const float* bf_pair, const float* ff
 
 template <typename FrameT, int MASK, typename Cfg, bool EDGE, bool MIXED>
 __device__ __forceinline__ float lean_tile(const FwdParams& p, const float* s_bu, const float* s_ff, const int* meta, const TileId& t,
-                                           int warp, int lane, const float (&cur)[Cfg::kPPL][3], const float (&mk)[Cfg::kPPL]) {
+                                           int warp, int lane, const float (&cur)[Cfg::kPPL][Cfg::kC], const float (&mk)[Cfg::kPPL]) {
   constexpr int P = Cfg::kPPL, BW = Cfg::BW, BFW = Cfg::kBfW, PL = Cfg::BH * Cfg::BW;
   constexpr float kHi = 1.0f + kFilterEps, kLo = 1.0f - kFilterEps;
   const Geo& g = p.geo;
@@ -714,7 +716,7 @@ __global__ void __launch_bounds__(kWsThreads, 1) fused_forward_ws_kernel(const F
     auto place_src = [&](int k) -> Placement {
       const int sb = k % NB;
       const TileId t = ctl->tinfo[sb];
-      int ox = 0, oy = 0, mode = 0;   // mode: 0 = nothing staged, 1 = every tap inside the boxes, 2 = mixed (LEAN only)
+      int ox = 0, oy = 0, mode = 0;   // mode: 0 = nothing staged, 1 = every tap inside the boxes, 2 = mixed
       if (want_occ || want_frames) {
         const float xmin = ord2f(ctl->box[sb][0]), ymin = ord2f(ctl->box[sb][1]), xmax = ord2f(ctl->box[sb][2]), ymax = ord2f(ctl->box[sb][3]);
         const float lim = 1048576.0f;
@@ -731,11 +733,10 @@ __global__ void __launch_bounds__(kWsThreads, 1) fused_forward_ws_kernel(const F
           oy = by0;
           // taps span [x0, x0+1] x [y0, y0+1]
           const bool fitx = bx1 + 1 - ox < Cfg::BW, fity = by1 + 1 - oy < Cfg::BH;
-          mode = (fitx && fity) ? 1 : (LEAN ? 2 : 0);
+          mode = (fitx && fity) ? 1 : 2;
           if (mode == 2) {
             // a motion boundary runs through the tile: centre the box on the extent (per axis, where it does not fit);
-            // pixels whose taps fall outside take the global path one by one.  The feature-complete path has no
-            // per-pixel fallback: there the whole tile is gathered from global memory (mode 0).
+            // pixels whose taps fall outside take the global path one by one
             if (!fitx) ox = ((bx0 + bx1 + 1 - Cfg::BW) / 2) & ~(Cfg::kXAlign - 1);
             if (!fity) oy = (by0 + by1 + 1 - Cfg::BH) / 2;
           }
@@ -831,19 +832,20 @@ __global__ void __launch_bounds__(kWsThreads, 1) fused_forward_ws_kernel(const F
   for (int k = 0; visit(k); ++k) {
     float err = 0.0f;
     const TileId t = ctl->tinfo[sb];
-    if (LEAN) {
-      // this tile's `cur` (and dataset mask) values: coalesced 64-byte row segments, streaming; requested before the wait
-      // for the source boxes and first used at the very end of the per-pixel work
-      float cur[P][3], mk[P];
+    // this tile's `cur` (and dataset mask) values: coalesced 64-byte row segments, streaming; requested before the wait
+    // for the source boxes and first used at the very end of the per-pixel work
+    float cur[P][Cfg::kC], mk[P];
+    const bool have_cur = CT > 0 && (LEAN || p.cur != nullptr);
+    {
       const size_t pix = (size_t)(t.y0 * g.W + t.x0) + lane_off;
-      const FrameT* cb = reinterpret_cast<const FrameT*>(p.cur) + (size_t)t.pair * 3 * plane + pix;
+      const FrameT* cb = reinterpret_cast<const FrameT*>(p.cur) + (size_t)t.pair * Cfg::kC * plane + pix;
       const float* mb = MASK == MASK_GIVEN ? p.mask_in + (size_t)t.pair * plane + pix : nullptr;
       if (!t.edge) {
 #pragma unroll
-        for (int c = 0; c < 3; ++c) {
+        for (int c = 0; c < Cfg::kC; ++c) {
           const FrameT* pc = cb + (size_t)c * plane;
 #pragma unroll
-          for (int i = 0; i < P; ++i) cur[i][c] = ld_stream(pc + (i >> 1) * row16 + 16 * (i & 1));
+          for (int i = 0; i < P; ++i) cur[i][c] = have_cur ? ld_stream(pc + (i >> 1) * row16 + 16 * (i & 1)) : 0.0f;
         }
 #pragma unroll
         for (int i = 0; i < P; ++i) mk[i] = MASK == MASK_GIVEN ? __ldcs(mb + (i >> 1) * row16 + 16 * (i & 1)) : 0.0f;
@@ -853,26 +855,24 @@ __global__ void __launch_bounds__(kWsThreads, 1) fused_forward_ws_kernel(const F
           const bool inside = t.x0 + lx0 + 16 * (i & 1) < g.W && t.y0 + ly0 + 16 * (i >> 1) < g.H;
           const ptrdiff_t off = (i >> 1) * row16 + 16 * (i & 1);
 #pragma unroll
-          for (int c = 0; c < 3; ++c) cur[i][c] = inside ? ld_stream(cb + off + (size_t)c * plane) : 0.0f;
+          for (int c = 0; c < Cfg::kC; ++c) cur[i][c] = (have_cur && inside) ? ld_stream(cb + off + (size_t)c * plane) : 0.0f;
           mk[i] = (MASK == MASK_GIVEN && inside) ? __ldcs(mb + off) : 0.0f;
         }
       }
-      if (threadIdx.x == 0) TCL_STAMP(k, 1);
-      mbar_wait(&ctl->src_full[ss], ps);
-      if (threadIdx.x == 0) TCL_STAMP(k, 2);
-      const int mode = ctl->meta[ss][2];
-      if (mode == 1) {
-        if (t.edge) err = lean_tile<FrameT, MASK, Cfg, true, false>(p, bf_stage(sb), ff_stage(ss), ctl->meta[ss], t, warp, lane, cur, mk);
-        else err = lean_tile<FrameT, MASK, Cfg, false, false>(p, bf_stage(sb), ff_stage(ss), ctl->meta[ss], t, warp, lane, cur, mk);
-      } else if (mode == 2) {
-        err = lean_tile<FrameT, MASK, Cfg, true, true>(p, bf_stage(sb), ff_stage(ss), ctl->meta[ss], t, warp, lane, cur, mk);
-      } else {
-        err = full_tile<FrameT, MASK, REDUCE, CT, true, Cfg, true>(p, bf_stage(sb), ff_stage(ss), prev_stage(ss), ctl->meta[ss], t, warp, lane, near);
-      }
+    }
+    if (threadIdx.x == 0) TCL_STAMP(k, 1);
+    mbar_wait(&ctl->src_full[ss], ps);
+    if (threadIdx.x == 0) TCL_STAMP(k, 2);
+    const int mode = ctl->meta[ss][2];
+    if (LEAN && mode == 1) {
+      if (t.edge) err = lean_tile<FrameT, MASK, Cfg, true, false>(p, bf_stage(sb), ff_stage(ss), ctl->meta[ss], t, warp, lane, cur, mk);
+      else err = lean_tile<FrameT, MASK, Cfg, false, false>(p, bf_stage(sb), ff_stage(ss), ctl->meta[ss], t, warp, lane, cur, mk);
+    } else if (LEAN && mode == 2) {
+      err = lean_tile<FrameT, MASK, Cfg, true, true>(p, bf_stage(sb), ff_stage(ss), ctl->meta[ss], t, warp, lane, cur, mk);
+    } else if (LEAN || t.edge) {
+      err = full_tile<FrameT, MASK, REDUCE, CT, LEAN, Cfg, true>(p, bf_stage(sb), ff_stage(ss), prev_stage(ss), ctl->meta[ss], t, warp, lane, cur, mk, have_cur, near);
     } else {
-      mbar_wait(&ctl->src_full[ss], ps);
-      if (t.edge) err = full_tile<FrameT, MASK, REDUCE, CT, false, Cfg, true>(p, bf_stage(sb), ff_stage(ss), prev_stage(ss), ctl->meta[ss], t, warp, lane, near);
-      else err = full_tile<FrameT, MASK, REDUCE, CT, false, Cfg, false>(p, bf_stage(sb), ff_stage(ss), prev_stage(ss), ctl->meta[ss], t, warp, lane, near);
+      err = full_tile<FrameT, MASK, REDUCE, CT, LEAN, Cfg, false>(p, bf_stage(sb), ff_stage(ss), prev_stage(ss), ctl->meta[ss], t, warp, lane, cur, mk, have_cur, near);
     }
     // <= 3 * P fp32 terms per lane, fixed butterfly over the lanes; fp64 from here on (warps: index order in the producer)
     if (REDUCE) {

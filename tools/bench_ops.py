@@ -1,0 +1,72 @@
+"""Kernel-level timing of every public op on the BASELINE shapes (tuning aid; bench.py is the contract)."""
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import tcl_b200 as tcl  # noqa: E402
+
+dev = torch.device("cuda:0")
+PEAK = 6548.2
+
+
+def timeit(fn, n=20, warm=3):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(n):
+        fn()
+    b.record()
+    torch.cuda.synchronize()
+    return a.elapsed_time(b) / n
+
+
+def report(name, ms, px, bpp):
+    print(f"{name:44s} {ms*1e3:9.1f} us  {px/ms/1e6:7.1f} Gpix/s  {px*bpp/ms/1e6:7.0f} GB/s  {px*bpp/ms/1e6/PEAK*100:5.1f}% of measured peak", flush=True)
+
+
+def run(cfg_name, pairs):
+    cfg = tcl.synth.CONFIGS[cfg_name]
+    H, W = cfg["H"], cfg["W"]
+    chunks = []
+    for s in range(0, pairs, 32):
+        n = min(32, pairs - s)
+        ff, bf = tcl.synth.make_flows(n, H, W, seed=11 + s, max_shift=cfg["max_shift"], max_rot_deg=cfg["max_rot_deg"], device=dev)
+        prev, cur = tcl.synth.make_frames(n, 3, H, W, seed=11 + s, device=dev)
+        chunks.append((ff, bf, prev, cur))
+    ff, bf, prev, cur = (torch.cat([c[i] for c in chunks]) for i in range(4))
+    del chunks
+    px = pairs * H * W
+    tag = f"{cfg_name}[{pairs}] "
+    report(tag + "warp fp32", timeit(lambda: tcl.warp(prev, bf)), px, 32)
+    report(tag + "fs_warp fp32", timeit(lambda: tcl.fs_warp(prev, bf)), px, 32)
+    report(tag + "fbcCheckTorch", timeit(lambda: tcl.fbcCheckTorch(ff, bf)), px, 20)
+    report(tag + "fbcCheckTorch_mob", timeit(lambda: tcl.fbcCheckTorch_mob(None, bf)), px, 12)
+    report(tag + "gradient(u)", timeit(lambda: tcl.gradient(bf[:, 0])), px, 12)
+    m = tcl.fbcCheckTorch(ff, bf)
+    report(tag + "temporal_error (fused, ff)", timeit(lambda: tcl.temporal_error(ff, bf, prev, cur)), px, 40)
+    report(tag + "temporal_loss fwd (mask)", timeit(lambda: tcl.temporal_loss(m, cur, prev, bf)), px, 36)
+    report(tag + "temporal_loss L1 fwd (mask)", timeit(lambda: tcl.temporal_loss(m, cur, prev, bf, loss="l1")), px, 36)
+    report(tag + "warp_blend", timeit(lambda: tcl.warp_blend(m, prev, bf, cur)), px, 48)
+    report(tag + "fused + warp/mask outputs", timeit(lambda: tcl.fused_forward(bf, prev, cur, ff=ff, want_warp=True, want_mask=True)), px, 56)
+    p2 = prev.clone().requires_grad_(True)
+    c2 = cur.clone().requires_grad_(True)
+
+    def fb():
+        p2.grad = None
+        c2.grad = None
+        tcl.temporal_loss(m, c2, p2, bf).backward()
+    report(tag + "temporal_loss fwd+bwd", timeit(fb), px, 36 + 36 + 24 + 12)
+    pb = prev.to(torch.bfloat16)
+    cb = cur.to(torch.bfloat16)
+    report(tag + "temporal_error bf16 frames", timeit(lambda: tcl.temporal_error(ff, bf, pb, cb)), px, 28)
+    report(tag + "warp bf16", timeit(lambda: tcl.warp(pb, bf)), px, 20)
+
+
+if __name__ == "__main__":
+    run("sintel_full", 128)
+    run("train_b16_256", 256)
+    run("train_b16_256", 16)
