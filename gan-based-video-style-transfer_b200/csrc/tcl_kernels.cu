@@ -47,6 +47,9 @@
 #ifndef TCL_NB
 #define TCL_NB (TCL_NS + 2)   // flow-tile stages in flight
 #endif
+#ifndef TCL_GROUPS
+#define TCL_GROUPS 1  // consumer groups: the 16 consumer warps work on this many tiles at a time
+#endif
 
 namespace tcl {
 
@@ -243,13 +246,14 @@ __device__ __forceinline__ unsigned long long gtime() { unsigned long long t; as
 constexpr int kCWarps = 16;                      // consumer warps
 constexpr int kWsThreads = 32 * (kCWarps + 1);   // + 1 producer warp
 
-template <typename FrameT, int CT, int TW_, int TH_, int BH_, int NB_, int NS_>
+template <typename FrameT, int CT, int TW_, int TH_, int BH_, int NB_, int NS_, int G_>
 struct WsCfg {
   static constexpr int TW = TW_, TH = TH_, BW = TW_ + 16, BH = BH_, NB = NB_, NS = NS_;
+  static constexpr int G = G_, WPG = kCWarps / G_;   // consumer groups (each works on its own tile), warps per group
   static constexpr int kHaloX = 8;               // TMA needs the box's innermost start on a 16-byte boundary
   static constexpr int kBfW = TW + 2 * kHaloX, kBfH = TH + 2;
   static constexpr int kXAlign = 16 / (int)sizeof(FrameT);   // source-box origin is rounded down to this many pixels
-  static constexpr int kPPL = TW * TH / (32 * kCWarps);      // pixels per lane per tile
+  static constexpr int kPPL = TW * TH / (32 * WPG);          // pixels per lane per tile
   static constexpr int kC = CT > 0 ? CT : 1;
   static constexpr unsigned kBfLoad = 2u * kBfH * kBfW * 4u;
   static constexpr unsigned kFfLoad = 2u * BH * BW * 4u;
@@ -261,9 +265,9 @@ struct WsCfg {
   static constexpr size_t kSrcOff = kBfOff + NB * kBfStage;
   static constexpr size_t kCtlOff = kSrcOff + NS * kSrcStage;
   static constexpr size_t kSmemBytes = kCtlOff + 1024 + 128;  // control block + slack for manual 128-byte alignment
-  static_assert(TW == 64 && TH % 16 == 0 && kPPL % 2 == 0, "lane mapping assumes 64-wide tiles, 16 consumer warps");
+  static_assert(TW == 64 && TH % WPG == 0 && kPPL % 2 == 0 && kCWarps % G == 0 && NS % G == 0, "lane mapping: 64-wide tiles, TH/WPG rows per warp");
   static_assert(BW % 32 == 16 && kBfW % 32 == 16, "pitch must be 16 (mod 32) words for the 16 x 2 lane footprint");
-  static_assert(NB > NS, "the flow tile of a tile must be requested before its source boxes");
+  static_assert(NB >= NS + 2, "the flow tile of a tile is scanned NS tiles ahead: it must have been requested a tile before that");
 };
 
 struct TileId { int pair, tile, x0, y0, edge, pad[3]; };
@@ -274,7 +278,7 @@ struct WsCtl {              // control block in shared memory
   TileId tinfo[NB];         // written by the producer with the flow-tile request
   int meta[NS][4];          // per source stage: ox, oy, staged?
   int box[NB][4];           // per flow stage: extent of x+u, y+v over the tile (ordered-int encoding): xmin, ymin, xmax, ymax
-  double red[NS][kCWarps];
+  double red[NS][kCWarps];  // [stage][warp of the tile's group]
 };
 
 // order-preserving float <-> int (total order of IEEE bit patterns; NaNs land beyond +-Inf): lets redux.sync and
@@ -288,7 +292,7 @@ __device__ __forceinline__ float fmax_nan(float a, float b) { float r; asm("max.
 // start from) folded into box[4].  Non-finite flow propagates (min/max.NaN) and is rejected by the placement.
 template <typename Cfg>
 __device__ __forceinline__ void scan_flow_rows(const float* s_bu, const TileId& t, const Geo& g, int* box, int warp, int lane) {
-  constexpr int RPW = Cfg::TH / kCWarps;   // rows per warp: 1 or 2
+  constexpr int RPW = Cfg::TH / Cfg::WPG;   // rows per warp: 1 or 2
   const float* s_bv = s_bu + Cfg::kBfH * Cfg::kBfW;
   const int c4 = 4 * (lane & 15);
   const int r = warp * RPW + (lane >> 4);
@@ -372,8 +376,9 @@ __device__ __forceinline__ TileId tile_id(const FwdParams& p, int tg, int TW, in
 }
 
 // lane -> pixel k of the tile: a warp instruction covers 16 columns x 2 rows
-__device__ __forceinline__ void lane_pixel(int warp, int lane, int k, int& lx, int& ly) {
-  const int task = warp + kCWarps * (k >> 1);   // 32 x 2 pixel strip of the tile
+template <int WPG>
+__device__ __forceinline__ void lane_pixel(int warp, int lane, int k, int& lx, int& ly) {   // warp = index within its group
+  const int task = warp + WPG * (k >> 1);   // 32 x 2 pixel strip of the tile
   lx = 32 * (task & 1) + 16 * (k & 1) + (lane & 15);
   ly = 2 * (task >> 1) + (lane >> 4);
 }
@@ -399,7 +404,7 @@ __device__ __forceinline__ float full_tile(const FwdParams& p, const float* s_bu
 #pragma unroll
   for (int k = 0; k < Cfg::kPPL; ++k) {   // fully unrolled: cur[k] / mk[k] must stay in registers
     int lx, ly;
-    lane_pixel(warp, lane, k, lx, ly);
+    lane_pixel<Cfg::WPG>(warp, lane, k, lx, ly);
     const int x = t.x0 + lx, y = t.y0 + ly;
     if (EDGE && (x >= W || y >= H)) continue;
     const int c = (ly + 1) * Cfg::kBfW + lx + Cfg::kHaloX;
@@ -531,15 +536,16 @@ __device__ __forceinline__ float lean_tile(const FwdParams& p, const float* s_bu
   lg.i2x = __fmul_rn(2.0f, g.inv_dx); lg.i2y = __fmul_rn(2.0f, g.inv_dy);   // exact doubling: (2a)*r == a*(2r)
   lg.Wf = g.Wf; lg.Hf = g.Hf;
   int lx0, ly0;
-  lane_pixel(warp, lane, 0, lx0, ly0);
+  lane_pixel<Cfg::WPG>(warp, lane, 0, lx0, ly0);
   // pixel k of this lane: 16 columns right of pixel k-1 (k odd) / 16 rows below pixel k-2
-  const float xs[2] = {(float)(t.x0 + lx0), (float)(t.x0 + lx0 + 16)}, ys[2] = {(float)(t.y0 + ly0), (float)(t.y0 + ly0 + 16)};
+  constexpr int DY = Cfg::WPG;   // pixel k of this lane: 16 columns right of pixel k-1 (k odd) / WPG rows below pixel k-2
+  const float xs[2] = {(float)(t.x0 + lx0), (float)(t.x0 + lx0 + 16)}, ys[2] = {(float)(t.y0 + ly0), (float)(t.y0 + ly0 + DY)};
   const int c0 = (ly0 + 1) * BFW + lx0 + Cfg::kHaloX;
   float e[P];
   unsigned keepbits = 0, ambbits = 0, outbits = 0;
 #pragma unroll
   for (int k = 0; k < P; ++k) {
-    const int dxk = 16 * (k & 1), dyk = 16 * (k >> 1);
+    const int dxk = 16 * (k & 1), dyk = DY * (k >> 1);
     const bool inside = !EDGE || (t.x0 + lx0 + dxk < g.W && t.y0 + ly0 + dyk < g.H);
     const int c = c0 + dyk * BFW + dxk;
     const float u = s_bu[c], v = s_bv[c];
@@ -620,7 +626,7 @@ __device__ __forceinline__ float lean_tile(const FwdParams& p, const float* s_bu
 #pragma unroll
     for (int k = 0; k < P; ++k)
       if ((ambbits >> k) & 1u) {
-        const bool kp = exact_keep<Cfg>(s_bu, s_ff, c0 + 16 * (k >> 1) * BFW + 16 * (k & 1), xs[k & 1], ys[k >> 1], lg, box_xf, box_yf);
+        const bool kp = exact_keep<Cfg>(s_bu, s_ff, c0 + DY * (k >> 1) * BFW + 16 * (k & 1), xs[k & 1], ys[k >> 1], lg, box_xf, box_yf);
         keepbits = (keepbits & ~(1u << k)) | ((kp ? 1u : 0u) << k);
       }
   }
@@ -632,7 +638,7 @@ __device__ __forceinline__ float lean_tile(const FwdParams& p, const float* s_bu
       if ((outbits >> k) & 1u) {
         e[k] = pixel_global<FrameT, MASK>(p.bf + (size_t)t.pair * 2 * plane, MASK == MASK_COMPUTED ? p.ff + (size_t)t.pair * 2 * plane : nullptr,
                                           reinterpret_cast<const FrameT*>(p.prev) + (size_t)t.pair * 3 * plane, g, t.x0 + lx0 + 16 * (k & 1),
-                                          t.y0 + ly0 + 16 * (k >> 1), cur[k][0], cur[k][1], cur[k][2], mk[k]);
+                                          t.y0 + ly0 + DY * (k >> 1), cur[k][0], cur[k][1], cur[k][2], mk[k]);
         keepbits |= 1u << k;   // the verdict is already applied
       }
   }
@@ -675,7 +681,7 @@ __global__ void __launch_bounds__(kWsThreads, 1) fused_forward_ws_kernel(const F
   if (REDUCE) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // let the fold kernel get resident early
   if (threadIdx.x == 0) {
     for (int i = 0; i < NB; ++i) mbar_init(&ctl->bf_full[i], 1);
-    for (int i = 0; i < NS; ++i) { mbar_init(&ctl->src_full[i], 1); mbar_init(&ctl->done[i], kCWarps); }
+    for (int i = 0; i < NS; ++i) { mbar_init(&ctl->src_full[i], 1); mbar_init(&ctl->done[i], Cfg::WPG); }
     mbar_init(&ctl->scan0, kCWarps);
     for (int i = 0; i < NB; ++i) { ctl->box[i][0] = INT_MAX; ctl->box[i][1] = INT_MAX; ctl->box[i][2] = INT_MIN; ctl->box[i][3] = INT_MIN; }
     fence_barrier_init();
@@ -773,17 +779,16 @@ __global__ void __launch_bounds__(kWsThreads, 1) fused_forward_ws_kernel(const F
     __syncwarp();
     for (int j = 0; real(j); ++j) {
       // consumers are finished with tile j (its stages are free) and have scanned the flow tile of tile j + NS
-      mbar_wait_idle(&ctl->done[j % NS], (j / NS) & 1);
-      const TileId t = ctl->tinfo[j % NB];
-      // the 16 consumer warps' sums of this tile, folded in index order (lanes 0..15, fixed tree): one fp64 partial per tile
-      double ts = 0.0;
-      if (REDUCE && lane < kCWarps) ts = ctl->red[j % NS][lane];
+      mbar_wait_idle(&ctl->done[j % NS], (j / NS) & 1);   // consumers are finished with tile j: its stages are free
+      const TileId t = ctl->tinfo[j % NB];   // (before issue_bf recycles the slot)
+      double ts = (REDUCE && lane < Cfg::WPG) ? ctl->red[j % NS][lane] : 0.0;
       __syncwarp();
       if (lane == 0) {
         if (real(j + NS)) issue_src(j + NS, place_src(j + NS));
         issue_bf(j + NB);
       }
       __syncwarp();
+      // the consumer warps' sums of this tile, folded in index order (lanes 0..WPG-1, fixed tree): one fp64 partial per tile
       if (REDUCE) {
         ts = warp_sum(ts);
         if (lane == 0) __stcg(&p.scratch.partials[(size_t)t.pair * p.tiles_per_pair + t.tile], ts);
@@ -804,9 +809,10 @@ __global__ void __launch_bounds__(kWsThreads, 1) fused_forward_ws_kernel(const F
   unsigned near = 0;
   const size_t plane = (size_t)g.H * g.W;
   int lx0, ly0;
-  lane_pixel(warp, lane, 0, lx0, ly0);
+  const int grp = warp / Cfg::WPG, wg = warp % Cfg::WPG;   // consumer group (works on local tiles grp, grp + G, ...), warp within it
+  lane_pixel<Cfg::WPG>(wg, lane, 0, lx0, ly0);
   const int lane_off = ly0 * g.W + lx0;
-  const ptrdiff_t row16 = (ptrdiff_t)16 * g.W;
+  const ptrdiff_t row16 = (ptrdiff_t)Cfg::WPG * g.W;   // a lane's pixels 2, 3 lie WPG rows below its pixels 0, 1
   // the source boxes of a tile are placed from the extent of its sampling positions: every consumer warp scans its rows
   // of the flow tile NS tiles ahead (the first NS ones here, tile k + NS at the end of tile k)
   const bool want_scan = want_occ || want_frames;
@@ -822,15 +828,15 @@ __global__ void __launch_bounds__(kWsThreads, 1) fused_forward_ws_kernel(const F
   auto scan_tile = [&](int k2) {
     if (!visit(k2) || !want_scan) return;
     const int s2 = k2 % NB;
-    scan_flow_rows<Cfg>(bf_stage(s2), ctl->tinfo[s2], g, ctl->box[s2], warp, lane);
+    scan_flow_rows<Cfg>(bf_stage(s2), ctl->tinfo[s2], g, ctl->box[s2], wg, lane);
   };
-  for (int j = 0; j < NS; ++j) scan_tile(j);
+  for (int j = grp; j < NS; j += Cfg::G) scan_tile(j);
   __syncwarp();
   if (lane == 0) mbar_arrive(&ctl->scan0);
-  int sb = 0, ss = 0;
-  unsigned ps = 0;   // stage indices of the current tile, phase parity of its source stage
-  for (int k = 0; visit(k); ++k) {
+  for (int k = grp; visit(k); k += Cfg::G) {
     float err = 0.0f;
+    const int sb = k % NB, ss = k % NS;   // stage indices of this tile, phase parity of its source stage
+    const unsigned ps = (k / NS) & 1;
     const TileId t = ctl->tinfo[sb];
     // this tile's `cur` (and dataset mask) values: coalesced 64-byte row segments, streaming; requested before the wait
     // for the source boxes and first used at the very end of the per-pixel work
@@ -852,7 +858,7 @@ __global__ void __launch_bounds__(kWsThreads, 1) fused_forward_ws_kernel(const F
       } else {
 #pragma unroll
         for (int i = 0; i < P; ++i) {
-          const bool inside = t.x0 + lx0 + 16 * (i & 1) < g.W && t.y0 + ly0 + 16 * (i >> 1) < g.H;
+          const bool inside = t.x0 + lx0 + 16 * (i & 1) < g.W && t.y0 + ly0 + Cfg::WPG * (i >> 1) < g.H;
           const ptrdiff_t off = (i >> 1) * row16 + 16 * (i & 1);
 #pragma unroll
           for (int c = 0; c < Cfg::kC; ++c) cur[i][c] = (have_cur && inside) ? ld_stream(cb + off + (size_t)c * plane) : 0.0f;
@@ -865,26 +871,24 @@ __global__ void __launch_bounds__(kWsThreads, 1) fused_forward_ws_kernel(const F
     if (threadIdx.x == 0) TCL_STAMP(k, 2);
     const int mode = ctl->meta[ss][2];
     if (LEAN && mode == 1) {
-      if (t.edge) err = lean_tile<FrameT, MASK, Cfg, true, false>(p, bf_stage(sb), ff_stage(ss), ctl->meta[ss], t, warp, lane, cur, mk);
-      else err = lean_tile<FrameT, MASK, Cfg, false, false>(p, bf_stage(sb), ff_stage(ss), ctl->meta[ss], t, warp, lane, cur, mk);
+      if (t.edge) err = lean_tile<FrameT, MASK, Cfg, true, false>(p, bf_stage(sb), ff_stage(ss), ctl->meta[ss], t, wg, lane, cur, mk);
+      else err = lean_tile<FrameT, MASK, Cfg, false, false>(p, bf_stage(sb), ff_stage(ss), ctl->meta[ss], t, wg, lane, cur, mk);
     } else if (LEAN && mode == 2) {
-      err = lean_tile<FrameT, MASK, Cfg, true, true>(p, bf_stage(sb), ff_stage(ss), ctl->meta[ss], t, warp, lane, cur, mk);
+      err = lean_tile<FrameT, MASK, Cfg, true, true>(p, bf_stage(sb), ff_stage(ss), ctl->meta[ss], t, wg, lane, cur, mk);
     } else if (LEAN || t.edge) {
-      err = full_tile<FrameT, MASK, REDUCE, CT, LEAN, Cfg, true>(p, bf_stage(sb), ff_stage(ss), prev_stage(ss), ctl->meta[ss], t, warp, lane, cur, mk, have_cur, near);
+      err = full_tile<FrameT, MASK, REDUCE, CT, LEAN, Cfg, true>(p, bf_stage(sb), ff_stage(ss), prev_stage(ss), ctl->meta[ss], t, wg, lane, cur, mk, have_cur, near);
     } else {
-      err = full_tile<FrameT, MASK, REDUCE, CT, LEAN, Cfg, false>(p, bf_stage(sb), ff_stage(ss), prev_stage(ss), ctl->meta[ss], t, warp, lane, cur, mk, have_cur, near);
+      err = full_tile<FrameT, MASK, REDUCE, CT, LEAN, Cfg, false>(p, bf_stage(sb), ff_stage(ss), prev_stage(ss), ctl->meta[ss], t, wg, lane, cur, mk, have_cur, near);
     }
     // <= 3 * P fp32 terms per lane, fixed butterfly over the lanes; fp64 from here on (warps: index order in the producer)
     if (REDUCE) {
       const float ws = warp_sum(err);
-      if (lane == 0) ctl->red[ss][warp] = (double)ws;
+      if (lane == 0) ctl->red[ss][wg] = (double)ws;
     }
-    scan_tile(k + NS);
+    scan_tile(k + NS);   // extent of the flow tile NS tiles ahead, for the placement of its source boxes
     __syncwarp();   // every lane is done reading the stages of tile k
     if (lane == 0) mbar_arrive(&ctl->done[ss]);
     if (threadIdx.x == 0) TCL_STAMP(k, 3);
-    if (++sb == NB) sb = 0;
-    if (++ss == NS) { ss = 0; ps ^= 1u; }
   }
   if (!LEAN) count_near(near, p.near_threshold);
 }
@@ -1088,7 +1092,7 @@ static int sm_count() {
 template <typename FrameT, int MASK, bool REDUCE, int CT, bool LEAN>
 static cudaError_t launch_tma(const FwdParams& p, const CUtensorMap& tb, const CUtensorMap& tf, const CUtensorMap& tp, const CUtensorMap& tc,
                               cudaStream_t s) {
-  using Cfg = WsCfg<FrameT, CT, kTW, kTH, kBH, TCL_NB, TCL_NS>;
+  using Cfg = WsCfg<FrameT, CT, kTW, kTH, kBH, TCL_NB, TCL_NS, TCL_GROUPS>;
   auto kern = fused_forward_ws_kernel<FrameT, MASK, REDUCE, CT, LEAN, Cfg>;
   static bool configured = false;  // per instantiation
   if (!configured) {

@@ -7,12 +7,9 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 CSRC = os.path.join(ROOT, "gan-based-video-style-transfer_b200", "csrc")
 OUT = os.path.join(ROOT, "tools", "_sweep")
 VARIANTS = {
-    "th32_ns2_nb4": {},
+    "g1_th32_ns2_nb4": {},
+    "g2_th16_ns4_nb6": {"TCL_TH": 16, "TCL_BH": 24, "TCL_NS": 4, "TCL_NB": 6, "TCL_GROUPS": 2},
     "trace": {"TCL_TRACE": 1},
-    "th16_ns4_nb6": {"TCL_TH": 16, "TCL_BH": 24, "TCL_NS": 4, "TCL_NB": 6},
-    "th32_ns2_nb3": {"TCL_NB": 3},
-    "th16_ns4_nb5": {"TCL_TH": 16, "TCL_BH": 24, "TCL_NS": 4, "TCL_NB": 5},
-    "th16_ns3_nb5": {"TCL_TH": 16, "TCL_BH": 24, "TCL_NS": 3, "TCL_NB": 5},
 }
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
