@@ -330,3 +330,57 @@ def test_nonfinite_flow_matches_torch_cuda(tcl):
     t = tp.backward_warp(prev, bf)
     assert torch.equal(torch.isnan(k), torch.isnan(t))
     assert torch.equal(torch.nan_to_num(k), torch.nan_to_num(t))
+
+
+# ------------------------------------------------------------------ the hot (LEAN) configuration against the exact path
+def _sums64(mask, cur, warp):
+    return ((mask.double() * (cur.double() - warp.double())) ** 2).sum(dim=(1, 2, 3))
+
+
+@pytest.mark.parametrize("B,H,W,shift,rect_shift", [(12, 436, 1024, 32.0, 30.0), (1, 2160, 3840, 224.0, 40.0), (3, 256, 256, 24.0, 20.0)])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_hot_path_equals_exact_path_with_mixed_tiles_and_dynamic_schedule(tcl, B, H, W, shift, rect_shift, dtype):
+    """The compile-time specialised hot path (sqrt-free filtered mask tests, mixed tiles, dynamic tile schedule when the
+    launch is long) must make exactly the mask decisions of the feature-complete exact path: its per-pair sums equal the
+    fp64 sums over the exact path's mask / warp outputs up to summation order."""
+    import ctypes
+    d = dev()
+    ff, bf = tcl.synth.make_flows(B, H, W, seed=31 + W, max_shift=shift, max_rot_deg=3.0, n_rects=10, rect_shift=rect_shift, device=d)
+    prev, cur = tcl.synth.make_frames(B, 3, H, W, seed=31 + W, kind="white", device=d, dtype=dtype)
+    lib = tcl._cabi.lib()
+    lib.tclb200_debug_tile_stats(None, 1)
+    hot = tcl.fused_forward(bf, prev, cur, ff=ff)
+    torch.cuda.synchronize()
+    st = (ctypes.c_ulonglong * 2)()
+    lib.tclb200_debug_tile_stats(st, 1)
+    exact = tcl.fused_forward(bf, prev, cur, ff=ff, want_warp=True, want_mask=True)
+    want = _sums64(exact.mask, cur, exact.warp if dtype == torch.float32 else tp.backward_warp(prev.float(), bf))
+    rtol = 1e-6 if dtype == torch.float32 else 1e-5
+    assert torch.allclose(hot.pair_sums, want, rtol=rtol, atol=0), (hot.pair_sums, want)
+    assert torch.allclose(exact.pair_sums, want, rtol=rtol, atol=0)
+    print(f"{B}x{H}x{W} {dtype}: mixed tiles {st[1]}, global tiles {st[0]}")
+    assert st[1] > 0, "this case is meant to exercise mixed tiles"
+    # dataset-mask form (training loss), same tiles
+    given = tcl.fused_forward(bf, prev, cur, mask=exact.mask, finalize=tcl.ops.FIN_MEAN)
+    assert torch.allclose(given.pair_sums, want, rtol=rtol, atol=0)
+    # the tile schedule must not show in the results
+    again = tcl.fused_forward(bf, prev, cur, ff=ff)
+    assert torch.equal(hot.pair_sums, again.pair_sums) and torch.equal(hot.total_sums, again.total_sums)
+
+
+def test_hot_path_with_nonfinite_and_extreme_flow(tcl):
+    d = dev()
+    B, H, W = 2, 96, 192
+    ff, bf = tcl.synth.make_flows(B, H, W, seed=2, max_shift=6.0, device=d)
+    prev, cur = tcl.synth.make_frames(B, 3, H, W, seed=2, kind="white", device=d)
+    bf[0, 0, 10, 20] = float("inf"); bf[0, 1, 50, 100] = float("nan"); bf[1, 0, 70:80, 30:60] = 1e7; bf[1, 1, 5, 5] = -3e9
+    hot = tcl.fused_forward(bf, prev, cur, ff=ff)
+    exact = tcl.fused_forward(bf, prev, cur, ff=ff, want_warp=True, want_mask=True)
+    with torch.no_grad():
+        t_mask = tp.fb_consistency(ff, bf)
+        t_warp = tp.backward_warp(prev, bf)
+    assert torch.equal(exact.mask, t_mask)
+    assert torch.equal(torch.nan_to_num(exact.warp), torch.nan_to_num(t_warp))
+    want = _sums64(t_mask, cur, t_warp)
+    assert torch.allclose(hot.pair_sums, want, rtol=1e-6, atol=0, equal_nan=True)
+    assert torch.allclose(exact.pair_sums, want, rtol=1e-6, atol=0, equal_nan=True)
