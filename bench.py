@@ -204,8 +204,11 @@ def run_reference(args, tcl):
             "gpix_per_s": rate * H * W / 1e9, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": el / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": args.workload, "shape": f"{W}x{H}", "pairs_per_step": sample_pairs,
-                       "note": "bounded sample of the workload; each step = fbcCheckTorch + warp + masked RMSE per pair"},
+            "config": {"workload": args.workload, "shape": f"{W}x{H}", "channels": C,
+                       "pairs_per_gpu_per_step": cfg["pairs"], "frames": args.frames,
+                       "reference_sample_pairs_per_step": sample_pairs,
+                       "note": "same workload as the GPU arm; each reference step = a bounded sample of it "
+                               "(fbcCheckTorch + warp + masked RMSE per pair, all host threads)"},
             "cpu_baseline": {"value": rate, "unit": "pairs/s", "cores": cores, "kind": "port",
                              "sample": f"{sample_pairs} pairs/step x {args.steps} steps, oracle/torch_port.py (ATen op sequence of "
                                        f"utils/flowtools.py + sintel_eval.py:110), torch threads={cores}"},
@@ -386,23 +389,26 @@ def main():
         dist.barrier()
     torch.cuda.synchronize()
     elapsed_ms = start.elapsed_time(end)
-    # nvidia-smi samples every 100 ms: when the timed region was shorter than ~1 s keep the same step running (untimed)
-    # so that the clock / throttle record covers the load the timed region ran under
+    if dist:   # max over ranks (the step contains a collective: every rank must run the same number of steps below)
+        t = torch.tensor([elapsed_ms], device=device, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        elapsed_ms = float(t[0])
+    # nvidia-smi samples every 100 ms: when the timed region was shorter than ~1 s keep the same step running (untimed,
+    # the same count on every rank) so that the clock / throttle record covers the load the timed region ran under
     probe_steps = 0
-    if rank == 0 and elapsed_ms < 1000.0:
-        t_end = time.perf_counter() + (1000.0 - elapsed_ms) / 1e3
-        while time.perf_counter() < t_end:
+    if elapsed_ms < 1000.0:
+        probe_steps = int((1000.0 - elapsed_ms) / max(elapsed_ms / args.steps, 1e-3)) + 1
+        for _ in range(probe_steps):
             step()
-            probe_steps += 1
         torch.cuda.synchronize()
     # dominant kernel alone, same inputs, CUDA events per launch (the roofline numerator)
     _, per = time_kernel(kernel_only, args.steps, 1)
     clocks = sampler.stop() if rank == 0 else None
     k_ms = sum(per) / len(per)
     if dist:
-        t = torch.tensor([elapsed_ms, k_ms], device=device, dtype=torch.float64)
+        t = torch.tensor([k_ms], device=device, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        elapsed_ms, k_ms = float(t[0]), float(t[1])
+        k_ms = float(t[0])
     total_pairs = n_local * world * args.steps
     pairs_per_s = total_pairs / (elapsed_ms / 1e3)
     peak, peak_src = load_peaks()
@@ -437,20 +443,21 @@ def main():
     if clocks is not None and probe_steps:
         line["clocks"]["note"] = f"timed region {elapsed_ms:.0f} ms + {probe_steps} untimed identical steps so that nvidia-smi (100 ms period) sees the load"
     if not args.no_extras:
+        if dist:
+            dist.barrier()
         try:
-            if dist:
-                dist.barrier()
             e = e2e_rate(tcl, shard, n_local, max(3, args.steps // 2), 2, device)
-            if dist:  # whole-job rate = all ranks' pairs over the slowest rank's time
-                t = torch.tensor([e["ms_per_step"]], device=device, dtype=torch.float64)
-                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        except Exception as ex:   # report, never hide; keep the collectives below symmetric across ranks
+            e = {"error": repr(ex), "ms_per_step": float("inf")}
+        if dist:  # whole-job rate = all ranks' pairs over the slowest rank's time
+            t = torch.tensor([e["ms_per_step"]], device=device, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            if "error" not in e and float(t[0]) != float("inf"):
                 e["ms_per_step"] = float(t[0])
                 e["value"] = n_local * world / (e["ms_per_step"] / 1e3)
                 e["h2d_bytes_per_step"] *= world
                 e["d2h_bytes_per_step"] *= world
-            line["e2e"] = e
-        except Exception as ex:
-            line["e2e"] = {"error": repr(ex)}
+        line["e2e"] = e
         del shard
         torch.cuda.empty_cache()
         if world == 1:
