@@ -133,7 +133,7 @@ __device__ __forceinline__ void finish_pixel(const FwdParams& p, const PixTaps& 
     if (occluded(wu, wv, u, v, nb, kV, &margin)) keep = 0.0f;
     if (!LEAN) near += fabsf(margin) < kNearBand;
   }
-  if (!LEAN && p.mask_out) __stcs(p.mask_out + (size_t)pair * plane + o, keep);
+  if ((!LEAN || CT == 0) && p.mask_out) __stcs(p.mask_out + (size_t)pair * plane + o, keep);
   if (p.prev == nullptr) return;
   const bool validity = !LEAN && (p.flags & TCLB200_VALIDITY);
   float valid = 1.0f;
@@ -485,7 +485,7 @@ __device__ __noinline__ bool exact_keep(const float* s_bu, const float* s_ff, in
 
 // one pixel of the hot configuration entirely from global memory with the exact sequences: the pixels of a "mixed" tile
 // (a motion boundary runs through it) whose taps lie outside the staged source boxes.  Returns the masked squared error.
-template <typename FrameT, int MASK>
+template <typename FrameT, int MASK, bool KEEP_ONLY>
 __device__ __noinline__ float pixel_global(const float* bf_pair, const float* ff_pair, const FrameT* prev_pair, Geo g, int x, int y,
                                            float c0, float c1, float c2, float mkv) {
   const int W = g.W, H = g.H;
@@ -511,6 +511,7 @@ __device__ __noinline__ float pixel_global(const float* bf_pair, const float* ff
     float margin;
     if (occluded(wu, wv, u, v, nb, kV, &margin)) keep = false;
   }
+  if (KEEP_ONLY) return keep ? 1.0f : 0.0f;
   const GlobalSrc<FrameT> psrc{prev_pair, plane, g};
   const float d0 = __fsub_rn(c0, psrc.sample(0, s)), d1 = __fsub_rn(c1, psrc.sample(1, s)), d2 = __fsub_rn(c2, psrc.sample(2, s));
   const float acc = __fmaf_rn(d2, d2, __fmaf_rn(d1, d1, __fmul_rn(d0, d0)));
@@ -518,7 +519,8 @@ __device__ __noinline__ float pixel_global(const float* bf_pair, const float* ff
   return keep ? acc : 0.0f;
 }
 
-template <typename FrameT, int MASK, typename Cfg, bool EDGE, bool MIXED>
+// CT == 3: masked squared error against `cur` (returned); CT == 0: mask-only (fbcCheckTorch), the verdicts go to mask_out
+template <typename FrameT, int MASK, int CT, typename Cfg, bool EDGE, bool MIXED>
 __device__ __forceinline__ float lean_tile(const FwdParams& p, const float* s_bu, const float* s_ff, const int* meta, const TileId& t,
                                            int warp, int lane, const float (&cur)[Cfg::kPPL][Cfg::kC], const float (&mk)[Cfg::kPPL]) {
   constexpr int P = Cfg::kPPL, BW = Cfg::BW, BFW = Cfg::kBfW, PL = Cfg::BH * Cfg::BW;
@@ -531,7 +533,7 @@ __device__ __forceinline__ float lean_tile(const FwdParams& p, const float* s_bu
   const float box_xf = (float)box_x, box_yf = (float)box_y;
   const ptrdiff_t gplane = (ptrdiff_t)g.H * g.W;
   const float* gff = (MIXED && MASK == MASK_COMPUTED) ? p.ff + (size_t)t.pair * 2 * gplane : nullptr;
-  const FrameT* gprev = MIXED ? reinterpret_cast<const FrameT*>(p.prev) + (size_t)t.pair * 3 * gplane : nullptr;
+  const FrameT* gprev = (MIXED && CT == 3) ? reinterpret_cast<const FrameT*>(p.prev) + (size_t)t.pair * 3 * gplane : nullptr;
   LeanGeo lg;
   lg.i2x = __fmul_rn(2.0f, g.inv_dx); lg.i2y = __fmul_rn(2.0f, g.inv_dy);   // exact doubling: (2a)*r == a*(2r)
   lg.Wf = g.Wf; lg.Hf = g.Hf;
@@ -577,7 +579,7 @@ __device__ __forceinline__ float lean_tile(const FwdParams& p, const float* s_bu
       const int gx = (int)tp.rx + box_x, gy = (int)tp.ry + box_y;   // top-left tap in the image (sane: the placement checked)
       const ptrdiff_t off = (ptrdiff_t)gy * g.W + gx;
       if (MASK == MASK_COMPUTED) pf = gff + off;
-      pp = gprev + off;
+      if (CT == 3) pp = gprev + off;
       rs = g.W; ps = gplane;
       const bool xin0 = (unsigned)gx < (unsigned)g.W, xin1 = (unsigned)(gx + 1) < (unsigned)g.W;
       const bool yin0 = (unsigned)gy < (unsigned)g.H, yin1 = (unsigned)(gy + 1) < (unsigned)g.H;
@@ -611,7 +613,7 @@ __device__ __forceinline__ float lean_tile(const FwdParams& p, const float* s_bu
     }
     float acc = 0.0f;
 #pragma unroll
-    for (int ch = 0; ch < 3; ++ch) {
+    for (int ch = 0; ch < CT; ++ch) {
       const float w = tap4(MIXED ? pp + ch * ps : pp + ch * PL);
       const float d = __fsub_rn(cur[k][ch], w);
       acc = __fmaf_rn(d, d, acc);
@@ -636,11 +638,26 @@ __device__ __forceinline__ float lean_tile(const FwdParams& p, const float* s_bu
 #pragma unroll
     for (int k = 0; k < P; ++k)
       if ((outbits >> k) & 1u) {
-        e[k] = pixel_global<FrameT, MASK>(p.bf + (size_t)t.pair * 2 * plane, MASK == MASK_COMPUTED ? p.ff + (size_t)t.pair * 2 * plane : nullptr,
-                                          reinterpret_cast<const FrameT*>(p.prev) + (size_t)t.pair * 3 * plane, g, t.x0 + lx0 + 16 * (k & 1),
-                                          t.y0 + ly0 + DY * (k >> 1), cur[k][0], cur[k][1], cur[k][2], mk[k]);
-        keepbits |= 1u << k;   // the verdict is already applied
+        if (CT == 3) {
+          e[k] = pixel_global<FrameT, MASK, false>(p.bf + (size_t)t.pair * 2 * plane, p.ff + (size_t)t.pair * 2 * plane,
+                                                   reinterpret_cast<const FrameT*>(p.prev) + (size_t)t.pair * 3 * plane, g, t.x0 + lx0 + 16 * (k & 1),
+                                                   t.y0 + ly0 + DY * (k >> 1), cur[k][0], cur[k][1], cur[k][2], mk[k]);
+          keepbits |= 1u << k;   // the verdict is already applied
+        } else {
+          const float kp = pixel_global<FrameT, MASK, true>(p.bf + (size_t)t.pair * 2 * plane, p.ff + (size_t)t.pair * 2 * plane, nullptr, g,
+                                                            t.x0 + lx0 + 16 * (k & 1), t.y0 + ly0 + DY * (k >> 1), 0.0f, 0.0f, 0.0f, 0.0f);
+          keepbits = (keepbits & ~(1u << k)) | ((kp != 0.0f ? 1u : 0u) << k);
+        }
       }
+  }
+  if (CT == 0) {   // mask-only: store the verdicts (two coalesced 64-byte row segments per warp instruction)
+    float* mo = p.mask_out + (size_t)t.pair * gplane + (size_t)(t.y0 + ly0) * g.W + (t.x0 + lx0);
+#pragma unroll
+    for (int k = 0; k < P; ++k) {
+      const bool inside = !EDGE || (t.x0 + lx0 + 16 * (k & 1) < g.W && t.y0 + ly0 + DY * (k >> 1) < g.H);
+      if (inside) __stcs(mo + (ptrdiff_t)DY * (k >> 1) * g.W + 16 * (k & 1), ((keepbits >> k) & 1u) ? 1.0f : 0.0f);
+    }
+    return 0.0f;
   }
   float err = 0.0f;
 #pragma unroll
@@ -713,7 +730,7 @@ __global__ void __launch_bounds__(kWsThreads, 1) fused_forward_ws_kernel(const F
       mbar_expect_tx(&ctl->bf_full[s], Cfg::kBfLoad);
       tma_load_4d(bf_stage(s), &tm_bf, &ctl->bf_full[s], t.x0 - Cfg::kHaloX, t.y0 - 1, 0, t.pair);
       // the consumers read this tile's `cur` values straight from global memory NB tiles from now: have them in L2 by then
-      if (LEAN) tma_prefetch_l2_4d(&tm_cur, t.x0, t.y0, 0, t.pair);
+      if (LEAN && CT > 0) tma_prefetch_l2_4d(&tm_cur, t.x0, t.y0, 0, t.pair);
     };
     // lane 0: the consumers have folded the extent of x+u, y+v over local tile k into box[k % NB] -> origin of the source
     // boxes.  The coordinate map is monotone in x+u (every step is a correctly rounded monotone operation), so the
@@ -871,10 +888,10 @@ __global__ void __launch_bounds__(kWsThreads, 1) fused_forward_ws_kernel(const F
     if (threadIdx.x == 0) TCL_STAMP(k, 2);
     const int mode = ctl->meta[ss][2];
     if (LEAN && mode == 1) {
-      if (t.edge) err = lean_tile<FrameT, MASK, Cfg, true, false>(p, bf_stage(sb), ff_stage(ss), ctl->meta[ss], t, wg, lane, cur, mk);
-      else err = lean_tile<FrameT, MASK, Cfg, false, false>(p, bf_stage(sb), ff_stage(ss), ctl->meta[ss], t, wg, lane, cur, mk);
+      if (t.edge) err = lean_tile<FrameT, MASK, CT, Cfg, true, false>(p, bf_stage(sb), ff_stage(ss), ctl->meta[ss], t, wg, lane, cur, mk);
+      else err = lean_tile<FrameT, MASK, CT, Cfg, false, false>(p, bf_stage(sb), ff_stage(ss), ctl->meta[ss], t, wg, lane, cur, mk);
     } else if (LEAN && mode == 2) {
-      err = lean_tile<FrameT, MASK, Cfg, true, true>(p, bf_stage(sb), ff_stage(ss), ctl->meta[ss], t, wg, lane, cur, mk);
+      err = lean_tile<FrameT, MASK, CT, Cfg, true, true>(p, bf_stage(sb), ff_stage(ss), ctl->meta[ss], t, wg, lane, cur, mk);
     } else if (LEAN || t.edge) {
       err = full_tile<FrameT, MASK, REDUCE, CT, LEAN, Cfg, true>(p, bf_stage(sb), ff_stage(ss), prev_stage(ss), ctl->meta[ss], t, wg, lane, cur, mk, have_cur, near);
     } else {
@@ -1135,12 +1152,16 @@ static cudaError_t dispatch(const FwdParams& p, int mask_kind, bool reduce, bool
   if (mask_kind == MK && reduce == RD) {                                                       \
     if (!tma) return launch_generic<FrameT, MK, RD>(p, s);                                     \
     if (p.C == 3 && lean) return launch_tma<FrameT, MK, RD, 3, true>(p, tb, tf, tp, tc, s);    \
+    if (MK == MASK_COMPUTED && !RD && lean_mask) return launch_tma<float, MASK_COMPUTED, false, 0, true>(p, tb, tf, tp, tc, s); \
     return p.C == 3 ? launch_tma<FrameT, MK, RD, 3, false>(p, tb, tf, tp, tc, s) : launch_tma<FrameT, MK, RD, 0, false>(p, tb, tf, tp, tc, s); \
   }
   // LEAN = the measured hot configurations, fixed at compile time: computeTCL / training loss with C == 3
   const bool lean = reduce && p.prev && p.cur && !p.warp_out && !p.mask_out && !p.blend_out && !p.near_threshold &&
                     p.loss == TCLB200_L2 && !(p.flags & TCLB200_VALIDITY) && mask_kind != MASK_NONE &&
                     (mask_kind != MASK_COMPUTED || (p.flags & (TCLB200_OCC | TCLB200_MOB)) == (TCLB200_OCC | TCLB200_MOB));
+  // ... and fbcCheckTorch on its own: both tests, mask_out only
+  const bool lean_mask = !reduce && !p.prev && p.mask_out && !p.near_threshold && mask_kind == MASK_COMPUTED &&
+                         (p.flags & (TCLB200_OCC | TCLB200_MOB)) == (TCLB200_OCC | TCLB200_MOB);
   TCL_CASE(MASK_COMPUTED, true)
   TCL_CASE(MASK_COMPUTED, false)
   TCL_CASE(MASK_GIVEN, true)
