@@ -123,7 +123,7 @@ struct PairPtrs {
 // LEAN fixes the hot configuration at compile time (both mask tests, L2 error, no optional outputs, no
 // near-threshold count) so the per-pixel code carries no runtime feature checks.
 // `cv` = this pixel's prefetched `cur` values (CT of them) or nullptr to load them here.
-template <typename FrameT, int MASK, bool REDUCE, int CT, bool LEAN, typename FlowSrc, typename FrameSrc>
+template <typename FrameT, int MASK, bool REDUCE, int CT, int LEAN, typename FlowSrc, typename FrameSrc>
 __device__ __forceinline__ void finish_pixel(const FwdParams& p, const PixTaps& s, float u, float v, float nb, float keep,
                                              size_t o, size_t plane, int pair, const FlowSrc& fsrc, const FrameSrc& psrc,
                                              const PairPtrs<FrameT>& io, const float* cv, float& err, unsigned& near) {
@@ -147,7 +147,7 @@ __device__ __forceinline__ void finish_pixel(const FwdParams& p, const PixTaps& 
     if (LEAN || io.cur) {
       const float x = cv ? cv[c] : ld_stream(io.cur + (size_t)c * plane + o);
       if (REDUCE) {
-        if (LEAN || p.loss == TCLB200_L2) {
+        if (LEAN == 1 || (!LEAN && p.loss == TCLB200_L2)) {   // LEAN: 1 = L2, 2 = L1 fixed at compile time
           const float md = __fmul_rn(keep, __fsub_rn(x, w));     // mask*(cur - warp)   sintel_eval.py:110
           err = __fmaf_rn(md, md, err);
         } else {
@@ -384,7 +384,7 @@ __device__ __forceinline__ void lane_pixel(int warp, int lane, int k, int& lx, i
 }
 
 // ---- consumer: exact per-pixel path (all features; staged boxes, global gathers, or both in a mixed tile) -------
-template <typename FrameT, int MASK, bool REDUCE, int CT, bool LEAN, typename Cfg, bool EDGE>
+template <typename FrameT, int MASK, bool REDUCE, int CT, int LEAN, typename Cfg, bool EDGE>
 __device__ __forceinline__ float full_tile(const FwdParams& p, const float* s_bu, const float* s_ff, const FrameT* s_prev,
                                            const int* meta, const TileId& t, int warp, int lane,
                                            const float (&cur)[Cfg::kPPL][Cfg::kC], const float (&mk)[Cfg::kPPL], bool have_cur,
@@ -485,7 +485,7 @@ __device__ __noinline__ bool exact_keep(const float* s_bu, const float* s_ff, in
 
 // one pixel of the hot configuration entirely from global memory with the exact sequences: the pixels of a "mixed" tile
 // (a motion boundary runs through it) whose taps lie outside the staged source boxes.  Returns the masked squared error.
-template <typename FrameT, int MASK, bool KEEP_ONLY>
+template <typename FrameT, int MASK, bool KEEP_ONLY, int LOSS>
 __device__ __noinline__ float pixel_global(const float* bf_pair, const float* ff_pair, const FrameT* prev_pair, Geo g, int x, int y,
                                            float c0, float c1, float c2, float mkv) {
   const int W = g.W, H = g.H;
@@ -514,13 +514,13 @@ __device__ __noinline__ float pixel_global(const float* bf_pair, const float* ff
   if (KEEP_ONLY) return keep ? 1.0f : 0.0f;
   const GlobalSrc<FrameT> psrc{prev_pair, plane, g};
   const float d0 = __fsub_rn(c0, psrc.sample(0, s)), d1 = __fsub_rn(c1, psrc.sample(1, s)), d2 = __fsub_rn(c2, psrc.sample(2, s));
-  const float acc = __fmaf_rn(d2, d2, __fmaf_rn(d1, d1, __fmul_rn(d0, d0)));
-  if (MASK == MASK_GIVEN) return __fmul_rn(__fmul_rn(mkv, mkv), acc);
+  const float acc = LOSS == TCLB200_L1 ? __fadd_rn(__fadd_rn(fabsf(d0), fabsf(d1)), fabsf(d2)) : __fmaf_rn(d2, d2, __fmaf_rn(d1, d1, __fmul_rn(d0, d0)));
+  if (MASK == MASK_GIVEN) return __fmul_rn(LOSS == TCLB200_L1 ? mkv : __fmul_rn(mkv, mkv), acc);
   return keep ? acc : 0.0f;
 }
 
 // CT == 3: masked squared error against `cur` (returned); CT == 0: mask-only (fbcCheckTorch), the verdicts go to mask_out
-template <typename FrameT, int MASK, int CT, typename Cfg, bool EDGE, bool MIXED>
+template <typename FrameT, int MASK, int CT, int LOSS, typename Cfg, bool EDGE, bool MIXED>
 __device__ __forceinline__ float lean_tile(const FwdParams& p, const float* s_bu, const float* s_ff, const int* meta, const TileId& t,
                                            int warp, int lane, const float (&cur)[Cfg::kPPL][Cfg::kC], const float (&mk)[Cfg::kPPL]) {
   constexpr int P = Cfg::kPPL, BW = Cfg::BW, BFW = Cfg::kBfW, PL = Cfg::BH * Cfg::BW;
@@ -616,9 +616,10 @@ __device__ __forceinline__ float lean_tile(const FwdParams& p, const float* s_bu
     for (int ch = 0; ch < CT; ++ch) {
       const float w = tap4(MIXED ? pp + ch * ps : pp + ch * PL);
       const float d = __fsub_rn(cur[k][ch], w);
-      acc = __fmaf_rn(d, d, acc);
+      acc = LOSS == TCLB200_L1 ? __fadd_rn(acc, fabsf(d)) : __fmaf_rn(d, d, acc);   // mask*|warp - cur| (MoGAN :281) / (mask*(cur - warp))^2
     }
-    e[k] = MASK == MASK_GIVEN ? __fmul_rn(__fmul_rn(mk[k], mk[k]), acc) : acc;   // (m*d)^2 summed over channels (mk = 0 outside)
+    // (m*d)^2 resp. m*|d| summed over channels (mk = 0 outside the image)
+    e[k] = MASK == MASK_GIVEN ? __fmul_rn(LOSS == TCLB200_L1 ? mk[k] : __fmul_rn(mk[k], mk[k]), acc) : acc;
     keepbits |= (keep ? 1u : 0u) << k;
     ambbits |= (amb && inside && inbox ? 1u : 0u) << k;
     if (MIXED) outbits |= (amb && inside && !inbox ? 1u : 0u) << k;
@@ -639,12 +640,12 @@ __device__ __forceinline__ float lean_tile(const FwdParams& p, const float* s_bu
     for (int k = 0; k < P; ++k)
       if ((outbits >> k) & 1u) {
         if (CT == 3) {
-          e[k] = pixel_global<FrameT, MASK, false>(p.bf + (size_t)t.pair * 2 * plane, p.ff + (size_t)t.pair * 2 * plane,
+          e[k] = pixel_global<FrameT, MASK, false, LOSS>(p.bf + (size_t)t.pair * 2 * plane, p.ff + (size_t)t.pair * 2 * plane,
                                                    reinterpret_cast<const FrameT*>(p.prev) + (size_t)t.pair * 3 * plane, g, t.x0 + lx0 + 16 * (k & 1),
                                                    t.y0 + ly0 + DY * (k >> 1), cur[k][0], cur[k][1], cur[k][2], mk[k]);
           keepbits |= 1u << k;   // the verdict is already applied
         } else {
-          const float kp = pixel_global<FrameT, MASK, true>(p.bf + (size_t)t.pair * 2 * plane, p.ff + (size_t)t.pair * 2 * plane, nullptr, g,
+          const float kp = pixel_global<FrameT, MASK, true, LOSS>(p.bf + (size_t)t.pair * 2 * plane, p.ff + (size_t)t.pair * 2 * plane, nullptr, g,
                                                             t.x0 + lx0 + 16 * (k & 1), t.y0 + ly0 + DY * (k >> 1), 0.0f, 0.0f, 0.0f, 0.0f);
           keepbits = (keepbits & ~(1u << k)) | ((kp != 0.0f ? 1u : 0u) << k);
         }
@@ -668,7 +669,7 @@ __device__ __forceinline__ float lean_tile(const FwdParams& p, const float* s_bu
   return err;
 }
 
-template <typename FrameT, int MASK, bool REDUCE, int CT, bool LEAN, typename Cfg>
+template <typename FrameT, int MASK, bool REDUCE, int CT, int LEAN, typename Cfg>
 __global__ void __launch_bounds__(kWsThreads, 1) fused_forward_ws_kernel(const FwdParams p, const __grid_constant__ CUtensorMap tm_bf,
                                                                          const __grid_constant__ CUtensorMap tm_ff,
                                                                          const __grid_constant__ CUtensorMap tm_prev,
@@ -888,10 +889,10 @@ __global__ void __launch_bounds__(kWsThreads, 1) fused_forward_ws_kernel(const F
     if (threadIdx.x == 0) TCL_STAMP(k, 2);
     const int mode = ctl->meta[ss][2];
     if (LEAN && mode == 1) {
-      if (t.edge) err = lean_tile<FrameT, MASK, CT, Cfg, true, false>(p, bf_stage(sb), ff_stage(ss), ctl->meta[ss], t, wg, lane, cur, mk);
-      else err = lean_tile<FrameT, MASK, CT, Cfg, false, false>(p, bf_stage(sb), ff_stage(ss), ctl->meta[ss], t, wg, lane, cur, mk);
+      if (t.edge) err = lean_tile<FrameT, MASK, CT, (LEAN == 2 ? TCLB200_L1 : TCLB200_L2), Cfg, true, false>(p, bf_stage(sb), ff_stage(ss), ctl->meta[ss], t, wg, lane, cur, mk);
+      else err = lean_tile<FrameT, MASK, CT, (LEAN == 2 ? TCLB200_L1 : TCLB200_L2), Cfg, false, false>(p, bf_stage(sb), ff_stage(ss), ctl->meta[ss], t, wg, lane, cur, mk);
     } else if (LEAN && mode == 2) {
-      err = lean_tile<FrameT, MASK, CT, Cfg, true, true>(p, bf_stage(sb), ff_stage(ss), ctl->meta[ss], t, wg, lane, cur, mk);
+      err = lean_tile<FrameT, MASK, CT, (LEAN == 2 ? TCLB200_L1 : TCLB200_L2), Cfg, true, true>(p, bf_stage(sb), ff_stage(ss), ctl->meta[ss], t, wg, lane, cur, mk);
     } else if (LEAN || t.edge) {
       err = full_tile<FrameT, MASK, REDUCE, CT, LEAN, Cfg, true>(p, bf_stage(sb), ff_stage(ss), prev_stage(ss), ctl->meta[ss], t, wg, lane, cur, mk, have_cur, near);
     } else {
@@ -1106,7 +1107,7 @@ static int sm_count() {
   return n;
 }
 
-template <typename FrameT, int MASK, bool REDUCE, int CT, bool LEAN>
+template <typename FrameT, int MASK, bool REDUCE, int CT, int LEAN>
 static cudaError_t launch_tma(const FwdParams& p, const CUtensorMap& tb, const CUtensorMap& tf, const CUtensorMap& tp, const CUtensorMap& tc,
                               cudaStream_t s) {
   using Cfg = WsCfg<FrameT, CT, kTW, kTH, kBH, TCL_NB, TCL_NS, TCL_GROUPS>;
@@ -1151,13 +1152,14 @@ static cudaError_t dispatch(const FwdParams& p, int mask_kind, bool reduce, bool
 #define TCL_CASE(MK, RD)                                                                       \
   if (mask_kind == MK && reduce == RD) {                                                       \
     if (!tma) return launch_generic<FrameT, MK, RD>(p, s);                                     \
-    if (p.C == 3 && lean) return launch_tma<FrameT, MK, RD, 3, true>(p, tb, tf, tp, tc, s);    \
-    if (MK == MASK_COMPUTED && !RD && lean_mask) return launch_tma<float, MASK_COMPUTED, false, 0, true>(p, tb, tf, tp, tc, s); \
-    return p.C == 3 ? launch_tma<FrameT, MK, RD, 3, false>(p, tb, tf, tp, tc, s) : launch_tma<FrameT, MK, RD, 0, false>(p, tb, tf, tp, tc, s); \
+    if (p.C == 3 && lean && RD) return p.loss == TCLB200_L1 ? launch_tma<FrameT, MK, true, 3, 2>(p, tb, tf, tp, tc, s)   \
+                                                            : launch_tma<FrameT, MK, true, 3, 1>(p, tb, tf, tp, tc, s);  \
+    if (MK == MASK_COMPUTED && !RD && lean_mask) return launch_tma<float, MASK_COMPUTED, false, 0, 1>(p, tb, tf, tp, tc, s); \
+    return p.C == 3 ? launch_tma<FrameT, MK, RD, 3, 0>(p, tb, tf, tp, tc, s) : launch_tma<FrameT, MK, RD, 0, 0>(p, tb, tf, tp, tc, s); \
   }
   // LEAN = the measured hot configurations, fixed at compile time: computeTCL / training loss with C == 3
   const bool lean = reduce && p.prev && p.cur && !p.warp_out && !p.mask_out && !p.blend_out && !p.near_threshold &&
-                    p.loss == TCLB200_L2 && !(p.flags & TCLB200_VALIDITY) && mask_kind != MASK_NONE &&
+                    !(p.flags & TCLB200_VALIDITY) && mask_kind != MASK_NONE &&
                     (mask_kind != MASK_COMPUTED || (p.flags & (TCLB200_OCC | TCLB200_MOB)) == (TCLB200_OCC | TCLB200_MOB));
   // ... and fbcCheckTorch on its own: both tests, mask_out only
   const bool lean_mask = !reduce && !p.prev && p.mask_out && !p.near_threshold && mask_kind == MASK_COMPUTED &&
