@@ -949,16 +949,19 @@ struct BwdParams {
 };
 
 // FUSED_LOSS: the upstream gradient of warp is derived in-kernel from the masked loss.
-template <bool FUSED_LOSS>
+// CT > 0 fixes the channel count at compile time: all 4*CT gathers and the CT `cur` / grad_out loads of a pixel are then
+// issued back to back (the kernel is latency-bound otherwise: measured 10 long-scoreboard stall cycles per issue).
+template <bool FUSED_LOSS, int CT>
 __global__ void __launch_bounds__(256) warp_backward_kernel(const BwdParams p) {
   const Geo& g = p.geo;
-  const int W = g.W, H = g.H, C = p.C;
+  const int W = g.W, H = g.H, C = CT > 0 ? CT : p.C;
   const size_t plane = (size_t)H * W;
-  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= (size_t)p.B * plane) return;
-  const int b = (int)(idx / plane);
-  const size_t o = idx - (size_t)b * plane;
-  const int y = (int)(o / W), x = (int)(o - (size_t)y * W);
+  // 32 x 8 pixel tiles: lanes along x (coalesced loads / stores, neighbouring lanes scatter into neighbouring addresses)
+  const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
+  const int b = blockIdx.z;
+  const int x = blockIdx.x * 32 + lane, y = blockIdx.y * 8 + wrp;
+  if (x >= W || y >= H) return;
+  const size_t o = (size_t)y * W + x;
   const float u = __ldg(p.f + (size_t)b * 2 * plane + o), v = __ldg(p.f + ((size_t)b * 2 + 1) * plane + o);
 
   // taps, with the un-multiplied fractional parts kept for the coordinate gradient
@@ -983,13 +986,12 @@ __global__ void __launch_bounds__(256) warp_backward_kernel(const BwdParams p) {
     m = p.mask ? __ldg(p.mask + (size_t)b * plane + o) : 1.0f;
     scale = __ldg(p.grad_scale);
   }
+  const bool need_taps = FUSED_LOSS || p.grad_f != nullptr;   // the source values themselves are only needed for these
 
+  constexpr int CU = CT > 0 ? CT : 1;
   float gix = 0.0f, giy = 0.0f;
-  for (int c = 0; c < C; ++c) {
+  auto channel = [&](int c, float v00, float v10, float v01, float v11, float in) {
     const size_t base = ((size_t)b * C + c) * plane;
-    const float* xp = p.x + base;
-    const float v00 = p00 ? __ldg(xp + o00) : 0.0f, v10 = p10 ? __ldg(xp + o00 + 1) : 0.0f;
-    const float v01 = p01 ? __ldg(xp + o00 + W) : 0.0f, v11 = p11 ? __ldg(xp + o00 + W + 1) : 0.0f;
     float go;  // d loss / d warp[b,c,y,x]
     if (FUSED_LOSS) {
       float wv = 0.0f;
@@ -998,18 +1000,17 @@ __global__ void __launch_bounds__(256) warp_backward_kernel(const BwdParams p) {
       if (p01) wv = fmaf(v01, sw, wv);
       if (p11) wv = fmaf(v11, se, wv);
       wv *= valid;
-      const float cv = __ldg(p.cur + base + o);
       float gc;  // d loss / d cur
       if (p.loss == TCLB200_L2) {
-        gc = 2.0f * scale * m * m * (cv - wv);
+        gc = 2.0f * scale * m * m * (in - wv);
       } else {
-        const float d = wv - cv;
+        const float d = wv - in;
         gc = -scale * m * (d > 0.0f ? 1.0f : (d < 0.0f ? -1.0f : 0.0f));
       }
-      if (p.grad_cur) p.grad_cur[base + o] = gc;
+      if (p.grad_cur) __stcs(p.grad_cur + base + o, gc);
       go = -gc;
     } else {
-      go = __ldg(p.grad_out + base + o);
+      go = in;
     }
     go *= valid;
     if (p.grad_x) {
@@ -1022,6 +1023,29 @@ __global__ void __launch_bounds__(256) warp_backward_kernel(const BwdParams p) {
     if (p.grad_f) {
       gix += go * ((v10 - v00) * fy1 + (v11 - v01) * fy0);
       giy += go * ((v01 - v00) * fx1 + (v11 - v10) * fx0);
+    }
+  };
+  if (CT > 0) {
+    float v00[CU], v10[CU], v01[CU], v11[CU], in[CU];
+#pragma unroll
+    for (int c = 0; c < CU; ++c) {   // every load of this pixel in flight before the first use
+      const size_t base = ((size_t)b * C + c) * plane;
+      const float* xp = p.x + base;
+      v00[c] = (need_taps && p00) ? __ldg(xp + o00) : 0.0f;
+      v10[c] = (need_taps && p10) ? __ldg(xp + o00 + 1) : 0.0f;
+      v01[c] = (need_taps && p01) ? __ldg(xp + o00 + W) : 0.0f;
+      v11[c] = (need_taps && p11) ? __ldg(xp + o00 + W + 1) : 0.0f;
+      in[c] = FUSED_LOSS ? __ldcs(p.cur + base + o) : __ldcs(p.grad_out + base + o);
+    }
+#pragma unroll
+    for (int c = 0; c < CU; ++c) channel(c, v00[c], v10[c], v01[c], v11[c], in[c]);
+  } else {
+    for (int c = 0; c < C; ++c) {
+      const size_t base = ((size_t)b * C + c) * plane;
+      const float* xp = p.x + base;
+      const float a00 = (need_taps && p00) ? __ldg(xp + o00) : 0.0f, a10 = (need_taps && p10) ? __ldg(xp + o00 + 1) : 0.0f;
+      const float a01 = (need_taps && p01) ? __ldg(xp + o00 + W) : 0.0f, a11 = (need_taps && p11) ? __ldg(xp + o00 + W + 1) : 0.0f;
+      channel(c, a00, a10, a01, a11, FUSED_LOSS ? __ldcs(p.cur + base + o) : __ldcs(p.grad_out + base + o));
     }
   }
   if (p.grad_f) {
@@ -1301,10 +1325,17 @@ extern "C" int tclb200_gradient(const float* x, float* out, int B, int H, int W,
 static int run_backward(const BwdParams& p, bool fused, cudaStream_t s) {
   const size_t n = (size_t)p.B * p.geo.H * p.geo.W;
   if (p.grad_x) CUDA_TRY(cudaMemsetAsync(p.grad_x, 0, n * p.C * sizeof(float), s));
-  const size_t blocks = (n + 255) / 256;
-  if (blocks >= 0x7fffffffu) return fail(TCLB200_ERR_UNSUPPORTED, "too many pixels for one launch");
-  if (fused) warp_backward_kernel<true><<<(unsigned)blocks, 256, 0, s>>>(p);
-  else warp_backward_kernel<false><<<(unsigned)blocks, 256, 0, s>>>(p);
+  if (p.B > 65535) return fail(TCLB200_ERR_UNSUPPORTED, "batch too large for one backward launch");
+  const dim3 grid((unsigned)cdiv(p.geo.W, 32), (unsigned)cdiv(p.geo.H, 8), (unsigned)p.B);
+  if (grid.y > 65535) return fail(TCLB200_ERR_UNSUPPORTED, "image too tall for one backward launch");
+  if (fused) {
+    if (p.C == 3) warp_backward_kernel<true, 3><<<grid, 256, 0, s>>>(p);
+    else warp_backward_kernel<true, 0><<<grid, 256, 0, s>>>(p);
+  } else {
+    if (p.C == 3) warp_backward_kernel<false, 3><<<grid, 256, 0, s>>>(p);
+    else if (p.C == 2) warp_backward_kernel<false, 2><<<grid, 256, 0, s>>>(p);
+    else warp_backward_kernel<false, 0><<<grid, 256, 0, s>>>(p);
+  }
   ++g_launches;
   CUDA_TRY(cudaGetLastError());
   return TCLB200_OK;
