@@ -12,6 +12,8 @@ from .ops import (FusedResult, fbcCheckTorch, fbcCheckTorch_mob, fbcheck_with_ne
 from .sintel_eval import (aggregate_means, computeTCL, computeTCL_from_flows, save_dict_as_json)  # noqa: F401
 from .sharding import (ShardPlan, plan_shards, evaluate_sharded, allreduce_sums)  # noqa: F401
 from . import synth  # noqa: F401
+from . import ingest  # noqa: F401
+from .ingest import hwc_split, split_fc2_block, flow_hw2_to_planar, load_flo_planar  # noqa: F401
 
 __all__ = ["gradient", "warp", "fbcCheckTorch", "fbcCheckTorch_mob", "fs_warp", "fused_forward",
            "temporal_error", "temporal_error_per_pair", "temporal_loss", "temporal_rmse_per_sample",

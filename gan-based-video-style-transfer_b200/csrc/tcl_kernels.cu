@@ -1055,6 +1055,44 @@ __global__ void __launch_bounds__(256) warp_backward_kernel(const BwdParams p) {
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// dataset ingest: HWC -> planar NCHW de-interleave (the 9-channel FC2 / Hollywood2 .npy blocks and .flo payloads)
+// ---------------------------------------------------------------------------------------------
+// A CTA moves kSplitPx consecutive pixels of one sample: the interleaved floats are read as one contiguous, fully
+// coalesced run into shared memory (pitch Cs | 1 words per pixel: conflict-free for any Cs), then every requested
+// channel is written as a coalesced run of its destination plane.  Pure data movement: 4*Cs B/px read, 4*sum(Cd) written.
+constexpr int kSplitPx = 256;
+constexpr int kSplitMaxOut = 8;
+struct SplitParams {
+  const float* src;
+  float* dst[kSplitMaxOut];
+  int c0[kSplitMaxOut], cd[kSplitMaxOut];
+  int n_out, Cs;
+  long long plane;       // H * W
+  int chunks_per_sample; // ceil(plane / kSplitPx)
+};
+
+__global__ void __launch_bounds__(kSplitPx) hwc_split_kernel(const SplitParams p) {
+  extern __shared__ float s_px[];
+  const int Cs = p.Cs, pitch = Cs | 1;
+  const int n = blockIdx.x / p.chunks_per_sample;
+  const long long px0 = (long long)(blockIdx.x - n * p.chunks_per_sample) * kSplitPx;
+  const int npx = (int)min((long long)kSplitPx, p.plane - px0);
+  const float* src = p.src + ((long long)n * p.plane + px0) * Cs;
+  const int nfl = npx * Cs;
+  for (int i = threadIdx.x; i < nfl; i += kSplitPx) {
+    const int px = i / Cs, c = i - px * Cs;
+    s_px[px * pitch + c] = __ldcs(src + i);
+  }
+  __syncthreads();
+  const int t = threadIdx.x;
+  if (t >= npx) return;
+  for (int o = 0; o < p.n_out; ++o) {
+    float* dst = p.dst[o] + (long long)n * p.cd[o] * p.plane + px0 + t;
+    for (int c = 0; c < p.cd[o]; ++c) __stcs(dst + (long long)c * p.plane, s_px[t * pitch + p.c0[o] + c]);
+  }
+}
+
 }  // namespace tcl
 
 // =============================================================================================
@@ -1136,11 +1174,13 @@ static cudaError_t launch_tma(const FwdParams& p, const CUtensorMap& tb, const C
                               cudaStream_t s) {
   using Cfg = WsCfg<FrameT, CT, kTW, kTH, kBH, TCL_NB, TCL_NS, TCL_GROUPS>;
   auto kern = fused_forward_ws_kernel<FrameT, MASK, REDUCE, CT, LEAN, Cfg>;
-  static bool configured = false;  // per instantiation
-  if (!configured) {
+  static bool configured[64] = {};  // per instantiation and device (the attribute is a per-device property of the function)
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) dev = 63;   // (an uncached slot: set the attribute every time)
+  if (!configured[dev] || dev == 63) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::kSmemBytes);
     if (e != cudaSuccess) return e;
-    configured = true;
+    configured[dev] = true;
   }
   // persistent: one CTA per SM (or fewer when there are fewer tiles)
   const size_t tiles = (size_t)p.B * p.tiles_per_pair;
@@ -1366,4 +1406,30 @@ extern "C" int tclb200_tcl_backward(const float* bf, const float* mask, const fl
   p.grad_x = grad_prev; p.grad_cur = grad_cur;
   p.geo = make_geo(H, W); p.B = B; p.C = C; p.flags = flags & TCLB200_VALIDITY; p.loss = loss;
   return run_backward(p, true, reinterpret_cast<cudaStream_t>(stream));
+}
+
+extern "C" int tclb200_hwc_split(const float* src, int N, int H, int W, int Cs, int n_out, float* const* dst, const int* c0,
+                                 const int* cd, tclb200_stream_t stream) {
+  if (!src || !dst || !c0 || !cd) return fail(TCLB200_ERR_INVALID, "src, dst, c0 and cd are required");
+  if (N <= 0 || H <= 0 || W <= 0 || Cs <= 0) return fail(TCLB200_ERR_INVALID, "N, H, W, Cs must be positive");
+  if (n_out <= 0 || n_out > kSplitMaxOut) return fail(TCLB200_ERR_INVALID, "n_out must be in 1..8");
+  if (Cs > 64) return fail(TCLB200_ERR_UNSUPPORTED, "at most 64 interleaved channels");
+  SplitParams p;
+  memset(&p, 0, sizeof(p));
+  p.src = src; p.n_out = n_out; p.Cs = Cs; p.plane = (long long)H * W;
+  for (int i = 0; i < n_out; ++i) {
+    if (!dst[i] || c0[i] < 0 || cd[i] <= 0 || c0[i] + cd[i] > Cs) return fail(TCLB200_ERR_INVALID, "bad output channel range");
+    p.dst[i] = dst[i]; p.c0[i] = c0[i]; p.cd[i] = cd[i];
+  }
+  const long long chunks = (p.plane + kSplitPx - 1) / kSplitPx;
+  if (chunks * N >= 0x7fffffffLL) return fail(TCLB200_ERR_UNSUPPORTED, "too many chunks for one launch");
+  p.chunks_per_sample = (int)chunks;
+  const size_t smem = (size_t)kSplitPx * (Cs | 1) * sizeof(float);
+  if (smem > 48 * 1024) {
+    CUDA_TRY(cudaFuncSetAttribute(hwc_split_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  }
+  hwc_split_kernel<<<(unsigned)(chunks * N), kSplitPx, smem, reinterpret_cast<cudaStream_t>(stream)>>>(p);
+  ++g_launches;
+  CUDA_TRY(cudaGetLastError());
+  return TCLB200_OK;
 }

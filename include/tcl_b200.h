@@ -131,6 +131,15 @@ int tclb200_tcl_backward(const float* bf, const float* mask, const float* prev, 
                          const float* grad_scale, float* grad_prev, float* grad_cur, int B, int C, int H, int W,
                          int flags, int loss, tclb200_stream_t stream);
 
+/* Dataset ingest ("next" row of the scope table): HWC -> planar NCHW de-interleave on the GPU.
+ *   - the 9-channel FlyingChairs2 / Hollywood2 blocks [img1 3 | img2 3 | mask 1 | flow 2]
+ *     (StarGANv2AdvCon/core/data_loader.py:243-245, methods/learning-based/datasets.py:52-54: np.moveaxis(np_data[:,:,6:7], 2, 0) ...)
+ *   - the payload of a .flo file, H x W x 2 (utils/flowlib.py:33-48 readFlow)
+ * src (N,H,W,Cs) fp32; output i, dst[i] (N,cd[i],H,W) fp32, receives channels [c0[i], c0[i]+cd[i]) of src.  The
+ * arrays dst / c0 / cd are HOST arrays of n_out <= 8 entries (dst[i] are device pointers). */
+int tclb200_hwc_split(const float* src, int N, int H, int W, int Cs, int n_out, float* const* dst, const int* c0,
+                      const int* cd, tclb200_stream_t stream);
+
 /* Test hook (process-global, not for production use): route TMA-capable shapes through the generic
  * global-memory kernel so that both kernels are exercised on the same inputs.  0 = off (default). */
 void tclb200_debug_force_generic(int on);

@@ -384,3 +384,27 @@ def test_hot_path_with_nonfinite_and_extreme_flow(tcl):
     want = _sums64(t_mask, cur, t_warp)
     assert torch.allclose(hot.pair_sums, want, rtol=1e-6, atol=0, equal_nan=True)
     assert torch.allclose(exact.pair_sums, want, rtol=1e-6, atol=0, equal_nan=True)
+
+
+# ------------------------------------------------------------------ dataset ingest (HWC -> planar), pure data movement: bit-exact
+@pytest.mark.parametrize("N,H,W,Cs", [(2, 256, 256, 9), (1, 436, 1024, 2), (3, 7, 5, 9), (1, 1, 1, 4), (2, 33, 129, 15)])
+def test_hwc_split_matches_moveaxis(tcl, tmp_path, N, H, W, Cs):
+    d = dev()
+    g = torch.Generator().manual_seed(Cs * 100 + W)
+    block = torch.randn(N, H, W, Cs, generator=g)
+    if Cs == 9:     # the reference's slicing: core/data_loader.py:243-245
+        img1, img2, mask, flow = tcl.split_fc2_block(block.to(d))
+        for got, (a, b) in zip((img1, img2, mask, flow), ((0, 3), (3, 6), (6, 7), (7, 9))):
+            want = np.stack([np.moveaxis(block[n].numpy()[:, :, a:b], 2, 0) for n in range(N)])
+            assert np.array_equal(got.cpu().numpy(), want)
+    elif Cs == 2:   # .flo payload: utils/flowlib.py:33-48 round trip through a file
+        path = str(tmp_path / "x.flo")
+        tcl.ingest.write_flo(path, block[0].numpy())
+        assert np.array_equal(tcl.ingest.read_flo(path), block[0].numpy())
+        got = tcl.load_flo_planar(path, d)
+        assert got.shape == (1, 2, H, W) and np.array_equal(got[0].cpu().numpy(), np.moveaxis(block[0].numpy(), 2, 0))
+    else:
+        parts = [("a", 1, 2), ("b", 0, Cs), ("c", Cs - 1, 1)]
+        o = tcl.hwc_split(block.to(d), parts)
+        for name, c0, cd in parts:
+            assert np.array_equal(o[name].cpu().numpy(), block[..., c0:c0 + cd].permute(0, 3, 1, 2).numpy())

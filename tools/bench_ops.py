@@ -66,7 +66,16 @@ def run(cfg_name, pairs):
     report(tag + "warp bf16", timeit(lambda: tcl.warp(pb, bf)), px, 20)
 
 
+def run_ingest():
+    N, H, W = 64, 256, 256
+    block = torch.randn(N, H, W, 9, device=dev)
+    report(f"ingest fc2 block[{N}] HWC9 -> planar", timeit(lambda: tcl.split_fc2_block(block)), N * H * W, 72)
+    flo = torch.randn(8, 436, 1024, 2, device=dev)
+    report("ingest .flo payload[8] HW2 -> planar", timeit(lambda: tcl.flow_hw2_to_planar(flo)), 8 * 436 * 1024, 16)
+
+
 if __name__ == "__main__":
+    run_ingest()
     run("sintel_full", 128)
     run("train_b16_256", 256)
     run("train_b16_256", 16)
