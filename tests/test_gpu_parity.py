@@ -408,3 +408,41 @@ def test_hwc_split_matches_moveaxis(tcl, tmp_path, N, H, W, Cs):
         o = tcl.hwc_split(block.to(d), parts)
         for name, c0, cd in parts:
             assert np.array_equal(o[name].cpu().numpy(), block[..., c0:c0 + cd].permute(0, 3, 1, 2).numpy())
+
+
+# ------------------------------------------------------------------ streams and CUDA graphs
+def test_concurrent_streams_and_graph_replay(tcl):
+    """Calls are asynchronous on the caller's stream and re-entrant across streams (each stream gets its own scratch);
+    a captured graph (fused kernel + its programmatic-dependent fold kernel) replays to the same bits."""
+    d = dev()
+    cases = []
+    for i, (B, H, W) in enumerate([(3, 128, 256), (2, 96, 512), (5, 64, 128)]):
+        ff, bf = tcl.synth.make_flows(B, H, W, seed=40 + i, max_shift=10.0, device=d)
+        prev, cur = tcl.synth.make_frames(B, 3, H, W, seed=40 + i, kind="white", device=d)
+        cases.append((ff, bf, prev, cur))
+    ref = [tcl.fused_forward(bf, prev, cur, ff=ff).pair_sums.clone() for ff, bf, prev, cur in cases]
+    torch.cuda.synchronize()
+    streams = [torch.cuda.Stream(d) for _ in cases]
+    outs = [[] for _ in cases]
+    for rep in range(8):
+        for s, (ff, bf, prev, cur), o in zip(streams, cases, outs):
+            with torch.cuda.stream(s):
+                o.append(tcl.fused_forward(bf, prev, cur, ff=ff).pair_sums)
+    torch.cuda.synchronize()
+    for r, o in zip(ref, outs):
+        for x in o:
+            assert torch.equal(x, r)
+    # graph capture / replay
+    ff, bf, prev, cur = cases[0]
+    side = torch.cuda.Stream(d)
+    with torch.cuda.stream(side):
+        tcl.fused_forward(bf, prev, cur, ff=ff)   # allocate this stream's scratch outside the capture
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g, stream=side):
+        res = tcl.fused_forward(bf, prev, cur, ff=ff)
+    for _ in range(3):
+        res.pair_sums.zero_()
+        g.replay()
+        torch.cuda.synchronize()
+        assert torch.equal(res.pair_sums, ref[0])
