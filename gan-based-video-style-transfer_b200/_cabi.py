@@ -12,7 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.environ.get("TCL_B200_LIB") or os.path.join(CSRC, "libtcl_b200.so")  # env override: tuning sweeps only
 HEADER = os.path.join(os.path.dirname(_HERE), "include", "tcl_b200.h")
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 # enums mirrored from include/tcl_b200.h
 F32, BF16 = 0, 1
@@ -38,6 +38,8 @@ class TclArgs(ctypes.Structure):
         ("scratch", ctypes.c_void_p), ("scratch_bytes", ctypes.c_size_t),
         ("B", ctypes.c_int), ("C", ctypes.c_int), ("H", ctypes.c_int), ("W", ctypes.c_int),
         ("dtype", ctypes.c_int), ("flags", ctypes.c_int), ("loss", ctypes.c_int), ("finalize", ctypes.c_int),
+        ("prev_index", ctypes.c_void_p), ("cur_index", ctypes.c_void_p),
+        ("n_prev_frames", ctypes.c_int), ("n_cur_frames", ctypes.c_int),
     ]
 
 

@@ -75,6 +75,8 @@ struct FwdParams {
   const float* mask_in;
   const void* prev;
   const void* cur;
+  const int* prev_index;   // clip mode: frame of `prev` / `cur` each pair reads (nullptr: its own)
+  const int* cur_index;
   void* warp_out;
   float* mask_out;
   void* blend_out;

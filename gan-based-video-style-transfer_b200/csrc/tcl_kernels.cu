@@ -160,11 +160,16 @@ __device__ __forceinline__ void finish_pixel(const FwdParams& p, const PixTaps& 
   }
 }
 
+// frame of `prev` / `cur` pair b reads: its own, or -- clip mode -- the one an index array names, so that a video frame
+// stored once can be the `cur` of pair t and the `prev` of pair t+1 (the second read then comes out of L2)
+__device__ __forceinline__ int prev_frame(const FwdParams& p, int pair) { return p.prev_index ? __ldg(p.prev_index + pair) : pair; }
+__device__ __forceinline__ int cur_frame(const FwdParams& p, int pair) { return p.cur_index ? __ldg(p.cur_index + pair) : pair; }
+
 template <typename FrameT>
-__device__ __forceinline__ PairPtrs<FrameT> pair_ptrs(const FwdParams& p, int pair, int C, size_t plane) {
+__device__ __forceinline__ PairPtrs<FrameT> pair_ptrs(const FwdParams& p, int pair, int cf, int C, size_t plane) {
   PairPtrs<FrameT> io;
   const size_t off = (size_t)pair * C * plane;
-  io.cur = p.cur ? reinterpret_cast<const FrameT*>(p.cur) + off : nullptr;
+  io.cur = p.cur ? reinterpret_cast<const FrameT*>(p.cur) + (size_t)cf * C * plane : nullptr;
   io.wout = p.warp_out ? reinterpret_cast<FrameT*>(p.warp_out) + off : nullptr;
   io.bout = p.blend_out ? reinterpret_cast<FrameT*>(p.blend_out) + off : nullptr;
   return io;
@@ -205,9 +210,9 @@ __global__ void __launch_bounds__(kThreads) fused_forward_generic_kernel(const F
     }
     const PixTaps s = pix_taps(u, v, x, y, g);
     GlobalSrc<float> fsrc{p.ff ? p.ff + (size_t)pair * 2 * plane : nullptr, plane, g};
-    GlobalSrc<FrameT> psrc{p.prev ? reinterpret_cast<const FrameT*>(p.prev) + (size_t)pair * C * plane : nullptr, plane, g};
+    GlobalSrc<FrameT> psrc{p.prev ? reinterpret_cast<const FrameT*>(p.prev) + (size_t)prev_frame(p, pair) * C * plane : nullptr, plane, g};
     finish_pixel<FrameT, MASK, REDUCE, CT, false>(p, s, u, v, nb, keep, o, plane, pair, fsrc, psrc,
-                                                  pair_ptrs<FrameT>(p, pair, C, plane), nullptr, err, near);
+                                                  pair_ptrs<FrameT>(p, pair, cur_frame(p, pair), C, plane), nullptr, err, near);
   }
   count_near(near, p.near_threshold);
   if (REDUCE) reduce_and_finalise(err, p, pair, tile);
@@ -270,7 +275,7 @@ struct WsCfg {
   static_assert(NB >= NS + 2, "the flow tile of a tile is scanned NS tiles ahead: it must have been requested a tile before that");
 };
 
-struct TileId { int pair, tile, x0, y0, edge, pad[3]; };
+struct TileId { int pair, tile, x0, y0, edge, pf, cf, pad; };   // pf / cf: frame of `prev` / `cur` this pair reads
 
 template <int NB, int NS>
 struct WsCtl {              // control block in shared memory
@@ -372,6 +377,7 @@ __device__ __forceinline__ TileId tile_id(const FwdParams& p, int tg, int TW, in
   const int ty = t.tile / p.tiles_x, tx = t.tile - ty * p.tiles_x;
   t.x0 = tx * TW; t.y0 = ty * TH;
   t.edge = ((t.x0 + TW > p.geo.W) || (t.y0 + TH > p.geo.H)) ? 1 : 0;
+  t.pf = prev_frame(p, t.pair); t.cf = cur_frame(p, t.pair);
   return t;
 }
 
@@ -394,12 +400,12 @@ __device__ __forceinline__ float full_tile(const FwdParams& p, const float* s_bu
   const size_t plane = (size_t)H * W;
   const bool want_mob = MASK == MASK_COMPUTED && (LEAN || (p.flags & TCLB200_MOB));
   const float* s_bv = s_bu + Cfg::kBfH * Cfg::kBfW;
-  const PairPtrs<FrameT> io = pair_ptrs<FrameT>(p, t.pair, CT > 0 ? CT : p.C, plane);
+  const PairPtrs<FrameT> io = pair_ptrs<FrameT>(p, t.pair, t.cf, CT > 0 ? CT : p.C, plane);
   const int ox = meta[0], oy = meta[1], mode = meta[2];   // mode 0: nothing staged, 1: every tap in the boxes, 2: mixed
   const SmemSrc<float, Cfg::BW, Cfg::BH * Cfg::BW> fs{s_ff, ox, oy};
   const SmemSrc<FrameT, Cfg::BW, Cfg::BH * Cfg::BW> ps{s_prev, ox, oy};
   const GlobalSrc<float> fg{p.ff ? p.ff + (size_t)t.pair * 2 * plane : nullptr, plane, g};
-  const GlobalSrc<FrameT> pg{p.prev ? reinterpret_cast<const FrameT*>(p.prev) + (size_t)t.pair * (CT > 0 ? CT : p.C) * plane : nullptr, plane, g};
+  const GlobalSrc<FrameT> pg{p.prev ? reinterpret_cast<const FrameT*>(p.prev) + (size_t)t.pf * (CT > 0 ? CT : p.C) * plane : nullptr, plane, g};
   float err = 0.0f;
 #pragma unroll
   for (int k = 0; k < Cfg::kPPL; ++k) {   // fully unrolled: cur[k] / mk[k] must stay in registers
@@ -533,7 +539,7 @@ __device__ __forceinline__ float lean_tile(const FwdParams& p, const float* s_bu
   const float box_xf = (float)box_x, box_yf = (float)box_y;
   const ptrdiff_t gplane = (ptrdiff_t)g.H * g.W;
   const float* gff = (MIXED && MASK == MASK_COMPUTED) ? p.ff + (size_t)t.pair * 2 * gplane : nullptr;
-  const FrameT* gprev = (MIXED && CT == 3) ? reinterpret_cast<const FrameT*>(p.prev) + (size_t)t.pair * 3 * gplane : nullptr;
+  const FrameT* gprev = (MIXED && CT == 3) ? reinterpret_cast<const FrameT*>(p.prev) + (size_t)t.pf * 3 * gplane : nullptr;
   LeanGeo lg;
   lg.i2x = __fmul_rn(2.0f, g.inv_dx); lg.i2y = __fmul_rn(2.0f, g.inv_dy);   // exact doubling: (2a)*r == a*(2r)
   lg.Wf = g.Wf; lg.Hf = g.Hf;
@@ -641,7 +647,7 @@ __device__ __forceinline__ float lean_tile(const FwdParams& p, const float* s_bu
       if ((outbits >> k) & 1u) {
         if (CT == 3) {
           e[k] = pixel_global<FrameT, MASK, false, LOSS>(p.bf + (size_t)t.pair * 2 * plane, p.ff + (size_t)t.pair * 2 * plane,
-                                                   reinterpret_cast<const FrameT*>(p.prev) + (size_t)t.pair * 3 * plane, g, t.x0 + lx0 + 16 * (k & 1),
+                                                   reinterpret_cast<const FrameT*>(p.prev) + (size_t)t.pf * 3 * plane, g, t.x0 + lx0 + 16 * (k & 1),
                                                    t.y0 + ly0 + DY * (k >> 1), cur[k][0], cur[k][1], cur[k][2], mk[k]);
           keepbits |= 1u << k;   // the verdict is already applied
         } else {
@@ -731,12 +737,12 @@ __global__ void __launch_bounds__(kWsThreads, 1) fused_forward_ws_kernel(const F
       mbar_expect_tx(&ctl->bf_full[s], Cfg::kBfLoad);
       tma_load_4d(bf_stage(s), &tm_bf, &ctl->bf_full[s], t.x0 - Cfg::kHaloX, t.y0 - 1, 0, t.pair);
       // the consumers read this tile's `cur` values straight from global memory NB tiles from now: have them in L2 by then
-      if (LEAN && CT > 0) tma_prefetch_l2_4d(&tm_cur, t.x0, t.y0, 0, t.pair);
+      if (LEAN && CT > 0) tma_prefetch_l2_4d(&tm_cur, t.x0, t.y0, 0, t.cf);
     };
     // lane 0: the consumers have folded the extent of x+u, y+v over local tile k into box[k % NB] -> origin of the source
     // boxes.  The coordinate map is monotone in x+u (every step is a correctly rounded monotone operation), so the
     // extreme taps come from the extreme sums.
-    struct Placement { int ox, oy, mode, pair; };
+    struct Placement { int ox, oy, mode, pair, pf; };
     auto place_src = [&](int k) -> Placement {
       const int sb = k % NB;
       const TileId t = ctl->tinfo[sb];
@@ -768,7 +774,7 @@ __global__ void __launch_bounds__(kWsThreads, 1) fused_forward_ws_kernel(const F
         if (mode != 1) atomicAdd(&g_tile_stats[mode == 2 ? 1 : 0], 1ull);
       }
       ctl->box[sb][0] = INT_MAX; ctl->box[sb][1] = INT_MAX; ctl->box[sb][2] = INT_MIN; ctl->box[sb][3] = INT_MIN;
-      return Placement{ox, oy, mode, t.pair};
+      return Placement{ox, oy, mode, t.pair, t.pf};
     };
     // ... and, once the source stage is free, the request itself (lane 0)
     auto issue_src = [&](int k, const Placement& pl) {
@@ -778,7 +784,7 @@ __global__ void __launch_bounds__(kWsThreads, 1) fused_forward_ws_kernel(const F
         TCL_STAMP(k, 0);
         mbar_expect_tx(&ctl->src_full[ss], (want_occ ? Cfg::kFfLoad : 0u) + (want_frames ? Cfg::kPrevLoad : 0u));
         if (want_occ) tma_load_4d(ff_stage(ss), &tm_ff, &ctl->src_full[ss], pl.ox, pl.oy, 0, pl.pair);
-        if (want_frames) tma_load_4d(prev_stage(ss), &tm_prev, &ctl->src_full[ss], pl.ox, pl.oy, 0, pl.pair);
+        if (want_frames) tma_load_4d(prev_stage(ss), &tm_prev, &ctl->src_full[ss], pl.ox, pl.oy, 0, pl.pf);
       } else {
         mbar_arrive(&ctl->src_full[ss]);
       }
@@ -862,9 +868,19 @@ __global__ void __launch_bounds__(kWsThreads, 1) fused_forward_ws_kernel(const F
     const bool have_cur = CT > 0 && (LEAN || p.cur != nullptr);
     {
       const size_t pix = (size_t)(t.y0 * g.W + t.x0) + lane_off;
-      const FrameT* cb = reinterpret_cast<const FrameT*>(p.cur) + (size_t)t.pair * Cfg::kC * plane + pix;
+      const FrameT* cb = reinterpret_cast<const FrameT*>(p.cur) + (size_t)t.cf * Cfg::kC * plane + pix;
       const float* mb = MASK == MASK_GIVEN ? p.mask_in + (size_t)t.pair * plane + pix : nullptr;
-      if (!t.edge) {
+      if (!t.edge && p.cur_index != nullptr) {
+        // clip mode: this frame is read again as the `prev` of the next pair -- do not mark its lines evict-first
+#pragma unroll
+        for (int c = 0; c < Cfg::kC; ++c) {
+          const FrameT* pc = cb + (size_t)c * plane;
+#pragma unroll
+          for (int i = 0; i < P; ++i) cur[i][c] = have_cur ? to_f32(__ldg(pc + (i >> 1) * row16 + 16 * (i & 1))) : 0.0f;
+        }
+#pragma unroll
+        for (int i = 0; i < P; ++i) mk[i] = MASK == MASK_GIVEN ? __ldcs(mb + (i >> 1) * row16 + 16 * (i & 1)) : 0.0f;
+      } else if (!t.edge) {
 #pragma unroll
         for (int c = 0; c < Cfg::kC; ++c) {
           const FrameT* pc = cb + (size_t)c * plane;
@@ -1272,6 +1288,8 @@ static int run_fused(const tclb200_tcl_args* a, cudaStream_t s) {
   if (a->prev && a->C <= 0) return fail(TCLB200_ERR_INVALID, "C must be positive when frames are given");
   if ((a->cur || a->warp_out || a->blend_out) && !a->prev) return fail(TCLB200_ERR_INVALID, "prev is required with cur / warp_out / blend_out");
   if (a->blend_out && !a->cur) return fail(TCLB200_ERR_INVALID, "blend_out needs cur");
+  if ((a->prev_index && a->n_prev_frames <= 0) || (a->cur_index && a->n_cur_frames <= 0))
+    return fail(TCLB200_ERR_INVALID, "prev_index / cur_index need n_prev_frames / n_cur_frames");
   if ((size_t)a->H * a->W >= (1u << 30)) return fail(TCLB200_ERR_UNSUPPORTED, "H*W must be below 2^30");
   const bool reduce = a->cur && (a->pair_sums || a->total_sums || a->pair_vals || a->total_val);
   const int mask_kind = a->ff ? MASK_COMPUTED : (a->mask_in ? MASK_GIVEN : MASK_NONE);
@@ -1288,13 +1306,14 @@ static int run_fused(const tclb200_tcl_args* a, cudaStream_t s) {
   if (tma) {
     tma = make_map(&tb, a->bf, 4, a->W, a->H, 2, a->B, kTW + 16, kTH + 2, 2);
     if (tma && mask_kind == MASK_COMPUTED && (a->flags & TCLB200_OCC)) tma = make_map(&tf, a->ff, 4, a->W, a->H, 2, a->B, kBW, kBH, 2);
-    if (tma && a->prev) tma = make_map(&tp, a->prev, esz, a->W, a->H, 3, a->B, kBW, kBH, 3);
-    if (tma && a->prev && a->cur) tma = make_map(&tc, a->cur, esz, a->W, a->H, 3, a->B, kTW, kTH, 3);
+    if (tma && a->prev) tma = make_map(&tp, a->prev, esz, a->W, a->H, 3, a->prev_index ? a->n_prev_frames : a->B, kBW, kBH, 3);
+    if (tma && a->prev && a->cur) tma = make_map(&tc, a->cur, esz, a->W, a->H, 3, a->cur_index ? a->n_cur_frames : a->B, kTW, kTH, 3);
   }
 
   FwdParams p;
   memset(&p, 0, sizeof(p));
   p.ff = a->ff; p.bf = a->bf; p.mask_in = a->mask_in; p.prev = a->prev; p.cur = a->cur;
+  p.prev_index = a->prev ? a->prev_index : nullptr; p.cur_index = a->cur ? a->cur_index : nullptr;
   p.warp_out = a->warp_out; p.mask_out = a->mask_out; p.blend_out = a->blend_out;
   p.pair_sums = a->pair_sums; p.total_sums = a->total_sums; p.pair_vals = a->pair_vals; p.total_val = a->total_val;
   p.near_threshold = a->near_threshold;

@@ -195,21 +195,43 @@ class FusedResult:
             setattr(self, s, None)
 
 
+def _index(idx, B, n_frames, name, validate=True):
+    if idx is None:
+        return None
+    if idx.dim() != 1 or idx.numel() != B:
+        raise RuntimeError(f"tcl_b200: {name} must hold one frame index per pair ({B}), got {tuple(idx.shape)}")
+    if validate and idx.numel() and (int(idx.min()) < 0 or int(idx.max()) >= n_frames):   # (a device sync: skip with validate=False)
+        raise RuntimeError(f"tcl_b200: {name} outside [0, {n_frames})")
+    return idx.to(dtype=torch.int32).contiguous()
+
+
 def fused_forward(bf, prev, cur, ff=None, mask=None, loss=L2, finalize=FIN_RMSE, flags=OCC | MOB,
-                  want_warp=False, want_mask=False, want_blend=False, want_near=False, want_sums=True):
+                  want_warp=False, want_mask=False, want_blend=False, want_near=False, want_sums=True,
+                  prev_index=None, cur_index=None, validate_index=True):
     """One launch: warp ``prev`` by ``bf``, build or read the mask, reduce the masked error against ``cur``.
 
     ``ff`` given -> the mask is computed (fbcCheckTorch semantics, tests per ``flags``);
     else ``mask`` given -> dataset mask (B,1,H,W); else no mask.  Returns a ``FusedResult``.
+
+    Clip mode: with ``prev_index`` / ``cur_index`` (int tensors, one entry per pair) ``prev`` / ``cur`` are banks of
+    frames (F,C,H,W) and pair b reads frame ``prev_index[b]`` / ``cur_index[b]`` -- a video stored once serves as
+    ``cur`` of pair t and ``prev`` of pair t+1 (see ``temporal_error_clip``).
     """
     _require_cuda(bf, prev, cur, ff, mask)
     bf = _flow(bf, "bf")
     B, _, H, W = bf.shape
     ff = _flow(ff, "ff") if ff is not None else None
-    if prev.dim() != 4 or prev.shape[0] != B or prev.shape[2:] != bf.shape[2:]:
+    if prev.dim() != 4 or (prev_index is None and prev.shape[0] != B) or prev.shape[2:] != bf.shape[2:]:
         raise RuntimeError(f"tcl_b200: prev {tuple(prev.shape)} does not match flow {tuple(bf.shape)}")
-    if cur.shape != prev.shape or cur.dtype != prev.dtype:
-        raise RuntimeError("tcl_b200: prev and cur must have the same shape and dtype")
+    if cur.dim() != 4 or cur.shape[1:] != prev.shape[1:] or cur.dtype != prev.dtype or (cur_index is None and cur.shape[0] != B):
+        raise RuntimeError("tcl_b200: prev and cur must have the same frame shape and dtype")
+    _require_cuda(prev_index, cur_index)
+    prev_index = _index(prev_index, B, prev.shape[0], "prev_index", validate_index)
+    cur_index = _index(cur_index, B, cur.shape[0], "cur_index", validate_index)
+    if (want_warp or want_blend) and (prev_index is not None or cur_index is not None):
+        out_like = torch.empty((B,) + tuple(prev.shape[1:]), dtype=prev.dtype, device=prev.device)
+    else:
+        out_like = None
     dt = _frame_dtype(prev)
     prev, cur = prev.contiguous(), cur.contiguous()
     C = prev.shape[1]
@@ -227,11 +249,11 @@ def fused_forward(bf, prev, cur, ff=None, mask=None, loss=L2, finalize=FIN_RMSE,
         res.pair_vals, res.total_val = f32[:B], f32[B]
         res.pair_sums, res.total_sums = f64[:B], f64[B:]
     if want_warp:
-        res.warp = torch.empty_like(prev)
+        res.warp = torch.empty_like(prev) if out_like is None else torch.empty_like(out_like)
     if want_mask:
         res.mask = torch.empty((B, 1, H, W), dtype=torch.float32, device=dev)
     if want_blend:
-        res.blend = torch.empty_like(prev)
+        res.blend = torch.empty_like(prev) if out_like is None else torch.empty_like(out_like)
     if want_near:
         res.near_threshold = torch.zeros(1, dtype=torch.int64, device=dev)
     with torch.cuda.device(dev):
@@ -246,6 +268,8 @@ def fused_forward(bf, prev, cur, ff=None, mask=None, loss=L2, finalize=FIN_RMSE,
         a.near_threshold = _ptr(res.near_threshold)
         a.B, a.C, a.H, a.W = B, C, H, W
         a.dtype, a.flags, a.loss, a.finalize = dt, flags, loss, finalize
+        a.prev_index, a.cur_index = _ptr(prev_index), _ptr(cur_index)
+        a.n_prev_frames, a.n_cur_frames = prev.shape[0], cur.shape[0]
         check(_cabi.lib().tclb200_tcl_forward(ctypes.byref(a), _stream_handle()))
     return res
 
@@ -258,6 +282,19 @@ def temporal_error(ff, bf, prev, cur):
 def temporal_error_per_pair(ff, bf, prev, cur):
     """Per-pair RMSE (B,) with the mask computed from (ff,bf) -- the batched form of ``computeTCL``."""
     return fused_forward(bf, prev, cur, ff=ff, finalize=FIN_RMSE).pair_vals
+
+
+def temporal_error_clip(frames, ff, bf):
+    """Per-pair RMSE (T-1,) over a clip of T stylised frames stored ONCE: pair i warps ``frames[i]`` by ``bf[i]`` and
+    compares with ``frames[i+1]`` under the mask of (``ff[i]``, ``bf[i]``) -- the evaluation loop of
+    utils/sintel_eval.py:206-222 for a deterministic generator.  Every frame is read from HBM once (28 instead of
+    40 B/px): its second use comes out of L2."""
+    T = frames.shape[0]
+    if bf.shape[0] != T - 1:
+        raise RuntimeError(f"tcl_b200: a clip of {T} frames has {T - 1} consecutive pairs, got {bf.shape[0]} flows")
+    idx = torch.arange(T, dtype=torch.int32, device=frames.device)
+    return fused_forward(bf, frames, frames, ff=ff, finalize=FIN_RMSE, prev_index=idx[:-1], cur_index=idx[1:],
+                         validate_index=False).pair_vals
 
 
 def temporal_rmse_per_sample(mask, cur, prev, flow):

@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define TCLB200_ABI_VERSION 1
+#define TCLB200_ABI_VERSION 2
 
 #define TCLB200_OK 0
 #define TCLB200_ERR_INVALID 1     /* bad argument (null pointer, non-positive size, unknown enum) */
@@ -118,6 +118,13 @@ typedef struct tclb200_tcl_args {
   int flags;            /* TCLB200_OCC | TCLB200_MOB tests when ff is given; TCLB200_VALIDITY */
   int loss;             /* TCLB200_L2 / TCLB200_L1 */
   int finalize;         /* TCLB200_FIN_MEAN / TCLB200_FIN_RMSE */
+  /* clip mode (optional, NULL = off): `prev` / `cur` hold n_*_frames frames (F,C,H,W) and pair b reads frame
+   * prev_index[b] / cur_index[b] (device int32 arrays of B entries, values in [0, n_*_frames)).  A video frame stored
+   * once can then be the `cur` of pair t and the `prev` of pair t+1 (utils/sintel_eval.py:206-222 evaluates consecutive
+   * frames of a clip): its second read is served by the 126 MB L2 instead of HBM.  Per-pixel outputs stay per pair. */
+  const int* prev_index;
+  const int* cur_index;
+  int n_prev_frames, n_cur_frames;
 } tclb200_tcl_args;
 
 int tclb200_tcl_forward(const tclb200_tcl_args* args, tclb200_stream_t stream);

@@ -446,3 +446,26 @@ def test_concurrent_streams_and_graph_replay(tcl):
         g.replay()
         torch.cuda.synchronize()
         assert torch.equal(res.pair_sums, ref[0])
+
+
+# ------------------------------------------------------------------ clip mode: frames stored once, pairs index them
+@pytest.mark.parametrize("T,H,W", [(6, 96, 256), (4, 436, 1024), (3, 37, 53)])
+def test_clip_mode_equals_pairwise(tcl, force_generic, T, H, W):
+    d = dev()
+    ff, bf = tcl.synth.make_flows(T - 1, H, W, seed=T + W, max_shift=10.0, device=d)
+    frames, _ = tcl.synth.make_frames(T, 3, H, W, seed=T + W, kind="white", device=d)
+    want = tcl.temporal_error_per_pair(ff, bf, frames[:-1].contiguous(), frames[1:].contiguous())
+    got = tcl.temporal_error_clip(frames, ff, bf)
+    assert torch.equal(got, want)     # same tiles, same arithmetic: identical bits
+    # arbitrary indices (long-term pairs: gap 2) with per-pair outputs, both kernels
+    idx_prev = torch.arange(0, T - 2, device=d)
+    idx_cur = idx_prev + 2
+    n = T - 2
+    for generic in (False, True):
+        force_generic(generic)
+        r = tcl.fused_forward(bf[:n], frames, frames, ff=ff[:n], prev_index=idx_prev, cur_index=idx_cur, want_warp=True, want_mask=True)
+        e = tcl.fused_forward(bf[:n], frames[idx_prev].contiguous(), frames[idx_cur].contiguous(), ff=ff[:n], want_warp=True, want_mask=True)
+        assert torch.equal(r.warp, e.warp) and torch.equal(r.mask, e.mask) and torch.equal(r.pair_sums, e.pair_sums)
+    force_generic(False)
+    with pytest.raises(RuntimeError):
+        tcl.fused_forward(bf, frames, frames, ff=ff, prev_index=torch.full((T - 1,), T, device=d), cur_index=idx_cur[:1].repeat(T - 1))

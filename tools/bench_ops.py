@@ -74,7 +74,26 @@ def run_ingest():
     report("ingest .flo payload[8] HW2 -> planar", timeit(lambda: tcl.flow_hw2_to_planar(flo)), 8 * 436 * 1024, 16)
 
 
+def run_clip(T=257):
+    cfg = tcl.synth.CONFIGS["sintel_full"]
+    H, W = cfg["H"], cfg["W"]
+    chunks, fr = [], []
+    for s0 in range(0, T - 1, 32):
+        n = min(32, T - 1 - s0)
+        ff, bf = tcl.synth.make_flows(n, H, W, seed=21 + s0, max_shift=32.0, max_rot_deg=3.0, device=dev)
+        chunks.append((ff, bf))
+    for s0 in range(0, T, 32):
+        n = min(32, T - s0)
+        fr.append(tcl.synth.make_frames(n, 3, H, W, seed=21 + s0, device=dev)[0])
+    ff = torch.cat([c[0] for c in chunks]); bf = torch.cat([c[1] for c in chunks]); frames = torch.cat(fr)
+    prev, cur = frames[:-1].contiguous(), frames[1:].contiguous()
+    px = (T - 1) * H * W
+    report(f"clip[{T}] pairwise tensors (40 B/px)", timeit(lambda: tcl.temporal_error_per_pair(ff, bf, prev, cur)), px, 40)
+    report(f"clip[{T}] frames stored once (28 B/px)", timeit(lambda: tcl.temporal_error_clip(frames, ff, bf)), px, 28)
+
+
 if __name__ == "__main__":
+    run_clip()
     run_ingest()
     run("sintel_full", 128)
     run("train_b16_256", 256)
