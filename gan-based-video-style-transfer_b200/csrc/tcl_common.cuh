@@ -170,7 +170,23 @@ __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, unsigned bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
+#ifndef TCL_WAIT_HINT_NS
+#define TCL_WAIT_HINT_NS 0   // > 0: let the hardware park a waiting warp for up to this many ns per poll
+#endif
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
+#if TCL_WAIT_HINT_NS > 0
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity), "r"((unsigned)TCL_WAIT_HINT_NS)
+      : "memory");
+#else
   asm volatile(
       "{\n"
       ".reg .pred p;\n"
@@ -182,6 +198,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
       "}\n" ::"r"(smem_u32(bar)),
       "r"(parity)
       : "memory");
+#endif
 }
 // same, for a warp that has nothing else to do while it waits: sleeps between polls so that its polling does not
 // take issue slots from the warps that share its scheduler

@@ -1229,6 +1229,13 @@ static cudaError_t launch_generic(const FwdParams& p, cudaStream_t s) {
 template <typename FrameT>
 static cudaError_t dispatch(const FwdParams& p, int mask_kind, bool reduce, bool tma, const CUtensorMap& tb, const CUtensorMap& tf,
                             const CUtensorMap& tp, const CUtensorMap& tc, cudaStream_t s) {
+#ifdef TCL_HOT_ONLY   // tuning builds (tools/sweep_build.py): only the fp32 computeTCL configuration, compiles in seconds
+  if (sizeof(FrameT) == 4 && mask_kind == MASK_COMPUTED && reduce && tma && p.C == 3 && p.prev && p.cur && !p.warp_out && !p.mask_out &&
+      !p.blend_out && !p.near_threshold && p.loss == TCLB200_L2)
+    return launch_tma<float, MASK_COMPUTED, true, 3, 1>(p, tb, tf, tp, tc, s);
+  if (mask_kind == MASK_COMPUTED && !reduce && !p.prev) return launch_generic<float, MASK_COMPUTED, false>(p, s);
+  return cudaErrorNotSupported;
+#else
 #define TCL_CASE(MK, RD)                                                                       \
   if (mask_kind == MK && reduce == RD) {                                                       \
     if (!tma) return launch_generic<FrameT, MK, RD>(p, s);                                     \
@@ -1252,6 +1259,7 @@ static cudaError_t dispatch(const FwdParams& p, int mask_kind, bool reduce, bool
   TCL_CASE(MASK_NONE, false)
 #undef TCL_CASE
   return cudaErrorInvalidValue;
+#endif
 }
 
 extern "C" int tclb200_debug_tile_stats(unsigned long long* out2, int reset) {

@@ -7,8 +7,10 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 CSRC = os.path.join(ROOT, "gan-based-video-style-transfer_b200", "csrc")
 OUT = os.path.join(ROOT, "tools", "_sweep")
 VARIANTS = {
-    "g1_th32_ns2_nb4": {},
-    "g2_th16_ns4_nb6": {"TCL_TH": 16, "TCL_BH": 24, "TCL_NS": 4, "TCL_NB": 6, "TCL_GROUPS": 2},
+    "hot": {"TCL_HOT_ONLY": 1},
+    "hot_hint500": {"TCL_HOT_ONLY": 1, "TCL_WAIT_HINT_NS": 500},
+    "hot_hint2000": {"TCL_HOT_ONLY": 1, "TCL_WAIT_HINT_NS": 2000},
+    "hot_bh38": {"TCL_HOT_ONLY": 1, "TCL_BH": 38},
     "trace": {"TCL_TRACE": 1},
 }
 if __name__ == "__main__":
