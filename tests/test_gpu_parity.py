@@ -469,3 +469,48 @@ def test_clip_mode_equals_pairwise(tcl, force_generic, T, H, W):
     force_generic(False)
     with pytest.raises(RuntimeError):
         tcl.fused_forward(bf, frames, frames, ff=ff, prev_index=torch.full((T - 1,), T, device=d), cur_index=idx_cur[:1].repeat(T - 1))
+
+
+# ------------------------------------------------------------------ adversarial near-threshold inputs for the filtered mask tests
+def test_masks_bit_exact_on_near_threshold_flows(tcl):
+    """The hot path decides the mask tests without the sqrt-then-square of torch.norm(.)**2 whenever lhs is outside
+    rhs*(1 +- 4e-6) and replays the exact sequence otherwise.  Here a large share of the pixels sits inside that band
+    (occlusion test: constant flows with |wf+bf|^2 tuned onto the threshold, perturbed by a few ulp; motion-boundary
+    test: linear ramps whose squared gradient crosses 0.01*|bf|^2+0.002): the masks must still be torch-CUDA's bit for bit."""
+    d = dev()
+    H, W = 96, 512
+    g = torch.Generator(device=d).manual_seed(123)
+    a = 3.0
+    # delta^2 = 0.01*((a-delta)^2 + a^2) + 0.5  (occlusion threshold for wf = (-a+delta, 0), bf = (a, 0))
+    delta = 1.0
+    for _ in range(200):
+        delta = (0.01 * ((a - delta) ** 2 + a ** 2) + 0.5) ** 0.5
+    eps = (torch.rand(1, 1, H, W, generator=g, device=d) * 2 - 1) * 4e-6
+    bf = torch.zeros(1, 2, H, W, device=d)
+    bf[:, 0] = a
+    ff = torch.zeros(1, 2, H, W, device=d)
+    ff[:, 0:1] = -a + delta * (1 + eps)
+    # second pair: motion-boundary stress.  u = g_y * x with per-row slopes: g_y^2 crosses 0.01*u^2 + 0.002 along each row
+    ys = torch.arange(H, device=d, dtype=torch.float32).view(H, 1)
+    xs = torch.arange(W, device=d, dtype=torch.float32).view(1, W)
+    slope = 0.0448 + 0.0004 * ys / H          # sqrt(0.002) = 0.04472...
+    bf2 = torch.zeros(1, 2, H, W, device=d)
+    bf2[0, 0] = slope * (xs - W / 2) * (1 + (torch.rand(H, W, generator=g, device=d) * 2 - 1) * 2e-6)
+    ff2 = -bf2.clone()
+    ff_all, bf_all = torch.cat([ff, ff2]), torch.cat([bf, bf2])
+    with torch.no_grad():
+        t_mask, t_mo, t_mm = tp.fb_consistency(ff_all, bf_all, return_margins=True)
+    rel_occ = (t_mo[0].abs() / 0.6) < 4e-6
+    print("pixels inside the occlusion filter band:", int(rel_occ.sum()), "of", H * W,
+          "| near-threshold (1e-6 abs) px:", int(((t_mo.abs() < BAND) | (t_mm.abs() < BAND)).sum()),
+          "| keep fractions:", [round(float(t_mask[i].mean()), 3) for i in range(2)])
+    assert int(rel_occ.sum()) > H * W // 4                     # the case really is adversarial
+    assert 0.05 < float(t_mask[0].mean()) < 0.95              # and the verdicts are genuinely mixed
+    k_mask = tcl.fbcCheckTorch(ff_all, bf_all)                 # mask-only hot path
+    assert torch.equal(k_mask, t_mask)
+    prev, cur = tcl.synth.make_frames(2, 3, H, W, seed=9, kind="white", device=d)
+    hot = tcl.fused_forward(bf_all, prev, cur, ff=ff_all)      # fused hot path
+    exact = tcl.fused_forward(bf_all, prev, cur, ff=ff_all, want_warp=True, want_mask=True)
+    assert torch.equal(exact.mask, t_mask)
+    want = _sums64(t_mask, cur, exact.warp)
+    assert torch.allclose(hot.pair_sums, want, rtol=1e-6, atol=0)
