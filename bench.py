@@ -416,6 +416,14 @@ def main():
     alg_bytes = n_local * H * W * bpp
     achieved = alg_bytes / (k_ms / 1e3) / 1e9
     res = last["out"]
+    # mask statistics of the workload (keep fraction and near-threshold pixel count with every run);
+    # outside the timed region, on a bounded sample of this rank's pairs, through the exact (counting) path
+    ns = min(64, n_local)
+    m_s, near_s = tcl.fbcheck_with_near_count(shard["ff"][:ns], shard["bf"][:ns])
+    mask_stats = {"sample_pairs": ns, "keep_fraction": float(m_s.mean()), "near_threshold_px": int(near_s),
+                  "sample_px": int(m_s.numel()),
+                  "note": "pixels whose occlusion / motion-boundary margin is within 1e-6 of the threshold (the north-star exemption band)"}
+    del m_s
     line = {
         "metric": "warped frame-pairs/sec", "value": pairs_per_s, "unit": "pairs/s",
         "gpix_per_s": pairs_per_s * H * W / 1e9,
@@ -431,6 +439,7 @@ def main():
         "tiles": {"per_step": n_local * ((W + 63) // 64) * ((H + 31) // 32),
                   "mixed_per_step": int(tile_stats[1]) // max(args.steps, 1), "global_per_step": int(tile_stats[0]) // max(args.steps, 1),
                   "note": "mixed = a motion boundary runs through the 64x32 tile, some pixels gather from global memory"},
+        "mask_stats": mask_stats,
         "result_check": {"mean_over_sequences_rmse": float(res["mean_over_sequences"]), "pooled_rmse": float(res["pooled_rmse"]),
                          "n_pairs": int(res["n_pairs"])},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
