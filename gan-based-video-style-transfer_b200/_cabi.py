@@ -68,6 +68,7 @@ _PROTOTYPES = {
     "tclb200_tcl_forward": (_c.c_int, [_c.POINTER(TclArgs), _vp]),
     "tclb200_tcl_backward": (_c.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     "tclb200_hwc_split": (_c.c_int, [_vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
+    "tclb200_upsample_flow": (_c.c_int, [_vp, _vp, _vp, _i, _i, _i, _vp]),
     "tclb200_debug_force_generic": (None, [_i]),
     "tclb200_debug_tile_stats": (_c.c_int, [_vp, _i]),
     "tclb200_debug_launch_count": (_c.c_ulonglong, [_i]),

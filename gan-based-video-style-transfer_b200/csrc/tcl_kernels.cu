@@ -1109,6 +1109,57 @@ __global__ void __launch_bounds__(kSplitPx) hwc_split_kernel(const SplitParams p
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// RAFT's convex 8x flow upsampling (utils/raft/raft/raft.py:72-83), the step right before the path: the flows the
+// kernels above consume are produced by it.  softmax over the 9 mask logits, convex combination of the 3x3 coarse
+// neighbourhood of 8*flow (zero padded, F.unfold), pixel shuffle to (N,2,8H,8W) -- one pass: the (N,576,H,W) mask is
+// read once (2304 B per coarse pixel, coalesced along w), the fine flow is written once (coalesced through a shared tile).
+// ---------------------------------------------------------------------------------------------
+constexpr int kUpW = 32;   // coarse cells per CTA (one coarse row segment)
+__global__ void __launch_bounds__(256) upsample_flow_kernel(const float* __restrict__ flow, const float* __restrict__ mask,
+                                                            float* __restrict__ out, int H, int W, int segs) {
+  __shared__ float s_fl[2][3][kUpW + 2];          // 8 * coarse flow, rows h-1..h+1, cols w0-1..w0+32 (zero padded)
+  __shared__ float s_out[2][8][8 * kUpW + 4];     // fine rows 8h..8h+7, cols 8*w0 .. 8*w0+255
+  const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
+  const int seg = blockIdx.x % segs, h = (blockIdx.x / segs) % H, n = blockIdx.x / (segs * H);
+  const int w0 = seg * kUpW;
+  const size_t cplane = (size_t)H * W;
+  for (int i = threadIdx.x; i < 2 * 3 * (kUpW + 2); i += 256) {
+    const int c = i / (3 * (kUpW + 2)), r = (i / (kUpW + 2)) % 3, x = i % (kUpW + 2);
+    const int hh = h + r - 1, ww = w0 + x - 1;
+    s_fl[c][r][x] = (hh >= 0 && hh < H && ww >= 0 && ww < W) ? 8.0f * __ldg(flow + ((size_t)n * 2 + c) * cplane + (size_t)hh * W + ww) : 0.0f;
+  }
+  __syncthreads();
+  const int w = w0 + lane;
+  if (w < W) {
+    const float* mp = mask + (size_t)n * 576 * cplane + (size_t)h * W + w;
+#pragma unroll 2
+    for (int ij = wrp; ij < 64; ij += 8) {          // sub-pixel (i, j) = (ij / 8, ij % 8); lanes = 32 coarse columns
+      float m[9], mx = -3.4e38f;
+#pragma unroll
+      for (int k = 0; k < 9; ++k) { m[k] = __ldcs(mp + (size_t)(k * 64 + ij) * cplane); mx = fmaxf(mx, m[k]); }
+      float sum = 0.0f, au = 0.0f, av = 0.0f;
+#pragma unroll
+      for (int k = 0; k < 9; ++k) {
+        const float e = __expf(m[k] - mx);
+        sum += e;
+        au = fmaf(e, s_fl[0][k / 3][lane + k % 3], au);   // unfold order: k = 3 * (dy + 1) + (dx + 1)
+        av = fmaf(e, s_fl[1][k / 3][lane + k % 3], av);
+      }
+      const float inv = 1.0f / sum;
+      s_out[0][ij >> 3][8 * lane + (ij & 7)] = au * inv;
+      s_out[1][ij >> 3][8 * lane + (ij & 7)] = av * inv;
+    }
+  }
+  __syncthreads();
+  const int ncol = min(8 * kUpW, 8 * (W - w0));
+  const size_t fW = (size_t)8 * W, fplane = (size_t)64 * cplane;
+  for (int i = threadIdx.x; i < 2 * 8 * 8 * kUpW; i += 256) {
+    const int c = i / (8 * 8 * kUpW), r = (i / (8 * kUpW)) % 8, x = i % (8 * kUpW);
+    if (x < ncol) __stcs(out + ((size_t)n * 2 + c) * fplane + (size_t)(8 * h + r) * fW + 8 * w0 + x, s_out[c][r][x]);
+  }
+}
+
 }  // namespace tcl
 
 // =============================================================================================
@@ -1456,6 +1507,17 @@ extern "C" int tclb200_hwc_split(const float* src, int N, int H, int W, int Cs, 
     CUDA_TRY(cudaFuncSetAttribute(hwc_split_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   }
   hwc_split_kernel<<<(unsigned)(chunks * N), kSplitPx, smem, reinterpret_cast<cudaStream_t>(stream)>>>(p);
+  ++g_launches;
+  CUDA_TRY(cudaGetLastError());
+  return TCLB200_OK;
+}
+
+extern "C" int tclb200_upsample_flow(const float* flow, const float* mask, float* out, int N, int H, int W, tclb200_stream_t stream) {
+  if (!flow || !mask || !out) return fail(TCLB200_ERR_INVALID, "flow, mask and out are required");
+  if (N <= 0 || H <= 0 || W <= 0) return fail(TCLB200_ERR_INVALID, "N, H, W must be positive");
+  const long long segs = cdiv(W, kUpW), blocks = segs * H * (long long)N;
+  if (blocks >= 0x7fffffffLL) return fail(TCLB200_ERR_UNSUPPORTED, "too many blocks for one launch");
+  upsample_flow_kernel<<<(unsigned)blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(flow, mask, out, H, W, (int)segs);
   ++g_launches;
   CUDA_TRY(cudaGetLastError());
   return TCLB200_OK;

@@ -183,6 +183,25 @@ def fbcheck_with_near_count(ff, bf, flags=OCC | MOB):
     return _fbcheck(ff, bf, flags, None, return_near=True)
 
 
+def upsample_flow(flow, mask):
+    """RAFT's convex upsampling (utils/raft/raft/raft.py:72-83): flow (N,2,H,W), mask (N,576,H,W) -> (N,2,8H,8W).
+
+    Drop-in for ``RAFT.upsample_flow`` (bind it with ``raft_model.upsample_flow = tcl_b200.upsample_flow``); one fused
+    pass instead of softmax + unfold + mul + sum + permute.  No autograd (the reference uses it under ``no_grad``,
+    utils/sintel_eval.py:55-58)."""
+    _require_cuda(flow, mask)
+    if flow.dim() != 4 or flow.shape[1] != 2:
+        raise RuntimeError(f"tcl_b200: flow must be (N,2,H,W), got {tuple(flow.shape)}")
+    N, _, H, W = flow.shape
+    if mask.dim() != 4 or mask.shape != (N, 576, H, W):
+        raise RuntimeError(f"tcl_b200: mask must be (N,576,H,W) = {(N, 576, H, W)}, got {tuple(mask.shape)}")
+    flow, mask = flow.float().contiguous(), mask.float().contiguous()
+    out = torch.empty((N, 2, 8 * H, 8 * W), dtype=torch.float32, device=flow.device)
+    with torch.cuda.device(flow.device):
+        check(_cabi.lib().tclb200_upsample_flow(_ptr(flow), _ptr(mask), _ptr(out), N, H, W, _stream_handle()))
+    return out
+
+
 # ------------------------------------------------------------------------------------------------
 # fused path
 # ------------------------------------------------------------------------------------------------

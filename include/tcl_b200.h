@@ -147,6 +147,11 @@ int tclb200_tcl_backward(const float* bf, const float* mask, const float* prev, 
 int tclb200_hwc_split(const float* src, int N, int H, int W, int Cs, int n_out, float* const* dst, const int* c0,
                       const int* cd, tclb200_stream_t stream);
 
+/* RAFT's convex 8x upsampling of the coarse flow (utils/raft/raft/raft.py:72-83 upsample_flow), the producer of the
+ * flows this path consumes ("next" row of the scope table): softmax over the 9 mask logits, convex combination of the
+ * zero-padded 3x3 neighbourhood of 8*flow, pixel shuffle.  flow (N,2,H,W), mask (N,576,H,W) -> out (N,2,8H,8W), fp32. */
+int tclb200_upsample_flow(const float* flow, const float* mask, float* out, int N, int H, int W, tclb200_stream_t stream);
+
 /* Test hook (process-global, not for production use): route TMA-capable shapes through the generic
  * global-memory kernel so that both kernels are exercised on the same inputs.  0 = off (default). */
 void tclb200_debug_force_generic(int on);

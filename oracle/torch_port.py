@@ -140,3 +140,15 @@ def temporal_error(ff, bf, prev, cur):
     """computeTCL minus RAFT and the generator (utils/sintel_eval.py:104-110)."""
     m = fb_consistency(ff, bf)
     return tcl_rmse(m, cur, backward_warp(prev, bf))
+
+
+def upsample_flow(flow, mask):
+    """``RAFT.upsample_flow`` op for op (utils/raft/raft/raft.py:72-83)."""
+    N, _, H, W = flow.shape
+    mask = mask.view(N, 1, 9, 8, 8, H, W)
+    mask = torch.softmax(mask, dim=2)
+    up_flow = F.unfold(8 * flow, [3, 3], padding=1)
+    up_flow = up_flow.view(N, 2, 9, 1, 1, H, W)
+    up_flow = torch.sum(mask * up_flow, dim=2)
+    up_flow = up_flow.permute(0, 1, 4, 2, 5, 3)
+    return up_flow.reshape(N, 2, 8 * H, 8 * W)

@@ -514,3 +514,19 @@ def test_masks_bit_exact_on_near_threshold_flows(tcl):
     assert torch.equal(exact.mask, t_mask)
     want = _sums64(t_mask, cur, exact.warp)
     assert torch.allclose(hot.pair_sums, want, rtol=1e-6, atol=0)
+
+
+# ------------------------------------------------------------------ RAFT convex upsampling (the step before the path)
+@pytest.mark.parametrize("N,H,W", [(1, 55, 128), (2, 32, 32), (1, 7, 45), (1, 135, 240)])
+def test_upsample_flow_matches_raft(tcl, N, H, W):
+    d = dev()
+    g = torch.Generator(device=d).manual_seed(H * W)
+    flow = torch.randn(N, 2, H, W, generator=g, device=d) * 4
+    mask = torch.randn(N, 576, H, W, generator=g, device=d) * 3
+    with torch.no_grad():
+        want = tp.upsample_flow(flow, mask)
+    got = tcl.upsample_flow(flow, mask)
+    assert got.shape == want.shape
+    err = float((got - want).abs().max())
+    print(f"upsample_flow {N}x{H}x{W}: max abs err {err:.3e} (|flow| up to {float(want.abs().max()):.1f} px)")
+    assert torch.allclose(got, want, rtol=1e-5, atol=2e-5)

@@ -74,6 +74,18 @@ def run_ingest():
     report("ingest .flo payload[8] HW2 -> planar", timeit(lambda: tcl.flow_hw2_to_planar(flo)), 8 * 436 * 1024, 16)
 
 
+def run_upsample():
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    from oracle import torch_port as tp   # timing the reference op sequence beside the kernel (tool, not product)
+    N, H, W = 4, 55, 128                  # Sintel 436(->440)x1024 at 1/8 resolution
+    flow = torch.randn(N, 2, H, W, device=dev)
+    mask = torch.randn(N, 576, H, W, device=dev)
+    px = N * 64 * H * W
+    report(f"upsample_flow[{N}] fused kernel", timeit(lambda: tcl.upsample_flow(flow, mask)), px, 44)
+    with torch.no_grad():
+        report(f"upsample_flow[{N}] torch op sequence", timeit(lambda: tp.upsample_flow(flow, mask)), px, 44)
+
+
 def run_clip(T=257):
     cfg = tcl.synth.CONFIGS["sintel_full"]
     H, W = cfg["H"], cfg["W"]
@@ -93,6 +105,7 @@ def run_clip(T=257):
 
 
 if __name__ == "__main__":
+    run_upsample()
     run_clip()
     run_ingest()
     run("sintel_full", 128)
