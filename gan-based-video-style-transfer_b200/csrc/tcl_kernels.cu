@@ -7,21 +7,25 @@
 //
 // Data layout in HBM: planar NCHW, fp32 flows/masks, fp32 or bf16 frames.
 //
-// fused_forward_tma_kernel (the hot kernel).  A CTA owns a TW x TH tile of one frame pair.
-//   phase A  one TMA box brings the tile of the backward flow `bf` (+1 px halo, zero-filled outside the
-//            image = the zero padding of flowtools.gradient) into shared memory; every lane derives its
-//            pixels' sampling positions and the motion-boundary test, and the CTA reduces the bounding box
-//            of all bilinear taps (warp redux + shared-memory atomics).
-//   phase B  two TMA boxes bring exactly that source region of `ff` (2 planes) and `prev` (C planes) into
-//            shared memory -- the box origin follows the flow, its size is fixed (BW x BH), out-of-image
-//            parts are zero-filled = grid_sample's padding_mode='zeros'.  The 4*(2+C) taps per pixel are then
-//            unit-stride, bank-conflict-free shared-memory reads.  Lanes own pixels x = lane + 32k, so every
-//            global access (cur, mask, outputs) is a fully coalesced 128-byte line per warp instruction.
-//   tiles whose taps do not fit the box (motion boundaries, extreme flows, non-finite values) take the
-//   exact predicated global-gather path for that tile only.
-//   reduction: lane -> warp shuffle -> CTA -> pair -> batch inside the same launch (tickets, fixed order).
+// fused_forward_ws_kernel (the hot kernel, details at its definition): persistent, warp-specialised, one CTA per SM.
+//   producer warp    TMA pipeline: flow tiles of `bf` (+1 px halo, zero-filled outside the image = the zero padding of
+//                    flowtools.gradient) NB tiles ahead; source boxes of `ff` (2 planes) and `prev` (3 planes) NS tiles
+//                    ahead, placed where the flow points (fixed 80 x BH size, zero-filled outside the image =
+//                    grid_sample's padding_mode='zeros'); L2 prefetch of `cur`; one fp64 partial sum per tile.
+//   16 consumer warps one pass per pixel, 4 pixels per lane: motion-boundary test, sampling position (the reference's
+//                    exact rounding sequence), 4*(2+3) taps from shared memory (16 x 2 lane footprint, pitch 80:
+//                    conflict-free), occlusion test, masked error against `cur`.  They also fold the extent of x+u, y+v
+//                    of the flow tile two tiles ahead, from which the producer places that tile's boxes.
+//   mixed tiles      (a motion boundary runs through the tile): pixels whose taps leave the boxes gather from global
+//                    memory inside the same loop; non-finite / absurd flow: whole tile through the exact guarded path.
+//   tile schedule    static round robin for short launches, a global atomic counter for long ones (keeps the CTAs
+//                    within a few tiles of each other so that the overlapping box halos hit in L2).
+//   reduction        lane -> warp butterfly -> fp64 per tile (plain store) -> fold_partials_kernel (programmatic
+//                    dependent launch) sums tiles per pair, pairs per batch in index order: deterministic.
 // fused_forward_generic_kernel covers shapes TMA cannot describe (W % 4 != 0, unaligned views, C != 3).
-// HBM-bound integer-free fp32 streaming + gather: no tensor cores, nothing here is a contraction.
+// warp_backward_kernel: autograd of warp / fused backward of the training loss.  gradient_kernel.  hwc_split_kernel
+// (dataset ingest) and upsample_flow_kernel (RAFT's convex upsampling) are the steps either side of the path.
+// HBM-bound fp32 streaming + gather: no tensor cores, nothing here is a contraction.
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
