@@ -405,6 +405,11 @@ def main():
     _, per = time_kernel(kernel_only, args.steps, 1)
     clocks = sampler.stop() if rank == 0 else None
     k_ms = sum(per) / len(per)
+    # the same kernel after a one-second pause: the first launches run before the 1000 W power cap pulls the SM clock
+    # down (what MEASURED_PEAKS' best-of-10 copy peak is: a burst figure).  Reported beside the sustained number.
+    time.sleep(1.0)
+    _, per_b = time_kernel(kernel_only, 3, 0)
+    burst_ms = min(per_b)
     if dist:
         t = torch.tensor([k_ms], device=device, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -446,7 +451,11 @@ def main():
                      "traffic": load_traffic(args.workload, n_local), "peak_source": peak_src,
                      "kernel": "tcl::fused_forward_ws_kernel<float, MASK_COMPUTED, reduce, C=3, lean> (+ fold_partials_kernel, <0.1 % of the time)",
                      "kernel_ms_per_launch": k_ms, "algorithmic_bytes_per_launch": alg_bytes, "bytes_per_px": bpp,
-                     "frac_of_nominal_8TBs": achieved / 8000.0},
+                     "frac_of_nominal_8TBs": achieved / 8000.0,
+                     "burst": {"kernel_ms_per_launch": burst_ms, "achieved": alg_bytes / (burst_ms / 1e3) / 1e9,
+                               "frac": alg_bytes / (burst_ms / 1e3) / 1e9 / peak,
+                               "note": "best of 3 launches after a 1 s pause (before the power cap lowers the SM clock); "
+                                       "`achieved` / `frac` above are the back-to-back (power-capped) figures"}},
         "clocks": clocks,
     }
     if clocks is not None and probe_steps:
