@@ -252,7 +252,10 @@ __device__ __forceinline__ unsigned long long gtime() { unsigned long long t; as
 #else
 #define TCL_STAMP(k, slot) do { } while (0)
 #endif
-constexpr int kCWarps = 16;                      // consumer warps
+#ifndef TCL_CWARPS
+#define TCL_CWARPS 16
+#endif
+constexpr int kCWarps = TCL_CWARPS;              // consumer warps
 constexpr int kWsThreads = 32 * (kCWarps + 1);   // + 1 producer warp
 
 template <typename FrameT, int CT, int TW_, int TH_, int BH_, int NB_, int NS_, int G_>

@@ -17,8 +17,9 @@ del chunks
 px = pairs * cfg["H"] * cfg["W"]
 fn = lambda: tcl.fused_forward(bf, prev, cur, ff=ff)
 for _ in range(3):
-    fn()
+    r = fn()
 torch.cuda.synchronize()
+check = float(r.total_val)
 a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 a.record()
 for _ in range(20):
@@ -47,4 +48,4 @@ t1 = time.time(); stop.set()
 ms = a.elapsed_time(b) / n
 sel = [s for (t, s) in samples if t0 + 1.0 < t < t1]
 clk = [float(s.split(",")[0]) for s in sel]; pw = [float(s.split(",")[1]) for s in sel]
-print(f"burst {px/burst/1e6:6.1f} Gpix/s | sustained {px/ms/1e6:6.1f} Gpix/s  sm {sum(clk)/max(len(clk),1):5.0f} MHz {sum(pw)/max(len(pw),1):5.0f} W  [{os.path.basename(os.environ.get('TCL_B200_LIB','default'))}]", flush=True)
+print(f"burst {px/burst/1e6:6.1f} Gpix/s | sustained {px/ms/1e6:6.1f} Gpix/s  sm {sum(clk)/max(len(clk),1):5.0f} MHz {sum(pw)/max(len(pw),1):5.0f} W  rmse {check:.9f}  [{os.path.basename(os.environ.get('TCL_B200_LIB','default'))}]", flush=True)

@@ -8,6 +8,8 @@ CSRC = os.path.join(ROOT, "gan-based-video-style-transfer_b200", "csrc")
 OUT = os.path.join(ROOT, "tools", "_sweep")
 VARIANTS = {
     "hot": {"TCL_HOT_ONLY": 1},
+    "hot_w12_th24_ns3": {"TCL_HOT_ONLY": 1, "TCL_CWARPS": 12, "TCL_TH": 24, "TCL_BH": 30, "TCL_NS": 3, "TCL_NB": 5},
+    "hot_w12_th24_ns2": {"TCL_HOT_ONLY": 1, "TCL_CWARPS": 12, "TCL_TH": 24, "TCL_BH": 32, "TCL_NS": 2, "TCL_NB": 4},
     "hot_hint500": {"TCL_HOT_ONLY": 1, "TCL_WAIT_HINT_NS": 500},
     "hot_hint2000": {"TCL_HOT_ONLY": 1, "TCL_WAIT_HINT_NS": 2000},
     "hot_bh38": {"TCL_HOT_ONLY": 1, "TCL_BH": 38},
