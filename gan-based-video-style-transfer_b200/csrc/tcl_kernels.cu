@@ -975,7 +975,10 @@ struct BwdParams {
 // CT > 0 fixes the channel count at compile time: all 4*CT gathers and the CT `cur` / grad_out loads of a pixel are then
 // issued back to back (the kernel is latency-bound otherwise: measured 10 long-scoreboard stall cycles per issue).
 template <bool FUSED_LOSS, int CT>
-__global__ void __launch_bounds__(256) warp_backward_kernel(const BwdParams p) {
+#ifndef TCL_BWD_MINB
+#define TCL_BWD_MINB 5   // measured: 5 CTAs per SM (48 registers) beats 4 (59) and 6 (40, spills)
+#endif
+__global__ void __launch_bounds__(256, TCL_BWD_MINB) warp_backward_kernel(const BwdParams p) {
   const Geo& g = p.geo;
   const int W = g.W, H = g.H, C = CT > 0 ? CT : p.C;
   const size_t plane = (size_t)H * W;
