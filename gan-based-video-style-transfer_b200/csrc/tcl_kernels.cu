@@ -147,8 +147,8 @@ __device__ __forceinline__ void finish_pixel(const FwdParams& p, const PixTaps& 
   for (int c = 0; c < C; ++c) {
     float w = psrc.sample(c, s);
     if (validity) w = __fmul_rn(w, valid);
-    if (!LEAN && io.wout) st_stream(io.wout + (size_t)c * plane + o, w);
-    if (LEAN || io.cur) {
+    if ((!LEAN || MASK == MASK_NONE) && io.wout) st_stream(io.wout + (size_t)c * plane + o, w);   // (LEAN + MASK_NONE = warp only)
+    if ((LEAN && MASK != MASK_NONE) || (!LEAN && io.cur)) {
       const float x = cv ? cv[c] : ld_stream(io.cur + (size_t)c * plane + o);
       if (REDUCE) {
         if (LEAN == 1 || (!LEAN && p.loss == TCLB200_L2)) {   // LEAN: 1 = L2, 2 = L1 fixed at compile time
@@ -628,6 +628,11 @@ __device__ __forceinline__ float lean_tile(const FwdParams& p, const float* s_bu
 #pragma unroll
     for (int ch = 0; ch < CT; ++ch) {
       const float w = tap4(MIXED ? pp + ch * ps : pp + ch * PL);
+      if (MASK == MASK_NONE) {   // warp() on its own: store the warped frame (two coalesced row segments per warp instruction)
+        if (inside)
+          st_stream(reinterpret_cast<FrameT*>(p.warp_out) + ((size_t)t.pair * 3 + ch) * gplane + (size_t)(t.y0 + ly0 + dyk) * g.W + (t.x0 + lx0 + dxk), w);
+        continue;
+      }
       const float d = __fsub_rn(cur[k][ch], w);
       acc = LOSS == TCLB200_L1 ? __fadd_rn(acc, fabsf(d)) : __fmaf_rn(d, d, acc);   // mask*|warp - cur| (MoGAN :281) / (mask*(cur - warp))^2
     }
@@ -744,7 +749,7 @@ __global__ void __launch_bounds__(kWsThreads, 1) fused_forward_ws_kernel(const F
       mbar_expect_tx(&ctl->bf_full[s], Cfg::kBfLoad);
       tma_load_4d(bf_stage(s), &tm_bf, &ctl->bf_full[s], t.x0 - Cfg::kHaloX, t.y0 - 1, 0, t.pair);
       // the consumers read this tile's `cur` values straight from global memory NB tiles from now: have them in L2 by then
-      if (LEAN && CT > 0) tma_prefetch_l2_4d(&tm_cur, t.x0, t.y0, 0, t.cf);
+      if (LEAN && CT > 0 && p.cur != nullptr) tma_prefetch_l2_4d(&tm_cur, t.x0, t.y0, 0, t.cf);
     };
     // lane 0: the consumers have folded the extent of x+u, y+v over local tile k into box[k % NB] -> origin of the source
     // boxes.  The coordinate map is monotone in x+u (every step is a correctly rounded monotone operation), so the
@@ -872,7 +877,7 @@ __global__ void __launch_bounds__(kWsThreads, 1) fused_forward_ws_kernel(const F
     // this tile's `cur` (and dataset mask) values: coalesced 64-byte row segments, streaming; requested before the wait
     // for the source boxes and first used at the very end of the per-pixel work
     float cur[P][Cfg::kC], mk[P];
-    const bool have_cur = CT > 0 && (LEAN || p.cur != nullptr);
+    const bool have_cur = CT > 0 && p.cur != nullptr;
     {
       const size_t pix = (size_t)(t.y0 * g.W + t.x0) + lane_off;
       const FrameT* cb = reinterpret_cast<const FrameT*>(p.cur) + (size_t)t.cf * Cfg::kC * plane + pix;
@@ -1303,6 +1308,7 @@ static cudaError_t dispatch(const FwdParams& p, int mask_kind, bool reduce, bool
     if (p.C == 3 && lean && RD) return p.loss == TCLB200_L1 ? launch_tma<FrameT, MK, true, 3, 2>(p, tb, tf, tp, tc, s)   \
                                                             : launch_tma<FrameT, MK, true, 3, 1>(p, tb, tf, tp, tc, s);  \
     if (MK == MASK_COMPUTED && !RD && lean_mask) return launch_tma<float, MASK_COMPUTED, false, 0, 1>(p, tb, tf, tp, tc, s); \
+    if (MK == MASK_NONE && !RD && lean_warp) return launch_tma<FrameT, MASK_NONE, false, 3, 1>(p, tb, tf, tp, tc, s); \
     return p.C == 3 ? launch_tma<FrameT, MK, RD, 3, 0>(p, tb, tf, tp, tc, s) : launch_tma<FrameT, MK, RD, 0, 0>(p, tb, tf, tp, tc, s); \
   }
   // LEAN = the measured hot configurations, fixed at compile time: computeTCL / training loss with C == 3
@@ -1312,6 +1318,9 @@ static cudaError_t dispatch(const FwdParams& p, int mask_kind, bool reduce, bool
   // ... and fbcCheckTorch on its own: both tests, mask_out only
   const bool lean_mask = !reduce && !p.prev && p.mask_out && !p.near_threshold && mask_kind == MASK_COMPUTED &&
                          (p.flags & (TCLB200_OCC | TCLB200_MOB)) == (TCLB200_OCC | TCLB200_MOB);
+  // ... and warp() on its own (C == 3, no validity mask): warp_out only
+  const bool lean_warp = !reduce && p.prev && p.C == 3 && !p.cur && p.warp_out && !p.mask_out && !p.blend_out && mask_kind == MASK_NONE &&
+                         !(p.flags & TCLB200_VALIDITY);
   TCL_CASE(MASK_COMPUTED, true)
   TCL_CASE(MASK_COMPUTED, false)
   TCL_CASE(MASK_GIVEN, true)
