@@ -143,12 +143,16 @@ def temporal_error(ff, bf, prev, cur):
 
 
 def upsample_flow(flow, mask):
-    """``RAFT.upsample_flow`` op for op (utils/raft/raft/raft.py:72-83)."""
-    N, _, H, W = flow.shape
-    mask = mask.view(N, 1, 9, 8, 8, H, W)
-    mask = torch.softmax(mask, dim=2)
-    up_flow = F.unfold(8 * flow, [3, 3], padding=1)
-    up_flow = up_flow.view(N, 2, 9, 1, 1, H, W)
-    up_flow = torch.sum(mask * up_flow, dim=2)
-    up_flow = up_flow.permute(0, 1, 4, 2, 5, 3)
-    return up_flow.reshape(N, 2, 8 * H, 8 * W)
+    """Convex 8x upsampling of a coarse flow as RAFT defines it (utils/raft/raft/raft.py:72-83): per fine pixel a
+    softmax over 9 logits weights the zero-padded 3x3 coarse neighbourhood of 8*flow.  Written with explicit
+    neighbour shifts instead of unfold; same arithmetic up to summation order."""
+    n, _, hc, wc = flow.shape
+    weights = torch.softmax(mask.reshape(n, 9, 64, hc, wc), dim=1)          # (n, neighbour, 8*8 sub-pixel, h, w)
+    padded = F.pad(8.0 * flow, (1, 1, 1, 1))                                # zero border, like unfold(padding=1)
+    fine = torch.zeros(n, 2, 64, hc, wc, dtype=flow.dtype, device=flow.device)
+    for k in range(9):
+        dy, dx = divmod(k, 3)
+        neighbour = padded[:, :, dy:dy + hc, dx:dx + wc]                     # coarse flow at (h + dy - 1, w + dx - 1)
+        fine = fine + weights[:, k].unsqueeze(1) * neighbour.unsqueeze(2)
+    fine = fine.reshape(n, 2, 8, 8, hc, wc).permute(0, 1, 4, 2, 5, 3)       # (n, 2, h, i, w, j)
+    return fine.reshape(n, 2, 8 * hc, 8 * wc)

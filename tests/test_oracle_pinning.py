@@ -166,3 +166,28 @@ def test_cuda_and_cpu_flavours_differ_only_at_ulp_level(oracle_mod, tcl):
     ma = oracle_mod.fbcheck(ff.numpy(), bf.numpy(), variant=oracle_mod.ATEN_CPU)
     mb = oracle_mod.fbcheck(ff.numpy(), bf.numpy(), variant=oracle_mod.ATEN_CUDA)
     assert (ma != mb).mean() < 1e-3
+
+
+def test_upsample_restatement_matches_reference_raft():
+    """oracle/torch_port.upsample_flow against the reference's own RAFT.upsample_flow (imported by path, CPU)."""
+    import os
+    import sys
+    import torch
+    from conftest import REFERENCE_ROOT
+    raft_dir = os.path.join(REFERENCE_ROOT, "utils", "raft", "raft")
+    if not os.path.isdir(raft_dir):
+        pytest.skip("reference checkout not present (GPU box)")
+    sys.path.insert(0, raft_dir)
+    try:
+        import raft as ref_raft
+    except Exception as ex:   # the vendored RAFT has path-dependent imports
+        pytest.skip(f"reference RAFT not importable here: {ex!r}")
+    from oracle import torch_port as tp
+    g = torch.Generator().manual_seed(7)
+    for (n, h, w) in [(1, 6, 7), (2, 9, 11), (1, 55, 128)]:
+        flow = torch.randn(n, 2, h, w, generator=g) * 5
+        mask = torch.randn(n, 576, h, w, generator=g) * 3
+        want = ref_raft.RAFT.upsample_flow(None, flow, mask)     # utils/raft/raft/raft.py:72-83
+        got = tp.upsample_flow(flow, mask)
+        assert got.shape == want.shape
+        assert torch.allclose(got, want, rtol=1e-6, atol=1e-6)
