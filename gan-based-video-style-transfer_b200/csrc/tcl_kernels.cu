@@ -139,7 +139,7 @@ __device__ __forceinline__ void finish_pixel(const FwdParams& p, const PixTaps& 
   }
   if ((!LEAN || CT == 0) && p.mask_out) __stcs(p.mask_out + (size_t)pair * plane + o, keep);
   if (p.prev == nullptr) return;
-  const bool validity = !LEAN && (p.flags & TCLB200_VALIDITY);
+  const bool validity = (!LEAN || MASK == MASK_NONE) && (p.flags & TCLB200_VALIDITY);
   float valid = 1.0f;
   if (validity) valid = binarise_validity(ones_sample(full_taps(s, p.geo), kV));
   const int C = CT > 0 ? CT : p.C;
@@ -556,6 +556,7 @@ __device__ __forceinline__ float lean_tile(const FwdParams& p, const float* s_bu
   constexpr int DY = Cfg::WPG;   // pixel k of this lane: 16 columns right of pixel k-1 (k odd) / WPG rows below pixel k-2
   const float xs[2] = {(float)(t.x0 + lx0), (float)(t.x0 + lx0 + 16)}, ys[2] = {(float)(t.y0 + ly0), (float)(t.y0 + ly0 + DY)};
   const int c0 = (ly0 + 1) * BFW + lx0 + Cfg::kHaloX;
+  const bool validity = MASK == MASK_NONE && (p.flags & TCLB200_VALIDITY);
   float e[P];
   unsigned keepbits = 0, ambbits = 0, outbits = 0;
 #pragma unroll
@@ -625,12 +626,23 @@ __device__ __forceinline__ float lean_tile(const FwdParams& p, const float* s_bu
       amb = amb || !(occ || L < Rlo);
     }
     float acc = 0.0f;
+    float valid = 1.0f;
+    if (MASK == MASK_NONE && validity) {   // fs_lib.warp: times the binarised warp of an all-ones image (fs_lib.py:29-37)
+      const int gx = (int)tp.rx + box_x, gy = (int)tp.ry + box_y;
+      Taps vt;
+      const bool xin0 = (unsigned)gx < (unsigned)g.W, xin1 = (unsigned)(gx + 1) < (unsigned)g.W;
+      const bool yin0 = (unsigned)gy < (unsigned)g.H, yin1 = (unsigned)(gy + 1) < (unsigned)g.H;
+      vt.p00 = xin0 && yin0; vt.p10 = xin1 && yin0; vt.p01 = xin0 && yin1; vt.p11 = xin1 && yin1;
+      vt.nw = tp.nw; vt.ne = tp.ne; vt.sw = tp.sw; vt.se = tp.se; vt.o00 = 0;
+      valid = binarise_validity(ones_sample(vt, kV));
+    }
 #pragma unroll
     for (int ch = 0; ch < CT; ++ch) {
       const float w = tap4(MIXED ? pp + ch * ps : pp + ch * PL);
       if (MASK == MASK_NONE) {   // warp() on its own: store the warped frame (two coalesced row segments per warp instruction)
         if (inside)
-          st_stream(reinterpret_cast<FrameT*>(p.warp_out) + ((size_t)t.pair * 3 + ch) * gplane + (size_t)(t.y0 + ly0 + dyk) * g.W + (t.x0 + lx0 + dxk), w);
+          st_stream(reinterpret_cast<FrameT*>(p.warp_out) + ((size_t)t.pair * 3 + ch) * gplane + (size_t)(t.y0 + ly0 + dyk) * g.W + (t.x0 + lx0 + dxk),
+                    validity ? __fmul_rn(w, valid) : w);
         continue;
       }
       const float d = __fsub_rn(cur[k][ch], w);
@@ -1319,8 +1331,7 @@ static cudaError_t dispatch(const FwdParams& p, int mask_kind, bool reduce, bool
   const bool lean_mask = !reduce && !p.prev && p.mask_out && !p.near_threshold && mask_kind == MASK_COMPUTED &&
                          (p.flags & (TCLB200_OCC | TCLB200_MOB)) == (TCLB200_OCC | TCLB200_MOB);
   // ... and warp() on its own (C == 3, no validity mask): warp_out only
-  const bool lean_warp = !reduce && p.prev && p.C == 3 && !p.cur && p.warp_out && !p.mask_out && !p.blend_out && mask_kind == MASK_NONE &&
-                         !(p.flags & TCLB200_VALIDITY);
+  const bool lean_warp = !reduce && p.prev && p.C == 3 && !p.cur && p.warp_out && !p.mask_out && !p.blend_out && mask_kind == MASK_NONE;
   TCL_CASE(MASK_COMPUTED, true)
   TCL_CASE(MASK_COMPUTED, false)
   TCL_CASE(MASK_GIVEN, true)
