@@ -12,7 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.environ.get("TCL_B200_LIB") or os.path.join(CSRC, "libtcl_b200.so")  # env override: tuning sweeps only
 HEADER = os.path.join(os.path.dirname(_HERE), "include", "tcl_b200.h")
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 # enums mirrored from include/tcl_b200.h
 F32, BF16 = 0, 1
@@ -22,7 +22,7 @@ FIN_MEAN, FIN_RMSE = 0, 1
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
-SOURCES = ["tcl_kernels.cu"]
+SOURCES = ["tcl_kernels.cu", "tcl_host.cu"]
 HEADERS = ["tcl_math.cuh", "tcl_common.cuh"]
 
 
@@ -40,6 +40,19 @@ class TclArgs(ctypes.Structure):
         ("dtype", ctypes.c_int), ("flags", ctypes.c_int), ("loss", ctypes.c_int), ("finalize", ctypes.c_int),
         ("prev_index", ctypes.c_void_p), ("cur_index", ctypes.c_void_p),
         ("n_prev_frames", ctypes.c_int), ("n_cur_frames", ctypes.c_int),
+    ]
+
+
+class HostArgs(ctypes.Structure):
+    """``tclb200_host_args`` (include/tcl_b200.h): every pointer is a HOST pointer except ``workspace``."""
+    _fields_ = [
+        ("ff", ctypes.c_void_p), ("bf", ctypes.c_void_p), ("mask_in", ctypes.c_void_p), ("frames", ctypes.c_void_p),
+        ("prev_index", ctypes.c_void_p), ("cur_index", ctypes.c_void_p),
+        ("pair_vals", ctypes.c_void_p), ("pair_sums", ctypes.c_void_p),
+        ("workspace", ctypes.c_void_p), ("workspace_bytes", ctypes.c_size_t),
+        ("P", ctypes.c_int), ("F", ctypes.c_int), ("C", ctypes.c_int), ("H", ctypes.c_int), ("W", ctypes.c_int),
+        ("dtype", ctypes.c_int), ("flags", ctypes.c_int), ("loss", ctypes.c_int), ("finalize", ctypes.c_int),
+        ("chunk_pairs", ctypes.c_int),
     ]
 
 
@@ -66,6 +79,8 @@ _PROTOTYPES = {
     "tclb200_warp_backward": (_c.c_int, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "tclb200_fbcheck": (_c.c_int, [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp]),
     "tclb200_tcl_forward": (_c.c_int, [_c.POINTER(TclArgs), _vp]),
+    "tclb200_host_workspace_bytes": (_c.c_size_t, [_i, _i, _i, _i, _i, _i, _i, _i]),
+    "tclb200_tcl_forward_host": (_c.c_int, [_c.POINTER(HostArgs), _vp]),
     "tclb200_tcl_backward": (_c.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     "tclb200_hwc_split": (_c.c_int, [_vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "tclb200_upsample_flow": (_c.c_int, [_vp, _vp, _vp, _i, _i, _i, _vp]),

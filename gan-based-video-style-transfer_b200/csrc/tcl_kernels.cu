@@ -1197,6 +1197,8 @@ using namespace tcl;
 static thread_local char g_err[512] = "";
 static unsigned long long g_launches = 0;   // kernels of this library launched by this process (diagnostics / bench.py)
 
+namespace tcl { void set_last_error(const char* msg) { snprintf(g_err, sizeof(g_err), "%s", msg); } }   // for tcl_host.cu
+
 static int fail(int code, const char* fmt, const char* detail = "") {
   snprintf(g_err, sizeof(g_err), fmt, detail);
   return code;

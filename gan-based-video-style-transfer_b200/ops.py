@@ -12,6 +12,7 @@ it replaces (upstream paths relative to the repository root):
 * ``temporal_loss(...)``                  StarGANv2AdvCon/core/solver.py:427-446, fs_ruder.py:97, MoGAN ...:280-281
 * ``temporal_rmse_per_sample(...)``       utils/metrics/eval.py:137-138
 * ``warp_blend(...)``                     methods/optimization-based/obst_eval.py:500
+* ``temporal_error_host(...)``            the evaluation loop of utils/sintel_eval.py:206-222 with HOST tensors in and out
 
 PyTorch is used for device memory, streams and autograd plumbing only; all arithmetic runs in
 ``csrc/tcl_kernels.cu``.  There is no CPU path: CPU tensors raise, like the reference's hard-coded
@@ -22,7 +23,7 @@ import ctypes
 import torch
 
 from . import _cabi
-from ._cabi import BF16, F32, FIN_MEAN, FIN_RMSE, L1, L2, MOB, OCC, VALIDITY, TclArgs, check
+from ._cabi import BF16, F32, FIN_MEAN, FIN_RMSE, L1, L2, MOB, OCC, VALIDITY, HostArgs, TclArgs, check
 
 _scratch_cache = {}
 
@@ -314,6 +315,81 @@ def temporal_error_clip(frames, ff, bf):
     idx = torch.arange(T, dtype=torch.int32, device=frames.device)
     return fused_forward(bf, frames, frames, ff=ff, finalize=FIN_RMSE, prev_index=idx[:-1], cur_index=idx[1:],
                          validate_index=False).pair_vals
+
+
+_host_ws_cache = {}
+
+
+def _host_tensor(t, name, dtype=None):
+    if t is None:
+        return None
+    if t.is_cuda:
+        raise RuntimeError(f"tcl_b200: {name} must be a host (CPU) tensor for the host-buffer entry")
+    if dtype is not None and t.dtype != dtype:
+        t = t.to(dtype)
+    return t.contiguous()
+
+
+def temporal_error_host(frames, ff, bf, prev_index=None, cur_index=None, mask=None, loss=L2, finalize=FIN_RMSE,
+                        flags=OCC | MOB, chunk_pairs=0, device=None, sync=True):
+    """The evaluation loop of utils/sintel_eval.py:206-222 (and solver.py:336-347) on HOST tensors.
+
+    ``frames`` (F,C,H,W) fp32/bf16: the stylised frames of one or more clips, each stored once; ``ff`` / ``bf``
+    (P,2,H,W) fp32; pair p warps ``frames[prev_index[p]]`` by ``bf[p]`` and compares with ``frames[cur_index[p]]``
+    under the mask of (``ff[p]``, ``bf[p]``) -- or under ``mask[p]`` (P,1,H,W) when ``ff`` is None
+    (utils/metrics/eval.py:137-138).  Default indices: the consecutive pairs of ONE clip (P = F-1).
+    All tensors are CPU tensors (pinned memory runs at PCIe speed); the result is a pinned CPU tensor (P,) of per-pair
+    values per ``finalize``.  One C-ABI call (``tclb200_tcl_forward_host``) pipelines H2D copies and fused launches
+    on ``device`` (default: the current CUDA device); there is no CPU arithmetic anywhere.
+    """
+    if not torch.cuda.is_available():
+        raise RuntimeError("tcl_b200: temporal_error_host needs a CUDA device; this path has no CPU implementation")
+    frames = _host_tensor(frames, "frames")
+    dt = _frame_dtype(frames)
+    bf = _host_tensor(bf, "bf", torch.float32)
+    ff = _host_tensor(ff, "ff", torch.float32)
+    mask = _host_tensor(mask, "mask", torch.float32) if ff is None else None
+    if frames.dim() != 4 or bf.dim() != 4 or bf.shape[1] != 2 or bf.shape[2:] != frames.shape[2:]:
+        raise RuntimeError(f"tcl_b200: frames {tuple(frames.shape)} / bf {tuple(bf.shape)} must be (F,C,H,W) / (P,2,H,W)")
+    F_, C, H, W = frames.shape
+    P = bf.shape[0]
+    if ff is not None and ff.shape != bf.shape:
+        raise RuntimeError(f"tcl_b200: ff {tuple(ff.shape)} and bf {tuple(bf.shape)} do not match")
+    if mask is not None and tuple(mask.shape) != (P, 1, H, W):
+        raise RuntimeError(f"tcl_b200: mask must be (P,1,H,W), got {tuple(mask.shape)}")
+    if prev_index is None and cur_index is None:
+        if P != F_ - 1:
+            raise RuntimeError(f"tcl_b200: a clip of {F_} frames has {F_ - 1} consecutive pairs, got {P} flows")
+        idx = torch.arange(F_, dtype=torch.int32)
+        prev_index, cur_index = idx[:-1], idx[1:]
+    prev_index = _host_tensor(prev_index, "prev_index", torch.int32)
+    cur_index = _host_tensor(cur_index, "cur_index", torch.int32)
+    if prev_index.numel() != P or cur_index.numel() != P:
+        raise RuntimeError(f"tcl_b200: prev_index / cur_index must hold one frame index per pair ({P})")
+    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    lib = _cabi.lib()
+    need = lib.tclb200_host_workspace_bytes(P, F_, C, H, W, dt, chunk_pairs, 1 if mask is not None else 0)
+    ws = _host_ws_cache.get(dev.index)
+    if ws is None or ws.numel() < need:
+        _host_ws_cache.pop(dev.index, None)
+        ws = torch.empty(need, dtype=torch.uint8, device=dev)
+        _host_ws_cache[dev.index] = ws
+    out = torch.empty(P, dtype=torch.float32, pin_memory=True)
+    a = HostArgs()
+    a.ff, a.bf, a.mask_in, a.frames = _ptr(ff), _ptr(bf), _ptr(mask), _ptr(frames)
+    a.prev_index, a.cur_index = _ptr(prev_index), _ptr(cur_index)
+    a.pair_vals, a.pair_sums = _ptr(out), None
+    a.workspace, a.workspace_bytes = _ptr(ws), ws.numel()
+    a.P, a.F, a.C, a.H, a.W = P, F_, C, H, W
+    a.dtype, a.flags, a.loss, a.finalize, a.chunk_pairs = dt, flags, loss, finalize, chunk_pairs
+    with torch.cuda.device(dev):
+        stream = torch.cuda.current_stream()
+        check(lib.tclb200_tcl_forward_host(ctypes.byref(a), ctypes.c_void_p(stream.cuda_stream)))
+        if sync:
+            stream.synchronize()
+        else:   # the caller synchronises the stream; keep the host inputs alive until then
+            out._tcl_keepalive = (frames, ff, bf, mask, prev_index, cur_index)
+    return out
 
 
 def temporal_rmse_per_sample(mask, cur, prev, flow):

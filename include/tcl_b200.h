@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define TCLB200_ABI_VERSION 2
+#define TCLB200_ABI_VERSION 3
 
 #define TCLB200_OK 0
 #define TCLB200_ERR_INVALID 1     /* bad argument (null pointer, non-positive size, unknown enum) */
@@ -128,6 +128,34 @@ typedef struct tclb200_tcl_args {
 } tclb200_tcl_args;
 
 int tclb200_tcl_forward(const tclb200_tcl_args* args, tclb200_stream_t stream);
+
+/* Host-buffer entry: the job of the reference's evaluation loops with the data where those loops hold it -- in HOST
+ * memory (utils/sintel_eval.py:206-222 and StarGANv2AdvCon/core/solver.py:336-347 walk a clip frame by frame and pull
+ * every pair's value back with .cpu().numpy(); utils/metrics/eval.py:137-149 does the same per FC2 batch).
+ * All pointers below are HOST pointers except `workspace` (page-locked memory gives full PCIe speed; pageable works).
+ * The call enqueues a software pipeline -- chunks of `chunk_pairs` pairs: H2D of the frames the chunk needs that are
+ * not on the device yet (each frame of the bank crosses PCIe once), H2D of its flows into a 3-slot ring on an internal
+ * copy stream, one fused launch (clip mode of tclb200_tcl_forward) per chunk on `stream`, one D2H of the per-pair
+ * results at the end -- and returns; pair_vals / pair_sums are valid once `stream` has been synchronised, and the host
+ * inputs must stay untouched until then. */
+typedef struct tclb200_host_args {
+  const float* ff;       /* (P,2,H,W) forward flows, or NULL (then mask_in or no mask) */
+  const float* bf;       /* (P,2,H,W) flows the warp samples with; required */
+  const float* mask_in;  /* (P,1,H,W) dataset masks, or NULL; ignored when ff is given */
+  const void* frames;    /* (F,C,H,W) `dtype`: the stylised frames, each stored once */
+  const int* prev_index; /* [P] frame warped by pair p's flow, in [0,F) */
+  const int* cur_index;  /* [P] frame pair p is compared with */
+  float* pair_vals;      /* [P] out, per `finalize`; or NULL */
+  double* pair_sums;     /* [P] out, S_p; or NULL */
+  void* workspace;       /* DEVICE memory, 256-byte aligned, >= tclb200_host_workspace_bytes(...) */
+  size_t workspace_bytes;
+  int P, F, C, H, W;
+  int dtype, flags, loss, finalize; /* as in tclb200_tcl_args */
+  int chunk_pairs;       /* pairs per launch, 0 = 32 */
+} tclb200_host_args;
+
+size_t tclb200_host_workspace_bytes(int P, int F, int C, int H, int W, int dtype, int chunk_pairs, int with_mask);
+int tclb200_tcl_forward_host(const tclb200_host_args* args, tclb200_stream_t stream);
 
 /* Backward of the fused training loss  L = grad_scale * sum (m*(cur-warp(prev,bf)))^2   (L2)
  *                                   or L = grad_scale * sum  m*|warp(prev,bf)-cur|      (L1)

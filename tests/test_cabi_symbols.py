@@ -40,9 +40,10 @@ def test_header_version_matches_wrappers(tcl):
         assert int(re.search(rf"#define TCLB200_{name} (\d+)", text).group(1)) == getattr(tcl._cabi, name)
 
 
-def test_struct_layout_matches_header(tcl):
+@pytest.mark.parametrize("struct,mirror", [("tclb200_tcl_args", "TclArgs"), ("tclb200_host_args", "HostArgs")])
+def test_struct_layout_matches_header(tcl, struct, mirror):
     text = open(os.path.join(ROOT, "include", "tcl_b200.h")).read()
-    body = re.search(r"typedef struct tclb200_tcl_args \{(.*?)\} tclb200_tcl_args;", text, re.S).group(1)
+    body = re.search(r"typedef struct %s \{(.*?)\} %s;" % (struct, struct), text, re.S).group(1)
     body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
     fields = []
     for decl in body.split(";"):
@@ -53,7 +54,7 @@ def test_struct_layout_matches_header(tcl):
         first = re.findall(r"[A-Za-z_][A-Za-z0-9_]*", names[0])[-1]
         fields.append(first)
         fields += [n.strip().lstrip("*").strip() for n in names[1:]]
-    assert fields == [f[0] for f in tcl._cabi.TclArgs._fields_]
+    assert fields == [f[0] for f in getattr(tcl._cabi, mirror)._fields_]
 
 
 def test_argument_validation_without_gpu(tcl):
@@ -71,6 +72,31 @@ def test_argument_validation_without_gpu(tcl):
     a.H = 4
     assert lib.tclb200_tcl_forward(ctypes.byref(a), None) == 1           # bf missing
     assert b"bf" in lib.tclb200_last_error()
+
+
+def test_host_entry_validation_without_gpu(tcl):
+    import numpy as np
+    lib = tcl._cabi.lib()
+    assert lib.tclb200_host_workspace_bytes(0, 2, 3, 8, 8, 0, 0, 0) == 0
+    small = lib.tclb200_host_workspace_bytes(4, 5, 3, 64, 64, 0, 0, 0)
+    # frame bank + 3 ring slots of two flows each, at least
+    assert small >= 5 * 3 * 64 * 64 * 4 + 3 * 2 * 4 * 2 * 64 * 64 * 4
+    assert lib.tclb200_host_workspace_bytes(4, 5, 3, 64, 64, 0, 0, 1) > small          # + dataset-mask ring
+    assert lib.tclb200_host_workspace_bytes(4, 5, 3, 64, 64, 1, 0, 0) < small          # bf16 frame bank
+    assert lib.tclb200_tcl_forward_host(None, None) == 1
+    a = tcl._cabi.HostArgs()
+    a.P, a.F, a.C, a.H, a.W = 1, 2, 3, 8, 8
+    assert lib.tclb200_tcl_forward_host(ctypes.byref(a), None) == 1           # bf / frames / indices missing
+    assert b"required" in lib.tclb200_last_error()
+    bf = np.zeros((1, 2, 8, 8), np.float32); fr = np.zeros((2, 3, 8, 8), np.float32)
+    pi = np.array([0], np.int32); ci = np.array([2], np.int32); out = np.zeros(1, np.float32)
+    a.bf, a.frames, a.prev_index, a.cur_index, a.pair_vals = (bf.ctypes.data, fr.ctypes.data, pi.ctypes.data, ci.ctypes.data,
+                                                              out.ctypes.data)
+    assert lib.tclb200_tcl_forward_host(ctypes.byref(a), None) == 1           # cur_index outside [0, F)
+    assert b"outside" in lib.tclb200_last_error()
+    ci[0] = 1
+    assert lib.tclb200_tcl_forward_host(ctypes.byref(a), None) == 1           # no workspace
+    assert b"workspace" in lib.tclb200_last_error()
 
 
 def test_missing_library_fails_loudly(tcl, monkeypatch):

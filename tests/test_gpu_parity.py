@@ -471,6 +471,48 @@ def test_clip_mode_equals_pairwise(tcl, force_generic, T, H, W):
         tcl.fused_forward(bf, frames, frames, ff=ff, prev_index=torch.full((T - 1,), T, device=d), cur_index=idx_cur[:1].repeat(T - 1))
 
 
+# ------------------------------------------------------------------ host-buffer entry (the e2e path of bench.py)
+@pytest.mark.gpu
+@pytest.mark.parametrize("clips,H,W,chunk,dtype", [([5], 96, 256, 0, torch.float32), ([4, 7, 3], 436, 1024, 4, torch.float32),
+                                                   ([9], 37, 53, 2, torch.float32), ([6, 2], 128, 192, 3, torch.bfloat16)])
+def test_host_entry_equals_device_path(tcl, oracle_mod, clips, H, W, chunk, dtype):
+    """tclb200_tcl_forward_host (host tensors in, pipelined H2D + clip-mode launches, host values out) returns the
+    bits of the device-resident path, which the other tests tie to the oracle; one pair is checked against the oracle
+    directly as well."""
+    d = dev()
+    T = sum(clips)
+    P = T - len(clips)
+    ff, bf = tcl.synth.make_flows(P, H, W, seed=H + T, max_shift=10.0)
+    frames, _ = tcl.synth.make_frames(T, 3, H, W, seed=H + T, kind="white", dtype=dtype)
+    prev_i, cur_i, base = [], [], 0
+    for n in clips:
+        prev_i += list(range(base, base + n - 1)); cur_i += list(range(base + 1, base + n)); base += n
+    pi, ci = torch.tensor(prev_i, dtype=torch.int32), torch.tensor(cur_i, dtype=torch.int32)
+    pin = lambda t: t.pin_memory()
+    got = tcl.temporal_error_host(pin(frames), pin(ff), pin(bf), pi, ci, chunk_pairs=chunk)
+    assert got.device.type == "cpu" and got.shape == (P,)
+    fd = frames.to(d)
+    want = tcl.temporal_error_per_pair(ff.to(d), bf.to(d), fd[pi.long()].contiguous(), fd[ci.long()].contiguous()).cpu()
+    assert torch.equal(got, want)
+    # pageable inputs and a second call on the cached workspace give the same bits
+    assert torch.equal(tcl.temporal_error_host(frames, ff, bf, pi, ci, chunk_pairs=chunk), want)
+    if len(clips) == 1:   # default indices = the consecutive pairs of one clip
+        assert torch.equal(tcl.temporal_error_host(frames, ff, bf), want)
+    if dtype == torch.float32:
+        s = oracle_mod.temporal_error_sums(ff[:1].numpy(), bf[:1].numpy(), frames[pi[:1].long()].numpy(),
+                                           frames[ci[:1].long()].numpy(), variant=oracle_mod.ATEN_CUDA)
+        assert abs(float(got[0]) - float(np.sqrt(s[0] / (3 * H * W)))) <= LOSS_RTOL * float(got[0])
+    # dataset-mask variant (utils/metrics/eval.py:137-138) through the same entry
+    mask = tcl.fbcCheckTorch(ff.to(d), bf.to(d)).cpu()
+    got_m = tcl.temporal_error_host(frames, None, bf, pi, ci, mask=mask, chunk_pairs=chunk)
+    want_m = tcl.temporal_rmse_per_sample(mask.to(d), fd[ci.long()].contiguous(), fd[pi.long()].contiguous(), bf.to(d)).cpu()
+    assert torch.equal(got_m, want_m)
+    with pytest.raises(RuntimeError):
+        tcl.temporal_error_host(frames.to(d), ff, bf, pi, ci)          # device tensor where host memory is expected
+    with pytest.raises(RuntimeError):
+        tcl.temporal_error_host(frames, ff, bf, pi, ci + T)            # index outside the frame bank
+
+
 # ------------------------------------------------------------------ adversarial near-threshold inputs for the filtered mask tests
 def test_masks_bit_exact_on_near_threshold_flows(tcl):
     """The hot path decides the mask tests without the sqrt-then-square of torch.norm(.)**2 whenever lhs is outside
