@@ -22,7 +22,7 @@ FIN_MEAN, FIN_RMSE = 0, 1
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
-SOURCES = ["tcl_kernels.cu", "tcl_host.cu"]
+SOURCES = ["tcl_kernels.cu", "tcl_host.cu", "tcl_cv2.cu"]
 HEADERS = ["tcl_math.cuh", "tcl_common.cuh"]
 
 
@@ -57,14 +57,26 @@ class HostArgs(ctypes.Structure):
 
 
 def build(force=False, verbose=False):
-    """nvcc the kernels for sm_100a, in-tree (cross-compiles without a GPU)."""
-    srcs = [os.path.join(CSRC, s) for s in SOURCES]
-    deps = srcs + [os.path.join(CSRC, h) for h in HEADERS] + [HEADER]
-    if (not force and os.path.exists(LIB_PATH)
-            and all(os.path.getmtime(LIB_PATH) >= os.path.getmtime(d) for d in deps)):
-        return LIB_PATH
-    cmd = ["nvcc"] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_PATH] + srcs
-    subprocess.run(cmd, check=True, cwd=CSRC)
+    """nvcc the kernels for sm_100a, in-tree (cross-compiles without a GPU): one object per source (stale ones only,
+    compiled in parallel), then one link into ``libtcl_b200.so``."""
+    deps_common = [os.path.join(CSRC, h) for h in HEADERS] + [HEADER]
+    compile_flags = [f for f in NVCC_FLAGS if f != "-shared"]
+    objs, jobs = [], []
+    for src in SOURCES:
+        path = os.path.join(CSRC, src)
+        obj = os.path.join(CSRC, os.path.splitext(src)[0] + ".o")
+        objs.append(obj)
+        stale = (force or not os.path.exists(obj)
+                 or any(os.path.getmtime(obj) < os.path.getmtime(d) for d in [path] + deps_common))
+        if stale:
+            cmd = ["nvcc"] + compile_flags + (["-Xptxas", "-v"] if verbose else []) + ["-c", "-o", obj, path]
+            jobs.append((cmd, subprocess.Popen(cmd, cwd=CSRC)))
+    for cmd, proc in jobs:
+        if proc.wait() != 0:
+            raise subprocess.CalledProcessError(proc.returncode, cmd)
+    if jobs or not os.path.exists(LIB_PATH) or any(os.path.getmtime(LIB_PATH) < os.path.getmtime(o) for o in objs):
+        subprocess.run(["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", LIB_PATH] + objs,
+                       check=True, cwd=CSRC)
     return LIB_PATH
 
 
@@ -84,6 +96,8 @@ _PROTOTYPES = {
     "tclb200_tcl_backward": (_c.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     "tclb200_hwc_split": (_c.c_int, [_vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "tclb200_upsample_flow": (_c.c_int, [_vp, _vp, _vp, _i, _i, _i, _vp]),
+    "tclb200_cv2_remap": (_c.c_int, [_vp, _vp, _vp, _i, _i, _i, _i, _vp]),
+    "tclb200_cv2_fb_check": (_c.c_int, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp]),
     "tclb200_debug_force_generic": (None, [_i]),
     "tclb200_debug_tile_stats": (_c.c_int, [_vp, _i]),
     "tclb200_debug_launch_count": (_c.c_ulonglong, [_i]),

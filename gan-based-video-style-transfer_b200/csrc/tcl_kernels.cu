@@ -478,7 +478,7 @@ __device__ __forceinline__ LeanTaps lean_taps(float xf, float yf, float u, float
 }
 
 // exact mask verdict of one pixel of a staged tile (the rare replay of lean_tile)
-template <typename Cfg>
+template <typename Cfg, bool OCC>
 __device__ __noinline__ bool exact_keep(const float* s_bu, const float* s_ff, int c, float xf, float yf, LeanGeo lg, float box_xf, float box_yf) {
   constexpr int BW = Cfg::BW, BFW = Cfg::kBfW, PL = Cfg::BH * Cfg::BW;
   const float* s_bv = s_bu + Cfg::kBfH * BFW;
@@ -486,6 +486,7 @@ __device__ __noinline__ bool exact_keep(const float* s_bu, const float* s_ff, in
   float nb, m1, m2;
   const bool mob = motion_boundary(u, v, s_bu[c - 1], s_bu[c + 1], s_bu[c - BFW], s_bu[c + BFW], s_bv[c - 1], s_bv[c + 1],
                                    s_bv[c - BFW], s_bv[c + BFW], kV, &nb, &m1);
+  if (!OCC) return !mob;   // the optimisation-based variant: motion-boundary test only
   const LeanTaps t = lean_taps(xf, yf, u, v, lg, box_xf, box_yf);
   const float* f0 = s_ff + (int)__fmaf_rn(t.ry, (float)BW, t.rx);
   float a = __fmul_rn(f0[0], t.nw);
@@ -533,7 +534,9 @@ __device__ __noinline__ float pixel_global(const float* bf_pair, const float* ff
 }
 
 // CT == 3: masked squared error against `cur` (returned); CT == 0: mask-only (fbcCheckTorch), the verdicts go to mask_out
-template <typename FrameT, int MASK, int CT, int LOSS, typename Cfg, bool EDGE, bool MIXED>
+// OCC == false (mask-only): the optimisation-based variant of fbcCheckTorch, motion-boundary test alone -- no source
+// boxes are staged and no sampling position is needed (methods/optimization-based/flowtools.py:34-58)
+template <typename FrameT, int MASK, int CT, int LOSS, typename Cfg, bool EDGE, bool MIXED, bool OCC = true>
 __device__ __forceinline__ float lean_tile(const FwdParams& p, const float* s_bu, const float* s_ff, const int* meta, const TileId& t,
                                            int warp, int lane, const float (&cur)[Cfg::kPPL][Cfg::kC], const float (&mk)[Cfg::kPPL]) {
   constexpr int P = Cfg::kPPL, BW = Cfg::BW, BFW = Cfg::kBfW, PL = Cfg::BH * Cfg::BW;
@@ -614,7 +617,7 @@ __device__ __forceinline__ float lean_tile(const FwdParams& p, const float* s_bu
       }
       return w;
     };
-    if (MASK == MASK_COMPUTED) {
+    if (MASK == MASK_COMPUTED && OCC) {
       const float a = tap4(pf), b = tap4(MIXED ? pf + ps : pf + PL);
       // occlusion: |wf+bf|^2  vs  0.01*(|wf|^2+|bf|^2) + 0.5
       const float su = __fadd_rn(a, u), sv = __fadd_rn(b, v);
@@ -659,7 +662,7 @@ __device__ __forceinline__ float lean_tile(const FwdParams& p, const float* s_bu
 #pragma unroll
     for (int k = 0; k < P; ++k)
       if ((ambbits >> k) & 1u) {
-        const bool kp = exact_keep<Cfg>(s_bu, s_ff, c0 + DY * (k >> 1) * BFW + 16 * (k & 1), xs[k & 1], ys[k >> 1], lg, box_xf, box_yf);
+        const bool kp = exact_keep<Cfg, OCC>(s_bu, s_ff, c0 + DY * (k >> 1) * BFW + 16 * (k & 1), xs[k & 1], ys[k >> 1], lg, box_xf, box_yf);
         keepbits = (keepbits & ~(1u << k)) | ((kp ? 1u : 0u) << k);
       }
   }
@@ -715,7 +718,8 @@ __global__ void __launch_bounds__(kWsThreads, 1) fused_forward_ws_kernel(const F
   auto prev_stage = [&](int s) { return reinterpret_cast<FrameT*>(smem + Cfg::kSrcOff + (size_t)s * Cfg::kSrcStage + Cfg::kFfStage); };
 
   const int total_tiles = p.B * p.tiles_per_pair;
-  const bool want_occ = MASK == MASK_COMPUTED && (LEAN || (p.flags & TCLB200_OCC));
+  // LEAN: 1 = both mask tests / L2, 2 = both mask tests / L1, 3 = mask-only with the motion-boundary test alone
+  const bool want_occ = MASK == MASK_COMPUTED && (LEAN ? LEAN != 3 : (p.flags & TCLB200_OCC) != 0);
   const bool want_frames = CT > 0 && (LEAN || p.prev != nullptr);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const Geo& g = p.geo;
@@ -928,7 +932,10 @@ __global__ void __launch_bounds__(kWsThreads, 1) fused_forward_ws_kernel(const F
     mbar_wait(&ctl->src_full[ss], ps);
     if (threadIdx.x == 0) TCL_STAMP(k, 2);
     const int mode = ctl->meta[ss][2];
-    if (LEAN && mode == 1) {
+    if (LEAN == 3) {   // nothing staged, nothing sampled: the flow tile alone decides
+      if (t.edge) lean_tile<FrameT, MASK, CT, TCLB200_L2, Cfg, true, false, false>(p, bf_stage(sb), ff_stage(ss), ctl->meta[ss], t, wg, lane, cur, mk);
+      else lean_tile<FrameT, MASK, CT, TCLB200_L2, Cfg, false, false, false>(p, bf_stage(sb), ff_stage(ss), ctl->meta[ss], t, wg, lane, cur, mk);
+    } else if (LEAN && mode == 1) {
       if (t.edge) err = lean_tile<FrameT, MASK, CT, (LEAN == 2 ? TCLB200_L1 : TCLB200_L2), Cfg, true, false>(p, bf_stage(sb), ff_stage(ss), ctl->meta[ss], t, wg, lane, cur, mk);
       else err = lean_tile<FrameT, MASK, CT, (LEAN == 2 ? TCLB200_L1 : TCLB200_L2), Cfg, false, false>(p, bf_stage(sb), ff_stage(ss), ctl->meta[ss], t, wg, lane, cur, mk);
     } else if (LEAN && mode == 2) {
@@ -969,6 +976,40 @@ __global__ void __launch_bounds__(kThreads) gradient_kernel(const float* __restr
   const float up = y > 0 ? __ldg(src + o - W) : 0.0f, dn = y + 1 < H ? __ldg(src + o + W) : 0.0f;
   __stcs(out + (size_t)img * plane + o, __fmul_rn(__fsub_rn(r, l), 0.5f));
   __stcs(out + ((size_t)B + img) * plane + o, __fmul_rn(__fsub_rn(dn, up), 0.5f));
+}
+
+// W % 4 == 0 and 16-byte aligned planes: four pixels per lane.  The centre row's float4 gives every x-difference but
+// the two that reach into the neighbouring lanes' quads (warp shuffles; one scalar load at a warp's ends), the rows
+// above / below are two more float4 loads (the three reads of a row are L1 / L2 hits); two float4 stores.
+// 4 B/px read + 8 B/px written, all 16-byte accesses.
+__global__ void __launch_bounds__(kThreads) gradient_vec4_kernel(const float* __restrict__ xin, float* __restrict__ out, int B, int H,
+                                                                 int W, int tiles_x, int tiles_per_img) {
+  const size_t plane = (size_t)H * W;
+  const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
+  const int img = blockIdx.x / tiles_per_img;
+  const int tile = blockIdx.x - img * tiles_per_img;
+  const int ty = tile / tiles_x, tx = tile - ty * tiles_x;
+  const int x = tx * 128 + 4 * lane, y = ty * kWarps + wrp;   // warp = one 128-pixel row segment
+  if (y >= H) return;
+  const bool in = x < W;
+  const float* src = xin + (size_t)img * plane;
+  const size_t o = (size_t)y * W + x;
+  const float4 z = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+  const float4 c = in ? __ldg(reinterpret_cast<const float4*>(src + o)) : z;
+  const float4 up = (in && y > 0) ? __ldg(reinterpret_cast<const float4*>(src + o - W)) : z;
+  const float4 dn = (in && y + 1 < H) ? __ldg(reinterpret_cast<const float4*>(src + o + W)) : z;
+  float l = __shfl_up_sync(0xffffffffu, c.w, 1), r = __shfl_down_sync(0xffffffffu, c.x, 1);
+  if (lane == 0) l = (in && x > 0) ? __ldg(src + o - 1) : 0.0f;
+  if (lane == 31) r = (in && x + 4 < W) ? __ldg(src + o + 4) : 0.0f;
+  if (in && x + 4 >= W) r = 0.0f;   // the lane right of the image edge holds zeros anyway; explicit for clarity
+  if (!in) return;
+  float4 dx, dy;
+  dx.x = __fmul_rn(__fsub_rn(c.y, l), 0.5f);   dx.y = __fmul_rn(__fsub_rn(c.z, c.x), 0.5f);
+  dx.z = __fmul_rn(__fsub_rn(c.w, c.y), 0.5f); dx.w = __fmul_rn(__fsub_rn(r, c.z), 0.5f);
+  dy.x = __fmul_rn(__fsub_rn(dn.x, up.x), 0.5f); dy.y = __fmul_rn(__fsub_rn(dn.y, up.y), 0.5f);
+  dy.z = __fmul_rn(__fsub_rn(dn.z, up.z), 0.5f); dy.w = __fmul_rn(__fsub_rn(dn.w, up.w), 0.5f);
+  __stcs(reinterpret_cast<float4*>(out + (size_t)img * plane + o), dx);
+  __stcs(reinterpret_cast<float4*>(out + ((size_t)B + img) * plane + o), dy);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1197,7 +1238,10 @@ using namespace tcl;
 static thread_local char g_err[512] = "";
 static unsigned long long g_launches = 0;   // kernels of this library launched by this process (diagnostics / bench.py)
 
-namespace tcl { void set_last_error(const char* msg) { snprintf(g_err, sizeof(g_err), "%s", msg); } }   // for tcl_host.cu
+namespace tcl {   // for tcl_host.cu / tcl_cv2.cu
+void set_last_error(const char* msg) { snprintf(g_err, sizeof(g_err), "%s", msg); }
+void count_launch() { ++g_launches; }
+}
 
 static int fail(int code, const char* fmt, const char* detail = "") {
   snprintf(g_err, sizeof(g_err), fmt, detail);
@@ -1322,6 +1366,7 @@ static cudaError_t dispatch(const FwdParams& p, int mask_kind, bool reduce, bool
     if (p.C == 3 && lean && RD) return p.loss == TCLB200_L1 ? launch_tma<FrameT, MK, true, 3, 2>(p, tb, tf, tp, tc, s)   \
                                                             : launch_tma<FrameT, MK, true, 3, 1>(p, tb, tf, tp, tc, s);  \
     if (MK == MASK_COMPUTED && !RD && lean_mask) return launch_tma<float, MASK_COMPUTED, false, 0, 1>(p, tb, tf, tp, tc, s); \
+    if (MK == MASK_COMPUTED && !RD && lean_mob) return launch_tma<float, MASK_COMPUTED, false, 0, 3>(p, tb, tf, tp, tc, s); \
     if (MK == MASK_NONE && !RD && lean_warp) return launch_tma<FrameT, MASK_NONE, false, 3, 1>(p, tb, tf, tp, tc, s); \
     return p.C == 3 ? launch_tma<FrameT, MK, RD, 3, 0>(p, tb, tf, tp, tc, s) : launch_tma<FrameT, MK, RD, 0, 0>(p, tb, tf, tp, tc, s); \
   }
@@ -1332,6 +1377,9 @@ static cudaError_t dispatch(const FwdParams& p, int mask_kind, bool reduce, bool
   // ... and fbcCheckTorch on its own: both tests, mask_out only
   const bool lean_mask = !reduce && !p.prev && p.mask_out && !p.near_threshold && mask_kind == MASK_COMPUTED &&
                          (p.flags & (TCLB200_OCC | TCLB200_MOB)) == (TCLB200_OCC | TCLB200_MOB);
+  // ... and its optimisation-based variant: the motion-boundary test alone
+  const bool lean_mob = !reduce && !p.prev && p.mask_out && !p.near_threshold && mask_kind == MASK_COMPUTED &&
+                        (p.flags & (TCLB200_OCC | TCLB200_MOB)) == TCLB200_MOB;
   // ... and warp() on its own (C == 3, no validity mask): warp_out only
   const bool lean_warp = !reduce && p.prev && p.C == 3 && !p.cur && p.warp_out && !p.mask_out && !p.blend_out && mask_kind == MASK_NONE;
   TCL_CASE(MASK_COMPUTED, true)
@@ -1464,9 +1512,11 @@ extern "C" int tclb200_gradient(const float* x, float* out, int B, int H, int W,
   if (!x || !out) return fail(TCLB200_ERR_INVALID, "x and out are required");
   if (B <= 0 || H <= 0 || W <= 0) return fail(TCLB200_ERR_INVALID, "B, H, W must be positive");
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-  const int tx = cdiv(W, 32), tpi = tx * cdiv(H, kWarps);
+  const bool vec4 = !g_force_generic && W % 4 == 0 && aligned16(x) && aligned16(out) && ((size_t)H * W) % 4 == 0;
+  const int tx = cdiv(W, vec4 ? 128 : 32), tpi = tx * cdiv(H, kWarps);
   if ((size_t)B * tpi >= 0x7fffffffu) return fail(TCLB200_ERR_UNSUPPORTED, "too many tiles for one launch");
-  gradient_kernel<<<(unsigned)((size_t)B * tpi), kThreads, 0, s>>>(x, out, B, H, W, tx, tpi);
+  if (vec4) gradient_vec4_kernel<<<(unsigned)((size_t)B * tpi), kThreads, 0, s>>>(x, out, B, H, W, tx, tpi);
+  else gradient_kernel<<<(unsigned)((size_t)B * tpi), kThreads, 0, s>>>(x, out, B, H, W, tx, tpi);
   ++g_launches;
   CUDA_TRY(cudaGetLastError());
   return TCLB200_OK;

@@ -12,6 +12,7 @@ it replaces (upstream paths relative to the repository root):
 * ``temporal_loss(...)``                  StarGANv2AdvCon/core/solver.py:427-446, fs_ruder.py:97, MoGAN ...:280-281
 * ``temporal_rmse_per_sample(...)``       utils/metrics/eval.py:137-138
 * ``warp_blend(...)``                     methods/optimization-based/obst_eval.py:500
+* ``generateMask(simg, prev, flow)``      ConGAN/models/cycle_gan_model.py:136-137 with the warp fused in
 * ``temporal_error_host(...)``            the evaluation loop of utils/sintel_eval.py:206-222 with HOST tensors in and out
 
 PyTorch is used for device memory, streams and autograd plumbing only; all arithmetic runs in
@@ -446,3 +447,11 @@ def temporal_loss(mask, cur, prev, flow, loss="l2", validity=False):
     if torch.is_grad_enabled() and (prev.requires_grad or cur.requires_grad):
         return _TemporalLossFn.apply(prev, cur, flow, mask, code, flags)
     return fused_forward(flow, prev, cur, mask=mask, loss=code, finalize=FIN_MEAN, flags=flags).total_val
+
+
+def generateMask(simg, prev, flow):
+    """ConGAN's scalar soft mask ``exp(-50 * |simg - warp(prev, flow)|.mean())`` (ConGAN/models/cycle_gan_model.py:136-137,
+    where ``wimg`` is ``warp(...)`` of the previous frame): the warp and the mean absolute difference are one fused
+    launch; differentiable like the reference expression.  ``loss_TCL_A`` (``:298``) is then
+    ``generateMask(...) * temporal_loss(None, fuse_B, prev_B, flow, loss='l1') * lambda_TCL``."""
+    return torch.exp(-50.0 * temporal_loss(None, simg, prev, flow, loss="l1"))

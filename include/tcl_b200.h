@@ -180,6 +180,20 @@ int tclb200_hwc_split(const float* src, int N, int H, int W, int Cs, int n_out, 
  * zero-padded 3x3 neighbourhood of 8*flow, pixel shuffle.  flow (N,2,H,W), mask (N,576,H,W) -> out (N,2,8H,8W), fp32. */
 int tclb200_upsample_flow(const float* flow, const float* mask, float* out, int N, int H, int W, tclb200_stream_t stream);
 
+/* NumPy / OpenCV flavour of the path ("next" row of the scope table): the reference's dataset generators restate warp and
+ * the forward-backward check on HWC arrays with cv2.remap / np.gradient / np.linalg.norm
+ * (methods/learning-based/dataset-generation/coco-generation.py:66-113, hollywood2-generation.py:63-111,
+ * sintel-generation.py:89-130).  Bit-compatible with OpenCV 4.x's remap(INTER_LINEAR, BORDER_CONSTANT 0) on float32: sample
+ * position exactly (x+u, y+v) in 1/32-pixel fixed point, table weights, unfused left-to-right sum.
+ *   tclb200_cv2_remap     warp_image / warp_flow: src (N,H,W,C), flow (N,H,W,2) -> out (N,H,W,C), all fp32 HWC
+ *   tclb200_cv2_fb_check  fb_check(warp_flow(ff, bf), bf) in one pass (prewarped != 0: ff is already the warped flow, the
+ *                         reference's two-argument fb_check); ff, bf (N,H,W,2) -> mask (N,H,W) fp32 in {0,1};
+ *                         flags = TCLB200_OCC (the COCO copy, :111 comments the boundary test out) | TCLB200_MOB;
+ *                         near_threshold as in tclb200_fbcheck. */
+int tclb200_cv2_remap(const float* src, const float* flow, float* out, int N, int H, int W, int C, tclb200_stream_t stream);
+int tclb200_cv2_fb_check(const float* ff, const float* bf, float* mask, int N, int H, int W, int flags, int prewarped,
+                         unsigned long long* near_threshold, tclb200_stream_t stream);
+
 /* Test hook (process-global, not for production use): route TMA-capable shapes through the generic
  * global-memory kernel so that both kernels are exercised on the same inputs.  0 = off (default). */
 void tclb200_debug_force_generic(int on);

@@ -74,3 +74,17 @@ def test_backward_matches_reference_autograd_golden(tcl, path):
     p = torch.from_numpy(g["prev"]).to(d)
     ((mask * (torch.from_numpy(g["cur"]).to(d) - tcl.warp(p, f))) ** 2).mean().backward()
     assert np.allclose(f.grad.cpu().numpy(), g["grad_flow"], rtol=1e-3, atol=1e-7)
+
+
+def test_congan_soft_mask_and_scalar_masked_l1(tcl):
+    """ConGAN/models/cycle_gan_model.py:136-137,298: exp(-50*|real2 - warp(real1)|.mean()) and mask*|fuse - warp|.mean()."""
+    ff, bf, prev, cur = _inputs(tcl, 4, 64, 96, 61, 6.0)
+    cur = prev + 0.01 * cur          # close frames: the soft mask is not vanishingly small
+    ref = torch.exp(-50 * torch.abs(cur - tp.backward_warp(prev, bf)).mean())
+    c = cur.clone().requires_grad_(True)
+    got = tcl.generateMask(c, prev, bf)
+    assert abs(float(got) - float(ref)) <= 1e-5 * float(ref)
+    c_ref = cur.clone().requires_grad_(True)
+    torch.exp(-50 * torch.abs(c_ref - tp.backward_warp(prev, bf)).mean()).backward()
+    got.backward()
+    assert float((c.grad - c_ref.grad).abs().max()) <= 1e-5 * float(c_ref.grad.abs().max())

@@ -471,6 +471,43 @@ def test_clip_mode_equals_pairwise(tcl, force_generic, T, H, W):
         tcl.fused_forward(bf, frames, frames, ff=ff, prev_index=torch.full((T - 1,), T, device=d), cur_index=idx_cur[:1].repeat(T - 1))
 
 
+# ------------------------------------------------------------------ specialised gradient / motion-boundary-only paths
+@pytest.mark.parametrize("B,H,W", [(1, 1, 4), (2, 5, 8), (3, 37, 52), (2, 436, 1024), (1, 64, 132), (2, 33, 129)])
+def test_gradient_vector_path_bit_exact(tcl, force_generic, B, H, W):
+    """gradient() (utils/flowtools.py:12-16): the float4 kernel (W % 4 == 0) and the scalar kernel give the bits of
+    the reference's pad / slice / subtract / halve sequence, including the zero padding at all four borders."""
+    d = dev()
+    x = torch.randn(B, H, W, device=d)
+    want = tp.central_diff(x)
+    for generic in (False, True):
+        force_generic(generic)
+        assert torch.equal(tcl.gradient(x), want)
+    force_generic(False)
+    xv = torch.randn(B, H, W + 4, device=d)[:, :, 1:W + 1]       # unaligned view -> made contiguous by the wrapper
+    assert torch.equal(tcl.gradient(xv), tp.central_diff(xv.contiguous()))
+
+
+@pytest.mark.parametrize("B,H,W,shift", [(2, 96, 256, 8.0), (1, 436, 1024, 32.0), (3, 37, 52, 6.0), (1, 70, 200, 300.0)])
+def test_mob_only_specialised_path_bit_exact(tcl, force_generic, B, H, W, shift):
+    """fbcCheckTorch of methods/optimization-based/flowtools.py (occlusion test off): the specialised mask-only path,
+    the feature-complete path (near-threshold count requested) and the generic kernel agree with the op sequence."""
+    d = dev()
+    ff, bf = tcl.synth.make_flows(B, H, W, seed=B + W, max_shift=shift, device=d)
+    want = tp.fb_consistency_mob(ff, bf)
+    got = tcl.fbcCheckTorch_mob(ff, bf)
+    assert torch.equal(got, want)
+    exact, _ = tcl.fbcheck_with_near_count(ff, bf, flags=tcl.ops.MOB)
+    assert torch.equal(exact, want)
+    force_generic(True)
+    assert torch.equal(tcl.fbcCheckTorch_mob(ff, bf), want)
+    force_generic(False)
+    # adversarial: gradients sitting on the threshold 0.01*|bf|^2 + 0.002
+    bf2 = bf.clone()
+    bf2[:, 0] = 0.0447214 * torch.arange(W, device=d).float()[None, None, :] + 1e-4 * torch.randn(B, H, W, device=d)
+    bf2[:, 1] = 0.0
+    assert torch.equal(tcl.fbcCheckTorch_mob(ff, bf2), tp.fb_consistency_mob(ff, bf2))
+
+
 # ------------------------------------------------------------------ host-buffer entry (the e2e path of bench.py)
 @pytest.mark.gpu
 @pytest.mark.parametrize("clips,H,W,chunk,dtype", [([5], 96, 256, 0, torch.float32), ([4, 7, 3], 436, 1024, 4, torch.float32),
