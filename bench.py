@@ -105,6 +105,19 @@ class ClockSampler:
                 "reasons": reasons, "samples": len(sm)}
 
 
+def bind_to_gpu_numa_node(index):
+    """Pin this rank's host threads to the CPUs next to its GPU (NVML's ideal affinity), so that the pinned host buffers
+    of the e2e leg are first-touched on the GPU's own NUMA node.  Best effort: silently skipped where NVML says no."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+        phys = int(visible.split(",")[index]) if visible and visible.split(",")[index].isdigit() else index
+        pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(phys))
+    except Exception:
+        pass
+
+
 def make_shard(tcl, cfg_name, n_pairs, seed, device, frames, chunk=32):
     """Synthetic shard resident in HBM: dict of (n,2,H,W)/(n,3,H,W) tensors, generated chunk-wise."""
     cfg = tcl.synth.CONFIGS[cfg_name]
@@ -331,6 +344,7 @@ def main():
         raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
     device = torch.device("cuda", local)
     torch.cuda.set_device(device)
+    bind_to_gpu_numa_node(local)
     dist = None
     if world > 1:
         import torch.distributed as dist
@@ -476,6 +490,7 @@ def main():
                 e["value"] = e["pairs_per_step"] * world / (e["ms_per_step"] / 1e3)
                 e["h2d_bytes_per_step"] *= world
                 e["d2h_bytes_per_step"] *= world
+                e["h2d_gb_per_s"] = e["h2d_bytes_per_step"] / (e["ms_per_step"] / 1e3) / 1e9
         line["e2e"] = e
         del shard
         torch.cuda.empty_cache()

@@ -87,6 +87,7 @@ _PROTOTYPES = {
     "tclb200_last_error": (_c.c_char_p, []),
     "tclb200_scratch_bytes": (_c.c_size_t, [_i, _i, _i]),
     "tclb200_gradient": (_c.c_int, [_vp, _vp, _i, _i, _i, _vp]),
+    "tclb200_gradient_strided": (_c.c_int, [_vp, _c.c_size_t, _vp, _i, _i, _i, _vp]),
     "tclb200_warp": (_c.c_int, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     "tclb200_warp_backward": (_c.c_int, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "tclb200_fbcheck": (_c.c_int, [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp]),

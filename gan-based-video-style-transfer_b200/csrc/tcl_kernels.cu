@@ -961,7 +961,7 @@ __global__ void __launch_bounds__(kWsThreads, 1) fused_forward_ws_kernel(const F
 // ---------------------------------------------------------------------------------------------
 // gradient(x): zero-padded central differences (flowtools.py:12-16); one pixel per lane, coalesced
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kThreads) gradient_kernel(const float* __restrict__ xin, float* __restrict__ out, int B, int H,
+__global__ void __launch_bounds__(kThreads) gradient_kernel(const float* __restrict__ xin, size_t in_stride, float* __restrict__ out, int B, int H,
                                                             int W, int tiles_x, int tiles_per_img) {
   const size_t plane = (size_t)H * W;
   const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
@@ -970,7 +970,7 @@ __global__ void __launch_bounds__(kThreads) gradient_kernel(const float* __restr
   const int ty = tile / tiles_x, tx = tile - ty * tiles_x;
   const int x = tx * 32 + lane, y = ty * kWarps + wrp;
   if (x >= W || y >= H) return;
-  const float* src = xin + (size_t)img * plane;
+  const float* src = xin + (size_t)img * in_stride;
   const size_t o = (size_t)y * W + x;
   const float l = x > 0 ? __ldg(src + o - 1) : 0.0f, r = x + 1 < W ? __ldg(src + o + 1) : 0.0f;
   const float up = y > 0 ? __ldg(src + o - W) : 0.0f, dn = y + 1 < H ? __ldg(src + o + W) : 0.0f;
@@ -982,7 +982,7 @@ __global__ void __launch_bounds__(kThreads) gradient_kernel(const float* __restr
 // the two that reach into the neighbouring lanes' quads (warp shuffles; one scalar load at a warp's ends), the rows
 // above / below are two more float4 loads (the three reads of a row are L1 / L2 hits); two float4 stores.
 // 4 B/px read + 8 B/px written, all 16-byte accesses.
-__global__ void __launch_bounds__(kThreads) gradient_vec4_kernel(const float* __restrict__ xin, float* __restrict__ out, int B, int H,
+__global__ void __launch_bounds__(kThreads) gradient_vec4_kernel(const float* __restrict__ xin, size_t in_stride, float* __restrict__ out, int B, int H,
                                                                  int W, int tiles_x, int tiles_per_img) {
   const size_t plane = (size_t)H * W;
   const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
@@ -992,7 +992,7 @@ __global__ void __launch_bounds__(kThreads) gradient_vec4_kernel(const float* __
   const int x = tx * 128 + 4 * lane, y = ty * kWarps + wrp;   // warp = one 128-pixel row segment
   if (y >= H) return;
   const bool in = x < W;
-  const float* src = xin + (size_t)img * plane;
+  const float* src = xin + (size_t)img * in_stride;
   const size_t o = (size_t)y * W + x;
   const float4 z = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
   const float4 c = in ? __ldg(reinterpret_cast<const float4*>(src + o)) : z;
@@ -1508,18 +1508,26 @@ extern "C" int tclb200_fbcheck(const float* ff, const float* bf, float* mask_out
   return run_fused(&a, reinterpret_cast<cudaStream_t>(stream));
 }
 
-extern "C" int tclb200_gradient(const float* x, float* out, int B, int H, int W, tclb200_stream_t stream) {
+static int run_gradient(const float* x, size_t in_stride, float* out, int B, int H, int W, cudaStream_t s) {
   if (!x || !out) return fail(TCLB200_ERR_INVALID, "x and out are required");
   if (B <= 0 || H <= 0 || W <= 0) return fail(TCLB200_ERR_INVALID, "B, H, W must be positive");
-  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-  const bool vec4 = !g_force_generic && W % 4 == 0 && aligned16(x) && aligned16(out) && ((size_t)H * W) % 4 == 0;
+  if (in_stride < (size_t)H * W) return fail(TCLB200_ERR_INVALID, "x_batch_stride must be at least H*W");
+  const bool vec4 = !g_force_generic && W % 4 == 0 && aligned16(x) && aligned16(out) && ((size_t)H * W) % 4 == 0 && in_stride % 4 == 0;
   const int tx = cdiv(W, vec4 ? 128 : 32), tpi = tx * cdiv(H, kWarps);
   if ((size_t)B * tpi >= 0x7fffffffu) return fail(TCLB200_ERR_UNSUPPORTED, "too many tiles for one launch");
-  if (vec4) gradient_vec4_kernel<<<(unsigned)((size_t)B * tpi), kThreads, 0, s>>>(x, out, B, H, W, tx, tpi);
-  else gradient_kernel<<<(unsigned)((size_t)B * tpi), kThreads, 0, s>>>(x, out, B, H, W, tx, tpi);
+  if (vec4) gradient_vec4_kernel<<<(unsigned)((size_t)B * tpi), kThreads, 0, s>>>(x, in_stride, out, B, H, W, tx, tpi);
+  else gradient_kernel<<<(unsigned)((size_t)B * tpi), kThreads, 0, s>>>(x, in_stride, out, B, H, W, tx, tpi);
   ++g_launches;
   CUDA_TRY(cudaGetLastError());
   return TCLB200_OK;
+}
+
+extern "C" int tclb200_gradient(const float* x, float* out, int B, int H, int W, tclb200_stream_t stream) {
+  return run_gradient(x, (size_t)(H > 0 && W > 0 ? (size_t)H * W : 0), out, B, H, W, reinterpret_cast<cudaStream_t>(stream));
+}
+
+extern "C" int tclb200_gradient_strided(const float* x, size_t x_batch_stride, float* out, int B, int H, int W, tclb200_stream_t stream) {
+  return run_gradient(x, x_batch_stride, out, B, H, W, reinterpret_cast<cudaStream_t>(stream));
 }
 
 static int run_backward(const BwdParams& p, bool fused, cudaStream_t s) {

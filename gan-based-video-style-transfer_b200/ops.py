@@ -79,11 +79,15 @@ def gradient(x):
     _require_cuda(x)
     if x.dim() != 3:
         raise RuntimeError(f"tcl_b200: gradient expects (B,H,W), got {tuple(x.shape)}")
-    x = x.float().contiguous()
+    x = x.float()
     B, H, W = x.shape
+    # one channel of a (B,2,H,W) flow (the reference's gradient(bf[:,0,:,:]), flowtools.py:47): planes are contiguous, only
+    # the batch stride differs -- handed to the kernel as is; anything else is made contiguous first
+    if not (x.stride(2) == 1 and x.stride(1) == W and (B == 1 or x.stride(0) >= H * W)):
+        x = x.contiguous()
     out = torch.empty((2, B, H, W), dtype=torch.float32, device=x.device)
     with torch.cuda.device(x.device):
-        check(_cabi.lib().tclb200_gradient(_ptr(x), _ptr(out), B, H, W, _stream_handle()))
+        check(_cabi.lib().tclb200_gradient_strided(_ptr(x), x.stride(0) if B > 1 else H * W, _ptr(out), B, H, W, _stream_handle()))
     return out
 
 

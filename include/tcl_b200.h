@@ -67,6 +67,9 @@ size_t tclb200_scratch_bytes(int B, int H, int W);
 /* gradient(x)  utils/flowtools.py:12-16
  * x (B,H,W) fp32 -> out (2,B,H,W) fp32 = [d/dx, d/dy], zero-padded central differences. */
 int tclb200_gradient(const float* x, float* out, int B, int H, int W, tclb200_stream_t stream);
+/* the same on B contiguous (H,W) planes that lie x_batch_stride floats apart: the reference calls gradient(bf[:,0,:,:])
+ * and gradient(bf[:,1,:,:]) (utils/flowtools.py:47-48), one channel of a (B,2,H,W) flow -- no gather copy needed. */
+int tclb200_gradient_strided(const float* x, size_t x_batch_stride, float* out, int B, int H, int W, tclb200_stream_t stream);
 
 /* warp(x, f)  utils/flowtools.py:18-32 (copies: utils/metrics/eval.py:43-57, StarGAN/solver.py:42-56;
  * inline: StarGANv2AdvCon/core/solver.py:427-443, CycleGANCon/models/cycle_gan_model.py:191-203)

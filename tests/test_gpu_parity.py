@@ -485,6 +485,9 @@ def test_gradient_vector_path_bit_exact(tcl, force_generic, B, H, W):
     force_generic(False)
     xv = torch.randn(B, H, W + 4, device=d)[:, :, 1:W + 1]       # unaligned view -> made contiguous by the wrapper
     assert torch.equal(tcl.gradient(xv), tp.central_diff(xv.contiguous()))
+    flow = torch.randn(B, 2, H, W, device=d)                     # the reference's call: gradient(bf[:,0,:,:]) (flowtools.py:47-48)
+    for ch in (0, 1):                                            # batch-strided planes go to the kernel as they are
+        assert torch.equal(tcl.gradient(flow[:, ch, :, :]), tp.central_diff(flow[:, ch, :, :]))
 
 
 @pytest.mark.parametrize("B,H,W,shift", [(2, 96, 256, 8.0), (1, 436, 1024, 32.0), (3, 37, 52, 6.0), (1, 70, 200, 300.0)])
