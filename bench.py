@@ -250,6 +250,8 @@ def e2e_rate(tcl, shard, pairs_in_seq, steps, warmup, device, chunk=32):
         seqs.append(n)
         need += b
     P, F = sum(seqs), sum(seqs) + len(seqs)
+    saved_affinity = os.sched_getaffinity(0)
+    bind_to_gpu_numa_node(device.index)     # (restored below: the cpu_baseline leg must see every host core)
     frames_h = torch.empty((F, C, H, W), dtype=shard["cur"].dtype, pin_memory=True)
     ff_h = torch.empty((P, 2, H, W), dtype=torch.float32, pin_memory=True)
     bf_h = torch.empty((P, 2, H, W), dtype=torch.float32, pin_memory=True)
@@ -278,6 +280,7 @@ def e2e_rate(tcl, shard, pairs_in_seq, steps, warmup, device, chunk=32):
     torch.cuda.synchronize()
     el = time.perf_counter() - t0
     launches = int(lib.tclb200_debug_launch_count(0))
+    os.sched_setaffinity(0, saved_affinity)
     h2d = F * frame_b + 2 * P * flow_b + 2 * 4 * P
     return dict(value=steps * P / el, unit="pairs/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=4 * P,
                 ms_per_step=el / steps * 1e3, h2d_gb_per_s=h2d * steps / el / 1e9, pairs_per_step=P, frames_per_step=F,
@@ -344,7 +347,6 @@ def main():
         raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
     device = torch.device("cuda", local)
     torch.cuda.set_device(device)
-    bind_to_gpu_numa_node(local)
     dist = None
     if world > 1:
         import torch.distributed as dist
