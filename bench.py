@@ -251,7 +251,8 @@ def e2e_rate(tcl, shard, pairs_in_seq, steps, warmup, device, chunk=32):
         need += b
     P, F = sum(seqs), sum(seqs) + len(seqs)
     saved_affinity = os.sched_getaffinity(0)
-    bind_to_gpu_numa_node(device.index)     # (restored below: the cpu_baseline leg must see every host core)
+    if world > 1:   # (N = 1 measured 55 GB/s unbound; the cpu_baseline leg that follows must see every host core)
+        bind_to_gpu_numa_node(device.index)
     frames_h = torch.empty((F, C, H, W), dtype=shard["cur"].dtype, pin_memory=True)
     ff_h = torch.empty((P, 2, H, W), dtype=torch.float32, pin_memory=True)
     bf_h = torch.empty((P, 2, H, W), dtype=torch.float32, pin_memory=True)
