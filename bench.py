@@ -330,7 +330,61 @@ def other_workloads(tcl, device, frames, peak):
             torch.cuda.empty_cache()
         except Exception as ex:  # report, never hide
             out.append(dict(workload=name, error=repr(ex)))
+    out.append(training_step(tcl, device, frames, peak))
     return out
+
+
+def training_step(tcl, device, frames, peak):
+    """BASELINE configs[1] as the trainer runs it (StarGANv2AdvCon/core/solver.py:427-446 + :181): the temporal loss
+    forward AND its backward to both frames, batch 16 at 256x256 fp32, dataset mask.  Device time of the two library
+    launches (+ the memset of grad_prev) from a CUDA graph over rotating buffers; the eager autograd call is timed
+    beside it (host-bound: Python + autograd bookkeeping of a 30 us job)."""
+    import ctypes
+    name, n, nbuf = "train_b16_256", 16, 12
+    try:
+        cfg = tcl.synth.CONFIGS[name]
+        H, W, C = cfg["H"], cfg["W"], cfg["C"]
+        bufs = [make_shard(tcl, name, n, 9500 + 97 * i, device, frames, chunk=8) for i in range(nbuf)]
+        masks = [tcl.fbcCheckTorch(b["ff"], b["bf"]) for b in bufs]
+        gp, gc = torch.empty_like(bufs[0]["prev"]), torch.empty_like(bufs[0]["cur"])
+        scale = torch.full((1,), 100.0 / (n * C * H * W), device=device)     # lambda_tcl = 100 (main.py:94) times 1/N
+        lib = tcl._cabi.lib()
+        ptr = lambda t: ctypes.c_void_p(t.data_ptr())
+
+        def launch(i):
+            b, m = bufs[i % nbuf], masks[i % nbuf]
+            tcl.fused_forward(b["bf"], b["prev"], b["cur"], mask=m, finalize=tcl.ops.FIN_MEAN)
+            tcl._cabi.check(lib.tclb200_tcl_backward(ptr(b["bf"]), ptr(m), ptr(b["prev"]), ptr(b["cur"]), ptr(scale), ptr(gp), ptr(gc),
+                                                     n, C, H, W, 0, tcl.ops.L2, ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)))
+        side = torch.cuda.Stream(device)
+        with torch.cuda.stream(side):
+            for i in range(nbuf):
+                launch(i)
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            for i in range(nbuf):
+                launch(i)
+        _, per = time_kernel(graph.replay, 20, 5)
+        per.sort()
+        ms = per[len(per) // 2] / nbuf
+        # the eager public call: tcl.temporal_loss(...).backward()
+        p2, c2 = bufs[0]["prev"].clone().requires_grad_(True), bufs[0]["cur"].clone().requires_grad_(True)
+
+        def eager():
+            p2.grad = None
+            c2.grad = None
+            (tcl.temporal_loss(masks[0], c2, p2, bufs[0]["bf"]) * 100.0).backward()
+        _, per_e = time_kernel(eager, 50, 10)
+        per_e.sort()
+        px = n * H * W
+        bpp = 36 + 36 + 24 + 12    # fwd reads; bwd reads again, writes grad_cur + grad_prev (zero-fill), + the scatter's read-for-ownership
+        return dict(workload=name + "_fwd_bwd", pairs=n, shape=f"{W}x{H}", dtype="fp32", mask="mask_in", loss="L2 mean, grads to prev and cur",
+                    ms_per_step_device=ms, ms_per_step_eager_autograd=per_e[len(per_e) // 2], gpix_per_s=px / ms / 1e6, bytes_per_px=bpp,
+                    achieved_gbs=px * bpp / ms / 1e6, frac_of_measured_peak=px * bpp / ms / 1e6 / peak, rotating_buffers=nbuf,
+                    timing="CUDA graph of fwd + bwd launches per rotating buffer, median of 20 replays; eager = public autograd call, median of 50")
+    except Exception as ex:
+        return dict(workload=name + "_fwd_bwd", error=repr(ex))
 
 
 def main():

@@ -536,7 +536,10 @@ __device__ __noinline__ float pixel_global(const float* bf_pair, const float* ff
 // CT == 3: masked squared error against `cur` (returned); CT == 0: mask-only (fbcCheckTorch), the verdicts go to mask_out
 // OCC == false (mask-only): the optimisation-based variant of fbcCheckTorch, motion-boundary test alone -- no source
 // boxes are staged and no sampling position is needed (methods/optimization-based/flowtools.py:34-58)
-template <typename FrameT, int MASK, int CT, int LOSS, typename Cfg, bool EDGE, bool MIXED, bool OCC = true>
+// OUTS (staged, non-mixed tiles of the reducing configurations): the optional per-pixel outputs -- warp_out, mask_out,
+// blend_out, whichever pointers are set -- are stored from the same pass (the warped values wait in registers until the
+// mask verdicts are final)
+template <typename FrameT, int MASK, int CT, int LOSS, typename Cfg, bool EDGE, bool MIXED, bool OCC = true, bool OUTS = false>
 __device__ __forceinline__ float lean_tile(const FwdParams& p, const float* s_bu, const float* s_ff, const int* meta, const TileId& t,
                                            int warp, int lane, const float (&cur)[Cfg::kPPL][Cfg::kC], const float (&mk)[Cfg::kPPL]) {
   constexpr int P = Cfg::kPPL, BW = Cfg::BW, BFW = Cfg::kBfW, PL = Cfg::BH * Cfg::BW;
@@ -561,6 +564,7 @@ __device__ __forceinline__ float lean_tile(const FwdParams& p, const float* s_bu
   const int c0 = (ly0 + 1) * BFW + lx0 + Cfg::kHaloX;
   const bool validity = MASK == MASK_NONE && (p.flags & TCLB200_VALIDITY);
   float e[P];
+  float wv[OUTS ? P : 1][3];
   unsigned keepbits = 0, ambbits = 0, outbits = 0;
 #pragma unroll
   for (int k = 0; k < P; ++k) {
@@ -648,6 +652,7 @@ __device__ __forceinline__ float lean_tile(const FwdParams& p, const float* s_bu
                     validity ? __fmul_rn(w, valid) : w);
         continue;
       }
+      if (OUTS) wv[k][ch] = w;
       const float d = __fsub_rn(cur[k][ch], w);
       acc = LOSS == TCLB200_L1 ? __fadd_rn(acc, fabsf(d)) : __fmaf_rn(d, d, acc);   // mask*|warp - cur| (MoGAN :281) / (mask*(cur - warp))^2
     }
@@ -684,6 +689,26 @@ __device__ __forceinline__ float lean_tile(const FwdParams& p, const float* s_bu
         }
       }
   }
+  if (OUTS && CT == 3) {
+    const size_t pix0 = (size_t)(t.y0 + ly0) * g.W + (t.x0 + lx0);
+    FrameT* wo = p.warp_out ? reinterpret_cast<FrameT*>(p.warp_out) + (size_t)t.pair * 3 * gplane + pix0 : nullptr;
+    FrameT* bo = p.blend_out ? reinterpret_cast<FrameT*>(p.blend_out) + (size_t)t.pair * 3 * gplane + pix0 : nullptr;
+    float* mo = (MASK == MASK_COMPUTED && p.mask_out) ? p.mask_out + (size_t)t.pair * gplane + pix0 : nullptr;
+#pragma unroll
+    for (int k = 0; k < P; ++k) {
+      const bool inside = !EDGE || (t.x0 + lx0 + 16 * (k & 1) < g.W && t.y0 + ly0 + DY * (k >> 1) < g.H);
+      if (!inside) continue;
+      const ptrdiff_t off = (ptrdiff_t)DY * (k >> 1) * g.W + 16 * (k & 1);
+      const float keepf = MASK == MASK_GIVEN ? mk[k] : (((keepbits >> k) & 1u) ? 1.0f : 0.0f);
+      if (mo) __stcs(mo + off, keepf);
+#pragma unroll
+      for (int ch = 0; ch < 3; ++ch) {
+        if (wo) st_stream(wo + ch * gplane + off, wv[k][ch]);
+        if (bo)   // m*warp + (1-m)*img   obst_eval.py:500
+          st_stream(bo + ch * gplane + off, __fadd_rn(__fmul_rn(keepf, wv[k][ch]), __fmul_rn(__fsub_rn(1.0f, keepf), cur[k][ch])));
+      }
+    }
+  }
   if (CT == 0) {   // mask-only: store the verdicts (two coalesced 64-byte row segments per warp instruction)
     float* mo = p.mask_out + (size_t)t.pair * gplane + (size_t)(t.y0 + ly0) * g.W + (t.x0 + lx0);
 #pragma unroll
@@ -718,7 +743,8 @@ __global__ void __launch_bounds__(kWsThreads, 1) fused_forward_ws_kernel(const F
   auto prev_stage = [&](int s) { return reinterpret_cast<FrameT*>(smem + Cfg::kSrcOff + (size_t)s * Cfg::kSrcStage + Cfg::kFfStage); };
 
   const int total_tiles = p.B * p.tiles_per_pair;
-  // LEAN: 1 = both mask tests / L2, 2 = both mask tests / L1, 3 = mask-only with the motion-boundary test alone
+  // LEAN: 1 = both mask tests / L2, 2 = both mask tests / L1, 3 = mask-only with the motion-boundary test alone,
+  //       4 = as 1 plus the optional per-pixel outputs (warp_out / mask_out / blend_out, whichever are set)
   const bool want_occ = MASK == MASK_COMPUTED && (LEAN ? LEAN != 3 : (p.flags & TCLB200_OCC) != 0);
   const bool want_frames = CT > 0 && (LEAN || p.prev != nullptr);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -936,8 +962,10 @@ __global__ void __launch_bounds__(kWsThreads, 1) fused_forward_ws_kernel(const F
       if (t.edge) lean_tile<FrameT, MASK, CT, TCLB200_L2, Cfg, true, false, false>(p, bf_stage(sb), ff_stage(ss), ctl->meta[ss], t, wg, lane, cur, mk);
       else lean_tile<FrameT, MASK, CT, TCLB200_L2, Cfg, false, false, false>(p, bf_stage(sb), ff_stage(ss), ctl->meta[ss], t, wg, lane, cur, mk);
     } else if (LEAN && mode == 1) {
-      if (t.edge) err = lean_tile<FrameT, MASK, CT, (LEAN == 2 ? TCLB200_L1 : TCLB200_L2), Cfg, true, false>(p, bf_stage(sb), ff_stage(ss), ctl->meta[ss], t, wg, lane, cur, mk);
-      else err = lean_tile<FrameT, MASK, CT, (LEAN == 2 ? TCLB200_L1 : TCLB200_L2), Cfg, false, false>(p, bf_stage(sb), ff_stage(ss), ctl->meta[ss], t, wg, lane, cur, mk);
+      if (t.edge) err = lean_tile<FrameT, MASK, CT, (LEAN == 2 ? TCLB200_L1 : TCLB200_L2), Cfg, true, false, true, LEAN == 4>(p, bf_stage(sb), ff_stage(ss), ctl->meta[ss], t, wg, lane, cur, mk);
+      else err = lean_tile<FrameT, MASK, CT, (LEAN == 2 ? TCLB200_L1 : TCLB200_L2), Cfg, false, false, true, LEAN == 4>(p, bf_stage(sb), ff_stage(ss), ctl->meta[ss], t, wg, lane, cur, mk);
+    } else if (LEAN == 4) {   // outputs wanted and the tile is mixed / unstaged: the feature-complete exact path
+      err = full_tile<FrameT, MASK, REDUCE, CT, 0, Cfg, true>(p, bf_stage(sb), ff_stage(ss), prev_stage(ss), ctl->meta[ss], t, wg, lane, cur, mk, have_cur, near);
     } else if (LEAN && mode == 2) {
       err = lean_tile<FrameT, MASK, CT, (LEAN == 2 ? TCLB200_L1 : TCLB200_L2), Cfg, true, true>(p, bf_stage(sb), ff_stage(ss), ctl->meta[ss], t, wg, lane, cur, mk);
     } else if (LEAN || t.edge) {
@@ -1363,6 +1391,7 @@ static cudaError_t dispatch(const FwdParams& p, int mask_kind, bool reduce, bool
 #define TCL_CASE(MK, RD)                                                                       \
   if (mask_kind == MK && reduce == RD) {                                                       \
     if (!tma) return launch_generic<FrameT, MK, RD>(p, s);                                     \
+    if (p.C == 3 && lean_out && MK != MASK_NONE) return launch_tma<FrameT, (MK == MASK_NONE ? MASK_GIVEN : MK), RD, 3, 4>(p, tb, tf, tp, tc, s); \
     if (p.C == 3 && lean && RD) return p.loss == TCLB200_L1 ? launch_tma<FrameT, MK, true, 3, 2>(p, tb, tf, tp, tc, s)   \
                                                             : launch_tma<FrameT, MK, true, 3, 1>(p, tb, tf, tp, tc, s);  \
     if (MK == MASK_COMPUTED && !RD && lean_mask) return launch_tma<float, MASK_COMPUTED, false, 0, 1>(p, tb, tf, tp, tc, s); \
@@ -1374,6 +1403,11 @@ static cudaError_t dispatch(const FwdParams& p, int mask_kind, bool reduce, bool
   const bool lean = reduce && p.prev && p.cur && !p.warp_out && !p.mask_out && !p.blend_out && !p.near_threshold &&
                     !(p.flags & TCLB200_VALIDITY) && mask_kind != MASK_NONE &&
                     (mask_kind != MASK_COMPUTED || (p.flags & (TCLB200_OCC | TCLB200_MOB)) == (TCLB200_OCC | TCLB200_MOB));
+  // ... the same with per-pixel outputs (warp / mask / blend), with or without the reduction
+  const bool lean_out = p.prev && p.cur && (p.warp_out || p.blend_out || (p.mask_out && mask_kind == MASK_COMPUTED)) &&
+                        !(p.mask_out && mask_kind == MASK_GIVEN) && !p.near_threshold && !(p.flags & TCLB200_VALIDITY) &&
+                        p.loss == TCLB200_L2 && mask_kind != MASK_NONE &&
+                        (mask_kind != MASK_COMPUTED || (p.flags & (TCLB200_OCC | TCLB200_MOB)) == (TCLB200_OCC | TCLB200_MOB));
   // ... and fbcCheckTorch on its own: both tests, mask_out only
   const bool lean_mask = !reduce && !p.prev && p.mask_out && !p.near_threshold && mask_kind == MASK_COMPUTED &&
                          (p.flags & (TCLB200_OCC | TCLB200_MOB)) == (TCLB200_OCC | TCLB200_MOB);

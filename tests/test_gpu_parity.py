@@ -353,7 +353,7 @@ def test_hot_path_equals_exact_path_with_mixed_tiles_and_dynamic_schedule(tcl, B
     torch.cuda.synchronize()
     st = (ctypes.c_ulonglong * 2)()
     lib.tclb200_debug_tile_stats(st, 1)
-    exact = tcl.fused_forward(bf, prev, cur, ff=ff, want_warp=True, want_mask=True)
+    exact = tcl.fused_forward(bf, prev, cur, ff=ff, want_warp=True, want_mask=True, want_near=True)   # (near count -> feature-complete path)
     want = _sums64(exact.mask, cur, exact.warp if dtype == torch.float32 else tp.backward_warp(prev.float(), bf))
     rtol = 1e-6 if dtype == torch.float32 else 1e-5
     assert torch.allclose(hot.pair_sums, want, rtol=rtol, atol=0), (hot.pair_sums, want)
@@ -375,7 +375,7 @@ def test_hot_path_with_nonfinite_and_extreme_flow(tcl):
     prev, cur = tcl.synth.make_frames(B, 3, H, W, seed=2, kind="white", device=d)
     bf[0, 0, 10, 20] = float("inf"); bf[0, 1, 50, 100] = float("nan"); bf[1, 0, 70:80, 30:60] = 1e7; bf[1, 1, 5, 5] = -3e9
     hot = tcl.fused_forward(bf, prev, cur, ff=ff)
-    exact = tcl.fused_forward(bf, prev, cur, ff=ff, want_warp=True, want_mask=True)
+    exact = tcl.fused_forward(bf, prev, cur, ff=ff, want_warp=True, want_mask=True, want_near=True)
     with torch.no_grad():
         t_mask = tp.fb_consistency(ff, bf)
         t_warp = tp.backward_warp(prev, bf)
@@ -469,6 +469,39 @@ def test_clip_mode_equals_pairwise(tcl, force_generic, T, H, W):
     force_generic(False)
     with pytest.raises(RuntimeError):
         tcl.fused_forward(bf, frames, frames, ff=ff, prev_index=torch.full((T - 1,), T, device=d), cur_index=idx_cur[:1].repeat(T - 1))
+
+
+# ------------------------------------------------------------------ specialised path with per-pixel outputs
+@pytest.mark.parametrize("B,H,W,shift,rect_shift", [(3, 436, 1024, 32.0, 30.0), (2, 256, 256, 24.0, 20.0), (2, 70, 132, 6.0, 4.0)])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_outputs_from_the_specialised_path_equal_the_exact_path(tcl, B, H, W, shift, rect_shift, dtype):
+    """warp_out / mask_out / blend_out requested together with the reduction run the specialised pipeline (staged tiles) and
+    the feature-complete path (mixed tiles); both must give the bits of the feature-complete path alone (near count requested)
+    and of the op sequence."""
+    d = dev()
+    ff, bf = tcl.synth.make_flows(B, H, W, seed=7 + W, max_shift=shift, max_rot_deg=3.0, n_rects=10, rect_shift=rect_shift, device=d)
+    prev, cur = tcl.synth.make_frames(B, 3, H, W, seed=7 + W, kind="white", device=d, dtype=dtype)
+    exact = tcl.fused_forward(bf, prev, cur, ff=ff, want_warp=True, want_mask=True, want_blend=True, want_near=True)
+    fast = tcl.fused_forward(bf, prev, cur, ff=ff, want_warp=True, want_mask=True, want_blend=True)
+    assert torch.equal(fast.mask, exact.mask)
+    assert torch.equal(fast.warp, exact.warp) and torch.equal(fast.blend, exact.blend)
+    assert torch.allclose(fast.pair_sums, exact.pair_sums, rtol=1e-6 if dtype == torch.float32 else 1e-5, atol=0)
+    if dtype == torch.float32:
+        with torch.no_grad():
+            t_mask, t_warp = tp.fb_consistency(ff, bf), tp.backward_warp(prev, bf)
+        assert torch.equal(fast.mask, t_mask) and torch.equal(fast.warp, t_warp)
+        assert torch.equal(fast.blend, tp.blend(t_mask, t_warp, cur))
+    # single outputs, dataset-mask form, no reduction (warp_blend) and with it
+    only_w = tcl.fused_forward(bf, prev, cur, ff=ff, want_warp=True)
+    assert torch.equal(only_w.warp, exact.warp) and only_w.mask is None
+    m = exact.mask
+    wb = tcl.warp_blend(m, prev, bf, cur)
+    assert torch.equal(wb, exact.blend)
+    soft = torch.rand_like(m)       # a non-binary dataset mask
+    g_exact = tcl.fused_forward(bf, prev, cur, mask=soft, want_blend=True, want_warp=True, want_near=True, finalize=tcl.ops.FIN_MEAN)
+    g_fast = tcl.fused_forward(bf, prev, cur, mask=soft, want_blend=True, want_warp=True, finalize=tcl.ops.FIN_MEAN)
+    assert torch.equal(g_fast.blend, g_exact.blend) and torch.equal(g_fast.warp, g_exact.warp)
+    assert torch.allclose(g_fast.pair_sums, g_exact.pair_sums, rtol=1e-6 if dtype == torch.float32 else 1e-5, atol=0)
 
 
 # ------------------------------------------------------------------ specialised gradient / motion-boundary-only paths
@@ -592,7 +625,7 @@ def test_masks_bit_exact_on_near_threshold_flows(tcl):
     assert torch.equal(k_mask, t_mask)
     prev, cur = tcl.synth.make_frames(2, 3, H, W, seed=9, kind="white", device=d)
     hot = tcl.fused_forward(bf_all, prev, cur, ff=ff_all)      # fused hot path
-    exact = tcl.fused_forward(bf_all, prev, cur, ff=ff_all, want_warp=True, want_mask=True)
+    exact = tcl.fused_forward(bf_all, prev, cur, ff=ff_all, want_warp=True, want_mask=True, want_near=True)
     assert torch.equal(exact.mask, t_mask)
     want = _sums64(t_mask, cur, exact.warp)
     assert torch.allclose(hot.pair_sums, want, rtol=1e-6, atol=0)
