@@ -1057,6 +1057,14 @@ struct BwdParams {
   int B, C, flags, loss;
 };
 
+// Where the time goes (64 Sintel-shape pairs, memset + kernel 527 us = 54 Gpix/s): the real DRAM traffic is 84 B/px
+// (36 inputs + 12 read-for-ownership of the scatter target + 24 written + 12 for the zero-fill), i.e. 4.5 TB/s = 0.69 of
+// the measured copy peak with reads and writes mixed.  Measured and dropped, none of them moved that number:
+//   - 2 / 4 pixels per lane (all flow-independent loads first, then all gathers): 43 / 19-26 Gpix/s (registers, occupancy)
+//   - warp-aggregated scatter (lane l adds lane l-1's right-hand taps to its own `red` where the flow is locally uniform,
+//     halving the atomics): 53.9 Gpix/s, no change -- the `red` drain is not the limit
+//   - the batch in L2-sized slices (memset of a slice, then its kernel) so that the `red`s find zeroed lines resident:
+//     556 / 573 / 614 / 712 us with 96 / 64 / 32 / 16 MB slices -- the tails between the short kernels cost more
 // FUSED_LOSS: the upstream gradient of warp is derived in-kernel from the masked loss.
 // CT > 0 fixes the channel count at compile time: all 4*CT gathers and the CT `cur` / grad_out loads of a pixel are then
 // issued back to back (the kernel is latency-bound otherwise: measured 10 long-scoreboard stall cycles per issue).
