@@ -12,7 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.environ.get("TCL_B200_LIB") or os.path.join(CSRC, "libtcl_b200.so")  # env override: tuning sweeps only
 HEADER = os.path.join(os.path.dirname(_HERE), "include", "tcl_b200.h")
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 # enums mirrored from include/tcl_b200.h
 F32, BF16 = 0, 1
@@ -40,6 +40,8 @@ class TclArgs(ctypes.Structure):
         ("dtype", ctypes.c_int), ("flags", ctypes.c_int), ("loss", ctypes.c_int), ("finalize", ctypes.c_int),
         ("prev_index", ctypes.c_void_p), ("cur_index", ctypes.c_void_p),
         ("n_prev_frames", ctypes.c_int), ("n_cur_frames", ctypes.c_int),
+        ("ff_plane_stride", ctypes.c_size_t), ("ff_batch_stride", ctypes.c_size_t),
+        ("bf_plane_stride", ctypes.c_size_t), ("bf_batch_stride", ctypes.c_size_t),
     ]
 
 

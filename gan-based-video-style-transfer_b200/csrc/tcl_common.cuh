@@ -75,6 +75,7 @@ struct FwdParams {
   const float* mask_in;
   const void* prev;
   const void* cur;
+  size_t ff_plane, ff_batch, bf_plane, bf_batch;   // element strides between the two flow components / between pairs (rows are dense)
   const int* prev_index;   // clip mode: frame of `prev` / `cur` each pair reads (nullptr: its own)
   const int* cur_index;
   void* warp_out;

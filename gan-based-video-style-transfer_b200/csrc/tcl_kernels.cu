@@ -197,8 +197,8 @@ __global__ void __launch_bounds__(kThreads) fused_forward_generic_kernel(const F
   unsigned near = 0;
   if (x < W && y < H) {
     const size_t o = (size_t)y * W + x;
-    const float* bu = p.bf + (size_t)pair * 2 * plane;
-    const float* bv = bu + plane;
+    const float* bu = p.bf + (size_t)pair * p.bf_batch;
+    const float* bv = bu + p.bf_plane;
     const float u = __ldg(bu + o), v = __ldg(bv + o);
     float nb = sqnorm2(u, v, kV);
     float keep = 1.0f;
@@ -213,7 +213,7 @@ __global__ void __launch_bounds__(kThreads) fused_forward_generic_kernel(const F
       near += fabsf(margin) < kNearBand;
     }
     const PixTaps s = pix_taps(u, v, x, y, g);
-    GlobalSrc<float> fsrc{p.ff ? p.ff + (size_t)pair * 2 * plane : nullptr, plane, g};
+    GlobalSrc<float> fsrc{p.ff ? p.ff + (size_t)pair * p.ff_batch : nullptr, p.ff_plane, g};
     GlobalSrc<FrameT> psrc{p.prev ? reinterpret_cast<const FrameT*>(p.prev) + (size_t)prev_frame(p, pair) * C * plane : nullptr, plane, g};
     finish_pixel<FrameT, MASK, REDUCE, CT, false>(p, s, u, v, nb, keep, o, plane, pair, fsrc, psrc,
                                                   pair_ptrs<FrameT>(p, pair, cur_frame(p, pair), C, plane), nullptr, err, near);
@@ -411,7 +411,7 @@ __device__ __forceinline__ float full_tile(const FwdParams& p, const float* s_bu
   const int ox = meta[0], oy = meta[1], mode = meta[2];   // mode 0: nothing staged, 1: every tap in the boxes, 2: mixed
   const SmemSrc<float, Cfg::BW, Cfg::BH * Cfg::BW> fs{s_ff, ox, oy};
   const SmemSrc<FrameT, Cfg::BW, Cfg::BH * Cfg::BW> ps{s_prev, ox, oy};
-  const GlobalSrc<float> fg{p.ff ? p.ff + (size_t)t.pair * 2 * plane : nullptr, plane, g};
+  const GlobalSrc<float> fg{p.ff ? p.ff + (size_t)t.pair * p.ff_batch : nullptr, p.ff_plane, g};
   const GlobalSrc<FrameT> pg{p.prev ? reinterpret_cast<const FrameT*>(p.prev) + (size_t)t.pf * (CT > 0 ? CT : p.C) * plane : nullptr, plane, g};
   float err = 0.0f;
 #pragma unroll
@@ -500,13 +500,13 @@ __device__ __noinline__ bool exact_keep(const float* s_bu, const float* s_ff, in
 // one pixel of the hot configuration entirely from global memory with the exact sequences: the pixels of a "mixed" tile
 // (a motion boundary runs through it) whose taps lie outside the staged source boxes.  Returns the masked squared error.
 template <typename FrameT, int MASK, bool KEEP_ONLY, int LOSS>
-__device__ __noinline__ float pixel_global(const float* bf_pair, const float* ff_pair, const FrameT* prev_pair, Geo g, int x, int y,
-                                           float c0, float c1, float c2, float mkv) {
+__device__ __noinline__ float pixel_global(const float* bf_pair, size_t bf_plane, const float* ff_pair, size_t ff_plane, const FrameT* prev_pair,
+                                           Geo g, int x, int y, float c0, float c1, float c2, float mkv) {
   const int W = g.W, H = g.H;
   const size_t plane = (size_t)H * W;
   const size_t o = (size_t)y * W + x;
   const float* bu = bf_pair;
-  const float* bv = bf_pair + plane;
+  const float* bv = bf_pair + bf_plane;
   const float u = __ldg(bu + o), v = __ldg(bv + o);
   bool keep = true;
   float nb = 0.0f;
@@ -520,7 +520,7 @@ __device__ __noinline__ float pixel_global(const float* bf_pair, const float* ff
   }
   const PixTaps s = pix_taps(u, v, x, y, g);
   if (MASK == MASK_COMPUTED) {
-    const GlobalSrc<float> fsrc{ff_pair, plane, g};
+    const GlobalSrc<float> fsrc{ff_pair, ff_plane, g};
     const float wu = fsrc.sample(0, s), wv = fsrc.sample(1, s);
     float margin;
     if (occluded(wu, wv, u, v, nb, kV, &margin)) keep = false;
@@ -551,7 +551,7 @@ __device__ __forceinline__ float lean_tile(const FwdParams& p, const float* s_bu
   const int box_x = meta[0], box_y = meta[1];
   const float box_xf = (float)box_x, box_yf = (float)box_y;
   const ptrdiff_t gplane = (ptrdiff_t)g.H * g.W;
-  const float* gff = (MIXED && MASK == MASK_COMPUTED) ? p.ff + (size_t)t.pair * 2 * gplane : nullptr;
+  const float* gff = (MIXED && MASK == MASK_COMPUTED) ? p.ff + (size_t)t.pair * p.ff_batch : nullptr;
   const FrameT* gprev = (MIXED && CT == 3) ? reinterpret_cast<const FrameT*>(p.prev) + (size_t)t.pf * 3 * gplane : nullptr;
   LeanGeo lg;
   lg.i2x = __fmul_rn(2.0f, g.inv_dx); lg.i2y = __fmul_rn(2.0f, g.inv_dy);   // exact doubling: (2a)*r == a*(2r)
@@ -594,14 +594,14 @@ __device__ __forceinline__ float lean_tile(const FwdParams& p, const float* s_bu
     const float* pf = s_ff + q;
     const FrameT* pp = s_prev + q;
     int rs = BW;
-    ptrdiff_t ps = PL;
+    ptrdiff_t ps = PL, psf = PL;   // plane pitch of the frame / flow planes behind pp / pf
     bool p00 = true, p10 = true, p01 = true, p11 = true;
     if (MIXED && !inbox) {
       const int gx = (int)tp.rx + box_x, gy = (int)tp.ry + box_y;   // top-left tap in the image (sane: the placement checked)
       const ptrdiff_t off = (ptrdiff_t)gy * g.W + gx;
       if (MASK == MASK_COMPUTED) pf = gff + off;
       if (CT == 3) pp = gprev + off;
-      rs = g.W; ps = gplane;
+      rs = g.W; ps = gplane; psf = (ptrdiff_t)p.ff_plane;
       const bool xin0 = (unsigned)gx < (unsigned)g.W, xin1 = (unsigned)(gx + 1) < (unsigned)g.W;
       const bool yin0 = (unsigned)gy < (unsigned)g.H, yin1 = (unsigned)(gy + 1) < (unsigned)g.H;
       p00 = xin0 && yin0; p10 = xin1 && yin0; p01 = xin0 && yin1; p11 = xin1 && yin1;
@@ -622,7 +622,7 @@ __device__ __forceinline__ float lean_tile(const FwdParams& p, const float* s_bu
       return w;
     };
     if (MASK == MASK_COMPUTED && OCC) {
-      const float a = tap4(pf), b = tap4(MIXED ? pf + ps : pf + PL);
+      const float a = tap4(pf), b = tap4(MIXED ? pf + psf : pf + PL);
       // occlusion: |wf+bf|^2  vs  0.01*(|wf|^2+|bf|^2) + 0.5
       const float su = __fadd_rn(a, u), sv = __fadd_rn(b, v);
       const float L = __fmaf_rn(su, su, __fmul_rn(sv, sv));
@@ -678,12 +678,12 @@ __device__ __forceinline__ float lean_tile(const FwdParams& p, const float* s_bu
     for (int k = 0; k < P; ++k)
       if ((outbits >> k) & 1u) {
         if (CT == 3) {
-          e[k] = pixel_global<FrameT, MASK, false, LOSS>(p.bf + (size_t)t.pair * 2 * plane, p.ff + (size_t)t.pair * 2 * plane,
+          e[k] = pixel_global<FrameT, MASK, false, LOSS>(p.bf + (size_t)t.pair * p.bf_batch, p.bf_plane, p.ff + (size_t)t.pair * p.ff_batch, p.ff_plane,
                                                    reinterpret_cast<const FrameT*>(p.prev) + (size_t)t.pf * 3 * plane, g, t.x0 + lx0 + 16 * (k & 1),
                                                    t.y0 + ly0 + DY * (k >> 1), cur[k][0], cur[k][1], cur[k][2], mk[k]);
           keepbits |= 1u << k;   // the verdict is already applied
         } else {
-          const float kp = pixel_global<FrameT, MASK, true, LOSS>(p.bf + (size_t)t.pair * 2 * plane, p.ff + (size_t)t.pair * 2 * plane, nullptr, g,
+          const float kp = pixel_global<FrameT, MASK, true, LOSS>(p.bf + (size_t)t.pair * p.bf_batch, p.bf_plane, p.ff + (size_t)t.pair * p.ff_batch, p.ff_plane, nullptr, g,
                                                             t.x0 + lx0 + 16 * (k & 1), t.y0 + ly0 + DY * (k >> 1), 0.0f, 0.0f, 0.0f, 0.0f);
           keepbits = (keepbits & ~(1u << k)) | ((kp != 0.0f ? 1u : 0u) << k);
         }
@@ -1322,12 +1322,16 @@ static EncodeTiledFn encode_fn() {
   return fn;
 }
 
-// (W, H, planes, B) view of an NCHW tensor with a (bw, bh, bp, 1) box
-static bool make_map(CUtensorMap* m, const void* base, int esize, int W, int H, int planes, int B, int bw, int bh, int bp) {
+// (W, H, planes, B) view of an NCHW tensor with a (bw, bh, bp, 1) box; plane_stride / batch_stride in elements
+// (0 = dense): rows are always dense, planes and images may lie further apart (a cropped view of a padded tensor)
+static bool make_map(CUtensorMap* m, const void* base, int esize, int W, int H, int planes, int B, int bw, int bh, int bp,
+                     size_t plane_stride = 0, size_t batch_stride = 0) {
   EncodeTiledFn fn = encode_fn();
   if (!fn || !base) return false;
+  if (!plane_stride) plane_stride = (size_t)W * H;
+  if (!batch_stride) batch_stride = plane_stride * planes;
   const cuuint64_t dims[4] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)planes, (cuuint64_t)B};
-  const cuuint64_t strides[3] = {(cuuint64_t)W * esize, (cuuint64_t)W * H * esize, (cuuint64_t)W * H * planes * esize};
+  const cuuint64_t strides[3] = {(cuuint64_t)W * esize, (cuuint64_t)plane_stride * esize, (cuuint64_t)batch_stride * esize};
   const cuuint32_t box[4] = {(cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)bp, 1u};
   const cuuint32_t estr[4] = {1u, 1u, 1u, 1u};
   const CUtensorMapDataType dt = esize == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
@@ -1479,14 +1483,22 @@ static int run_fused(const tclb200_tcl_args* a, cudaStream_t s) {
   if (!a->prev && !a->mask_out) return fail(TCLB200_ERR_INVALID, "nothing to compute: no frames and no mask_out");
 
   const int esz = a->dtype == TCLB200_BF16 ? 2 : 4;
+  // flows may be row-dense views with their own plane / pair strides (RAFT's padded output cropped by
+  // InputPadder.unpad or flow_up[:,:,:H,:]); 0 = dense
+  const size_t hw = (size_t)a->H * a->W;
+  const size_t bf_plane = a->bf_plane_stride ? a->bf_plane_stride : hw, bf_batch = a->bf_batch_stride ? a->bf_batch_stride : 2 * bf_plane;
+  const size_t ff_plane = a->ff_plane_stride ? a->ff_plane_stride : hw, ff_batch = a->ff_batch_stride ? a->ff_batch_stride : 2 * ff_plane;
+  if (bf_plane < hw || ff_plane < hw || (a->B > 1 && (bf_batch < hw || ff_batch < hw)))
+    return fail(TCLB200_ERR_INVALID, "flow plane / pair strides must be at least H*W");
+  const bool strides16 = bf_plane % 4 == 0 && bf_batch % 4 == 0 && ff_plane % 4 == 0 && ff_batch % 4 == 0;   // TMA: 16-byte strides
   // TMA needs 16-byte aligned bases and row strides; frames need C == 3 (the compiled box depth)
   bool tma = !g_force_generic && (a->W % 4 == 0) && ((a->W * esz) % 16 == 0) && aligned16(a->bf) && aligned16(a->ff) &&
-             aligned16(a->prev) && aligned16(a->cur) && (!a->prev || a->C == 3) && a->B <= 65535 * 16;
+             aligned16(a->prev) && aligned16(a->cur) && (!a->prev || a->C == 3) && a->B <= 65535 * 16 && strides16;
   CUtensorMap tb, tf, tp, tc;
   memset(&tb, 0, sizeof(tb)); memset(&tf, 0, sizeof(tf)); memset(&tp, 0, sizeof(tp)); memset(&tc, 0, sizeof(tc));
   if (tma) {
-    tma = make_map(&tb, a->bf, 4, a->W, a->H, 2, a->B, kTW + 16, kTH + 2, 2);
-    if (tma && mask_kind == MASK_COMPUTED && (a->flags & TCLB200_OCC)) tma = make_map(&tf, a->ff, 4, a->W, a->H, 2, a->B, kBW, kBH, 2);
+    tma = make_map(&tb, a->bf, 4, a->W, a->H, 2, a->B, kTW + 16, kTH + 2, 2, bf_plane, bf_batch);
+    if (tma && mask_kind == MASK_COMPUTED && (a->flags & TCLB200_OCC)) tma = make_map(&tf, a->ff, 4, a->W, a->H, 2, a->B, kBW, kBH, 2, ff_plane, ff_batch);
     if (tma && a->prev) tma = make_map(&tp, a->prev, esz, a->W, a->H, 3, a->prev_index ? a->n_prev_frames : a->B, kBW, kBH, 3);
     if (tma && a->prev && a->cur) tma = make_map(&tc, a->cur, esz, a->W, a->H, 3, a->cur_index ? a->n_cur_frames : a->B, kTW, kTH, 3);
   }
@@ -1494,6 +1506,7 @@ static int run_fused(const tclb200_tcl_args* a, cudaStream_t s) {
   FwdParams p;
   memset(&p, 0, sizeof(p));
   p.ff = a->ff; p.bf = a->bf; p.mask_in = a->mask_in; p.prev = a->prev; p.cur = a->cur;
+  p.ff_plane = ff_plane; p.ff_batch = ff_batch; p.bf_plane = bf_plane; p.bf_batch = bf_batch;
   p.prev_index = a->prev ? a->prev_index : nullptr; p.cur_index = a->cur ? a->cur_index : nullptr;
   p.warp_out = a->warp_out; p.mask_out = a->mask_out; p.blend_out = a->blend_out;
   p.pair_sums = a->pair_sums; p.total_sums = a->total_sums; p.pair_vals = a->pair_vals; p.total_val = a->total_val;

@@ -52,6 +52,21 @@ def _flow(f, name="flow"):
     return f.contiguous()
 
 
+def _flow_view(f, name="flow"):
+    """-> (tensor whose data_ptr is handed over, plane stride, pair stride) in elements; 0 strides = dense.
+
+    A row-dense view of a larger tensor -- what ``InputPadder.unpad`` (utils/raft/raft/utils/utils.py:21-24) or
+    ``flow_up[:,:,:H,:]`` (ConGAN/sintel_eval.py:61) make of RAFT's padded output when only rows were padded -- is read
+    in place through its strides; anything else is made contiguous like before."""
+    if f.dim() != 4 or f.shape[1] != 2:
+        raise RuntimeError(f"tcl_b200: {name} must be (B,2,H,W), got {tuple(f.shape)}")
+    B, _, H, W = f.shape
+    if (f.dtype == torch.float32 and not f.is_contiguous() and H * W > 0 and f.stride(3) == 1 and f.stride(2) == W
+            and f.stride(1) >= H * W and (B == 1 or f.stride(0) >= 2 * H * W)):
+        return f, f.stride(1), (f.stride(0) if B > 1 else 2 * f.stride(1))
+    return _flow(f, name), 0, 0
+
+
 def _frame_dtype(t):
     if t.dtype == torch.float32:
         return F32
@@ -91,12 +106,19 @@ def gradient(x):
     return out
 
 
-def _warp_forward(x, f, flags):
+def _warp_forward(x, f, flags, f_plane=0, f_batch=0):
     B, C, H, W = x.shape
     out = torch.empty_like(x)
     with torch.cuda.device(x.device):
-        check(_cabi.lib().tclb200_warp(_ptr(x), _ptr(f), _ptr(out), B, C, H, W, _frame_dtype(x), flags,
-                                       _stream_handle()))
+        if not (f_plane or f_batch):
+            check(_cabi.lib().tclb200_warp(_ptr(x), _ptr(f), _ptr(out), B, C, H, W, _frame_dtype(x), flags,
+                                           _stream_handle()))
+        else:   # a strided flow view: the same launch through the struct entry, which carries the strides
+            a = TclArgs()
+            a.bf, a.prev, a.warp_out = _ptr(f), _ptr(x), _ptr(out)
+            a.B, a.C, a.H, a.W, a.dtype, a.flags = B, C, H, W, _frame_dtype(x), flags & VALIDITY
+            a.bf_plane_stride, a.bf_batch_stride = f_plane, f_batch
+            check(_cabi.lib().tclb200_tcl_forward(ctypes.byref(a), _stream_handle()))
     return out
 
 
@@ -129,14 +151,16 @@ def _warp(x, f, flags):
     _require_cuda(x, f)
     if x.dim() != 4:
         raise RuntimeError(f"tcl_b200: warp expects x of shape (B,C,H,W), got {tuple(x.shape)}")
-    f = _flow(f, "f")
+    if f.dim() != 4 or f.shape[1] != 2:
+        raise RuntimeError(f"tcl_b200: f must be (B,2,H,W), got {tuple(f.shape)}")
     if f.shape[0] != x.shape[0] or f.shape[2:] != x.shape[2:]:
         raise RuntimeError(f"tcl_b200: x {tuple(x.shape)} and flow {tuple(f.shape)} do not match")
     _frame_dtype(x)
     x = x.contiguous()
     if torch.is_grad_enabled() and (x.requires_grad or f.requires_grad):
-        return _WarpFn.apply(x, f, flags)
-    return _warp_forward(x, f, flags)
+        return _WarpFn.apply(x, _flow(f, "f"), flags)
+    f, f_plane, f_batch = _flow_view(f, "f")
+    return _warp_forward(x, f, flags, f_plane, f_batch)
 
 
 def warp(x, f):
@@ -155,10 +179,11 @@ def fs_warp(x, flo):
 
 def _fbcheck(ff, bf, flags, device, return_near=False):
     _require_cuda(bf)
-    bf = _flow(bf, "bf")
+    bf, bf_plane, bf_batch = _flow_view(bf, "bf")
+    ff_plane = ff_batch = 0
     if flags & OCC:
         _require_cuda(ff)
-        ff = _flow(ff, "ff")
+        ff, ff_plane, ff_batch = _flow_view(ff, "ff")
         if ff.shape != bf.shape:
             raise RuntimeError(f"tcl_b200: ff {tuple(ff.shape)} and bf {tuple(bf.shape)} do not match")
     else:
@@ -167,8 +192,16 @@ def _fbcheck(ff, bf, flags, device, return_near=False):
     mask = torch.empty((B, 1, H, W), dtype=torch.float32, device=bf.device)
     near = torch.zeros(1, dtype=torch.int64, device=bf.device) if return_near else None
     with torch.cuda.device(bf.device):
-        check(_cabi.lib().tclb200_fbcheck(_ptr(ff), _ptr(bf), _ptr(mask), B, H, W, flags, _ptr(near),
-                                          _stream_handle()))
+        if not (bf_plane or ff_plane):
+            check(_cabi.lib().tclb200_fbcheck(_ptr(ff), _ptr(bf), _ptr(mask), B, H, W, flags, _ptr(near),
+                                              _stream_handle()))
+        else:   # strided flow views: the same launch through the struct entry, which carries the strides
+            a = TclArgs()
+            a.ff, a.bf, a.mask_out, a.near_threshold = _ptr(ff if ff is not None else bf), _ptr(bf), _ptr(mask), _ptr(near)
+            a.B, a.H, a.W, a.flags = B, H, W, flags
+            a.bf_plane_stride, a.bf_batch_stride = bf_plane, bf_batch
+            a.ff_plane_stride, a.ff_batch_stride = (ff_plane, ff_batch) if ff is not None else (bf_plane, bf_batch)
+            check(_cabi.lib().tclb200_tcl_forward(ctypes.byref(a), _stream_handle()))
     if device is not None and torch.device(device) != mask.device and torch.device(device).type != "cuda":
         mask = mask.to(device)
     return (mask, near) if return_near else mask
@@ -243,9 +276,9 @@ def fused_forward(bf, prev, cur, ff=None, mask=None, loss=L2, finalize=FIN_RMSE,
     ``cur`` of pair t and ``prev`` of pair t+1 (see ``temporal_error_clip``).
     """
     _require_cuda(bf, prev, cur, ff, mask)
-    bf = _flow(bf, "bf")
+    bf, bf_plane, bf_batch = _flow_view(bf, "bf")
     B, _, H, W = bf.shape
-    ff = _flow(ff, "ff") if ff is not None else None
+    ff, ff_plane, ff_batch = _flow_view(ff, "ff") if ff is not None else (None, 0, 0)
     if prev.dim() != 4 or (prev_index is None and prev.shape[0] != B) or prev.shape[2:] != bf.shape[2:]:
         raise RuntimeError(f"tcl_b200: prev {tuple(prev.shape)} does not match flow {tuple(bf.shape)}")
     if cur.dim() != 4 or cur.shape[1:] != prev.shape[1:] or cur.dtype != prev.dtype or (cur_index is None and cur.shape[0] != B):
@@ -295,6 +328,7 @@ def fused_forward(bf, prev, cur, ff=None, mask=None, loss=L2, finalize=FIN_RMSE,
         a.dtype, a.flags, a.loss, a.finalize = dt, flags, loss, finalize
         a.prev_index, a.cur_index = _ptr(prev_index), _ptr(cur_index)
         a.n_prev_frames, a.n_cur_frames = prev.shape[0], cur.shape[0]
+        a.ff_plane_stride, a.ff_batch_stride, a.bf_plane_stride, a.bf_batch_stride = ff_plane, ff_batch, bf_plane, bf_batch
         check(_cabi.lib().tclb200_tcl_forward(ctypes.byref(a), _stream_handle()))
     return res
 

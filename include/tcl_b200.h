@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define TCLB200_ABI_VERSION 3
+#define TCLB200_ABI_VERSION 4
 
 #define TCLB200_OK 0
 #define TCLB200_ERR_INVALID 1     /* bad argument (null pointer, non-positive size, unknown enum) */
@@ -128,6 +128,11 @@ typedef struct tclb200_tcl_args {
   const int* prev_index;
   const int* cur_index;
   int n_prev_frames, n_cur_frames;
+  /* strided flows (optional, 0 = dense): rows stay dense, but the two components of a flow / consecutive pairs may lie
+   * ff_plane_stride / ff_batch_stride (bf_...) floats apart.  That is what the reference hands over: RAFT's output on
+   * the /8-padded image cropped by InputPadder.unpad (utils/raft/raft/utils/utils.py:21-24) or flow_up[:,:,:H,:]
+   * (methods/GAN-based/ConGAN/sintel_eval.py:61) is such a view -- it is read in place, no gather copy. */
+  size_t ff_plane_stride, ff_batch_stride, bf_plane_stride, bf_batch_stride;
 } tclb200_tcl_args;
 
 int tclb200_tcl_forward(const tclb200_tcl_args* args, tclb200_stream_t stream);

@@ -471,6 +471,47 @@ def test_clip_mode_equals_pairwise(tcl, force_generic, T, H, W):
         tcl.fused_forward(bf, frames, frames, ff=ff, prev_index=torch.full((T - 1,), T, device=d), cur_index=idx_cur[:1].repeat(T - 1))
 
 
+# ------------------------------------------------------------------ strided flow views (RAFT's padded output, cropped)
+@pytest.mark.parametrize("B,H,W,pad", [(1, 436, 1024, (2, 2)), (3, 100, 256, (0, 4)), (2, 37, 53, (3, 1)), (1, 64, 96, (4, 4))])
+def test_cropped_views_of_padded_flows_are_read_in_place(tcl, B, H, W, pad):
+    """InputPadder.unpad (utils/raft/raft/utils/utils.py:21-24) and flow_up[:,:,:H,:] (ConGAN/sintel_eval.py:61) hand the path
+    row-dense views of RAFT's padded output; they go to the kernels through their strides (no gather copy) and must give the
+    bits of the contiguous copy -- fused error, mask, warp, on the TMA path and (W % 4 != 0) the generic one."""
+    d = dev()
+    top, bottom = pad
+    ff_c, bf_c = tcl.synth.make_flows(B, H, W, seed=H + W, max_shift=9.0, device=d)
+    prev, cur = tcl.synth.make_frames(B, 3, H, W, seed=H + W, kind="white", device=d)
+
+    def padded_view(t):
+        big = torch.full((B, 2, top + H + bottom, W), 7.5, device=d)      # the padding must never be read as flow
+        big[:, :, top:top + H] = t
+        v = big[:, :, top:top + H, :]
+        assert not v.is_contiguous() or (top + bottom == 0)
+        return v
+    ff_v, bf_v = padded_view(ff_c), padded_view(bf_c)
+    from importlib import import_module
+    ops = tcl.ops
+    _, plane, batch = ops._flow_view(bf_v, "bf")
+    assert plane == (top + H + bottom) * W and batch == 2 * plane, "the view must be handed over through its strides"
+    want = tcl.fused_forward(bf_c, prev, cur, ff=ff_c, want_warp=True, want_mask=True)
+    got = tcl.fused_forward(bf_v, prev, cur, ff=ff_v, want_warp=True, want_mask=True)
+    assert torch.equal(got.mask, want.mask) and torch.equal(got.warp, want.warp) and torch.equal(got.pair_sums, want.pair_sums)
+    assert torch.equal(tcl.temporal_error_per_pair(ff_v, bf_v, prev, cur), tcl.temporal_error_per_pair(ff_c, bf_c, prev, cur))
+    assert torch.equal(tcl.fbcCheckTorch(ff_v, bf_v), tcl.fbcCheckTorch(ff_c, bf_c))
+    assert torch.equal(tcl.fbcCheckTorch_mob(ff_v, bf_v), tcl.fbcCheckTorch_mob(ff_c, bf_c))
+    assert torch.equal(tcl.warp(prev, bf_v), tcl.warp(prev, bf_c))
+    assert torch.equal(tcl.fs_warp(prev, bf_v), tcl.fs_warp(prev, bf_c))
+    m, near = tcl.fbcheck_with_near_count(ff_v, bf_v)
+    assert torch.equal(m, want.mask)
+    # mixed strides: one flow dense, one a view; and autograd through warp still works on a view (made contiguous there)
+    assert torch.equal(tcl.fused_forward(bf_v, prev, cur, ff=ff_c).pair_sums, tcl.fused_forward(bf_c, prev, cur, ff=ff_c).pair_sums)
+    p = prev.clone().requires_grad_(True)
+    tcl.warp(p, bf_v).sum().backward()
+    p2 = prev.clone().requires_grad_(True)
+    tcl.warp(p2, bf_c).sum().backward()
+    assert torch.allclose(p.grad, p2.grad, rtol=1e-5, atol=1e-6)
+
+
 # ------------------------------------------------------------------ specialised path with per-pixel outputs
 @pytest.mark.parametrize("B,H,W,shift,rect_shift", [(3, 436, 1024, 32.0, 30.0), (2, 256, 256, 24.0, 20.0), (2, 70, 132, 6.0, 4.0)])
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
