@@ -14,7 +14,7 @@ from .sharding import (ShardPlan, plan_shards, evaluate_sharded, allreduce_sums)
 from . import synth  # noqa: F401
 from . import ingest  # noqa: F401
 from . import cv2compat  # noqa: F401
-from .ingest import hwc_split, split_fc2_block, flow_hw2_to_planar, load_flo_planar  # noqa: F401
+from .ingest import hwc_split, split_fc2_block, flow_hw2_to_planar, load_flo_planar, sintel_occlusion_mask  # noqa: F401
 
 __all__ = ["gradient", "warp", "fbcCheckTorch", "fbcCheckTorch_mob", "fs_warp", "fused_forward",
            "temporal_error", "temporal_error_per_pair", "temporal_error_clip", "temporal_error_host", "generateMask", "temporal_loss", "temporal_rmse_per_sample",

@@ -98,6 +98,7 @@ _PROTOTYPES = {
     "tclb200_tcl_forward_host": (_c.c_int, [_c.POINTER(HostArgs), _vp]),
     "tclb200_tcl_backward": (_c.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     "tclb200_hwc_split": (_c.c_int, [_vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
+    "tclb200_occlusion_u8_to_mask": (_c.c_int, [_vp, _vp, _c.c_size_t, _vp]),
     "tclb200_upsample_flow": (_c.c_int, [_vp, _vp, _vp, _i, _i, _i, _vp]),
     "tclb200_cv2_remap": (_c.c_int, [_vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "tclb200_cv2_fb_check": (_c.c_int, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp]),

@@ -144,6 +144,23 @@ __global__ void __launch_bounds__(256) cv2_fb_check_kernel(const float2* __restr
   }
 }
 
+// Sintel ground-truth occlusion PNG -> the mask the path consumes (utils/sintel_dataset.py:64-65):
+//   mask = io.imread(png) / 255.0 ; mask = 1.0 - mask   (float64) ; later .float()
+// 256 possible inputs: the table is computed on the host with exactly that float64 arithmetic, the kernel is a lookup.
+__constant__ float c_occ_lut[256];
+
+__global__ void __launch_bounds__(256) occlusion_u8_kernel(const uint8_t* __restrict__ src, float* __restrict__ dst, size_t n4, size_t n) {
+  const size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
+  if (i < n4) {   // four pixels per lane: one 32-bit load, one 128-bit store
+    const uchar4 v = __ldcs(reinterpret_cast<const uchar4*>(src) + i);
+    __stcs(reinterpret_cast<float4*>(dst) + i, make_float4(c_occ_lut[v.x], c_occ_lut[v.y], c_occ_lut[v.z], c_occ_lut[v.w]));
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (unsigned)(n - 4 * n4)) {   // the 0..3 trailing pixels
+    const size_t j = 4 * n4 + threadIdx.x;
+    dst[j] = c_occ_lut[src[j]];
+  }
+}
+
 int cfail(int code, const char* msg, const char* detail = "") {
   char buf[512];
   snprintf(buf, sizeof(buf), "%s%s", msg, detail);
@@ -192,5 +209,26 @@ extern "C" int tclb200_cv2_fb_check(const float* ff, const float* bf, float* mas
   tcl::count_launch();
   const cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return cfail(TCLB200_ERR_CUDA, "cv2_fb_check launch: ", cudaGetErrorString(e));
+  return TCLB200_OK;
+}
+
+extern "C" int tclb200_occlusion_u8_to_mask(const uint8_t* src, float* dst, size_t n, tclb200_stream_t stream) {
+  if (!src || !dst) return cfail(TCLB200_ERR_INVALID, "src and dst are required");
+  if (n == 0) return cfail(TCLB200_ERR_INVALID, "n must be positive");
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  float lut[256];
+  for (int v = 0; v < 256; ++v) lut[v] = (float)(1.0 - (double)v / 255.0);
+  // per call and stream-ordered (64 launches' worth of bytes; no process-global "initialised" flag to go stale across devices)
+  cudaError_t e = cudaMemcpyToSymbolAsync(c_occ_lut, lut, sizeof(lut), 0, cudaMemcpyHostToDevice, s);
+  if (e != cudaSuccess) return cfail(TCLB200_ERR_CUDA, "occlusion table upload: ", cudaGetErrorString(e));
+  const bool vec = ((reinterpret_cast<uintptr_t>(src) & 3u) == 0) && ((reinterpret_cast<uintptr_t>(dst) & 15u) == 0);
+  const size_t n4 = vec ? n / 4 : 0;
+  if (n - 4 * n4 > 256 || (n4 + 255) / 256 >= 0x7fffffffull)   // (the scalar tail covers at most one CTA's worth of pixels)
+    return cfail(TCLB200_ERR_UNSUPPORTED, "src must be 4-byte and dst 16-byte aligned (or n <= 256)");
+  const unsigned grid = (unsigned)(n4 ? (n4 + 255) / 256 : 1);
+  occlusion_u8_kernel<<<grid, 256, 0, s>>>(src, dst, n4, n);
+  tcl::count_launch();
+  e = cudaGetLastError();
+  if (e != cudaSuccess) return cfail(TCLB200_ERR_CUDA, "occlusion_u8 launch: ", cudaGetErrorString(e));
   return TCLB200_OK;
 }

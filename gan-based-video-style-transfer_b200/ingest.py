@@ -6,7 +6,9 @@ Upstream formats (paths relative to the reference repository):
   training sets (``methods/GAN-based/StarGANv2AdvCon/core/data_loader.py:243-245``,
   ``methods/learning-based/datasets.py:52-54``): the reference slices them with ``np.moveaxis(np_data[:,:,6:7], 2, 0)``
   per sample on the host;
-* ``.flo`` files (``utils/flowlib.py:33-48``): magic ``PIEH``, int32 width, int32 height, H x W x 2 float32.
+* ``.flo`` files (``utils/flowlib.py:33-48``): magic ``PIEH``, int32 width, int32 height, H x W x 2 float32;
+* Sintel's ground-truth occlusion PNGs (``utils/sintel_dataset.py:64-65``): ``mask = 1.0 - imread(png)/255.0``;
+* the long-term ``.npy`` blocks ``[flow 2 | mask 1]`` HWC (``utils/sintel_dataset.py:76-83``): ``hwc_split(block, LT_LAYOUT)``.
 
 Here the raw interleaved block is uploaded once and split on the GPU by ``tclb200_hwc_split`` (one pass, coalesced on both
 sides).  File reading itself stays plain numpy: it is I/O, not arithmetic.
@@ -20,6 +22,7 @@ from . import _cabi
 from ._cabi import check
 
 FC2_LAYOUT = (("img1", 0, 3), ("img2", 3, 3), ("mask", 6, 1), ("flow", 7, 2))
+LT_LAYOUT = (("flow", 0, 2), ("mask", 2, 1))   # utils/sintel_dataset.py:76-78: data[0,:,:,:2], data[0,:,:,2]
 
 
 def hwc_split(block, parts):
@@ -81,3 +84,21 @@ def write_flo(path, flow_hw2):
 def load_flo_planar(path, device="cuda"):
     """.flo file -> (1,2,H,W) CUDA tensor (upload interleaved, de-interleave on the GPU)."""
     return flow_hw2_to_planar(torch.from_numpy(read_flo(path)).to(device))
+
+
+def sintel_occlusion_mask(png_u8):
+    """Sintel occlusion PNG (uint8 CUDA tensor (H,W) or (N,H,W), 255 = occluded) -> mask (N,1,H,W) float32 =
+    ``(1.0 - png/255.0).float()`` exactly as utils/sintel_dataset.py:64-65 computes it (float64, then ``.float()``)."""
+    if not png_u8.is_cuda or png_u8.dtype != torch.uint8:
+        raise RuntimeError("tcl_b200: sintel_occlusion_mask expects a uint8 CUDA tensor (upload the decoded PNG as it is)")
+    if png_u8.dim() == 2:
+        png_u8 = png_u8.unsqueeze(0)
+    if png_u8.dim() != 3:
+        raise RuntimeError(f"tcl_b200: expected (H,W) or (N,H,W), got {tuple(png_u8.shape)}")
+    src = png_u8.contiguous()
+    N, H, W = src.shape
+    out = torch.empty((N, 1, H, W), dtype=torch.float32, device=src.device)
+    with torch.cuda.device(src.device):
+        stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+        check(_cabi.lib().tclb200_occlusion_u8_to_mask(ctypes.c_void_p(src.data_ptr()), ctypes.c_void_p(out.data_ptr()), src.numel(), stream))
+    return out

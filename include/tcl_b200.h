@@ -183,6 +183,10 @@ int tclb200_tcl_backward(const float* bf, const float* mask, const float* prev, 
 int tclb200_hwc_split(const float* src, int N, int H, int W, int Cs, int n_out, float* const* dst, const int* c0,
                       const int* cd, tclb200_stream_t stream);
 
+/* Sintel ground-truth occlusion PNG -> mask (utils/sintel_dataset.py:64-65: mask = 1.0 - imread(png)/255.0 in float64, later
+ * .float()): src n bytes (4-byte aligned), dst n floats (16-byte aligned), both device; exact for all 256 inputs. */
+int tclb200_occlusion_u8_to_mask(const uint8_t* src, float* dst, size_t n, tclb200_stream_t stream);
+
 /* RAFT's convex 8x upsampling of the coarse flow (utils/raft/raft/raft.py:72-83 upsample_flow), the producer of the
  * flows this path consumes ("next" row of the scope table): softmax over the 9 mask logits, convex combination of the
  * zero-padded 3x3 neighbourhood of 8*flow, pixel shuffle.  flow (N,2,H,W), mask (N,576,H,W) -> out (N,2,8H,8W), fp32. */

@@ -410,6 +410,24 @@ def test_hwc_split_matches_moveaxis(tcl, tmp_path, N, H, W, Cs):
             assert np.array_equal(o[name].cpu().numpy(), block[..., c0:c0 + cd].permute(0, 3, 1, 2).numpy())
 
 
+@pytest.mark.parametrize("shape", [(436, 1024), (2, 37, 53), (1, 1), (3, 5, 7)])
+def test_sintel_occlusion_png_to_mask_exact(tcl, shape):
+    """utils/sintel_dataset.py:64-65: mask = io.imread(png)/255.0 ; mask = 1.0 - mask (float64) ; torch .float()"""
+    d = dev()
+    rng = np.random.default_rng(sum(shape))
+    png = rng.integers(0, 256, size=shape, dtype=np.uint8)
+    png.reshape(-1)[:min(png.size, 256)] = np.arange(min(png.size, 256), dtype=np.uint8)     # every value where there is room
+    want = torch.from_numpy(1.0 - png / 255.0).float()
+    got = tcl.sintel_occlusion_mask(torch.from_numpy(png).to(d))
+    assert got.shape == ((1, 1) + shape if len(shape) == 2 else (shape[0], 1) + shape[1:])
+    assert torch.equal(got.cpu().reshape(want.shape), want)
+    # the long-term block layout [flow 2 | mask 1] (utils/sintel_dataset.py:76-83)
+    if len(shape) == 2:
+        blk = torch.randn(shape + (3,), device=d)
+        o = tcl.hwc_split(blk, tcl.ingest.LT_LAYOUT)
+        assert torch.equal(o["flow"][0], blk[..., :2].permute(2, 0, 1)) and torch.equal(o["mask"][0, 0], blk[..., 2])
+
+
 # ------------------------------------------------------------------ streams and CUDA graphs
 def test_concurrent_streams_and_graph_replay(tcl):
     """Calls are asynchronous on the caller's stream and re-entrant across streams (each stream gets its own scratch);
