@@ -150,14 +150,17 @@ __global__ void __launch_bounds__(256) cv2_fb_check_kernel(const float2* __restr
 __constant__ float c_occ_lut[256];
 
 __global__ void __launch_bounds__(256) occlusion_u8_kernel(const uint8_t* __restrict__ src, float* __restrict__ dst, size_t n4, size_t n) {
-  const size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
-  if (i < n4) {   // four pixels per lane: one 32-bit load, one 128-bit store
+  __shared__ float lut[256];   // (a warp's 128 lookups hit arbitrary entries: shared memory, not the constant cache)
+  lut[threadIdx.x] = c_occ_lut[threadIdx.x];
+  __syncthreads();
+  // four pixels per lane and step: one 32-bit load, one 128-bit store
+  for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n4; i += (size_t)gridDim.x * 256) {
     const uchar4 v = __ldcs(reinterpret_cast<const uchar4*>(src) + i);
-    __stcs(reinterpret_cast<float4*>(dst) + i, make_float4(c_occ_lut[v.x], c_occ_lut[v.y], c_occ_lut[v.z], c_occ_lut[v.w]));
+    __stcs(reinterpret_cast<float4*>(dst) + i, make_float4(lut[v.x], lut[v.y], lut[v.z], lut[v.w]));
   }
-  if (blockIdx.x == 0 && threadIdx.x < (unsigned)(n - 4 * n4)) {   // the 0..3 trailing pixels
+  if (blockIdx.x == 0 && threadIdx.x < (unsigned)(n - 4 * n4)) {   // the 0..3 trailing pixels (or a tiny unaligned buffer)
     const size_t j = 4 * n4 + threadIdx.x;
-    dst[j] = c_occ_lut[src[j]];
+    dst[j] = lut[src[j]];
   }
 }
 
@@ -223,9 +226,10 @@ extern "C" int tclb200_occlusion_u8_to_mask(const uint8_t* src, float* dst, size
   if (e != cudaSuccess) return cfail(TCLB200_ERR_CUDA, "occlusion table upload: ", cudaGetErrorString(e));
   const bool vec = ((reinterpret_cast<uintptr_t>(src) & 3u) == 0) && ((reinterpret_cast<uintptr_t>(dst) & 15u) == 0);
   const size_t n4 = vec ? n / 4 : 0;
-  if (n - 4 * n4 > 256 || (n4 + 255) / 256 >= 0x7fffffffull)   // (the scalar tail covers at most one CTA's worth of pixels)
+  if (n - 4 * n4 > 256)   // (the scalar tail covers at most one CTA's worth of pixels)
     return cfail(TCLB200_ERR_UNSUPPORTED, "src must be 4-byte and dst 16-byte aligned (or n <= 256)");
-  const unsigned grid = (unsigned)(n4 ? (n4 + 255) / 256 : 1);
+  const size_t want = n4 ? (n4 + 255) / 256 : 1, cap = 148 * 8 * 4;   // grid-stride beyond a few waves
+  const unsigned grid = (unsigned)(want < cap ? want : cap);
   occlusion_u8_kernel<<<grid, 256, 0, s>>>(src, dst, n4, n);
   tcl::count_launch();
   e = cudaGetLastError();

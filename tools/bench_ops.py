@@ -74,6 +74,22 @@ def run_ingest():
     report("ingest .flo payload[8] HW2 -> planar", timeit(lambda: tcl.flow_hw2_to_planar(flo)), 8 * 436 * 1024, 16)
 
 
+def run_cv2compat(N=64):
+    """the generators' NumPy / OpenCV flavour on HWC device tensors (Sintel shape)"""
+    cfg = tcl.synth.CONFIGS["sintel_full"]
+    H, W = cfg["H"], cfg["W"]
+    ff, bf = tcl.synth.make_flows(N, H, W, seed=5, max_shift=32.0, max_rot_deg=3.0, device=dev)
+    img, _ = tcl.synth.make_frames(N, 3, H, W, seed=5, device=dev)
+    ff, bf, img = (t.permute(0, 2, 3, 1).contiguous() for t in (ff, bf, img))
+    px = N * H * W
+    cc = tcl.cv2compat
+    report(f"cv2compat[{N}] fb_check_flows (fused)", timeit(lambda: cc.fb_check_flows(ff, bf)), px, 20)
+    report(f"cv2compat[{N}] warp_image C=3", timeit(lambda: cc.warp_image(img, bf)), px, 32)
+    report(f"cv2compat[{N}] warp_flow C=2", timeit(lambda: cc.warp_flow(ff, bf)), px, 24)
+    png = torch.randint(0, 256, (N, H, W), dtype=torch.uint8, device=dev)
+    report(f"ingest occlusion png[{N}] u8 -> mask", timeit(lambda: tcl.sintel_occlusion_mask(png)), px, 5)
+
+
 def run_upsample():
     sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
     from oracle import torch_port as tp   # timing the reference op sequence beside the kernel (tool, not product)
@@ -108,6 +124,7 @@ if __name__ == "__main__":
     run_upsample()
     run_clip()
     run_ingest()
+    run_cv2compat()
     run("sintel_full", 128)
     run("train_b16_256", 256)
     run("train_b16_256", 16)
