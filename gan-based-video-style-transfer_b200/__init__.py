@@ -6,7 +6,7 @@ the repository root.  ``dropin/`` holds modules named like the reference's (``fl
 ``sintel_eval``) for ``sys.path``-style drop-in use.
 """
 from . import _cabi  # noqa: F401
-from .ops import (FusedResult, generateMask, fbcCheckTorch, fbcCheckTorch_mob, fbcheck_with_near_count, fs_warp,  # noqa: F401
+from .ops import (FusedResult, free_workspaces, generateMask, fbcCheckTorch, fbcCheckTorch_mob, fbcheck_with_near_count, fs_warp,  # noqa: F401
                   fused_forward, gradient, temporal_error, temporal_error_clip, temporal_error_host, temporal_error_per_pair, temporal_loss,
                   temporal_rmse_per_sample, upsample_flow, warp, warp_blend)
 from .sintel_eval import (aggregate_means, computeTCL, computeTCL_from_flows, save_dict_as_json)  # noqa: F401

@@ -359,6 +359,14 @@ def temporal_error_clip(frames, ff, bf):
 _host_ws_cache = {}
 
 
+def free_workspaces():
+    """Drop the cached device buffers (per-stream reduction scratch, the host entry's frame bank / flow ring).  They are
+    re-allocated on demand; call this to hand the memory back to the caching allocator, e.g. after a one-off evaluation of a
+    long clip.  The caches are plain dicts: like the reference's loops, the wrappers assume one Python thread per device."""
+    _scratch_cache.clear()
+    _host_ws_cache.clear()
+
+
 def _host_tensor(t, name, dtype=None):
     if t is None:
         return None
