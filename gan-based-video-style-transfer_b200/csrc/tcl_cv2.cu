@@ -64,6 +64,12 @@ __device__ __forceinline__ float np_sqnorm2(float a, float b) {
   return __fmul_rn(s, s);
 }
 
+// the rounded sum of rounded squares inside it (what the sqrt-free filter compares)
+__device__ __forceinline__ float np_sumsq2(float a, float b) { return __fadd_rn(__fmul_rn(a, a), __fmul_rn(b, b)); }
+// sqrt-then-square moves a term by < 3 * 2^-24 relative; the sums and the 0.01 scaling keep a test's two sides within
+// 1e-6 relative of their sqrt-free values: 4e-6 is a safe band (same constant as the hot kernel's filter)
+constexpr float kCvFilterEps = 4e-6f;
+
 // cv2.remap(src, x+u, y+v, INTER_LINEAR): src (N,H,W,C), flow (N,H,W,2), out (N,H,W,C)
 template <int CT>
 __global__ void __launch_bounds__(256) cv2_remap_kernel(const float* __restrict__ src, const float2* __restrict__ flow,
@@ -114,14 +120,23 @@ __global__ void __launch_bounds__(256) cv2_fb_check_kernel(const float2* __restr
       wf.x = cv2_blend(v00.x, v01.x, v10.x, v11.x, t);
       wf.y = cv2_blend(v00.y, v01.y, v10.y, v11.y, t);
     }
-    const float norm_b = np_sqnorm2(c.x, c.y);
+    // np.linalg.norm(.)**2.0 is sqrt-then-square of a rounded sum of squares: each such term is within a few ulp of the plain
+    // sum.  The plain (sqrt-free) evaluation decides a test whenever lhs lies outside rhs * (1 +- kCvFilterEps); only the
+    // remaining pixels (a few per million) and calls that want the near-threshold count evaluate the exact sequence.
+    const bool exact_all = near_threshold != nullptr;
+    const float sb = np_sumsq2(c.x, c.y);
     bool keep = true;
     if (flags & TCLB200_OCC) {
-      const float norm_wb = np_sqnorm2(__fadd_rn(wf.x, c.x), __fadd_rn(wf.y, c.y));
-      const float norm_w = np_sqnorm2(wf.x, wf.y);
-      const float rhs = __fadd_rn(__fmul_rn(0.01f, __fadd_rn(norm_w, norm_b)), 0.5f);
-      if (norm_wb > rhs) keep = false;
-      near += fabsf(__fsub_rn(norm_wb, rhs)) < kNearBandCv;
+      const float swb = np_sumsq2(__fadd_rn(wf.x, c.x), __fadd_rn(wf.y, c.y)), sw = np_sumsq2(wf.x, wf.y);
+      const float r = __fadd_rn(__fmul_rn(0.01f, __fadd_rn(sw, sb)), 0.5f);
+      bool occ = swb > r * (1.0f + kCvFilterEps);
+      if (exact_all || (!occ && !(swb < r * (1.0f - kCvFilterEps)))) {
+        const float norm_wb = np_sqnorm2(__fadd_rn(wf.x, c.x), __fadd_rn(wf.y, c.y));
+        const float rhs = __fadd_rn(__fmul_rn(0.01f, __fadd_rn(np_sqnorm2(wf.x, wf.y), np_sqnorm2(c.x, c.y))), 0.5f);
+        occ = norm_wb > rhs;
+        near += fabsf(__fsub_rn(norm_wb, rhs)) < kNearBandCv;
+      }
+      if (occ) keep = false;
     }
     if (flags & TCLB200_MOB) {
       // np.gradient: one-sided on the border, halved central difference inside (H, W >= 2 checked by the host)
@@ -131,10 +146,16 @@ __global__ void __launch_bounds__(256) cv2_fb_check_kernel(const float2* __restr
       float ux = __fsub_rn(r.x, l.x), vx = __fsub_rn(r.y, l.y), uy = __fsub_rn(dn.x, up.x), vy = __fsub_rn(dn.y, up.y);
       if (!xe) { ux = __fmul_rn(ux, 0.5f); vx = __fmul_rn(vx, 0.5f); }
       if (!ye) { uy = __fmul_rn(uy, 0.5f); vy = __fmul_rn(vy, 0.5f); }
-      const float lhs = __fadd_rn(np_sqnorm2(uy, ux), np_sqnorm2(vy, vx));
-      const float rhs = __fadd_rn(__fmul_rn(0.01f, norm_b), 0.002f);
-      if (lhs > rhs) keep = false;
-      near += fabsf(__fsub_rn(lhs, rhs)) < kNearBandCv;
+      const float lq = __fadd_rn(np_sumsq2(uy, ux), np_sumsq2(vy, vx));
+      const float rq = __fadd_rn(__fmul_rn(0.01f, sb), 0.002f);
+      bool mob = lq > rq * (1.0f + kCvFilterEps);
+      if (exact_all || (!mob && !(lq < rq * (1.0f - kCvFilterEps)))) {
+        const float lhs = __fadd_rn(np_sqnorm2(uy, ux), np_sqnorm2(vy, vx));
+        const float rhs = __fadd_rn(__fmul_rn(0.01f, np_sqnorm2(c.x, c.y)), 0.002f);
+        mob = lhs > rhs;
+        near += fabsf(__fsub_rn(lhs, rhs)) < kNearBandCv;
+      }
+      if (mob) keep = false;
     }
     __stcs(mask + img + o, keep ? 1.0f : 0.0f);
   }
