@@ -62,6 +62,10 @@ def build(force=False, verbose=False):
     """nvcc the kernels for sm_100a, in-tree (cross-compiles without a GPU): one object per source (stale ones only,
     compiled in parallel), then one link into ``libtcl_b200.so``."""
     deps_common = [os.path.join(CSRC, h) for h in HEADERS] + [HEADER]
+    all_inputs = [os.path.join(CSRC, src) for src in SOURCES] + deps_common
+    if (not force and os.path.exists(LIB_PATH)
+            and all(os.path.getmtime(LIB_PATH) >= os.path.getmtime(d) for d in all_inputs)):
+        return LIB_PATH   # up to date (also when the intermediate objects did not travel with the library)
     compile_flags = [f for f in NVCC_FLAGS if f != "-shared"]
     objs, jobs = [], []
     for src in SOURCES:
