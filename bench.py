@@ -236,6 +236,15 @@ def e2e_rate(tcl, shard, pairs_in_seq, steps, warmup, device, chunk=32):
     device inside the call (each stylised frame once -- it is the `cur` of pair t and the `prev` of pair t+1, the way
     utils/sintel_eval.py:206-222 walks a clip), runs the fused launches and reads the per-pair values back to the host."""
     import psutil
+    import torch.distributed as tdist
+    multi = tdist.is_available() and tdist.is_initialized() and tdist.get_world_size() > 1
+
+    def all_ranks_ok(ok):   # the step below contains a collective: either every rank runs it or none does
+        if not multi:
+            return ok
+        flag = torch.tensor([1 if ok else 0], device=device, dtype=torch.int32)
+        tdist.all_reduce(flag, op=tdist.ReduceOp.MIN)
+        return bool(int(flag[0]))
     H, W = shard["bf"].shape[2:]
     C = shard["cur"].shape[1]
     esz = shard["cur"].element_size()
@@ -250,12 +259,24 @@ def e2e_rate(tcl, shard, pairs_in_seq, steps, warmup, device, chunk=32):
         seqs.append(n)
         need += b
     P, F = sum(seqs), sum(seqs) + len(seqs)
+    if multi:   # every rank evaluates the same number of sequences (the smallest any rank has room for)
+        t = torch.tensor([len(seqs)], device=device, dtype=torch.int32)
+        tdist.all_reduce(t, op=tdist.ReduceOp.MIN)
+        seqs = seqs[:int(t[0])]
+        P, F = sum(seqs), sum(seqs) + len(seqs)
     saved_affinity = os.sched_getaffinity(0)
     if world > 1:   # (N = 1 measured 55 GB/s unbound; the cpu_baseline leg that follows must see every host core)
         bind_to_gpu_numa_node(device.index)
-    frames_h = torch.empty((F, C, H, W), dtype=shard["cur"].dtype, pin_memory=True)
-    ff_h = torch.empty((P, 2, H, W), dtype=torch.float32, pin_memory=True)
-    bf_h = torch.empty((P, 2, H, W), dtype=torch.float32, pin_memory=True)
+    setup_error = None
+    try:
+        frames_h = torch.empty((F, C, H, W), dtype=shard["cur"].dtype, pin_memory=True)
+        ff_h = torch.empty((P, 2, H, W), dtype=torch.float32, pin_memory=True)
+        bf_h = torch.empty((P, 2, H, W), dtype=torch.float32, pin_memory=True)
+    except Exception as ex:
+        setup_error = ex
+    if not all_ranks_ok(setup_error is None):
+        os.sched_setaffinity(0, saved_affinity)
+        raise RuntimeError(f"pinned host buffers for the e2e leg could not be allocated on every rank: {setup_error!r}")
     ff_h.copy_(shard["ff"][:P]); bf_h.copy_(shard["bf"][:P])
     prev_i, cur_i, p0, f0 = [], [], 0, 0
     for n in seqs:    # frame bank of a clip: its first frame, then the frame each pair is compared with
@@ -267,9 +288,12 @@ def e2e_rate(tcl, shard, pairs_in_seq, steps, warmup, device, chunk=32):
     torch.cuda.synchronize()
     lib = tcl._cabi.lib()
 
+    seq_ids = torch.tensor([si for si, n in enumerate(seqs) for _ in range(n)], dtype=torch.long)
+
     def step():
-        out = tcl.temporal_error_host(frames_h, ff_h, bf_h, prev_i, cur_i, chunk_pairs=chunk)   # synchronises its stream
-        return float(out.mean())
+        # one C-ABI call for the shard (synchronises its stream), the packed sums, ONE all-reduce when N > 1, result on the host
+        res = tcl.evaluate_sharded_host(frames_h, ff_h, bf_h, prev_i, cur_i, seq_ids, len(pairs_in_seq), chunk_pairs=chunk)
+        return float(res["mean_over_pairs"])
 
     for _ in range(warmup):
         step()
@@ -283,12 +307,12 @@ def e2e_rate(tcl, shard, pairs_in_seq, steps, warmup, device, chunk=32):
     launches = int(lib.tclb200_debug_launch_count(0))
     os.sched_setaffinity(0, saved_affinity)
     h2d = F * frame_b + 2 * P * flow_b + 2 * 4 * P
-    return dict(value=steps * P / el, unit="pairs/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=4 * P,
+    return dict(value=steps * P / el, unit="pairs/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=12 * P + 8,
                 ms_per_step=el / steps * 1e3, h2d_gb_per_s=h2d * steps / el / 1e9, pairs_per_step=P, frames_per_step=F,
                 sequences_per_step=len(seqs), gpu_launches_per_step=launches // max(steps, 1), mean_rmse=mean_rmse,
-                note=f"tcl_b200.temporal_error_host (C ABI tclb200_tcl_forward_host): pinned host clips -> {chunk}-pair chunks, "
+                note=f"tcl_b200.evaluate_sharded_host = temporal_error_host (C ABI tclb200_tcl_forward_host) + packed sums + one all-reduce when N > 1: pinned host clips -> {chunk}-pair chunks, "
                      "3-slot device ring, internal copy stream; every frame crosses PCIe once per step (28.3 B/px per pair "
-                     "instead of 40), per-pair values copied back to the host")
+                     "instead of 40), per-pair values and sums copied back to the host (12 B per pair), the aggregate read on the host")
 
 
 def other_workloads(tcl, device, frames, peak):

@@ -378,7 +378,7 @@ def _host_tensor(t, name, dtype=None):
 
 
 def temporal_error_host(frames, ff, bf, prev_index=None, cur_index=None, mask=None, loss=L2, finalize=FIN_RMSE,
-                        flags=OCC | MOB, chunk_pairs=0, device=None, sync=True):
+                        flags=OCC | MOB, chunk_pairs=0, device=None, sync=True, return_sums=False):
     """The evaluation loop of utils/sintel_eval.py:206-222 (and solver.py:336-347) on HOST tensors.
 
     ``frames`` (F,C,H,W) fp32/bf16: the stylised frames of one or more clips, each stored once; ``ff`` / ``bf``
@@ -388,6 +388,7 @@ def temporal_error_host(frames, ff, bf, prev_index=None, cur_index=None, mask=No
     All tensors are CPU tensors (pinned memory runs at PCIe speed); the result is a pinned CPU tensor (P,) of per-pair
     values per ``finalize``.  One C-ABI call (``tclb200_tcl_forward_host``) pipelines H2D copies and fused launches
     on ``device`` (default: the current CUDA device); there is no CPU arithmetic anywhere.
+    ``return_sums=True`` returns ``(values, sums)`` with the per-pair float64 sums S_p as well (for pooled statistics).
     """
     if not torch.cuda.is_available():
         raise RuntimeError("tcl_b200: temporal_error_host needs a CUDA device; this path has no CPU implementation")
@@ -422,10 +423,11 @@ def temporal_error_host(frames, ff, bf, prev_index=None, cur_index=None, mask=No
         ws = torch.empty(need, dtype=torch.uint8, device=dev)
         _host_ws_cache[dev.index] = ws
     out = torch.empty(P, dtype=torch.float32, pin_memory=True)
+    sums = torch.empty(P, dtype=torch.float64, pin_memory=True) if return_sums else None
     a = HostArgs()
     a.ff, a.bf, a.mask_in, a.frames = _ptr(ff), _ptr(bf), _ptr(mask), _ptr(frames)
     a.prev_index, a.cur_index = _ptr(prev_index), _ptr(cur_index)
-    a.pair_vals, a.pair_sums = _ptr(out), None
+    a.pair_vals, a.pair_sums = _ptr(out), _ptr(sums)
     a.workspace, a.workspace_bytes = _ptr(ws), ws.numel()
     a.P, a.F, a.C, a.H, a.W = P, F_, C, H, W
     a.dtype, a.flags, a.loss, a.finalize, a.chunk_pairs = dt, flags, loss, finalize, chunk_pairs
@@ -436,7 +438,7 @@ def temporal_error_host(frames, ff, bf, prev_index=None, cur_index=None, mask=No
             stream.synchronize()
         else:   # the caller synchronises the stream; keep the host inputs alive until then
             out._tcl_keepalive = (frames, ff, bf, mask, prev_index, cur_index)
-    return out
+    return (out, sums) if return_sums else out
 
 
 def temporal_rmse_per_sample(mask, cur, prev, flow):

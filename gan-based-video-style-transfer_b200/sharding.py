@@ -102,3 +102,22 @@ def evaluate_sharded(ff, bf, prev, cur, seq_of_pair: torch.Tensor, n_seq: int,
             part = pack_local(res.pair_vals, res.total_sums[0], seq_of_pair[s:e], n_seq, C * H * W)
             packed = part if packed is None else packed + part
     return unpack(allreduce_sums(packed, group), n_seq)
+
+
+def evaluate_sharded_host(frames, ff, bf, prev_index, cur_index, seq_of_pair, n_seq: int,
+                          group: Optional[dist.ProcessGroup] = None, device=None, chunk_pairs: int = 0) -> dict:
+    """The same evaluation with this rank's shard in HOST memory (``ops.temporal_error_host``: frames of the rank's clips
+    stored once, pairs index them) + the one all-reduce.  ``seq_of_pair``: sequence id of each local pair (CPU or CUDA
+    long tensor).  Returns ``unpack``'s dict of device tensors."""
+    from . import ops
+    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    P = bf.shape[0]
+    C, H, W = frames.shape[1:]
+    if P == 0:
+        packed = torch.zeros(2 * n_seq + 2, dtype=torch.float64, device=dev)
+    else:
+        vals, sums = ops.temporal_error_host(frames, ff, bf, prev_index, cur_index, chunk_pairs=chunk_pairs, device=dev,
+                                             return_sums=True)
+        packed = pack_local(vals.to(dev, non_blocking=True), sums.to(dev, non_blocking=True).sum(),
+                            torch.as_tensor(seq_of_pair).to(dev), n_seq, C * H * W)
+    return unpack(allreduce_sums(packed, group), n_seq)

@@ -626,6 +626,13 @@ def test_host_entry_equals_device_path(tcl, oracle_mod, clips, H, W, chunk, dtyp
     fd = frames.to(d)
     want = tcl.temporal_error_per_pair(ff.to(d), bf.to(d), fd[pi.long()].contiguous(), fd[ci.long()].contiguous()).cpu()
     assert torch.equal(got, want)
+    # the sharded evaluation on host buffers (packed sums + the all-reduce, a no-op at world size 1) equals the device-resident one
+    seq_ids = torch.tensor([si for si, n in enumerate(clips) for _ in range(n - 1)], dtype=torch.long)
+    res_h = tcl.evaluate_sharded_host(pin(frames), pin(ff), pin(bf), pi, ci, seq_ids, len(clips), chunk_pairs=chunk)
+    res_d = tcl.evaluate_sharded(ff.to(d), bf.to(d), fd[pi.long()].contiguous(), fd[ci.long()].contiguous(), seq_ids.to(d), len(clips))
+    for key in ("per_sequence_mean", "mean_over_sequences", "mean_over_pairs", "n_pairs"):
+        assert torch.equal(res_h[key], res_d[key]), key
+    assert torch.allclose(res_h["pooled_rmse"], res_d["pooled_rmse"], rtol=1e-12, atol=0)
     # pageable inputs and a second call on the cached workspace give the same bits
     assert torch.equal(tcl.temporal_error_host(frames, ff, bf, pi, ci, chunk_pairs=chunk), want)
     if len(clips) == 1:   # default indices = the consecutive pairs of one clip
