@@ -6,7 +6,7 @@ never copied) on small seeded inputs.  Run in the build container, where /root/r
 The reference hard-codes ``.cuda()`` (utils/flowtools.py:25) and ``device="cuda"``; on this CPU-only
 container the former is neutralised by patching ``torch.Tensor.cuda`` to the identity and the latter
 by passing ``device="cpu"`` -- the arithmetic then runs in ATen's CPU kernels (torch 2.11.0).
-The CUDA-flavour vectors (``ref_cuda_*.npz``) are produced on a B200 by tools/probe_semantics.py with
+The CUDA-flavour vectors (``ref_cuda_*.npz``) are produced on a B200 by tests/golden/make_golden_cuda.py with
 oracle/torch_port.py, which tests/test_oracle_pinning.py proves bit-identical to these functions on CPU.
 """
 import os
