@@ -536,7 +536,8 @@ def main():
                    "l2": "inputs (%.1f GB per GPU) are larger than L2, no flush needed" % (alg_bytes / 1e9)},
         "gpu_launches": n_launches,
         "gpu_launches_note": "kernels of libtcl_b200.so inside the timed region: per step one fused_forward_ws_kernel + one "
-                             "fold_partials_kernel (programmatic dependent launch)",
+                             "fold_partials_kernel (programmatic dependent launch) + the two single-CTA aggregation kernels "
+                             "(pack / unpack of the per-sequence sums around the all-reduce)",
         "tiles": {"per_step": n_local * ((W + 63) // 64) * ((H + 31) // 32),
                   "mixed_per_step": int(tile_stats[1]) // max(args.steps, 1), "global_per_step": int(tile_stats[0]) // max(args.steps, 1),
                   "note": "mixed = a motion boundary runs through the 64x32 tile, some pixels gather from global memory"},

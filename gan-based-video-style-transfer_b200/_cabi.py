@@ -22,7 +22,7 @@ FIN_MEAN, FIN_RMSE = 0, 1
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
-SOURCES = ["tcl_kernels.cu", "tcl_host.cu", "tcl_cv2.cu"]
+SOURCES = ["tcl_kernels.cu", "tcl_host.cu", "tcl_cv2.cu", "tcl_agg.cu"]
 HEADERS = ["tcl_math.cuh", "tcl_common.cuh"]
 
 
@@ -106,6 +106,8 @@ _PROTOTYPES = {
     "tclb200_upsample_flow": (_c.c_int, [_vp, _vp, _vp, _i, _i, _i, _vp]),
     "tclb200_cv2_remap": (_c.c_int, [_vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "tclb200_cv2_fb_check": (_c.c_int, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp]),
+    "tclb200_pack_sequence_sums": (_c.c_int, [_vp, _vp, _vp, _i, _i, _c.c_double, _vp, _vp]),
+    "tclb200_unpack_sequence_means": (_c.c_int, [_vp, _i, _vp, _vp]),
     "tclb200_debug_force_generic": (None, [_i]),
     "tclb200_debug_tile_stats": (_c.c_int, [_vp, _i]),
     "tclb200_debug_launch_count": (_c.c_ulonglong, [_i]),

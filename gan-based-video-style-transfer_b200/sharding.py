@@ -50,8 +50,21 @@ def plan_shards(pairs_in_sequence: Sequence[int], world: int, rank: int) -> Shar
 
 def pack_local(pair_vals: torch.Tensor, sum_sq: torch.Tensor, seq_of_pair: torch.Tensor, n_seq: int,
                elems_per_pair: int) -> torch.Tensor:
-    """Local contribution to the packed vector (float64, on the tensors' device)."""
+    """Local contribution to the packed vector (float64, on the tensors' device).  CUDA tensors: one launch of
+    ``tclb200_pack_sequence_sums``; CPU tensors (the gloo tests of the host logic): the same arithmetic as torch ops."""
     n = pair_vals.numel()
+    if pair_vals.is_cuda:
+        import ctypes
+        from . import _cabi
+        packed = torch.empty(2 * n_seq + 2, dtype=torch.float64, device=pair_vals.device)
+        vals = pair_vals.float().contiguous()
+        seq = seq_of_pair.to(device=pair_vals.device, dtype=torch.long).contiguous()
+        ssq = sum_sq.double().reshape(1).contiguous() if n else None
+        ptr = lambda t: ctypes.c_void_p(t.data_ptr()) if t is not None else None
+        with torch.cuda.device(pair_vals.device):
+            _cabi.check(_cabi.lib().tclb200_pack_sequence_sums(ptr(vals), ptr(ssq), ptr(seq), n, n_seq, float(elems_per_pair), ptr(packed),
+                                                               ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)))
+        return packed
     packed = torch.zeros(2 * n_seq + 2, dtype=torch.float64, device=pair_vals.device)
     if n:
         packed[:n_seq].index_add_(0, seq_of_pair, pair_vals.double())
@@ -69,7 +82,18 @@ def allreduce_sums(packed: torch.Tensor, group: Optional[dist.ProcessGroup] = No
 
 
 def unpack(packed: torch.Tensor, n_seq: int) -> dict:
-    """Per-sequence mean RMSE, the reference's mean over sequences, pooled RMSE. Device tensors, no sync."""
+    """Per-sequence mean RMSE, the reference's mean over sequences, pooled RMSE. Device tensors, no sync.
+    CUDA: one launch of ``tclb200_unpack_sequence_means``; CPU (gloo tests): torch ops."""
+    if packed.is_cuda:
+        import ctypes
+        from . import _cabi
+        packed = packed.contiguous()
+        out = torch.empty(n_seq + 4, dtype=torch.float64, device=packed.device)
+        with torch.cuda.device(packed.device):
+            _cabi.check(_cabi.lib().tclb200_unpack_sequence_means(ctypes.c_void_p(packed.data_ptr()), n_seq, ctypes.c_void_p(out.data_ptr()),
+                                                                  ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)))
+        return {"per_sequence_mean": out[:n_seq], "mean_over_sequences": out[n_seq], "mean_over_pairs": out[n_seq + 1],
+                "pooled_rmse": out[n_seq + 2], "n_pairs": out[n_seq + 3]}
     sums, cnt = packed[:n_seq], packed[n_seq:2 * n_seq]
     per_seq = sums / cnt.clamp(min=1.0)
     present = (cnt > 0).double()

@@ -206,6 +206,16 @@ int tclb200_cv2_remap(const float* src, const float* flow, float* out, int N, in
 int tclb200_cv2_fb_check(const float* ff, const float* bf, float* mask, int N, int H, int W, int flags, int prewarped,
                          unsigned long long* near_threshold, tclb200_stream_t stream);
 
+/* Aggregation of the evaluation loop (per-video mean of the per-pair RMSE, StarGANv2AdvCon/core/solver.py:352-354; mean over
+ * videos, utils/sintel_eval.py:112-126) around the one all-reduce of the sharded evaluation.  All pointers are device pointers.
+ *   pack:   pair_vals [n_pairs] fp32, sum_sq [1] fp64 (sum of squared error of these pairs, or NULL), seq_of_pair [n_pairs] int64
+ *           -> packed [2*n_seq + 2] fp64 = { sum of values per sequence | pair count per sequence | sum_sq | n_pairs * elems_per_pair }
+ *   unpack: packed (summed over ranks) -> out [n_seq + 4] fp64 = { per-sequence mean ... | mean over sequences that have pairs |
+ *           mean over pairs | pooled RMSE | number of pairs } */
+int tclb200_pack_sequence_sums(const float* pair_vals, const double* sum_sq, const long long* seq_of_pair, int n_pairs, int n_seq,
+                               double elems_per_pair, double* packed, tclb200_stream_t stream);
+int tclb200_unpack_sequence_means(const double* packed, int n_seq, double* out, tclb200_stream_t stream);
+
 /* Test hook (process-global, not for production use): route TMA-capable shapes through the generic
  * global-memory kernel so that both kernels are exercised on the same inputs.  0 = off (default). */
 void tclb200_debug_force_generic(int on);

@@ -652,6 +652,24 @@ def test_host_entry_equals_device_path(tcl, oracle_mod, clips, H, W, chunk, dtyp
         tcl.temporal_error_host(frames, ff, bf, pi, ci + T)            # index outside the frame bank
 
 
+def test_aggregation_kernels_equal_the_host_logic(tcl):
+    """pack / unpack around the all-reduce (solver.py:352-354, utils/sintel_eval.py:112-126): the two device kernels give the
+    numbers of the torch-op form that the CPU (gloo) tests exercise -- including empty sequences and an empty shard."""
+    d = dev()
+    sh = tcl.sharding
+    g = torch.Generator().manual_seed(3)
+    for n, n_seq in ((1041, 23), (7, 5), (0, 3), (300, 300)):
+        vals = torch.rand(n, generator=g)
+        seq = torch.randint(0, max(n_seq - 1, 1), (n,), generator=g)       # the last sequence stays empty
+        ssq = torch.tensor(123.456, dtype=torch.float64)
+        want_p = sh.pack_local(vals, ssq, seq, n_seq, 3 * 436 * 1024)
+        got_p = sh.pack_local(vals.to(d), ssq.to(d), seq.to(d), n_seq, 3 * 436 * 1024)
+        assert got_p.is_cuda and torch.equal(got_p.cpu(), want_p)
+        want_u, got_u = sh.unpack(want_p * 2, n_seq), sh.unpack(got_p * 2, n_seq)    # "* 2": as if two ranks had contributed
+        for key in want_u:
+            assert torch.allclose(got_u[key].cpu(), want_u[key], rtol=1e-14, atol=0), key
+
+
 # ------------------------------------------------------------------ adversarial near-threshold inputs for the filtered mask tests
 def test_masks_bit_exact_on_near_threshold_flows(tcl):
     """The hot path decides the mask tests without the sqrt-then-square of torch.norm(.)**2 whenever lhs is outside
