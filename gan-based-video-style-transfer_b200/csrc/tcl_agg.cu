@@ -19,20 +19,21 @@ void count_launch();
 namespace {
 
 constexpr int kAggThreads = 256;
+constexpr int kPackThreads = 1024;   // pack: few dependent rounds of loads (1041 pairs = 2 rounds)
 
 // Sums of at most a few thousand fp32-valued doubles of similar magnitude are exact in fp64, so the order in which the
 // shared-memory atomics land does not show in the result.
-__global__ void __launch_bounds__(kAggThreads) pack_sequences_kernel(const float* __restrict__ pair_vals, const double* __restrict__ sum_sq,
+__global__ void __launch_bounds__(kPackThreads) pack_sequences_kernel(const float* __restrict__ pair_vals, const double* __restrict__ sum_sq,
                                                                      const long long* __restrict__ seq_of_pair, int n_pairs, int n_seq,
                                                                      double elems_per_pair, double* __restrict__ packed) {
   extern __shared__ double s_acc[];   // [n_seq] sums, [n_seq] counts
-  for (int i = threadIdx.x; i < 2 * n_seq; i += kAggThreads) s_acc[i] = 0.0;
+  for (int i = threadIdx.x; i < 2 * n_seq; i += kPackThreads) s_acc[i] = 0.0;
   __syncthreads();
   // warp-aggregated: the lanes of a warp that hold pairs of the same sequence (pairs of a clip are neighbours) fold their
   // values in the lowest such lane, which issues ONE shared-memory atomic per sequence and warp (a shared fp64 atomicAdd is a
-  // compare-and-swap loop: 32 lanes hammering one address took 23 us for 1041 pairs, this takes 3)
+  // compare-and-swap loop: 32 lanes hammering one address took 23 us for 1041 pairs under ncu, this takes 9, cold)
   const int lane = threadIdx.x & 31;
-  for (int base = 0; base < n_pairs; base += kAggThreads) {
+  for (int base = 0; base < n_pairs; base += kPackThreads) {
     const int i = base + (int)threadIdx.x;
     const bool live = i < n_pairs;
     long long s = live ? seq_of_pair[i] : -1;
@@ -51,7 +52,7 @@ __global__ void __launch_bounds__(kAggThreads) pack_sequences_kernel(const float
     }
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < 2 * n_seq; i += kAggThreads) packed[i] = s_acc[i];
+  for (int i = threadIdx.x; i < 2 * n_seq; i += kPackThreads) packed[i] = s_acc[i];
   if (threadIdx.x == 0) {
     packed[2 * n_seq] = (n_pairs > 0 && sum_sq) ? *sum_sq : 0.0;
     packed[2 * n_seq + 1] = (double)n_pairs * elems_per_pair;
@@ -101,7 +102,7 @@ extern "C" int tclb200_pack_sequence_sums(const float* pair_vals, const double* 
   if (!packed || n_seq <= 0 || n_pairs < 0) return afail(TCLB200_ERR_INVALID, "packed and a positive n_seq are required");
   if (n_pairs > 0 && (!pair_vals || !seq_of_pair)) return afail(TCLB200_ERR_INVALID, "pair_vals and seq_of_pair are required");
   if (n_seq > 2048) return afail(TCLB200_ERR_UNSUPPORTED, "at most 2048 sequences per call");
-  pack_sequences_kernel<<<1, kAggThreads, 2 * (size_t)n_seq * sizeof(double), reinterpret_cast<cudaStream_t>(stream)>>>(
+  pack_sequences_kernel<<<1, kPackThreads, 2 * (size_t)n_seq * sizeof(double), reinterpret_cast<cudaStream_t>(stream)>>>(
       pair_vals, sum_sq, seq_of_pair, n_pairs, n_seq, elems_per_pair, packed);
   tcl::count_launch();
   const cudaError_t e = cudaGetLastError();
