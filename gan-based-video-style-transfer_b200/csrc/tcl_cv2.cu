@@ -10,6 +10,7 @@
 // Layout is the reference's own: HWC (interleaved) images and flows.  One pixel per lane; the gathers of neighbouring
 // lanes land in neighbouring addresses, so the kernels run at L2 / HBM streaming speed (20 B/px for the fused check,
 // 8 + 8C B/px for remap).  No tensor cores: nothing here is a contraction.
+// Also here: the Sintel occlusion-PNG -> mask conversion of the dataset reader (utils/sintel_dataset.py:64-65), a table lookup.
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>

@@ -507,7 +507,6 @@ def test_cropped_views_of_padded_flows_are_read_in_place(tcl, B, H, W, pad):
         assert not v.is_contiguous() or (top + bottom == 0)
         return v
     ff_v, bf_v = padded_view(ff_c), padded_view(bf_c)
-    from importlib import import_module
     ops = tcl.ops
     _, plane, batch = ops._flow_view(bf_v, "bf")
     assert plane == (top + H + bottom) * W and batch == 2 * plane, "the view must be handed over through its strides"
