@@ -12,7 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.environ.get("TCL_B200_LIB") or os.path.join(CSRC, "libtcl_b200.so")  # env override: tuning sweeps only
 HEADER = os.path.join(os.path.dirname(_HERE), "include", "tcl_b200.h")
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 # enums mirrored from include/tcl_b200.h
 F32, BF16 = 0, 1
@@ -54,8 +54,22 @@ class HostArgs(ctypes.Structure):
         ("workspace", ctypes.c_void_p), ("workspace_bytes", ctypes.c_size_t),
         ("P", ctypes.c_int), ("F", ctypes.c_int), ("C", ctypes.c_int), ("H", ctypes.c_int), ("W", ctypes.c_int),
         ("dtype", ctypes.c_int), ("flags", ctypes.c_int), ("loss", ctypes.c_int), ("finalize", ctypes.c_int),
-        ("chunk_pairs", ctypes.c_int),
+        ("chunk_pairs", ctypes.c_int), ("frame_slots", ctypes.c_int),
     ]
+
+
+def _is_product_build(info):
+    """True for a library compiled with the default configuration (no TCL_HOT_ONLY / TCL_DIAG / TCL_TRACE tuning macros)."""
+    return all(tok in info.split() for tok in ("hot_only=0", "diag=0", "trace=0", f"abi={ABI_VERSION}"))
+
+
+def _existing_lib_is_product_build():
+    try:
+        h = ctypes.CDLL(LIB_PATH)
+        h.tclb200_build_info.restype = ctypes.c_char_p
+        return _is_product_build(h.tclb200_build_info().decode())
+    except Exception:
+        return False
 
 
 def build(force=False, verbose=False):
@@ -64,8 +78,11 @@ def build(force=False, verbose=False):
     deps_common = [os.path.join(CSRC, h) for h in HEADERS] + [HEADER]
     all_inputs = [os.path.join(CSRC, src) for src in SOURCES] + deps_common
     if (not force and os.path.exists(LIB_PATH)
-            and all(os.path.getmtime(LIB_PATH) >= os.path.getmtime(d) for d in all_inputs)):
+            and all(os.path.getmtime(LIB_PATH) >= os.path.getmtime(d) for d in all_inputs)
+            and (os.environ.get("TCL_B200_LIB") or _existing_lib_is_product_build())):
         return LIB_PATH   # up to date (also when the intermediate objects did not travel with the library)
+    if os.path.exists(LIB_PATH) and not os.environ.get("TCL_B200_LIB") and not _existing_lib_is_product_build():
+        force = True      # a library with another ABI or built with tuning macros: mtimes cannot tell, its build info can
     compile_flags = [f for f in NVCC_FLAGS if f != "-shared"]
     objs, jobs = [], []
     for src in SOURCES:
@@ -91,6 +108,7 @@ _vp, _i = ctypes.c_void_p, ctypes.c_int
 _PROTOTYPES = {
     "tclb200_abi_version": (_c.c_int, []),
     "tclb200_last_error": (_c.c_char_p, []),
+    "tclb200_build_info": (_c.c_char_p, []),
     "tclb200_scratch_bytes": (_c.c_size_t, [_i, _i, _i]),
     "tclb200_gradient": (_c.c_int, [_vp, _vp, _i, _i, _i, _vp]),
     "tclb200_gradient_strided": (_c.c_int, [_vp, _c.c_size_t, _vp, _i, _i, _i, _vp]),
@@ -136,6 +154,10 @@ def lib():
     got = handle.tclb200_abi_version()
     if got != ABI_VERSION:
         raise TclB200Error(f"ABI mismatch: library reports {got}, wrappers expect {ABI_VERSION}")
+    info = handle.tclb200_build_info().decode()
+    if not os.environ.get("TCL_B200_LIB") and not _is_product_build(info):
+        raise TclB200Error(f"{LIB_PATH} was built with tuning macros ({info}); rebuild it with _cabi.build(force=True) "
+                           "(tuning builds are loaded by name through TCL_B200_LIB only)")
     _lib = handle
     return _lib
 

@@ -12,12 +12,23 @@
 //                   device result array; after the last chunk one D2H copy of the per-pair results
 //
 // PCIe is the bound (a 1024x436 pair is 12.5 MB of flows + frames; its kernel time is 4 us): the ring only has to keep
-// the copy engine busy.  No state outlives the call except what the caller owns (workspace, streams are per call).
+// the copy engine busy.
+//
+// Device frame slots: the workspace holds `frame_slots` frames (0 = all F of them).  With fewer slots than frames the
+// bank becomes a ring: a frame's slot is handed out again once every chunk that reads it has completed (known from the
+// flow ring's own events: when chunk k is being staged, chunk k - 3 has finished), so long or 4K clips need device
+// memory for a window of frames only -- (3 + 1) chunks' worth -- not for the whole clip.  Pairs reach their frames
+// through per-pair slot indices written for each chunk.
+//
+// The copy stream and the events are kept in a per-device pool and reused by later calls (creating a stream and seven
+// events costs more than a small job).  On any failure the function drains both streams before it returns, so the
+// caller may free or reuse its host buffers as soon as it sees the error.
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
 #include <string.h>
 
+#include <mutex>
 #include <vector>
 
 #include "../../include/tcl_b200.h"
@@ -37,6 +48,7 @@ struct Layout {
   int chunk;
 };
 
+// F = device frame slots provisioned
 Layout make_layout(int P, int F, int C, int H, int W, int dtype, int chunk_pairs, bool with_mask) {
   Layout L;
   memset(&L, 0, sizeof(L));
@@ -69,11 +81,11 @@ int hfail(int code, const char* what, const char* detail = "") {
   return code;
 }
 
-// RAII for the per-call copy stream and ring events (destroying them is safe while work is pending: the runtime
-// releases the resources once the work has completed)
+// copy stream + ring events of one call in flight; pooled per device and reused (never destroyed: process lifetime)
 struct Pipe {
   cudaStream_t copy = nullptr;
   cudaEvent_t ready[kRing] = {}, done[kRing] = {}, fork = nullptr;
+  int device = -1;
   cudaError_t init() {
     cudaError_t e = cudaStreamCreateWithFlags(&copy, cudaStreamNonBlocking);
     if (e != cudaSuccess) return e;
@@ -83,7 +95,7 @@ struct Pipe {
     }
     return cudaEventCreateWithFlags(&fork, cudaEventDisableTiming);
   }
-  ~Pipe() {
+  void destroy() {
     for (int i = 0; i < kRing; ++i) {
       if (ready[i]) cudaEventDestroy(ready[i]);
       if (done[i]) cudaEventDestroy(done[i]);
@@ -93,6 +105,32 @@ struct Pipe {
   }
 };
 
+std::mutex g_pool_mutex;
+std::vector<Pipe*> g_pool;   // idle pipes of all devices
+
+Pipe* acquire_pipe(cudaError_t* err) {
+  int dev = 0;
+  if ((*err = cudaGetDevice(&dev)) != cudaSuccess) return nullptr;
+  {
+    std::lock_guard<std::mutex> lock(g_pool_mutex);
+    for (size_t i = 0; i < g_pool.size(); ++i)
+      if (g_pool[i]->device == dev) {
+        Pipe* p = g_pool[i];
+        g_pool.erase(g_pool.begin() + (long)i);
+        return p;
+      }
+  }
+  Pipe* p = new Pipe();
+  p->device = dev;
+  if ((*err = p->init()) != cudaSuccess) { p->destroy(); delete p; return nullptr; }
+  return p;
+}
+
+void release_pipe(Pipe* p) {
+  std::lock_guard<std::mutex> lock(g_pool_mutex);
+  g_pool.push_back(p);
+}
+
 }  // namespace
 
 extern "C" size_t tclb200_host_workspace_bytes(int P, int F, int C, int H, int W, int dtype, int chunk_pairs, int with_mask) {
@@ -100,63 +138,93 @@ extern "C" size_t tclb200_host_workspace_bytes(int P, int F, int C, int H, int W
   return make_layout(P, F, C, H, W, dtype, chunk_pairs, with_mask != 0).total;
 }
 
+// on failure: drain both streams (the caller may free its host buffers when it sees the error), give the pipe back
 #define HOST_TRY(expr)                                                                         \
   do {                                                                                         \
     cudaError_t e__ = (expr);                                                                  \
-    if (e__ != cudaSuccess) return hfail(TCLB200_ERR_CUDA, #expr ": ", cudaGetErrorString(e__)); \
+    if (e__ != cudaSuccess) return bail(hfail(TCLB200_ERR_CUDA, #expr ": ", cudaGetErrorString(e__))); \
   } while (0)
 
 extern "C" int tclb200_tcl_forward_host(const tclb200_host_args* a, tclb200_stream_t stream) {
   if (!a) return hfail(TCLB200_ERR_INVALID, "args is NULL");
-  if (a->P <= 0 || a->F <= 0 || a->C <= 0 || a->H <= 0 || a->W <= 0) return hfail(TCLB200_ERR_INVALID, "P, F, C, H, W must be positive");
+  if (a->P < 0 || a->F < 0) return hfail(TCLB200_ERR_INVALID, "P and F must not be negative");
+  if (a->P == 0) return TCLB200_OK;   // a clip of one frame has no pairs: nothing to do, nothing to return
+  if (a->F <= 0 || a->C <= 0 || a->H <= 0 || a->W <= 0) return hfail(TCLB200_ERR_INVALID, "F, C, H, W must be positive");
   if (!a->bf || !a->frames || !a->prev_index || !a->cur_index) return hfail(TCLB200_ERR_INVALID, "bf, frames, prev_index and cur_index are required");
   if (!a->pair_vals && !a->pair_sums) return hfail(TCLB200_ERR_INVALID, "nothing to return: pair_vals and pair_sums are both NULL");
   if (a->dtype != TCLB200_F32 && a->dtype != TCLB200_BF16) return hfail(TCLB200_ERR_INVALID, "unknown dtype");
+  if (a->frame_slots < 0) return hfail(TCLB200_ERR_INVALID, "frame_slots must not be negative");
   for (int p = 0; p < a->P; ++p)
     if (a->prev_index[p] < 0 || a->prev_index[p] >= a->F || a->cur_index[p] < 0 || a->cur_index[p] >= a->F)
       return hfail(TCLB200_ERR_INVALID, "prev_index / cur_index outside [0, F)");
   const bool with_mask = !a->ff && a->mask_in;
-  const Layout L = make_layout(a->P, a->F, a->C, a->H, a->W, a->dtype, a->chunk_pairs, with_mask);
+  const int S = (a->frame_slots > 0 && a->frame_slots < a->F) ? a->frame_slots : a->F;   // device frame slots
+  const Layout L = make_layout(a->P, S, a->C, a->H, a->W, a->dtype, a->chunk_pairs, with_mask);
   if (!a->workspace || a->workspace_bytes < L.total) return hfail(TCLB200_ERR_INVALID, "workspace missing or smaller than tclb200_host_workspace_bytes()");
   if ((reinterpret_cast<uintptr_t>(a->workspace) & 255u) != 0) return hfail(TCLB200_ERR_INVALID, "workspace must be 256-byte aligned");
 
   cudaStream_t comp = reinterpret_cast<cudaStream_t>(stream);
   char* ws = reinterpret_cast<char*>(a->workspace);
-  Pipe pipe;
-  HOST_TRY(pipe.init());
+  cudaError_t perr = cudaSuccess;
+  Pipe* pipe = acquire_pipe(&perr);
+  if (!pipe) return hfail(TCLB200_ERR_CUDA, "copy stream / events: ", cudaGetErrorString(perr));
+  auto bail = [&](int rc) {
+    cudaStreamSynchronize(pipe->copy);
+    cudaStreamSynchronize(comp);
+    release_pipe(pipe);
+    return rc;
+  };
   // the workspace may still be in use by earlier work on the caller's stream
-  HOST_TRY(cudaEventRecord(pipe.fork, comp));
-  HOST_TRY(cudaStreamWaitEvent(pipe.copy, pipe.fork, 0));
+  HOST_TRY(cudaEventRecord(pipe->fork, comp));
+  HOST_TRY(cudaStreamWaitEvent(pipe->copy, pipe->fork, 0));
   HOST_TRY(cudaMemsetAsync(ws + L.scratch, 0, tclb200_scratch_bytes(L.chunk, a->H, a->W), comp));
-  HOST_TRY(cudaMemcpyAsync(ws + L.prev_idx, a->prev_index, sizeof(int) * (size_t)a->P, cudaMemcpyHostToDevice, pipe.copy));
-  HOST_TRY(cudaMemcpyAsync(ws + L.cur_idx, a->cur_index, sizeof(int) * (size_t)a->P, cudaMemcpyHostToDevice, pipe.copy));
 
-  std::vector<char> on_device((size_t)a->F, 0);
+  // frame -> device slot; a slot is free again once the last chunk that reads its frame has completed
+  const int n_chunks = (a->P + L.chunk - 1) / L.chunk;
+  std::vector<int> slot_of((size_t)a->F, -1), last_use((size_t)a->F, -1), free_slots, h_prev((size_t)a->P), h_cur((size_t)a->P);
+  std::vector<std::vector<int>> dies((size_t)n_chunks);   // frames whose last reader is chunk k
+  for (int p = 0; p < a->P; ++p) { last_use[(size_t)a->prev_index[p]] = p / L.chunk; last_use[(size_t)a->cur_index[p]] = p / L.chunk; }
+  for (int f = 0; f < a->F; ++f) if (last_use[(size_t)f] >= 0) dies[(size_t)last_use[(size_t)f]].push_back(f);
+  free_slots.reserve((size_t)S);
+  for (int i = S - 1; i >= 0; --i) free_slots.push_back(i);   // handed out in increasing order: consecutive frames, consecutive slots
+  int released = 0;   // chunks whose frames have been released
   std::vector<int> want;
   const char* h_frames = reinterpret_cast<const char*>(a->frames);
   for (int s = 0, k = 0; s < a->P; s += L.chunk, ++k) {
     const int n = a->P - s < L.chunk ? a->P - s : L.chunk;
     const int slot = k % kRing;
-    // frames this chunk needs and the device does not hold yet; runs of consecutive frames go as one copy
+    if (k >= kRing) {
+      HOST_TRY(cudaStreamWaitEvent(pipe->copy, pipe->done[slot], 0));   // chunk k - kRing has been consumed: its flow slot is free ...
+      for (; released <= k - kRing; ++released)                           // ... and so are the frames nobody reads after it
+        for (int f : dies[(size_t)released]) { free_slots.push_back(slot_of[(size_t)f]); slot_of[(size_t)f] = -1; }
+    }
+    // frames this chunk needs and the device does not hold yet; runs of consecutive frames / slots go as one copy
     want.clear();
     for (int p = s; p < s + n; ++p) {
       const int f2[2] = {a->prev_index[p], a->cur_index[p]};
       for (int j = 0; j < 2; ++j)
-        if (!on_device[(size_t)f2[j]]) { on_device[(size_t)f2[j]] = 1; want.push_back(f2[j]); }
+        if (slot_of[(size_t)f2[j]] < 0) {
+          if (free_slots.empty()) return bail(hfail(TCLB200_ERR_INVALID, "frame_slots too small: a window of (3 + 1) chunks of pairs must fit the device frame ring"));
+          slot_of[(size_t)f2[j]] = free_slots.back(); free_slots.pop_back();
+          want.push_back(f2[j]);
+        }
+      h_prev[(size_t)p] = slot_of[(size_t)f2[0]]; h_cur[(size_t)p] = slot_of[(size_t)f2[1]];
     }
     for (size_t i = 0; i < want.size();) {
       size_t j = i + 1;
-      while (j < want.size() && want[j] == want[j - 1] + 1) ++j;
-      const size_t off = (size_t)want[i] * L.frame_bytes;
-      HOST_TRY(cudaMemcpyAsync(ws + L.frames + off, h_frames + off, (j - i) * L.frame_bytes, cudaMemcpyHostToDevice, pipe.copy));
+      while (j < want.size() && want[j] == want[j - 1] + 1 && slot_of[(size_t)want[j]] == slot_of[(size_t)want[j - 1]] + 1) ++j;
+      HOST_TRY(cudaMemcpyAsync(ws + L.frames + (size_t)slot_of[(size_t)want[i]] * L.frame_bytes, h_frames + (size_t)want[i] * L.frame_bytes,
+                               (j - i) * L.frame_bytes, cudaMemcpyHostToDevice, pipe->copy));
       i = j;
     }
-    if (k >= kRing) HOST_TRY(cudaStreamWaitEvent(pipe.copy, pipe.done[slot], 0));   // the slot's previous chunk has been consumed
-    if (a->ff) HOST_TRY(cudaMemcpyAsync(ws + L.flows[slot][0], a->ff + (size_t)s * 2 * a->H * a->W, (size_t)n * L.flow_bytes, cudaMemcpyHostToDevice, pipe.copy));
-    HOST_TRY(cudaMemcpyAsync(ws + L.flows[slot][1], a->bf + (size_t)s * 2 * a->H * a->W, (size_t)n * L.flow_bytes, cudaMemcpyHostToDevice, pipe.copy));
-    if (with_mask) HOST_TRY(cudaMemcpyAsync(ws + L.mask[slot], a->mask_in + (size_t)s * a->H * a->W, (size_t)n * L.mask_bytes, cudaMemcpyHostToDevice, pipe.copy));
-    HOST_TRY(cudaEventRecord(pipe.ready[slot], pipe.copy));
-    HOST_TRY(cudaStreamWaitEvent(comp, pipe.ready[slot], 0));
+    // (pageable host vectors: the runtime stages these small copies before the call returns)
+    HOST_TRY(cudaMemcpyAsync(ws + L.prev_idx + sizeof(int) * (size_t)s, h_prev.data() + s, sizeof(int) * (size_t)n, cudaMemcpyHostToDevice, pipe->copy));
+    HOST_TRY(cudaMemcpyAsync(ws + L.cur_idx + sizeof(int) * (size_t)s, h_cur.data() + s, sizeof(int) * (size_t)n, cudaMemcpyHostToDevice, pipe->copy));
+    if (a->ff) HOST_TRY(cudaMemcpyAsync(ws + L.flows[slot][0], a->ff + (size_t)s * 2 * a->H * a->W, (size_t)n * L.flow_bytes, cudaMemcpyHostToDevice, pipe->copy));
+    HOST_TRY(cudaMemcpyAsync(ws + L.flows[slot][1], a->bf + (size_t)s * 2 * a->H * a->W, (size_t)n * L.flow_bytes, cudaMemcpyHostToDevice, pipe->copy));
+    if (with_mask) HOST_TRY(cudaMemcpyAsync(ws + L.mask[slot], a->mask_in + (size_t)s * a->H * a->W, (size_t)n * L.mask_bytes, cudaMemcpyHostToDevice, pipe->copy));
+    HOST_TRY(cudaEventRecord(pipe->ready[slot], pipe->copy));
+    HOST_TRY(cudaStreamWaitEvent(comp, pipe->ready[slot], 0));
 
     tclb200_tcl_args t;
     memset(&t, 0, sizeof(t));
@@ -166,17 +234,20 @@ extern "C" int tclb200_tcl_forward_host(const tclb200_host_args* a, tclb200_stre
     t.prev = ws + L.frames; t.cur = ws + L.frames;
     t.prev_index = reinterpret_cast<const int*>(ws + L.prev_idx) + s;
     t.cur_index = reinterpret_cast<const int*>(ws + L.cur_idx) + s;
-    t.n_prev_frames = a->F; t.n_cur_frames = a->F;
+    t.n_prev_frames = S; t.n_cur_frames = S;
     t.pair_vals = reinterpret_cast<float*>(ws + L.vals) + s;
     t.pair_sums = reinterpret_cast<double*>(ws + L.sums) + s;
     t.scratch = ws + L.scratch; t.scratch_bytes = tclb200_scratch_bytes(L.chunk, a->H, a->W);
     t.B = n; t.C = a->C; t.H = a->H; t.W = a->W;
     t.dtype = a->dtype; t.flags = a->flags; t.loss = a->loss; t.finalize = a->finalize;
     const int rc = tclb200_tcl_forward(&t, stream);
-    if (rc != TCLB200_OK) return rc;   // tclb200_last_error() already holds the message
-    HOST_TRY(cudaEventRecord(pipe.done[slot], comp));
+    if (rc != TCLB200_OK) return bail(rc);   // tclb200_last_error() already holds the message
+    HOST_TRY(cudaEventRecord(pipe->done[slot], comp));
   }
   if (a->pair_vals) HOST_TRY(cudaMemcpyAsync(a->pair_vals, ws + L.vals, sizeof(float) * (size_t)a->P, cudaMemcpyDeviceToHost, comp));
   if (a->pair_sums) HOST_TRY(cudaMemcpyAsync(a->pair_sums, ws + L.sums, sizeof(double) * (size_t)a->P, cudaMemcpyDeviceToHost, comp));
+  // the pipe goes back to the pool once its last use (the final ready event the caller's stream waits for) is enqueued;
+  // a later call's work on the copy stream is ordered behind this call's by the stream itself
+  release_pipe(pipe);
   return TCLB200_OK;
 }

@@ -43,7 +43,13 @@
 #define TCL_TH 32     // tile height (the width is 64)
 #endif
 #ifndef TCL_BH
-#define TCL_BH 40     // source-box height (the width is 80)
+#define TCL_BH 40     // source-box height
+#endif
+#ifndef TCL_BW
+#define TCL_BW 80     // source-box width for fp32 frames: 16 (mod 32), see WsCfg
+#endif
+#ifndef TCL_BW16
+#define TCL_BW16 80   // ... for bf16 frames (TMA: rows are multiples of 16 bytes)
 #endif
 #ifndef TCL_NS
 #define TCL_NS 2      // source-box stages in flight
@@ -51,8 +57,17 @@
 #ifndef TCL_NB
 #define TCL_NB (TCL_NS + 2)   // flow-tile stages in flight
 #endif
-#ifndef TCL_GROUPS
-#define TCL_GROUPS 1  // consumer groups: the 16 consumer warps work on this many tiles at a time
+#ifndef TCL_SCANNERS
+#define TCL_SCANNERS 2   // scanner warps (one warp needs about a tile period per tile and would pace the pipeline)
+#endif
+#ifndef TCL_PACKED
+#define TCL_PACKED 1  // interior staged tiles of the reducing hot configurations use packed fp32 arithmetic (lean_tile_packed)
+#endif
+#ifndef TCL_PACKED_GIVEN
+#define TCL_PACKED_GIVEN 1   // ... also with a dataset mask (the training loss)
+#endif
+#ifndef TCL_DIAG
+#define TCL_DIAG 0    // tuning aids (tools/sweep_build.py): 1 = no source-box traffic, 3 = boxes at the tile's own position (no scan)
 #endif
 
 namespace tcl {
@@ -223,25 +238,8 @@ __global__ void __launch_bounds__(kThreads) fused_forward_generic_kernel(const F
 }
 
 // ---------------------------------------------------------------------------------------------
-// TMA-staged, persistent, warp-specialised forward kernel (the hot kernel)
+// pieces of the TMA-staged, persistent, warp-specialised forward kernel (the hot kernel, described at its definition)
 // ---------------------------------------------------------------------------------------------
-// One 544-thread CTA per SM walks tiles  t = blockIdx.x + k * gridDim.x  of TW x TH pixels.
-//
-//   producer warp (warp 16)   keeps NB flow tiles and NS source-box sets in flight with TMA:
-//       bf tile k   (TW+16) x (TH+2) x 2, 1 px halo (8 columns for the 16-byte TMA alignment), zero-filled
-//                   outside the image = the zero padding of flowtools.gradient
-//       when it lands: scan it (LDS.128) for the extent of x+u, y+v -> bounding box of all bilinear taps
-//       ff / prev   BW x BH boxes at that origin, zero-filled outside the image = grid_sample's
-//                   padding_mode='zeros'; tiles whose taps do not fit the box (or hold non-finite flow) are
-//                   flagged and take the exact predicated global-gather path
-//       when the consumers release a tile: fold its 16 warp partials, pair / batch tickets (fixed order)
-//   consumer warps (0..15)    one pass per pixel: flow + 4 neighbours from the flow tile, motion-boundary test,
-//                   sampling position, 4 x (2 + C) taps from the source boxes, occlusion test, masked error
-//                   against `cur` (coalesced global loads issued before the wait for the boxes).
-//
-// A warp instruction covers 16 x 2 pixels (lane = 16 * row + column) and both the flow tile and the source boxes
-// have a pitch of 80 words = 16 (mod 32): the two rows fall into disjoint halves of the 32 banks, also when the
-// flow shifts some lanes to the next source row, so the taps are (nearly) conflict-free shared-memory reads.
 __device__ unsigned long long g_tile_stats[2];   // debug statistics: tiles taken from global memory entirely / mixed tiles
 #ifdef TCL_TRACE
 // tuning aid (tools/trace_pipeline.py): per CTA and local tile, globaltimer stamps of the pipeline events
@@ -252,20 +250,36 @@ __device__ __forceinline__ unsigned long long gtime() { unsigned long long t; as
 #else
 #define TCL_STAMP(k, slot) do { } while (0)
 #endif
-#ifndef TCL_CWARPS
-#define TCL_CWARPS 16
+// consumer warps per CTA: 8 (eight pixels per lane and tile) for the packed-arithmetic configuration, 16 (four pixels
+// per lane) for everything else -- measured per configuration; TCL_CWARPS forces one value (tuning builds)
+#ifdef TCL_CWARPS
+constexpr int kCWarpsPacked = TCL_CWARPS, kCWarpsOther = TCL_CWARPS;
+#else
+constexpr int kCWarpsPacked = 8, kCWarpsOther = 16;
 #endif
-constexpr int kCWarps = TCL_CWARPS;              // consumer warps
-constexpr int kWsThreads = 32 * (kCWarps + 1);   // + 1 producer warp
 
-template <typename FrameT, int CT, int TW_, int TH_, int BH_, int NB_, int NS_, int G_>
+// Lane -> pixel mapping of the consumer warps.  A warp owns a 16-column x kRows-row block of the 64 x TH tile (4 column
+// blocks x CW/4 row blocks); lane = 16 * h + c works on column c and on rows h, h + 2, h + 4, ... of the block.  One
+// warp instruction therefore covers 16 columns x 2 ADJACENT rows, and all shared-memory pitches are 80 words = 16 (mod 32):
+// the two rows fall into disjoint halves of the 32 banks, also when the flow shifts some lanes to the next source row, so
+// the reads of the flow tile are conflict-free and the taps nearly so (measured: rows four apart -- vertical strips of
+// adjacent pixels per lane -- lose more to the shear of real flows, 1.5 wavefronts per tap read, than their register
+// reuse saves).  A lane's rows interleave with its partner's, so the column's flow values are still shared between a
+// lane's pixels: 2 * P + 1 + 2 * P shared-memory reads per flow component and P pixels instead of 5 * P.
+template <typename FrameT, int CT, int TW_, int TH_, int BW_, int BH_, int NB_, int NS_, int CW_>
 struct WsCfg {
-  static constexpr int TW = TW_, TH = TH_, BW = TW_ + 16, BH = BH_, NB = NB_, NS = NS_;
-  static constexpr int G = G_, WPG = kCWarps / G_;   // consumer groups (each works on its own tile), warps per group
-  static constexpr int kHaloX = 8;               // TMA needs the box's innermost start on a 16-byte boundary
-  static constexpr int kBfW = TW + 2 * kHaloX, kBfH = TH + 2;
+  static constexpr int TW = TW_, TH = TH_, BW = BW_, BH = BH_, NB = NB_, NS = NS_;
+  static constexpr int CW = CW_;                 // consumer warps; then the producer warp (TMA requests, box placement, per-tile
+  static constexpr int kProducerWarp = CW;       // fold of the partial sums) and the scanner warp (extent of the sampling
+  static constexpr int kScannerWarp = CW + 1;    // positions of every flow tile; kScanners of them take the tiles in turn)
+  static constexpr int kScanners = TCL_SCANNERS;
+  static constexpr int kThreads = 32 * (CW + 1 + kScanners);
+  static constexpr int kHaloL = 4;               // TMA needs the box's innermost start on a 16-byte boundary
+  static constexpr int kBfW = TW + 16, kBfH = TH + 2;   // 4 + 64 + 12 columns (the right halo needs 1; 80 = 16 mod 32)
   static constexpr int kXAlign = 16 / (int)sizeof(FrameT);   // source-box origin is rounded down to this many pixels
-  static constexpr int kPPL = TW * TH / (32 * WPG);          // pixels per lane per tile
+  static constexpr int kRowBlocks = CW / 4;
+  static constexpr int kRows = TH / kRowBlocks;  // rows of a warp's block
+  static constexpr int kPPL = kRows / 2;         // pixels per lane per tile
   static constexpr int kC = CT > 0 ? CT : 1;
   static constexpr unsigned kBfLoad = 2u * kBfH * kBfW * 4u;
   static constexpr unsigned kFfLoad = 2u * BH * BW * 4u;
@@ -276,61 +290,91 @@ struct WsCfg {
   static constexpr size_t kBfOff = 0;
   static constexpr size_t kSrcOff = kBfOff + NB * kBfStage;
   static constexpr size_t kCtlOff = kSrcOff + NS * kSrcStage;
-  static constexpr size_t kSmemBytes = kCtlOff + 1024 + 128;  // control block + slack for manual 128-byte alignment
-  static_assert(TW == 64 && TH % WPG == 0 && kPPL % 2 == 0 && kCWarps % G == 0 && NS % G == 0, "lane mapping: 64-wide tiles, TH/WPG rows per warp");
-  static_assert(BW % 32 == 16 && kBfW % 32 == 16, "pitch must be 16 (mod 32) words for the 16 x 2 lane footprint");
+  static constexpr size_t kCtlBytes = 1024 + (size_t)NS * CW * 32 * 4;
+  static constexpr size_t kSmemBytes = kCtlOff + kCtlBytes + 128;  // + slack for manual 128-byte alignment
+  static_assert(TW == 64 && CW % 4 == 0 && TH % kRowBlocks == 0 && kRows % 2 == 0, "lane mapping: 16-column blocks, row pairs");
+  static_assert(kBfW % 32 == 16, "flow-tile pitch must be 16 (mod 32) words: adjacent rows fall into disjoint bank halves");
+  static_assert((BW * (int)sizeof(FrameT)) % 16 == 0 && BW % 4 == 0, "TMA: box rows are multiples of 16 bytes");
+#if TCL_DIAG != 3
   static_assert(NB >= NS + 2, "the flow tile of a tile is scanned NS tiles ahead: it must have been requested a tile before that");
+#endif
 };
+// row of pixel k of a lane, relative to the lane's first row
+__host__ __device__ constexpr int pix_dy(int k) { return 2 * k; }
+template <typename Cfg>
+__device__ __forceinline__ void lane_origin(int warp, int lane, int& lx0, int& ly0) {
+  lx0 = 16 * (warp & 3) + (lane & 15);
+  ly0 = Cfg::kRows * (warp >> 2) + (lane >> 4);
+}
 
 struct TileId { int pair, tile, x0, y0, edge, pf, cf, pad; };   // pf / cf: frame of `prev` / `cur` this pair reads
 
-template <int NB, int NS>
+template <int NB, int NS, int CW>
 struct WsCtl {              // control block in shared memory
-  uint64_t bf_full[NB], src_full[NS], done[NS], scan0;
+  uint64_t bf_full[NB], scanned[NB], src_full[NS], done[NS];
   TileId tinfo[NB];         // written by the producer with the flow-tile request
   int meta[NS][4];          // per source stage: ox, oy, staged?
   int box[NB][4];           // per flow stage: extent of x+u, y+v over the tile (ordered-int encoding): xmin, ymin, xmax, ymax
-  double red[NS][kCWarps];  // [stage][warp of the tile's group]
+  float red[NS][CW * 32];   // per source stage: every consumer lane's error sum of the tile
 };
 
-// order-preserving float <-> int (total order of IEEE bit patterns; NaNs land beyond +-Inf): lets redux.sync and
-// shared-memory atomicMin / atomicMax work on float extents
+// order-preserving float <-> int (total order of IEEE bit patterns; NaNs land beyond +-Inf): lets redux.sync work on
+// float extents
 __device__ __forceinline__ int f2ord(float f) { const int i = __float_as_int(f); return i ^ ((i >> 31) & 0x7fffffff); }
 __device__ __forceinline__ float ord2f(int i) { return __int_as_float(i ^ ((i >> 31) & 0x7fffffff)); }
 __device__ __forceinline__ float fmin_nan(float a, float b) { float r; asm("min.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b)); return r; }
 __device__ __forceinline__ float fmax_nan(float a, float b) { float r; asm("max.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b)); return r; }
 
-// consumer warp `warp`: its TH/16 rows of the flow tile `t` -> extent of x+u, y+v (the same sums the sampling positions
-// start from) folded into box[4].  Non-finite flow propagates (min/max.NaN) and is rejected by the placement.
+// scanner warp: extent of x+u, y+v (the sums the sampling positions start from) over the pixels of flow tile `t` that lie
+// inside the image -> box[4].  Non-finite flow propagates (min/max.NaN; a NaN wins the min or the max of the ordered
+// encoding, depending on its sign) and is rejected by the placement.  One LDS.128 per component and four pixels.
 template <typename Cfg>
-__device__ __forceinline__ void scan_flow_rows(const float* s_bu, const TileId& t, const Geo& g, int* box, int warp, int lane) {
-  constexpr int RPW = Cfg::TH / Cfg::WPG;   // rows per warp: 1 or 2
+__device__ __forceinline__ void scan_flow_tile(const float* s_bu, const TileId& t, const Geo& g, int* box, int lane) {
   const float* s_bv = s_bu + Cfg::kBfH * Cfg::kBfW;
-  const int c4 = 4 * (lane & 15);
-  const int r = warp * RPW + (lane >> 4);
+  const int c4 = 4 * (lane & 15), rh = lane >> 4;
   // W % 4 == 0: a lane's four columns are all inside the image or all outside
-  const bool ok = (RPW == 2 || lane < 16) && t.x0 + c4 < g.W && t.y0 + r < g.H;
-  int ixmin = INT_MAX, iymin = INT_MAX, ixmax = INT_MIN, iymax = INT_MIN;
-  if (ok) {
-    const float4 u4 = *reinterpret_cast<const float4*>(s_bu + (r + 1) * Cfg::kBfW + Cfg::kHaloX + c4);
-    const float4 v4 = *reinterpret_cast<const float4*>(s_bv + (r + 1) * Cfg::kBfW + Cfg::kHaloX + c4);
-    const float xf = (float)(t.x0 + c4), yf = (float)(t.y0 + r);
-    const float a0 = __fadd_rn(xf, u4.x), a1 = __fadd_rn(xf + 1.0f, u4.y), a2 = __fadd_rn(xf + 2.0f, u4.z), a3 = __fadd_rn(xf + 3.0f, u4.w);
-    ixmin = f2ord(fmin_nan(fmin_nan(a0, a1), fmin_nan(a2, a3)));
-    ixmax = f2ord(fmax_nan(fmax_nan(a0, a1), fmax_nan(a2, a3)));
-    iymin = f2ord(__fadd_rn(yf, fmin_nan(fmin_nan(v4.x, v4.y), fmin_nan(v4.z, v4.w))));
-    iymax = f2ord(__fadd_rn(yf, fmax_nan(fmax_nan(v4.x, v4.y), fmax_nan(v4.z, v4.w))));
+  const bool colok = t.x0 + c4 < g.W;
+  const float xf = (float)(t.x0 + c4);
+  const float inf = __int_as_float(0x7f800000);
+  float xmin = inf, ymin = inf, xmax = -inf, ymax = -inf;
+  const int rows = min(Cfg::TH, g.H - t.y0);
+  if (colok) {
+#pragma unroll 4
+    for (int r = rh; r < rows; r += 2) {
+      const float4 u4 = *reinterpret_cast<const float4*>(s_bu + (r + 1) * Cfg::kBfW + Cfg::kHaloL + c4);
+      const float4 v4 = *reinterpret_cast<const float4*>(s_bv + (r + 1) * Cfg::kBfW + Cfg::kHaloL + c4);
+      const float yf = (float)(t.y0 + r);
+      const float a0 = __fadd_rn(xf, u4.x), a1 = __fadd_rn(xf + 1.0f, u4.y), a2 = __fadd_rn(xf + 2.0f, u4.z), a3 = __fadd_rn(xf + 3.0f, u4.w);
+      xmin = fmin_nan(xmin, fmin_nan(fmin_nan(a0, a1), fmin_nan(a2, a3)));
+      xmax = fmax_nan(xmax, fmax_nan(fmax_nan(a0, a1), fmax_nan(a2, a3)));
+      ymin = fmin_nan(ymin, __fadd_rn(yf, fmin_nan(fmin_nan(v4.x, v4.y), fmin_nan(v4.z, v4.w))));
+      ymax = fmax_nan(ymax, __fadd_rn(yf, fmax_nan(fmax_nan(v4.x, v4.y), fmax_nan(v4.z, v4.w))));
+    }
   }
-  ixmin = __reduce_min_sync(0xffffffffu, ixmin); iymin = __reduce_min_sync(0xffffffffu, iymin);
-  ixmax = __reduce_max_sync(0xffffffffu, ixmax); iymax = __reduce_max_sync(0xffffffffu, iymax);
-  if (lane == 0) {
-    atomicMin(&box[0], ixmin); atomicMin(&box[1], iymin);
-    atomicMax(&box[2], ixmax); atomicMax(&box[3], iymax);
-  }
+  const int ixmin = __reduce_min_sync(0xffffffffu, f2ord(xmin)), iymin = __reduce_min_sync(0xffffffffu, f2ord(ymin));
+  const int ixmax = __reduce_max_sync(0xffffffffu, f2ord(xmax)), iymax = __reduce_max_sync(0xffffffffu, f2ord(ymax));
+  if (lane == 0) { box[0] = ixmin; box[1] = iymin; box[2] = ixmax; box[3] = iymax; }
 }
 
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// the same on precomputed shared-memory addresses (the consumers' per-tile waits: no address arithmetic in the loop)
+__device__ __forceinline__ void mbar_arrive_s(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_s(uint32_t bar, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(bar),
+      "r"(parity)
+      : "memory");
 }
 
 // Fold kernel of the warp-specialised path: the hot kernel only stores one fp64 partial per tile (no fences, no
@@ -388,18 +432,11 @@ __device__ __forceinline__ TileId tile_id(const FwdParams& p, int tg, int TW, in
   return t;
 }
 
-// lane -> pixel k of the tile: a warp instruction covers 16 columns x 2 rows
-template <int WPG>
-__device__ __forceinline__ void lane_pixel(int warp, int lane, int k, int& lx, int& ly) {   // warp = index within its group
-  const int task = warp + WPG * (k >> 1);   // 32 x 2 pixel strip of the tile
-  lx = 32 * (task & 1) + 16 * (k & 1) + (lane & 15);
-  ly = 2 * (task >> 1) + (lane >> 4);
-}
 
 // ---- consumer: exact per-pixel path (all features; staged boxes, global gathers, or both in a mixed tile) -------
 template <typename FrameT, int MASK, bool REDUCE, int CT, int LEAN, typename Cfg, bool EDGE>
 __device__ __forceinline__ float full_tile(const FwdParams& p, const float* s_bu, const float* s_ff, const FrameT* s_prev,
-                                           const int* meta, const TileId& t, int warp, int lane,
+                                           const int* meta, const TileId& t, int lx0, int ly0,
                                            const float (&cur)[Cfg::kPPL][Cfg::kC], const float (&mk)[Cfg::kPPL], bool have_cur,
                                            unsigned& near) {
   const Geo& g = p.geo;
@@ -416,11 +453,10 @@ __device__ __forceinline__ float full_tile(const FwdParams& p, const float* s_bu
   float err = 0.0f;
 #pragma unroll
   for (int k = 0; k < Cfg::kPPL; ++k) {   // fully unrolled: cur[k] / mk[k] must stay in registers
-    int lx, ly;
-    lane_pixel<Cfg::WPG>(warp, lane, k, lx, ly);
+    const int lx = lx0, ly = ly0 + pix_dy(k);
     const int x = t.x0 + lx, y = t.y0 + ly;
     if (EDGE && (x >= W || y >= H)) continue;
-    const int c = (ly + 1) * Cfg::kBfW + lx + Cfg::kHaloX;
+    const int c = (ly + 1) * Cfg::kBfW + lx + Cfg::kHaloL;
     const float u = s_bu[c], v = s_bv[c];
     float nb, keep = 1.0f;
     if (want_mob) {
@@ -457,23 +493,22 @@ struct LeanGeo {   // per-thread constants of lean_tile
   float i2x, i2y, Wf, Hf;
 };
 
-// sampling position of one pixel of a staged tile, relative to the box origin (floor parts) + the four weights
+// sampling position of one pixel of a staged tile: floor parts (as floats: exact integers) + the four weights
 struct LeanTaps {
-  float rx, ry;   // floor(ix) - box_x, floor(iy) - box_y as floats (small exact integers inside the box)
+  float fxf, fyf;   // floor(ix), floor(iy)
   float nw, ne, sw, se;
 };
-__device__ __forceinline__ LeanTaps lean_taps(float xf, float yf, float u, float v, const LeanGeo& lg, float box_xf, float box_yf) {
+__device__ __forceinline__ LeanTaps lean_taps(float xf, float yf, float u, float v, const LeanGeo& lg) {
   // the reference's [-1,1] round trip (flowtools.py:28-29 + grid_sampler's unnormalise).  Inside a staged tile every
   // coordinate is finite and far inside the int range: no safe_downgrade guard needed.
   const float ax = __fadd_rn(xf, u), ay = __fadd_rn(yf, v);
   const float tx = __fadd_rn(__fsub_rn(__fmul_rn(ax, lg.i2x), 1.0f), 1.0f), ty = __fadd_rn(__fsub_rn(__fmul_rn(ay, lg.i2y), 1.0f), 1.0f);
   const float ix = __fmul_rn(__fmaf_rn(tx, lg.Wf, -1.0f), 0.5f), iy = __fmul_rn(__fmaf_rn(ty, lg.Hf, -1.0f), 0.5f);
-  const float fxf = floorf(ix), fyf = floorf(iy);
-  const float fx1 = __fsub_rn(__fadd_rn(fxf, 1.0f), ix), fx0 = __fsub_rn(ix, fxf);
-  const float fy1 = __fsub_rn(__fadd_rn(fyf, 1.0f), iy), fy0 = __fsub_rn(iy, fyf);
   LeanTaps t;
+  t.fxf = floorf(ix); t.fyf = floorf(iy);
+  const float fx1 = __fsub_rn(__fadd_rn(t.fxf, 1.0f), ix), fx0 = __fsub_rn(ix, t.fxf);
+  const float fy1 = __fsub_rn(__fadd_rn(t.fyf, 1.0f), iy), fy0 = __fsub_rn(iy, t.fyf);
   t.nw = __fmul_rn(fx1, fy1); t.ne = __fmul_rn(fx0, fy1); t.sw = __fmul_rn(fx1, fy0); t.se = __fmul_rn(fx0, fy0);
-  t.rx = __fsub_rn(fxf, box_xf); t.ry = __fsub_rn(fyf, box_yf);
   return t;
 }
 
@@ -487,8 +522,8 @@ __device__ __noinline__ bool exact_keep(const float* s_bu, const float* s_ff, in
   const bool mob = motion_boundary(u, v, s_bu[c - 1], s_bu[c + 1], s_bu[c - BFW], s_bu[c + BFW], s_bv[c - 1], s_bv[c + 1],
                                    s_bv[c - BFW], s_bv[c + BFW], kV, &nb, &m1);
   if (!OCC) return !mob;   // the optimisation-based variant: motion-boundary test only
-  const LeanTaps t = lean_taps(xf, yf, u, v, lg, box_xf, box_yf);
-  const float* f0 = s_ff + (int)__fmaf_rn(t.ry, (float)BW, t.rx);
+  const LeanTaps t = lean_taps(xf, yf, u, v, lg);
+  const float* f0 = s_ff + (int)__fmaf_rn(__fsub_rn(t.fyf, box_yf), (float)BW, __fsub_rn(t.fxf, box_xf));
   float a = __fmul_rn(f0[0], t.nw);
   a = __fmaf_rn(f0[1], t.ne, a); a = __fmaf_rn(f0[BW], t.sw, a); a = __fmaf_rn(f0[BW + 1], t.se, a);
   float b = __fmul_rn(f0[PL], t.nw);
@@ -533,6 +568,31 @@ __device__ __noinline__ float pixel_global(const float* bf_pair, size_t bf_plane
   return keep ? acc : 0.0f;
 }
 
+// shared-memory reads at a 32-bit shared address + compile-time offset (the tap reads of the staged tiles: the box
+// address of a pixel is computed in floating point straight from floor(ix), floor(iy) and serves all planes)
+template <int OFF>
+__device__ __forceinline__ float lds_tap(uint32_t a, float) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1+%2];" : "=f"(v) : "r"(a), "n"(OFF));
+  return v;
+}
+template <int OFF>
+__device__ __forceinline__ float lds_tap(uint32_t a, __nv_bfloat16) {
+  unsigned h;   // (ld may write a register wider than its type: zero-extended)
+  asm volatile("ld.shared.u16 %0, [%1+%2];" : "=r"(h) : "r"(a), "n"(OFF));
+  return __uint_as_float(h << 16);
+}
+// one plane of a staged box, grid_sampler_2d's accumulation order (zero-filled outside the image: all four taps are plain reads)
+template <typename T, int OFF, int PITCH>
+__device__ __forceinline__ float staged_tap4(uint32_t a, const LeanTaps& tp) {
+  constexpr int E = (int)sizeof(T);
+  float w = __fmul_rn(lds_tap<OFF>(a, T()), tp.nw);
+  w = __fmaf_rn(lds_tap<OFF + E>(a, T()), tp.ne, w);
+  w = __fmaf_rn(lds_tap<OFF + PITCH * E>(a, T()), tp.sw, w);
+  w = __fmaf_rn(lds_tap<OFF + PITCH * E + E>(a, T()), tp.se, w);
+  return w;
+}
+
 // CT == 3: masked squared error against `cur` (returned); CT == 0: mask-only (fbcCheckTorch), the verdicts go to mask_out
 // OCC == false (mask-only): the optimisation-based variant of fbcCheckTorch, motion-boundary test alone -- no source
 // boxes are staged and no sampling position is needed (methods/optimization-based/flowtools.py:34-58)
@@ -541,12 +601,13 @@ __device__ __noinline__ float pixel_global(const float* bf_pair, size_t bf_plane
 // mask verdicts are final)
 template <typename FrameT, int MASK, int CT, int LOSS, typename Cfg, bool EDGE, bool MIXED, bool OCC = true, bool OUTS = false>
 __device__ __forceinline__ float lean_tile(const FwdParams& p, const float* s_bu, const float* s_ff, const int* meta, const TileId& t,
-                                           int warp, int lane, const float (&cur)[Cfg::kPPL][Cfg::kC], const float (&mk)[Cfg::kPPL]) {
+                                           int lx0, int ly0, const float (&cur)[Cfg::kPPL][Cfg::kC], const float (&mk)[Cfg::kPPL]) {
   constexpr int P = Cfg::kPPL, BW = Cfg::BW, BFW = Cfg::kBfW, PL = Cfg::BH * Cfg::BW;
   constexpr float kHi = 1.0f + kFilterEps, kLo = 1.0f - kFilterEps;
+  constexpr int FE = (int)sizeof(FrameT);
   const Geo& g = p.geo;
   const float* s_bv = s_bu + Cfg::kBfH * BFW;
-  // the prev boxes follow the ff boxes in the stage: one address register serves both (fp32 frames)
+  // the prev boxes follow the ff boxes in the stage
   const FrameT* s_prev = reinterpret_cast<const FrameT*>(reinterpret_cast<const unsigned char*>(s_ff) + Cfg::kFfStage);
   const int box_x = meta[0], box_y = meta[1];
   const float box_xf = (float)box_x, box_yf = (float)box_y;
@@ -556,135 +617,179 @@ __device__ __forceinline__ float lean_tile(const FwdParams& p, const float* s_bu
   LeanGeo lg;
   lg.i2x = __fmul_rn(2.0f, g.inv_dx); lg.i2y = __fmul_rn(2.0f, g.inv_dy);   // exact doubling: (2a)*r == a*(2r)
   lg.Wf = g.Wf; lg.Hf = g.Hf;
-  int lx0, ly0;
-  lane_pixel<Cfg::WPG>(warp, lane, 0, lx0, ly0);
-  // pixel k of this lane: 16 columns right of pixel k-1 (k odd) / 16 rows below pixel k-2
-  constexpr int DY = Cfg::WPG;   // pixel k of this lane: 16 columns right of pixel k-1 (k odd) / WPG rows below pixel k-2
-  const float xs[2] = {(float)(t.x0 + lx0), (float)(t.x0 + lx0 + 16)}, ys[2] = {(float)(t.y0 + ly0), (float)(t.y0 + ly0 + DY)};
-  const int c0 = (ly0 + 1) * BFW + lx0 + Cfg::kHaloX;
+  const float xf = (float)(t.x0 + lx0), yf0 = (float)(t.y0 + ly0);
+  const int c0 = (ly0 + 1) * BFW + lx0 + Cfg::kHaloL;
+  const bool xin = !EDGE || t.x0 + lx0 < g.W;
   const bool validity = MASK == MASK_NONE && (p.flags & TCLB200_VALIDITY);
+  // staged tiles: byte address of a pixel's top-left tap = base + 4 * ((fyf - box_y) * BW + (fxf - box_x)), evaluated with two
+  // fmas on exact small integers (the placement keeps |box| < 2^15, so every intermediate is an integer below 2^24)
+  const uint32_t ff_base = smem_u32(s_ff), prev_base = smem_u32(s_prev);
+  const float ff_k = __fsub_rn((float)ff_base, 4.0f * __fmaf_rn(box_yf, (float)BW, box_xf));
+  const float prev_k = __fsub_rn((float)prev_base, (float)FE * __fmaf_rn(box_yf, (float)BW, box_xf));
   float e[P];
   float wv[OUTS ? P : 1][3];
   unsigned keepbits = 0, ambbits = 0, outbits = 0;
+  {
+    // this lane's column of the flow tile: rows -1 .. 2 * P - 1 relative to the lane's first row (its own pixels are the
+    // odd entries, the even ones belong to the partner lane)
+    float uc[2 * P + 1], vc[2 * P + 1], ul[P], ur[P], vl[P], vr[P];
 #pragma unroll
-  for (int k = 0; k < P; ++k) {
-    const int dxk = 16 * (k & 1), dyk = DY * (k >> 1);
-    const bool inside = !EDGE || (t.x0 + lx0 + dxk < g.W && t.y0 + ly0 + dyk < g.H);
-    const int c = c0 + dyk * BFW + dxk;
-    const float u = s_bu[c], v = s_bv[c];
-    const float s0 = __fmaf_rn(u, u, __fmul_rn(v, v));
-    bool keep = inside, amb = false;
-    if (MASK == MASK_COMPUTED) {
-      // motion boundary: 4*(|grad u|^2 + |grad v|^2)  vs  4*(0.01*|bf|^2 + 0.002)
-      const float dux = __fsub_rn(s_bu[c + 1], s_bu[c - 1]), duy = __fsub_rn(s_bu[c + BFW], s_bu[c - BFW]);
-      const float dvx = __fsub_rn(s_bv[c + 1], s_bv[c - 1]), dvy = __fsub_rn(s_bv[c + BFW], s_bv[c - BFW]);
-      const float G = __fmaf_rn(dux, dux, __fmaf_rn(duy, duy, __fmaf_rn(dvx, dvx, __fmul_rn(dvy, dvy))));
-      const float Rhi = __fmaf_rn(4.0f * 0.01f * kHi, s0, 4.0f * 0.002f * kHi), Rlo = __fmaf_rn(4.0f * 0.01f * kLo, s0, 4.0f * 0.002f * kLo);
-      const bool mob = G > Rhi;
-      keep = keep && !mob;
-      amb = !(mob || G < Rlo);
+    for (int r = 0; r < 2 * P + 1; ++r) {
+      if (MASK == MASK_COMPUTED || (r & 1)) { uc[r] = s_bu[c0 + (r - 1) * BFW]; vc[r] = s_bv[c0 + (r - 1) * BFW]; }
+      else { uc[r] = 0.0f; vc[r] = 0.0f; }
     }
-    LeanTaps tp = lean_taps(xs[k & 1], ys[k >> 1], u, v, lg, box_xf, box_yf);
-    // pixels beyond the image edge read any in-box address, their result is discarded
-    bool inbox = true;
-    if (MIXED) inbox = !inside || (tp.rx >= 0.0f && tp.rx < (float)(BW - 1) && tp.ry >= 0.0f && tp.ry < (float)(Cfg::BH - 1));
-    const int q = ((EDGE || MIXED) && !(inside && inbox)) ? 0 : (int)__fmaf_rn(tp.ry, (float)BW, tp.rx);
-    // where the four taps of each plane come from: the staged boxes (zero-filled outside the image), or -- pixels of a
-    // mixed tile whose taps left the boxes -- global memory with grid_sample's zero padding as per-tap predicates
-    const float* pf = s_ff + q;
-    const FrameT* pp = s_prev + q;
-    int rs = BW;
-    ptrdiff_t ps = PL, psf = PL;   // plane pitch of the frame / flow planes behind pp / pf
-    bool p00 = true, p10 = true, p01 = true, p11 = true;
-    if (MIXED && !inbox) {
-      const int gx = (int)tp.rx + box_x, gy = (int)tp.ry + box_y;   // top-left tap in the image (sane: the placement checked)
-      const ptrdiff_t off = (ptrdiff_t)gy * g.W + gx;
-      if (MASK == MASK_COMPUTED) pf = gff + off;
-      if (CT == 3) pp = gprev + off;
-      rs = g.W; ps = gplane; psf = (ptrdiff_t)p.ff_plane;
-      const bool xin0 = (unsigned)gx < (unsigned)g.W, xin1 = (unsigned)(gx + 1) < (unsigned)g.W;
-      const bool yin0 = (unsigned)gy < (unsigned)g.H, yin1 = (unsigned)(gy + 1) < (unsigned)g.H;
-      p00 = xin0 && yin0; p10 = xin1 && yin0; p01 = xin0 && yin1; p11 = xin1 && yin1;
+#pragma unroll
+    for (int j = 0; j < P; ++j) {
+      if (MASK == MASK_COMPUTED) {
+        ul[j] = s_bu[c0 + 2 * j * BFW - 1]; ur[j] = s_bu[c0 + 2 * j * BFW + 1];
+        vl[j] = s_bv[c0 + 2 * j * BFW - 1]; vr[j] = s_bv[c0 + 2 * j * BFW + 1];
+      } else { ul[j] = ur[j] = vl[j] = vr[j] = 0.0f; }
     }
-    auto tap4 = [&](auto* b) {   // one plane, grid_sampler_2d's accumulation order
-      float w;
+#pragma unroll
+    for (int j = 0; j < P; ++j) {
+      const int k = j, dyk = 2 * j;
+      const bool inside = !EDGE || (xin && t.y0 + ly0 + dyk < g.H);
+      const float u = uc[2 * j + 1], v = vc[2 * j + 1];
+      const float s0 = __fmaf_rn(u, u, __fmul_rn(v, v));
+      bool keep = inside, amb = false;
+      if (MASK == MASK_COMPUTED) {
+        // motion boundary: 4*(|grad u|^2 + |grad v|^2)  vs  4*(0.01*|bf|^2 + 0.002)
+        const float dux = __fsub_rn(ur[j], ul[j]), duy = __fsub_rn(uc[2 * j + 2], uc[2 * j]);
+        const float dvx = __fsub_rn(vr[j], vl[j]), dvy = __fsub_rn(vc[2 * j + 2], vc[2 * j]);
+        const float G = __fmaf_rn(dux, dux, __fmaf_rn(duy, duy, __fmaf_rn(dvx, dvx, __fmul_rn(dvy, dvy))));
+        const float Rhi = __fmaf_rn(4.0f * 0.01f * kHi, s0, 4.0f * 0.002f * kHi), Rlo = __fmaf_rn(4.0f * 0.01f * kLo, s0, 4.0f * 0.002f * kLo);
+        const bool mob = G > Rhi;
+        keep = keep && !mob;
+        amb = !(mob || G < Rlo);
+      }
+      const float yf = yf0 + (float)dyk;
+      const LeanTaps tp = lean_taps(xf, yf, u, v, lg);
+      // pixels beyond the image edge read any in-box address, their result is discarded
+      bool inbox = true;
+      float rx = 0.0f, ry = 0.0f;
       if (MIXED) {
-        w = __fmul_rn(p00 ? to_f32(b[0]) : 0.0f, tp.nw);
-        w = __fmaf_rn(p10 ? to_f32(b[1]) : 0.0f, tp.ne, w);
-        w = __fmaf_rn(p01 ? to_f32(b[rs]) : 0.0f, tp.sw, w);
-        w = __fmaf_rn(p11 ? to_f32(b[rs + 1]) : 0.0f, tp.se, w);
+        rx = __fsub_rn(tp.fxf, box_xf); ry = __fsub_rn(tp.fyf, box_yf);
+        inbox = !inside || (rx >= 0.0f && rx < (float)(BW - 1) && ry >= 0.0f && ry < (float)(Cfg::BH - 1));
+      }
+      float a = 0.0f, b = 0.0f, w3[3] = {0.0f, 0.0f, 0.0f};
+      if (!MIXED) {
+        // every tap of the tile lies inside the staged boxes (zero-filled outside the image)
+        uint32_t fa = (uint32_t)__float2int_rn(__fmaf_rn(tp.fyf, 4.0f * (float)BW, __fmaf_rn(tp.fxf, 4.0f, ff_k)));
+        if (EDGE && !inside) fa = ff_base;
+#if TCL_DIAG == 3
+        fa = ff_base + ((fa - ff_base) & 0xffcu);
+#endif
+        if (MASK == MASK_COMPUTED && OCC) {
+          a = staged_tap4<float, 0, BW>(fa, tp);
+          b = staged_tap4<float, PL * 4, BW>(fa, tp);
+        }
+        if (CT == 3) {
+          if (FE == 4) {   // fp32 frames: the prev planes sit behind the ff planes, the same address register serves them
+            w3[0] = staged_tap4<FrameT, (int)Cfg::kFfStage, BW>(fa, tp);
+            w3[1] = staged_tap4<FrameT, (int)Cfg::kFfStage + PL * FE, BW>(fa, tp);
+            w3[2] = staged_tap4<FrameT, (int)Cfg::kFfStage + 2 * PL * FE, BW>(fa, tp);
+          } else {
+            uint32_t pa = (uint32_t)__float2int_rn(__fmaf_rn(tp.fyf, (float)(FE * BW), __fmaf_rn(tp.fxf, (float)FE, prev_k)));
+            if (EDGE && !inside) pa = prev_base;
+            w3[0] = staged_tap4<FrameT, 0, BW>(pa, tp);
+            w3[1] = staged_tap4<FrameT, PL * FE, BW>(pa, tp);
+            w3[2] = staged_tap4<FrameT, 2 * PL * FE, BW>(pa, tp);
+          }
+        }
       } else {
-        w = __fmul_rn(to_f32(b[0]), tp.nw);
-        w = __fmaf_rn(to_f32(b[1]), tp.ne, w);
-        w = __fmaf_rn(to_f32(b[BW]), tp.sw, w);
-        w = __fmaf_rn(to_f32(b[BW + 1]), tp.se, w);
-      }
-      return w;
-    };
-    if (MASK == MASK_COMPUTED && OCC) {
-      const float a = tap4(pf), b = tap4(MIXED ? pf + psf : pf + PL);
-      // occlusion: |wf+bf|^2  vs  0.01*(|wf|^2+|bf|^2) + 0.5
-      const float su = __fadd_rn(a, u), sv = __fadd_rn(b, v);
-      const float L = __fmaf_rn(su, su, __fmul_rn(sv, sv));
-      const float nn = __fadd_rn(__fmaf_rn(a, a, __fmul_rn(b, b)), s0);
-      const float Rhi = __fmaf_rn(0.01f * kHi, nn, 0.5f * kHi), Rlo = __fmaf_rn(0.01f * kLo, nn, 0.5f * kLo);
-      const bool occ = L > Rhi;
-      keep = keep && !occ;
-      amb = amb || !(occ || L < Rlo);
-    }
-    float acc = 0.0f;
-    float valid = 1.0f;
-    if (MASK == MASK_NONE && validity) {   // fs_lib.warp: times the binarised warp of an all-ones image (fs_lib.py:29-37)
-      const int gx = (int)tp.rx + box_x, gy = (int)tp.ry + box_y;
-      Taps vt;
-      const bool xin0 = (unsigned)gx < (unsigned)g.W, xin1 = (unsigned)(gx + 1) < (unsigned)g.W;
-      const bool yin0 = (unsigned)gy < (unsigned)g.H, yin1 = (unsigned)(gy + 1) < (unsigned)g.H;
-      vt.p00 = xin0 && yin0; vt.p10 = xin1 && yin0; vt.p01 = xin0 && yin1; vt.p11 = xin1 && yin1;
-      vt.nw = tp.nw; vt.ne = tp.ne; vt.sw = tp.sw; vt.se = tp.se; vt.o00 = 0;
-      valid = binarise_validity(ones_sample(vt, kV));
-    }
+        // mixed tile: the staged boxes, or -- pixels whose taps left the boxes -- global memory with grid_sample's zero
+        // padding as per-tap predicates
+        const int q = !(inside && inbox) ? 0 : (int)__fmaf_rn(ry, (float)BW, rx);
+        const float* pf = s_ff + q;
+        const FrameT* pp = s_prev + q;
+        int rs = BW;
+        ptrdiff_t ps = PL, psf = PL;   // plane pitch of the frame / flow planes behind pp / pf
+        bool p00 = true, p10 = true, p01 = true, p11 = true;
+        if (!inbox) {
+          const int gx = (int)tp.fxf, gy = (int)tp.fyf;   // top-left tap in the image (sane: the placement checked)
+          const ptrdiff_t off = (ptrdiff_t)gy * g.W + gx;
+          if (MASK == MASK_COMPUTED) pf = gff + off;
+          if (CT == 3) pp = gprev + off;
+          rs = g.W; ps = gplane; psf = (ptrdiff_t)p.ff_plane;
+          const bool xin0 = (unsigned)gx < (unsigned)g.W, xin1 = (unsigned)(gx + 1) < (unsigned)g.W;
+          const bool yin0 = (unsigned)gy < (unsigned)g.H, yin1 = (unsigned)(gy + 1) < (unsigned)g.H;
+          p00 = xin0 && yin0; p10 = xin1 && yin0; p01 = xin0 && yin1; p11 = xin1 && yin1;
+        }
+        auto tap4 = [&](auto* bp) {   // one plane, grid_sampler_2d's accumulation order
+          float w = __fmul_rn(p00 ? to_f32(bp[0]) : 0.0f, tp.nw);
+          w = __fmaf_rn(p10 ? to_f32(bp[1]) : 0.0f, tp.ne, w);
+          w = __fmaf_rn(p01 ? to_f32(bp[rs]) : 0.0f, tp.sw, w);
+          w = __fmaf_rn(p11 ? to_f32(bp[rs + 1]) : 0.0f, tp.se, w);
+          return w;
+        };
+        if (MASK == MASK_COMPUTED && OCC) { a = tap4(pf); b = tap4(pf + psf); }
 #pragma unroll
-    for (int ch = 0; ch < CT; ++ch) {
-      const float w = tap4(MIXED ? pp + ch * ps : pp + ch * PL);
-      if (MASK == MASK_NONE) {   // warp() on its own: store the warped frame (two coalesced row segments per warp instruction)
-        if (inside)
-          st_stream(reinterpret_cast<FrameT*>(p.warp_out) + ((size_t)t.pair * 3 + ch) * gplane + (size_t)(t.y0 + ly0 + dyk) * g.W + (t.x0 + lx0 + dxk),
-                    validity ? __fmul_rn(w, valid) : w);
-        continue;
+        for (int ch = 0; ch < CT; ++ch) w3[ch] = tap4(pp + ch * ps);
       }
-      if (OUTS) wv[k][ch] = w;
-      const float d = __fsub_rn(cur[k][ch], w);
-      acc = LOSS == TCLB200_L1 ? __fadd_rn(acc, fabsf(d)) : __fmaf_rn(d, d, acc);   // mask*|warp - cur| (MoGAN :281) / (mask*(cur - warp))^2
+      if (MASK == MASK_COMPUTED && OCC) {
+        // occlusion: |wf+bf|^2  vs  0.01*(|wf|^2+|bf|^2) + 0.5
+        const float su = __fadd_rn(a, u), sv = __fadd_rn(b, v);
+        const float L = __fmaf_rn(su, su, __fmul_rn(sv, sv));
+        const float nn = __fadd_rn(__fmaf_rn(a, a, __fmul_rn(b, b)), s0);
+        const float Rhi = __fmaf_rn(0.01f * kHi, nn, 0.5f * kHi), Rlo = __fmaf_rn(0.01f * kLo, nn, 0.5f * kLo);
+        const bool occ = L > Rhi;
+        keep = keep && !occ;
+        amb = amb || !(occ || L < Rlo);
+      }
+      float acc = 0.0f;
+      float valid = 1.0f;
+      if (MASK == MASK_NONE && validity) {   // fs_lib.warp: times the binarised warp of an all-ones image (fs_lib.py:29-37)
+        const int gx = (int)tp.fxf, gy = (int)tp.fyf;
+        Taps vt;
+        const bool xin0 = (unsigned)gx < (unsigned)g.W, xin1 = (unsigned)(gx + 1) < (unsigned)g.W;
+        const bool yin0 = (unsigned)gy < (unsigned)g.H, yin1 = (unsigned)(gy + 1) < (unsigned)g.H;
+        vt.p00 = xin0 && yin0; vt.p10 = xin1 && yin0; vt.p01 = xin0 && yin1; vt.p11 = xin1 && yin1;
+        vt.nw = tp.nw; vt.ne = tp.ne; vt.sw = tp.sw; vt.se = tp.se; vt.o00 = 0;
+        valid = binarise_validity(ones_sample(vt, kV));
+      }
+#pragma unroll
+      for (int ch = 0; ch < CT; ++ch) {
+        const float w = w3[ch];
+        if (MASK == MASK_NONE) {   // warp() on its own: store the warped frame (two coalesced row segments per warp instruction)
+          if (inside)
+            st_stream(reinterpret_cast<FrameT*>(p.warp_out) + ((size_t)t.pair * 3 + ch) * gplane + (size_t)(t.y0 + ly0 + dyk) * g.W + (t.x0 + lx0),
+                      validity ? __fmul_rn(w, valid) : w);
+          continue;
+        }
+        if (OUTS) wv[k][ch] = w;
+        const float d = __fsub_rn(cur[k][ch], w);
+        acc = LOSS == TCLB200_L1 ? __fadd_rn(acc, fabsf(d)) : __fmaf_rn(d, d, acc);   // mask*|warp - cur| (MoGAN :281) / (mask*(cur - warp))^2
+      }
+      // (m*d)^2 resp. m*|d| summed over channels (mk = 0 outside the image)
+      e[k] = MASK == MASK_GIVEN ? __fmul_rn(LOSS == TCLB200_L1 ? mk[k] : __fmul_rn(mk[k], mk[k]), acc) : acc;
+      keepbits |= (keep ? 1u : 0u) << k;
+      ambbits |= (amb && inside && inbox ? 1u : 0u) << k;
+      if (MIXED) outbits |= (amb && inside && !inbox ? 1u : 0u) << k;
     }
-    // (m*d)^2 resp. m*|d| summed over channels (mk = 0 outside the image)
-    e[k] = MASK == MASK_GIVEN ? __fmul_rn(LOSS == TCLB200_L1 ? mk[k] : __fmul_rn(mk[k], mk[k]), acc) : acc;
-    keepbits |= (keep ? 1u : 0u) << k;
-    ambbits |= (amb && inside && inbox ? 1u : 0u) << k;
-    if (MIXED) outbits |= (amb && inside && !inbox ? 1u : 0u) << k;
   }
   // rare, divergent: tests too close to call replay the exact sequences (a few pixels per million) ...
   if (MASK == MASK_COMPUTED && __builtin_expect(ambbits != 0, 0)) {
 #pragma unroll
     for (int k = 0; k < P; ++k)
       if ((ambbits >> k) & 1u) {
-        const bool kp = exact_keep<Cfg, OCC>(s_bu, s_ff, c0 + DY * (k >> 1) * BFW + 16 * (k & 1), xs[k & 1], ys[k >> 1], lg, box_xf, box_yf);
+        const bool kp = exact_keep<Cfg, OCC>(s_bu, s_ff, c0 + pix_dy(k) * BFW, xf, yf0 + (float)pix_dy(k), lg, box_xf, box_yf);
         keepbits = (keepbits & ~(1u << k)) | ((kp ? 1u : 0u) << k);
       }
   }
   // ... the same for pixels of a mixed tile whose taps left the boxes: redone from global memory
-  if (MIXED && MASK == MASK_COMPUTED && __builtin_expect(outbits != 0, 0)) {
+  if (MIXED && __builtin_expect(outbits != 0, 0)) {
     const size_t plane = (size_t)g.H * g.W;
 #pragma unroll
     for (int k = 0; k < P; ++k)
       if ((outbits >> k) & 1u) {
         if (CT == 3) {
           e[k] = pixel_global<FrameT, MASK, false, LOSS>(p.bf + (size_t)t.pair * p.bf_batch, p.bf_plane, p.ff + (size_t)t.pair * p.ff_batch, p.ff_plane,
-                                                   reinterpret_cast<const FrameT*>(p.prev) + (size_t)t.pf * 3 * plane, g, t.x0 + lx0 + 16 * (k & 1),
-                                                   t.y0 + ly0 + DY * (k >> 1), cur[k][0], cur[k][1], cur[k][2], mk[k]);
+                                                   reinterpret_cast<const FrameT*>(p.prev) + (size_t)t.pf * 3 * plane, g, t.x0 + lx0,
+                                                   t.y0 + ly0 + pix_dy(k), cur[k][0], cur[k][1], cur[k][2], mk[k]);
           keepbits |= 1u << k;   // the verdict is already applied
         } else {
           const float kp = pixel_global<FrameT, MASK, true, LOSS>(p.bf + (size_t)t.pair * p.bf_batch, p.bf_plane, p.ff + (size_t)t.pair * p.ff_batch, p.ff_plane, nullptr, g,
-                                                            t.x0 + lx0 + 16 * (k & 1), t.y0 + ly0 + DY * (k >> 1), 0.0f, 0.0f, 0.0f, 0.0f);
+                                                            t.x0 + lx0, t.y0 + ly0 + pix_dy(k), 0.0f, 0.0f, 0.0f, 0.0f);
           keepbits = (keepbits & ~(1u << k)) | ((kp != 0.0f ? 1u : 0u) << k);
         }
       }
@@ -696,9 +801,9 @@ __device__ __forceinline__ float lean_tile(const FwdParams& p, const float* s_bu
     float* mo = (MASK == MASK_COMPUTED && p.mask_out) ? p.mask_out + (size_t)t.pair * gplane + pix0 : nullptr;
 #pragma unroll
     for (int k = 0; k < P; ++k) {
-      const bool inside = !EDGE || (t.x0 + lx0 + 16 * (k & 1) < g.W && t.y0 + ly0 + DY * (k >> 1) < g.H);
+      const bool inside = !EDGE || (xin && t.y0 + ly0 + pix_dy(k) < g.H);
       if (!inside) continue;
-      const ptrdiff_t off = (ptrdiff_t)DY * (k >> 1) * g.W + 16 * (k & 1);
+      const ptrdiff_t off = (ptrdiff_t)pix_dy(k) * g.W;
       const float keepf = MASK == MASK_GIVEN ? mk[k] : (((keepbits >> k) & 1u) ? 1.0f : 0.0f);
       if (mo) __stcs(mo + off, keepf);
 #pragma unroll
@@ -713,8 +818,8 @@ __device__ __forceinline__ float lean_tile(const FwdParams& p, const float* s_bu
     float* mo = p.mask_out + (size_t)t.pair * gplane + (size_t)(t.y0 + ly0) * g.W + (t.x0 + lx0);
 #pragma unroll
     for (int k = 0; k < P; ++k) {
-      const bool inside = !EDGE || (t.x0 + lx0 + 16 * (k & 1) < g.W && t.y0 + ly0 + DY * (k >> 1) < g.H);
-      if (inside) __stcs(mo + (ptrdiff_t)DY * (k >> 1) * g.W + 16 * (k & 1), ((keepbits >> k) & 1u) ? 1.0f : 0.0f);
+      const bool inside = !EDGE || (xin && t.y0 + ly0 + pix_dy(k) < g.H);
+      if (inside) __stcs(mo + (ptrdiff_t)pix_dy(k) * g.W, ((keepbits >> k) & 1u) ? 1.0f : 0.0f);
     }
     return 0.0f;
   }
@@ -727,14 +832,234 @@ __device__ __forceinline__ float lean_tile(const FwdParams& p, const float* s_bu
   return err;
 }
 
+// ---- consumer: the hot configurations on staged, interior tiles with packed fp32 arithmetic --------------------------
+// Same operation sequence as lean_tile, two of the lane's pixels per instruction: sm_100's FFMA2 / FADD2 / FMUL2 round
+// every component to nearest exactly like their scalar forms (results are bit-identical, the parity tests do not tell
+// the two paths apart), but halve the issue slots and the instruction energy of the ~70 floating-point operations a
+// pixel needs -- the kernel is bound by instruction issue and, sustained, by the board's power cap, not by the FMA pipe.
+// Loads, floor, float -> int and the comparisons stay scalar.
+__device__ __forceinline__ float2 f2(float a, float b) { return make_float2(a, b); }
+__device__ __forceinline__ float2 f2(float a) { return make_float2(a, a); }
+__device__ __forceinline__ float2 add2(float2 a, float2 b) { return __fadd2_rn(a, b); }
+__device__ __forceinline__ float2 sub2(float2 a, float2 b) { return __fadd2_rn(a, make_float2(-b.x, -b.y)); }
+__device__ __forceinline__ float2 mul2(float2 a, float2 b) { return __fmul2_rn(a, b); }
+__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
+
+template <typename T, int OFF, int PITCH>
+__device__ __forceinline__ float2 staged_tap4x2(uint32_t a0, uint32_t a1, float2 nw, float2 ne, float2 sw, float2 se) {
+  constexpr int E = (int)sizeof(T);
+  float2 w = mul2(f2(lds_tap<OFF>(a0, T()), lds_tap<OFF>(a1, T())), nw);
+  w = fma2(f2(lds_tap<OFF + E>(a0, T()), lds_tap<OFF + E>(a1, T())), ne, w);
+  w = fma2(f2(lds_tap<OFF + PITCH * E>(a0, T()), lds_tap<OFF + PITCH * E>(a1, T())), sw, w);
+  w = fma2(f2(lds_tap<OFF + PITCH * E + E>(a0, T()), lds_tap<OFF + PITCH * E + E>(a1, T())), se, w);
+  return w;
+}
+
+// EDGE: the tile overhangs the image (pixels outside are computed on a safe address and dropped); MIXED: a motion boundary
+// runs through the tile and the taps of some pixels lie outside the staged boxes -- those pixels are redone one by one
+// from global memory after the loop (pixel_global, exact), every other pixel of the tile keeps the fast path.
+template <typename FrameT, int MASK, int LOSS, typename Cfg, bool EDGE = false, bool MIXED = false>
+__device__ __forceinline__ float lean_tile_packed(const FwdParams& p, const float* s_bu, const float* s_ff, const int* meta, const TileId& t,
+                                                  int lx0, int ly0, const float (&cur)[Cfg::kPPL][Cfg::kC], const float (&mk)[Cfg::kPPL]) {
+  constexpr int P = Cfg::kPPL, BW = Cfg::BW, BFW = Cfg::kBfW, PL = Cfg::BH * Cfg::BW;
+  constexpr float kHi = 1.0f + kFilterEps, kLo = 1.0f - kFilterEps;
+  constexpr int FE = (int)sizeof(FrameT);
+  static_assert(P % 2 == 0 && Cfg::kC == 3 && MASK != MASK_NONE, "pixel pairs, three channels, a reducing configuration");
+  // mixed tiles, pixels whose taps left the boxes: computed masks fetch those taps from global memory inside the loop (a
+  // warp-uniform branch); with a dataset mask the pixel is so cheap that waiting for global loads inside the loop costs
+  // more than redoing the few pixels after it (measured: 131 vs 149 Gpix/s on the Sintel shape)
+  constexpr bool kFixInLoop = MASK == MASK_COMPUTED;
+  const Geo& g = p.geo;
+  const float* s_bv = s_bu + Cfg::kBfH * BFW;
+  const FrameT* s_prev = reinterpret_cast<const FrameT*>(reinterpret_cast<const unsigned char*>(s_ff) + Cfg::kFfStage);
+  const float box_xf = (float)meta[0], box_yf = (float)meta[1];
+  LeanGeo lg;
+  lg.i2x = __fmul_rn(2.0f, g.inv_dx); lg.i2y = __fmul_rn(2.0f, g.inv_dy);   // exact doubling: (2a)*r == a*(2r)
+  lg.Wf = g.Wf; lg.Hf = g.Hf;
+  const float xf = (float)(t.x0 + lx0), yf0 = (float)(t.y0 + ly0);
+  const int c0 = (ly0 + 1) * BFW + lx0 + Cfg::kHaloL;
+  const size_t gplane = (size_t)g.H * g.W;
+  const GlobalSrc<float> fg{(MIXED && MASK == MASK_COMPUTED) ? p.ff + (size_t)t.pair * p.ff_batch : nullptr, p.ff_plane, g};
+  const GlobalSrc<FrameT> pg{MIXED ? reinterpret_cast<const FrameT*>(p.prev) + (size_t)t.pf * 3 * gplane : nullptr, gplane, g};
+  const bool xin = !EDGE || t.x0 + lx0 < g.W;
+  const int rows_in = EDGE ? g.H - (t.y0 + ly0) : INT_MAX;   // pixel k is inside the image iff 2 * k < rows_in (and xin)
+  const float bx_hi = box_xf + (float)(BW - 2), by_hi = box_yf + (float)(Cfg::BH - 2);   // top-left taps inside the boxes: [box, box + size - 2]
+  // byte address of a pixel's top-left tap, in floating point (see lean_tile)
+  const uint32_t ff_base = smem_u32(s_ff), prev_base = smem_u32(s_prev);
+  const float ff_k = __fsub_rn((float)ff_base, 4.0f * __fmaf_rn(box_yf, (float)BW, box_xf));
+  const float prev_k = __fsub_rn((float)prev_base, (float)FE * __fmaf_rn(box_yf, (float)BW, box_xf));
+  // this lane's column of the flow tile (see lean_tile)
+  float uc[2 * P + 1], vc[2 * P + 1], ul[P], ur[P], vl[P], vr[P];
+#pragma unroll
+  for (int r = 0; r < 2 * P + 1; ++r) {
+    if (MASK == MASK_COMPUTED || (r & 1)) { uc[r] = s_bu[c0 + (r - 1) * BFW]; vc[r] = s_bv[c0 + (r - 1) * BFW]; }
+    else { uc[r] = 0.0f; vc[r] = 0.0f; }
+  }
+#pragma unroll
+  for (int j = 0; j < P; ++j) {
+    if (MASK == MASK_COMPUTED) {
+      ul[j] = s_bu[c0 + 2 * j * BFW - 1]; ur[j] = s_bu[c0 + 2 * j * BFW + 1];
+      vl[j] = s_bv[c0 + 2 * j * BFW - 1]; vr[j] = s_bv[c0 + 2 * j * BFW + 1];
+    } else { ul[j] = ur[j] = vl[j] = vr[j] = 0.0f; }
+  }
+  float e[P];
+  unsigned keepbits = 0, ambbits = 0, outbits = 0;
+#pragma unroll
+  for (int q = 0; q < P / 2; ++q) {
+    const int j0 = 2 * q, j1 = 2 * q + 1;   // the pair's pixels: rows ly0 + 2 * j0, ly0 + 2 * j1
+    const float2 u = f2(uc[2 * j0 + 1], uc[2 * j1 + 1]), v = f2(vc[2 * j0 + 1], vc[2 * j1 + 1]);
+    const float2 s0 = fma2(u, u, mul2(v, v));
+    const bool in0 = !EDGE || (xin && 2 * j0 < rows_in), in1 = !EDGE || (xin && 2 * j1 < rows_in);
+    bool keep0 = in0, keep1 = in1, amb0 = false, amb1 = false;
+    if (MASK == MASK_COMPUTED) {
+      // motion boundary: 4*(|grad u|^2 + |grad v|^2)  vs  4*(0.01*|bf|^2 + 0.002)
+      const float2 dux = sub2(f2(ur[j0], ur[j1]), f2(ul[j0], ul[j1])), duy = sub2(f2(uc[2 * j0 + 2], uc[2 * j1 + 2]), f2(uc[2 * j0], uc[2 * j1]));
+      const float2 dvx = sub2(f2(vr[j0], vr[j1]), f2(vl[j0], vl[j1])), dvy = sub2(f2(vc[2 * j0 + 2], vc[2 * j1 + 2]), f2(vc[2 * j0], vc[2 * j1]));
+      const float2 G = fma2(dux, dux, fma2(duy, duy, fma2(dvx, dvx, mul2(dvy, dvy))));
+      const float2 Rhi = fma2(f2(4.0f * 0.01f * kHi), s0, f2(4.0f * 0.002f * kHi)), Rlo = fma2(f2(4.0f * 0.01f * kLo), s0, f2(4.0f * 0.002f * kLo));
+      const bool mob0 = G.x > Rhi.x, mob1 = G.y > Rhi.y;
+      keep0 = keep0 && !mob0; keep1 = keep1 && !mob1;
+      amb0 = !(mob0 || G.x < Rlo.x); amb1 = !(mob1 || G.y < Rlo.y);
+    }
+    // sampling position: the reference's [-1,1] round trip (flowtools.py:28-29 + grid_sampler's unnormalise), see lean_taps
+    const float2 ax = add2(f2(xf), u), ay = add2(f2(yf0 + (float)(2 * j0), yf0 + (float)(2 * j1)), v);
+    const float2 tx = add2(add2(mul2(ax, f2(lg.i2x)), f2(-1.0f)), f2(1.0f)), ty = add2(add2(mul2(ay, f2(lg.i2y)), f2(-1.0f)), f2(1.0f));
+    const float2 ix = mul2(fma2(tx, f2(lg.Wf), f2(-1.0f)), f2(0.5f)), iy = mul2(fma2(ty, f2(lg.Hf), f2(-1.0f)), f2(0.5f));
+    const float2 fxf = f2(floorf(ix.x), floorf(ix.y)), fyf = f2(floorf(iy.x), floorf(iy.y));
+    const float2 fx1 = sub2(add2(fxf, f2(1.0f)), ix), fx0 = sub2(ix, fxf);
+    const float2 fy1 = sub2(add2(fyf, f2(1.0f)), iy), fy0 = sub2(iy, fyf);
+    const float2 nw = mul2(fx1, fy1), ne = mul2(fx0, fy1), sw = mul2(fx1, fy0), se = mul2(fx0, fy0);
+    const float2 faf = fma2(fyf, f2(4.0f * (float)BW), fma2(fxf, f2(4.0f), f2(ff_k)));
+    uint32_t fa0 = (uint32_t)__float2int_rn(faf.x), fa1 = (uint32_t)__float2int_rn(faf.y);
+    // pixels beyond the image edge, or -- mixed tiles -- with taps outside the boxes, read any in-box address; their
+    // result is discarded (the latter are redone from global memory below)
+    bool ok0 = in0, ok1 = in1;
+    if (MIXED) {
+      ok0 = ok0 && fxf.x >= box_xf && fxf.x <= bx_hi && fyf.x >= box_yf && fyf.x <= by_hi;
+      ok1 = ok1 && fxf.y >= box_xf && fxf.y <= bx_hi && fyf.y >= box_yf && fyf.y <= by_hi;
+    }
+    if (EDGE || MIXED) { fa0 = ok0 ? fa0 : ff_base; fa1 = ok1 ? fa1 : ff_base; }
+    float2 a = f2(0.0f), b = f2(0.0f), w3[3];
+    if (MASK == MASK_COMPUTED) {
+      a = staged_tap4x2<float, 0, BW>(fa0, fa1, nw, ne, sw, se);
+      b = staged_tap4x2<float, PL * 4, BW>(fa0, fa1, nw, ne, sw, se);
+    }
+    if (FE == 4) {   // fp32 frames: the prev planes sit behind the ff planes, the same address registers serve them
+      w3[0] = staged_tap4x2<FrameT, (int)Cfg::kFfStage, BW>(fa0, fa1, nw, ne, sw, se);
+      w3[1] = staged_tap4x2<FrameT, (int)Cfg::kFfStage + PL * FE, BW>(fa0, fa1, nw, ne, sw, se);
+      w3[2] = staged_tap4x2<FrameT, (int)Cfg::kFfStage + 2 * PL * FE, BW>(fa0, fa1, nw, ne, sw, se);
+    } else {
+      const float2 paf = fma2(fyf, f2((float)(FE * BW)), fma2(fxf, f2((float)FE), f2(prev_k)));
+      uint32_t pa0 = (uint32_t)__float2int_rn(paf.x), pa1 = (uint32_t)__float2int_rn(paf.y);
+      if (EDGE || MIXED) { pa0 = ok0 ? pa0 : prev_base; pa1 = ok1 ? pa1 : prev_base; }
+      w3[0] = staged_tap4x2<FrameT, 0, BW>(pa0, pa1, nw, ne, sw, se);
+      w3[1] = staged_tap4x2<FrameT, PL * FE, BW>(pa0, pa1, nw, ne, sw, se);
+      w3[2] = staged_tap4x2<FrameT, 2 * PL * FE, BW>(pa0, pa1, nw, ne, sw, se);
+    }
+    if (MIXED && kFixInLoop) {
+      // pixels of the pair whose taps left the boxes: the same taps from global memory with grid_sample's zero padding as
+      // per-tap predicates (exact); warp-uniform branch, most warps of a mixed tile never take it
+      const bool o0 = in0 && !ok0, o1 = in1 && !ok1;
+      if (__any_sync(0xffffffffu, o0 || o1)) {
+        if (o0) {
+          const PixTaps st{(int)fxf.x, (int)fyf.x, nw.x, ne.x, sw.x, se.x};
+          if (MASK == MASK_COMPUTED) { a.x = fg.sample(0, st); b.x = fg.sample(1, st); }
+          w3[0].x = pg.sample(0, st); w3[1].x = pg.sample(1, st); w3[2].x = pg.sample(2, st);
+        }
+        if (o1) {
+          const PixTaps st{(int)fxf.y, (int)fyf.y, nw.y, ne.y, sw.y, se.y};
+          if (MASK == MASK_COMPUTED) { a.y = fg.sample(0, st); b.y = fg.sample(1, st); }
+          w3[0].y = pg.sample(0, st); w3[1].y = pg.sample(1, st); w3[2].y = pg.sample(2, st);
+        }
+      }
+    }
+    if (MASK == MASK_COMPUTED) {
+      // occlusion: |wf+bf|^2  vs  0.01*(|wf|^2+|bf|^2) + 0.5
+      const float2 su = add2(a, u), sv = add2(b, v);
+      const float2 L = fma2(su, su, mul2(sv, sv));
+      const float2 nn = add2(fma2(a, a, mul2(b, b)), s0);
+      const float2 Rhi = fma2(f2(0.01f * kHi), nn, f2(0.5f * kHi)), Rlo = fma2(f2(0.01f * kLo), nn, f2(0.5f * kLo));
+      const bool occ0 = L.x > Rhi.x, occ1 = L.y > Rhi.y;
+      keep0 = keep0 && !occ0; keep1 = keep1 && !occ1;
+      amb0 = amb0 || !(occ0 || L.x < Rlo.x); amb1 = amb1 || !(occ1 || L.y < Rlo.y);
+    }
+    float2 acc = f2(0.0f);
+#pragma unroll
+    for (int ch = 0; ch < 3; ++ch) {
+      const float2 d = sub2(f2(cur[j0][ch], cur[j1][ch]), w3[ch]);
+      // mask*|warp - cur| (MoGAN :281) / (mask*(cur - warp))^2
+      acc = LOSS == TCLB200_L1 ? add2(acc, f2(fabsf(d.x), fabsf(d.y))) : fma2(d, d, acc);
+    }
+    if (MASK == MASK_GIVEN) {   // (m*d)^2 resp. m*|d| summed over channels
+      const float2 m = f2(mk[j0], mk[j1]);
+      acc = mul2(LOSS == TCLB200_L1 ? m : mul2(m, m), acc);
+    }
+    e[j0] = acc.x; e[j1] = acc.y;
+    keepbits |= ((keep0 ? 1u : 0u) << j0) | ((keep1 ? 1u : 0u) << j1);
+    ambbits |= ((amb0 && ok0 ? 1u : 0u) << j0) | ((amb1 && ok1 ? 1u : 0u) << j1);
+    // left for the exact replay from global memory below: out-of-box pixels whose test was too close to call (or, dataset
+    // mask, every out-of-box pixel)
+    if (MIXED) outbits |= (((amb0 || !kFixInLoop) && in0 && !ok0 ? 1u : 0u) << j0) | (((amb1 || !kFixInLoop) && in1 && !ok1 ? 1u : 0u) << j1);
+  }
+  // rare, divergent: tests too close to call replay the exact sequences (a few pixels per million)
+  if (MASK == MASK_COMPUTED && __builtin_expect(ambbits != 0, 0)) {
+#pragma unroll
+    for (int k = 0; k < P; ++k)
+      if ((ambbits >> k) & 1u) {
+        const bool kp = exact_keep<Cfg, true>(s_bu, s_ff, c0 + pix_dy(k) * BFW, xf, yf0 + (float)pix_dy(k), lg, box_xf, box_yf);
+        keepbits = (keepbits & ~(1u << k)) | ((kp ? 1u : 0u) << k);
+      }
+  }
+  // ... the same for pixels of a mixed tile whose taps left the boxes: redone from global memory
+  if (MIXED && __builtin_expect(outbits != 0, 0)) {
+    const size_t plane = (size_t)g.H * g.W;
+#pragma unroll
+    for (int k = 0; k < P; ++k)
+      if ((outbits >> k) & 1u) {
+        e[k] = pixel_global<FrameT, MASK, false, LOSS>(p.bf + (size_t)t.pair * p.bf_batch, p.bf_plane, MASK == MASK_COMPUTED ? p.ff + (size_t)t.pair * p.ff_batch : nullptr, p.ff_plane,
+                                                       reinterpret_cast<const FrameT*>(p.prev) + (size_t)t.pf * 3 * plane, g, t.x0 + lx0,
+                                                       t.y0 + ly0 + pix_dy(k), cur[k][0], cur[k][1], cur[k][2], mk[k]);
+        keepbits |= 1u << k;   // the verdict is already applied
+      }
+  }
+  float err = 0.0f;
+#pragma unroll
+  for (int k = 0; k < P; ++k) {
+    if (MASK == MASK_GIVEN) err = __fadd_rn(err, e[k]);
+    else err = ((keepbits >> k) & 1u) ? __fadd_rn(err, e[k]) : err;
+  }
+  return err;
+}
+
+// ---------------------------------------------------------------------------------------------
+// TMA-staged, persistent, warp-specialised forward kernel (the hot kernel)
+// ---------------------------------------------------------------------------------------------
+// One CTA per SM walks tiles of TW x TH pixels (static round robin, or a global counter for long launches).
+//
+//   producer warp   keeps NB flow tiles and NS source-box sets in flight with TMA:
+//       bf tile k   (TW+16) x (TH+2) x 2, 1 px halo (4 columns on the left for the 16-byte TMA alignment), zero-filled
+//                   outside the image = the zero padding of flowtools.gradient
+//       ff / prev   BW x BH boxes at the origin the scanner's extent dictates, zero-filled outside the image =
+//                   grid_sample's padding_mode='zeros'; tiles whose taps do not fit the box are "mixed", tiles with
+//                   non-finite / absurd flow are not staged at all (exact predicated global gathers)
+//       when the consumers release a tile: folds their 32 * CW partial sums in a fixed order -> one fp64 per tile
+//   scanner warp    as soon as a flow tile lands: extent of x+u, y+v over it (LDS.128) -> box[]; runs NS tiles ahead of
+//                   the consumers, off everybody's critical path
+//   consumer warps  one pass per pixel: flow + 4 neighbours from the flow tile (vertical strips, see WsCfg),
+//                   motion-boundary test, sampling position, 4 x (2 + C) taps from the source boxes, occlusion test,
+//                   masked error against `cur` (coalesced global loads issued before the wait for the boxes).
 template <typename FrameT, int MASK, bool REDUCE, int CT, int LEAN, typename Cfg>
-__global__ void __launch_bounds__(kWsThreads, 1) fused_forward_ws_kernel(const FwdParams p, const __grid_constant__ CUtensorMap tm_bf,
+__global__ void __launch_bounds__(Cfg::kThreads, 1) fused_forward_ws_kernel(const FwdParams p, const __grid_constant__ CUtensorMap tm_bf,
                                                                          const __grid_constant__ CUtensorMap tm_ff,
                                                                          const __grid_constant__ CUtensorMap tm_prev,
                                                                          const __grid_constant__ CUtensorMap tm_cur) {
   constexpr int NB = Cfg::NB, NS = Cfg::NS, P = Cfg::kPPL;
-  using Ctl = WsCtl<NB, NS>;
-  static_assert(sizeof(Ctl) <= 1024, "control block too large");
+  constexpr int kCWarps = Cfg::CW;
+  constexpr int kLoss = LEAN == 2 ? TCLB200_L1 : TCLB200_L2;
+  // interior / edge / mixed staged tiles of the reducing hot configurations: packed fp32 arithmetic (lean_tile_packed)
+  constexpr bool kPacked = TCL_PACKED && (LEAN == 1 || LEAN == 2) && CT == 3 && (MASK == MASK_COMPUTED || (MASK == MASK_GIVEN && TCL_PACKED_GIVEN));
+  using Ctl = WsCtl<NB, NS, kCWarps>;
+  static_assert(sizeof(Ctl) <= Cfg::kCtlBytes, "control block too large");
   extern __shared__ __align__(128) unsigned char smem_raw[];
   unsigned char* smem = smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u);  // TMA destinations: 128-byte aligned
   Ctl* ctl = reinterpret_cast<Ctl*>(smem + Cfg::kCtlOff);
@@ -747,6 +1072,7 @@ __global__ void __launch_bounds__(kWsThreads, 1) fused_forward_ws_kernel(const F
   //       4 = as 1 plus the optional per-pixel outputs (warp_out / mask_out / blend_out, whichever are set)
   const bool want_occ = MASK == MASK_COMPUTED && (LEAN ? LEAN != 3 : (p.flags & TCLB200_OCC) != 0);
   const bool want_frames = CT > 0 && (LEAN || p.prev != nullptr);
+  const bool want_scan = want_occ || want_frames;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const Geo& g = p.geo;
   // Local tile k of this CTA lives in flow stage k % NB / source stage k % NS.  Which tile that is, is decided when its
@@ -758,15 +1084,13 @@ __global__ void __launch_bounds__(kWsThreads, 1) fused_forward_ws_kernel(const F
 
   if (REDUCE) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // let the fold kernel get resident early
   if (threadIdx.x == 0) {
-    for (int i = 0; i < NB; ++i) mbar_init(&ctl->bf_full[i], 1);
-    for (int i = 0; i < NS; ++i) { mbar_init(&ctl->src_full[i], 1); mbar_init(&ctl->done[i], Cfg::WPG); }
-    mbar_init(&ctl->scan0, kCWarps);
-    for (int i = 0; i < NB; ++i) { ctl->box[i][0] = INT_MAX; ctl->box[i][1] = INT_MAX; ctl->box[i][2] = INT_MIN; ctl->box[i][3] = INT_MIN; }
+    for (int i = 0; i < NB; ++i) { mbar_init(&ctl->bf_full[i], 1); mbar_init(&ctl->scanned[i], 1); }
+    for (int i = 0; i < NS; ++i) { mbar_init(&ctl->src_full[i], 1); mbar_init(&ctl->done[i], kCWarps); }
     fence_barrier_init();
   }
   __syncthreads();
 
-  if (warp == kCWarps) {
+  if (warp == Cfg::kProducerWarp) {
     // ===================================== producer warp =====================================
     // lane 0 only: next tile of this CTA (prefetched one call ahead so the atomic's latency is off the critical path)
     const bool dynamic = p.scratch.tile_ctr != nullptr;
@@ -789,11 +1113,11 @@ __global__ void __launch_bounds__(kWsThreads, 1) fused_forward_ws_kernel(const F
       const TileId t = tile_id(p, tg, Cfg::TW, Cfg::TH);
       ctl->tinfo[s] = t;
       mbar_expect_tx(&ctl->bf_full[s], Cfg::kBfLoad);
-      tma_load_4d(bf_stage(s), &tm_bf, &ctl->bf_full[s], t.x0 - Cfg::kHaloX, t.y0 - 1, 0, t.pair);
+      tma_load_4d(bf_stage(s), &tm_bf, &ctl->bf_full[s], t.x0 - Cfg::kHaloL, t.y0 - 1, 0, t.pair);
       // the consumers read this tile's `cur` values straight from global memory NB tiles from now: have them in L2 by then
       if (LEAN && CT > 0 && p.cur != nullptr) tma_prefetch_l2_4d(&tm_cur, t.x0, t.y0, 0, t.cf);
     };
-    // lane 0: the consumers have folded the extent of x+u, y+v over local tile k into box[k % NB] -> origin of the source
+    // lane 0: the scanner has left the extent of x+u, y+v over local tile k in box[k % NB] -> origin of the source
     // boxes.  The coordinate map is monotone in x+u (every step is a correctly rounded monotone operation), so the
     // extreme taps come from the extreme sums.
     struct Placement { int ox, oy, mode, pair, pf; };
@@ -801,9 +1125,13 @@ __global__ void __launch_bounds__(kWsThreads, 1) fused_forward_ws_kernel(const F
       const int sb = k % NB;
       const TileId t = ctl->tinfo[sb];
       int ox = 0, oy = 0, mode = 0;   // mode: 0 = nothing staged, 1 = every tap inside the boxes, 2 = mixed
-      if (want_occ || want_frames) {
+#if TCL_DIAG == 3   // tuning aid: boxes at the tile's own position, no scan (results are garbage)
+      if (true) { ox = (t.x0 - 8) & ~3; oy = t.y0 - 4; mode = 1; } else
+#endif
+      if (want_scan) {
+        mbar_wait_idle(&ctl->scanned[sb], (k / NB) & 1);
         const float xmin = ord2f(ctl->box[sb][0]), ymin = ord2f(ctl->box[sb][1]), xmax = ord2f(ctl->box[sb][2]), ymax = ord2f(ctl->box[sb][3]);
-        const float lim = 1048576.0f;
+        const float lim = 30000.0f;   // (keeps the consumers' floating-point box addresses exact, see lean_tile)
         const bool sane = xmin > -lim && xmax < lim && ymin > -lim && ymax < lim && xmin <= xmax && ymin <= ymax;   // false for NaN / Inf
         if (sane) {
           const float i2x = __fmul_rn(2.0f, g.inv_dx), i2y = __fmul_rn(2.0f, g.inv_dy);
@@ -827,14 +1155,17 @@ __global__ void __launch_bounds__(kWsThreads, 1) fused_forward_ws_kernel(const F
         }
         if (mode != 1) atomicAdd(&g_tile_stats[mode == 2 ? 1 : 0], 1ull);
       }
-      ctl->box[sb][0] = INT_MAX; ctl->box[sb][1] = INT_MAX; ctl->box[sb][2] = INT_MIN; ctl->box[sb][3] = INT_MIN;
       return Placement{ox, oy, mode, t.pair, t.pf};
     };
     // ... and, once the source stage is free, the request itself (lane 0)
     auto issue_src = [&](int k, const Placement& pl) {
       const int ss = k % NS;
       ctl->meta[ss][0] = pl.ox; ctl->meta[ss][1] = pl.oy; ctl->meta[ss][2] = pl.mode;
+#if TCL_DIAG == 1   // tuning aid: no source-box traffic at all (results are garbage)
+      if (false) {
+#else
       if (pl.mode != 0) {
+#endif
         TCL_STAMP(k, 0);
         mbar_expect_tx(&ctl->src_full[ss], (want_occ ? Cfg::kFfLoad : 0u) + (want_frames ? Cfg::kPrevLoad : 0u));
         if (want_occ) tma_load_4d(ff_stage(ss), &tm_ff, &ctl->src_full[ss], pl.ox, pl.oy, 0, pl.pair);
@@ -849,24 +1180,26 @@ __global__ void __launch_bounds__(kWsThreads, 1) fused_forward_ws_kernel(const F
       if (want_occ) prefetch_tmap(&tm_ff);
       if (want_frames) prefetch_tmap(&tm_prev);
       for (int j = 0; j < NB; ++j) issue_bf(j);
+      for (int j = 0; j < NS && real(j); ++j) issue_src(j, place_src(j));
     }
     __syncwarp();
-    mbar_wait_idle(&ctl->scan0, 0);   // the consumers have scanned the first NS flow tiles
-    if (lane == 0)
-      for (int j = 0; j < NS && real(j); ++j) issue_src(j, place_src(j));
-    __syncwarp();
     for (int j = 0; real(j); ++j) {
-      // consumers are finished with tile j (its stages are free) and have scanned the flow tile of tile j + NS
       mbar_wait_idle(&ctl->done[j % NS], (j / NS) & 1);   // consumers are finished with tile j: its stages are free
       const TileId t = ctl->tinfo[j % NB];   // (before issue_bf recycles the slot)
-      double ts = (REDUCE && lane < Cfg::WPG) ? ctl->red[j % NS][lane] : 0.0;
-      __syncwarp();
+      // every consumer lane's sum of this tile: lane l folds the warps' lanes l in warp order (fp64 from here on)
+      double ts = 0.0;
+      if (REDUCE) {
+        const float* r = ctl->red[j % NS] + lane;
+#pragma unroll
+        for (int w = 0; w < kCWarps; ++w) ts += (double)r[32 * w];
+      }
+      __syncwarp();   // (all of red[] is in registers before the stage is handed out again)
       if (lane == 0) {
         if (real(j + NS)) issue_src(j + NS, place_src(j + NS));
         issue_bf(j + NB);
       }
       __syncwarp();
-      // the consumer warps' sums of this tile, folded in index order (lanes 0..WPG-1, fixed tree): one fp64 partial per tile
+      // ... then the lanes in a fixed butterfly: one fp64 partial per tile, independent of the tile schedule
       if (REDUCE) {
         ts = warp_sum(ts);
         if (lane == 0) __stcg(&p.scratch.partials[(size_t)t.pair * p.tiles_per_pair + t.tile], ts);
@@ -883,43 +1216,40 @@ __global__ void __launch_bounds__(kWsThreads, 1) fused_forward_ws_kernel(const F
     return;
   }
 
+  if (warp >= Cfg::kScannerWarp) {
+    // ===================================== scanner warps =====================================
+    if (!want_scan || TCL_DIAG == 3) return;
+    for (int k = warp - Cfg::kScannerWarp;; k += Cfg::kScanners) {
+      const int sb = k % NB;
+      mbar_wait_idle(&ctl->bf_full[sb], (k / NB) & 1);
+      if (ctl->tinfo[sb].pair < 0) return;
+      scan_flow_tile<Cfg>(bf_stage(sb), ctl->tinfo[sb], g, ctl->box[sb], lane);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&ctl->scanned[sb]);
+    }
+  }
+
   // ======================================= consumer warps =======================================
   unsigned near = 0;
   const size_t plane = (size_t)g.H * g.W;
   int lx0, ly0;
-  const int grp = warp / Cfg::WPG, wg = warp % Cfg::WPG;   // consumer group (works on local tiles grp, grp + G, ...), warp within it
-  lane_pixel<Cfg::WPG>(wg, lane, 0, lx0, ly0);
+  lane_origin<Cfg>(warp, lane, lx0, ly0);
   const int lane_off = ly0 * g.W + lx0;
-  const ptrdiff_t row16 = (ptrdiff_t)Cfg::WPG * g.W;   // a lane's pixels 2, 3 lie WPG rows below its pixels 0, 1
-  // the source boxes of a tile are placed from the extent of its sampling positions: every consumer warp scans its rows
-  // of the flow tile NS tiles ahead (the first NS ones here, tile k + NS at the end of tile k)
-  const bool want_scan = want_occ || want_frames;
-  int n_seen = INT_MAX;   // index of the end marker once it has been seen
-  // wait for the descriptor (and flow tile) of local tile i; false when the CTA has no such tile.  Called with
-  // non-decreasing i for new entries, so nothing beyond the end marker is ever waited for.
-  auto visit = [&](int i) {
-    if (i >= n_seen) return false;
-    mbar_wait(&ctl->bf_full[i % NB], (i / NB) & 1);
-    if (!real(i)) { n_seen = i; return false; }
-    return true;
-  };
-  auto scan_tile = [&](int k2) {
-    if (!visit(k2) || !want_scan) return;
-    const int s2 = k2 % NB;
-    scan_flow_rows<Cfg>(bf_stage(s2), ctl->tinfo[s2], g, ctl->box[s2], wg, lane);
-  };
-  for (int j = grp; j < NS; j += Cfg::G) scan_tile(j);
-  __syncwarp();
-  if (lane == 0) mbar_arrive(&ctl->scan0);
-  for (int k = grp; visit(k); k += Cfg::G) {
+  // shared-memory addresses the loop needs every tile, computed once (the empty asm keeps the compiler from
+  // re-deriving them from the generic pointers inside the loop)
+  uint32_t bf_full_s = smem_u32(&ctl->bf_full[0]), src_full_s = smem_u32(&ctl->src_full[0]), done_s = smem_u32(&ctl->done[0]);
+  uint32_t red_s = smem_u32(&ctl->red[0][threadIdx.x]);
+  asm volatile("" : "+r"(bf_full_s), "+r"(src_full_s), "+r"(done_s), "+r"(red_s));
+  const bool have_cur = CT > 0 && (LEAN ? MASK != MASK_NONE : p.cur != nullptr);   // (the LEAN configurations fix it at compile time)
+  for (int k = 0;; ++k) {
     float err = 0.0f;
-    const int sb = k % NB, ss = k % NS;   // stage indices of this tile, phase parity of its source stage
-    const unsigned ps = (k / NS) & 1;
+    const int sb = k % NB, ss = k % NS;   // stage indices of this tile
+    mbar_wait_s(bf_full_s + 8u * sb, (k / NB) & 1);
     const TileId t = ctl->tinfo[sb];
+    if (t.pair < 0) break;
     // this tile's `cur` (and dataset mask) values: coalesced 64-byte row segments, streaming; requested before the wait
     // for the source boxes and first used at the very end of the per-pixel work
     float cur[P][Cfg::kC], mk[P];
-    const bool have_cur = CT > 0 && p.cur != nullptr;
     {
       const size_t pix = (size_t)(t.y0 * g.W + t.x0) + lane_off;
       const FrameT* cb = reinterpret_cast<const FrameT*>(p.cur) + (size_t)t.cf * Cfg::kC * plane + pix;
@@ -930,24 +1260,24 @@ __global__ void __launch_bounds__(kWsThreads, 1) fused_forward_ws_kernel(const F
         for (int c = 0; c < Cfg::kC; ++c) {
           const FrameT* pc = cb + (size_t)c * plane;
 #pragma unroll
-          for (int i = 0; i < P; ++i) cur[i][c] = have_cur ? to_f32(__ldg(pc + (i >> 1) * row16 + 16 * (i & 1))) : 0.0f;
+          for (int i = 0; i < P; ++i) cur[i][c] = have_cur ? to_f32(__ldg(pc + (ptrdiff_t)pix_dy(i) * g.W)) : 0.0f;
         }
 #pragma unroll
-        for (int i = 0; i < P; ++i) mk[i] = MASK == MASK_GIVEN ? __ldcs(mb + (i >> 1) * row16 + 16 * (i & 1)) : 0.0f;
+        for (int i = 0; i < P; ++i) mk[i] = MASK == MASK_GIVEN ? __ldcs(mb + (ptrdiff_t)pix_dy(i) * g.W) : 0.0f;
       } else if (!t.edge) {
 #pragma unroll
         for (int c = 0; c < Cfg::kC; ++c) {
           const FrameT* pc = cb + (size_t)c * plane;
 #pragma unroll
-          for (int i = 0; i < P; ++i) cur[i][c] = have_cur ? ld_stream(pc + (i >> 1) * row16 + 16 * (i & 1)) : 0.0f;
+          for (int i = 0; i < P; ++i) cur[i][c] = have_cur ? ld_stream(pc + (ptrdiff_t)pix_dy(i) * g.W) : 0.0f;
         }
 #pragma unroll
-        for (int i = 0; i < P; ++i) mk[i] = MASK == MASK_GIVEN ? __ldcs(mb + (i >> 1) * row16 + 16 * (i & 1)) : 0.0f;
+        for (int i = 0; i < P; ++i) mk[i] = MASK == MASK_GIVEN ? __ldcs(mb + (ptrdiff_t)pix_dy(i) * g.W) : 0.0f;
       } else {
 #pragma unroll
         for (int i = 0; i < P; ++i) {
-          const bool inside = t.x0 + lx0 + 16 * (i & 1) < g.W && t.y0 + ly0 + Cfg::WPG * (i >> 1) < g.H;
-          const ptrdiff_t off = (i >> 1) * row16 + 16 * (i & 1);
+          const bool inside = t.x0 + lx0 < g.W && t.y0 + ly0 + pix_dy(i) < g.H;
+          const ptrdiff_t off = (ptrdiff_t)pix_dy(i) * g.W;
 #pragma unroll
           for (int c = 0; c < Cfg::kC; ++c) cur[i][c] = (have_cur && inside) ? ld_stream(cb + off + (size_t)c * plane) : 0.0f;
           mk[i] = (MASK == MASK_GIVEN && inside) ? __ldcs(mb + off) : 0.0f;
@@ -955,32 +1285,38 @@ __global__ void __launch_bounds__(kWsThreads, 1) fused_forward_ws_kernel(const F
       }
     }
     if (threadIdx.x == 0) TCL_STAMP(k, 1);
-    mbar_wait(&ctl->src_full[ss], ps);
+    mbar_wait_s(src_full_s + 8u * ss, (k / NS) & 1);
     if (threadIdx.x == 0) TCL_STAMP(k, 2);
+#if TCL_DIAG == 1
+    const int mode = 1;
+#else
     const int mode = ctl->meta[ss][2];
+#endif
     if (LEAN == 3) {   // nothing staged, nothing sampled: the flow tile alone decides
-      if (t.edge) lean_tile<FrameT, MASK, CT, TCLB200_L2, Cfg, true, false, false>(p, bf_stage(sb), ff_stage(ss), ctl->meta[ss], t, wg, lane, cur, mk);
-      else lean_tile<FrameT, MASK, CT, TCLB200_L2, Cfg, false, false, false>(p, bf_stage(sb), ff_stage(ss), ctl->meta[ss], t, wg, lane, cur, mk);
+      if (t.edge) lean_tile<FrameT, MASK, CT, TCLB200_L2, Cfg, true, false, false>(p, bf_stage(sb), ff_stage(ss), ctl->meta[ss], t, lx0, ly0, cur, mk);
+      else lean_tile<FrameT, MASK, CT, TCLB200_L2, Cfg, false, false, false>(p, bf_stage(sb), ff_stage(ss), ctl->meta[ss], t, lx0, ly0, cur, mk);
     } else if (LEAN && mode == 1) {
-      if (t.edge) err = lean_tile<FrameT, MASK, CT, (LEAN == 2 ? TCLB200_L1 : TCLB200_L2), Cfg, true, false, true, LEAN == 4>(p, bf_stage(sb), ff_stage(ss), ctl->meta[ss], t, wg, lane, cur, mk);
-      else err = lean_tile<FrameT, MASK, CT, (LEAN == 2 ? TCLB200_L1 : TCLB200_L2), Cfg, false, false, true, LEAN == 4>(p, bf_stage(sb), ff_stage(ss), ctl->meta[ss], t, wg, lane, cur, mk);
+      if constexpr (kPacked) {
+        if (t.edge) err = lean_tile_packed<FrameT, MASK, kLoss, Cfg, true, false>(p, bf_stage(sb), ff_stage(ss), ctl->meta[ss], t, lx0, ly0, cur, mk);
+        else err = lean_tile_packed<FrameT, MASK, kLoss, Cfg, false, false>(p, bf_stage(sb), ff_stage(ss), ctl->meta[ss], t, lx0, ly0, cur, mk);
+      } else {
+        if (t.edge) err = lean_tile<FrameT, MASK, CT, kLoss, Cfg, true, false, true, LEAN == 4>(p, bf_stage(sb), ff_stage(ss), ctl->meta[ss], t, lx0, ly0, cur, mk);
+        else err = lean_tile<FrameT, MASK, CT, kLoss, Cfg, false, false, true, LEAN == 4>(p, bf_stage(sb), ff_stage(ss), ctl->meta[ss], t, lx0, ly0, cur, mk);
+      }
     } else if (LEAN == 4) {   // outputs wanted and the tile is mixed / unstaged: the feature-complete exact path
-      err = full_tile<FrameT, MASK, REDUCE, CT, 0, Cfg, true>(p, bf_stage(sb), ff_stage(ss), prev_stage(ss), ctl->meta[ss], t, wg, lane, cur, mk, have_cur, near);
+      err = full_tile<FrameT, MASK, REDUCE, CT, 0, Cfg, true>(p, bf_stage(sb), ff_stage(ss), prev_stage(ss), ctl->meta[ss], t, lx0, ly0, cur, mk, have_cur, near);
     } else if (LEAN && mode == 2) {
-      err = lean_tile<FrameT, MASK, CT, (LEAN == 2 ? TCLB200_L1 : TCLB200_L2), Cfg, true, true>(p, bf_stage(sb), ff_stage(ss), ctl->meta[ss], t, wg, lane, cur, mk);
+      if constexpr (kPacked) err = lean_tile_packed<FrameT, MASK, kLoss, Cfg, true, true>(p, bf_stage(sb), ff_stage(ss), ctl->meta[ss], t, lx0, ly0, cur, mk);
+      else err = lean_tile<FrameT, MASK, CT, kLoss, Cfg, true, true>(p, bf_stage(sb), ff_stage(ss), ctl->meta[ss], t, lx0, ly0, cur, mk);
     } else if (LEAN || t.edge) {
-      err = full_tile<FrameT, MASK, REDUCE, CT, LEAN, Cfg, true>(p, bf_stage(sb), ff_stage(ss), prev_stage(ss), ctl->meta[ss], t, wg, lane, cur, mk, have_cur, near);
+      err = full_tile<FrameT, MASK, REDUCE, CT, LEAN, Cfg, true>(p, bf_stage(sb), ff_stage(ss), prev_stage(ss), ctl->meta[ss], t, lx0, ly0, cur, mk, have_cur, near);
     } else {
-      err = full_tile<FrameT, MASK, REDUCE, CT, LEAN, Cfg, false>(p, bf_stage(sb), ff_stage(ss), prev_stage(ss), ctl->meta[ss], t, wg, lane, cur, mk, have_cur, near);
+      err = full_tile<FrameT, MASK, REDUCE, CT, LEAN, Cfg, false>(p, bf_stage(sb), ff_stage(ss), prev_stage(ss), ctl->meta[ss], t, lx0, ly0, cur, mk, have_cur, near);
     }
-    // <= 3 * P fp32 terms per lane, fixed butterfly over the lanes; fp64 from here on (warps: index order in the producer)
-    if (REDUCE) {
-      const float ws = warp_sum(err);
-      if (lane == 0) ctl->red[ss][wg] = (double)ws;
-    }
-    scan_tile(k + NS);   // extent of the flow tile NS tiles ahead, for the placement of its source boxes
+    // <= 3 * P fp32 terms per lane; the producer folds the lanes (fixed order, fp64)
+    if (REDUCE) asm volatile("st.shared.f32 [%0], %1;" ::"r"(red_s + (uint32_t)(ss * kCWarps * 128)), "f"(err) : "memory");
     __syncwarp();   // every lane is done reading the stages of tile k
-    if (lane == 0) mbar_arrive(&ctl->done[ss]);
+    if (lane == 0) mbar_arrive_s(done_s + 8u * ss);
     if (threadIdx.x == 0) TCL_STAMP(k, 3);
   }
   if (!LEAN) count_near(near, p.near_threshold);
@@ -1294,10 +1630,34 @@ static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 
 extern "C" int tclb200_abi_version(void) { return TCLB200_ABI_VERSION; }
 extern "C" const char* tclb200_last_error(void) { return g_err; }
 
+#define TCL_STR2(x) #x
+#define TCL_STR(x) TCL_STR2(x)
+#ifdef TCL_HOT_ONLY
+#define TCL_HOT_ONLY_V 1
+#else
+#define TCL_HOT_ONLY_V 0
+#endif
+#ifdef TCL_TRACE
+#define TCL_TRACE_V 1
+#else
+#define TCL_TRACE_V 0
+#endif
+#ifdef TCL_CWARPS
+#define TCL_CWARPS_S TCL_STR(TCL_CWARPS)
+#else
+#define TCL_CWARPS_S "8/16"
+#endif
+extern "C" const char* tclb200_build_info(void) {
+  return "abi=" TCL_STR(TCLB200_ABI_VERSION) " th=" TCL_STR(TCL_TH) " bh=" TCL_STR(TCL_BH) " bw=" TCL_STR(TCL_BW) " bw16=" TCL_STR(TCL_BW16)
+         " ns=" TCL_STR(TCL_NS) " nb=" TCL_STR(TCL_NB) " cwarps=" TCL_CWARPS_S " scanners=" TCL_STR(TCL_SCANNERS) " packed=" TCL_STR(TCL_PACKED)
+         " packed_given=" TCL_STR(TCL_PACKED_GIVEN) " hot_only=" TCL_STR(TCL_HOT_ONLY_V) " diag=" TCL_STR(TCL_DIAG) " trace=" TCL_STR(TCL_TRACE_V);
+}
+
 // tile shape of the TMA kernel: 64 x TH pixels per tile, 80 x BH source boxes: after rounding the box origin down
 // to a 16-byte boundary the taps may still spread >= 8 px in x and BH-TH-1 px in y beyond the tile's own extent
 // before the tile falls back to global gathers
-constexpr int kTW = 64, kTH = TCL_TH, kBH = TCL_BH, kBW = kTW + 16;
+constexpr int kTW = 64, kTH = TCL_TH, kBH = TCL_BH;
+template <typename FrameT> constexpr int box_width() { return sizeof(FrameT) == 4 ? TCL_BW : TCL_BW16; }
 
 static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 // scratch is sized for the finest tiling any kernel uses (32 x 8 generic tiles)
@@ -1340,19 +1700,20 @@ static bool make_map(CUtensorMap* m, const void* base, int esize, int W, int H, 
 }
 
 // ---- launches ----------------------------------------------------------------------------------
-static int sm_count() {
-  static int n = []() {
-    int dev = 0, v = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return 148;
-    return v > 0 ? v : 148;
-  }();
-  return n;
+static int sm_count() {   // of the current device, cached per device index (a process may drive different GPUs / MIG slices)
+  static int cache[64] = {};
+  int dev = 0, v = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+  if (dev >= 0 && dev < 64 && cache[dev] > 0) return cache[dev];
+  if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) return 148;
+  if (dev >= 0 && dev < 64) cache[dev] = v;
+  return v;
 }
 
-template <typename FrameT, int MASK, bool REDUCE, int CT, int LEAN>
-static cudaError_t launch_tma(const FwdParams& p, const CUtensorMap& tb, const CUtensorMap& tf, const CUtensorMap& tp, const CUtensorMap& tc,
-                              cudaStream_t s) {
-  using Cfg = WsCfg<FrameT, CT, kTW, kTH, kBH, TCL_NB, TCL_NS, TCL_GROUPS>;
+template <typename FrameT, int MASK, bool REDUCE, int CT, int LEAN, int CW>
+static cudaError_t launch_tma_cw(const FwdParams& p, const CUtensorMap& tb, const CUtensorMap& tf, const CUtensorMap& tp, const CUtensorMap& tc,
+                                 cudaStream_t s) {
+  using Cfg = WsCfg<FrameT, CT, kTW, kTH, box_width<FrameT>(), kBH, TCL_NB, TCL_NS, CW>;
   auto kern = fused_forward_ws_kernel<FrameT, MASK, REDUCE, CT, LEAN, Cfg>;
   static bool configured[64] = {};  // per instantiation and device (the attribute is a per-device property of the function)
   int dev = 0;
@@ -1366,7 +1727,7 @@ static cudaError_t launch_tma(const FwdParams& p, const CUtensorMap& tb, const C
   const size_t tiles = (size_t)p.B * p.tiles_per_pair;
   const size_t slots = (size_t)sm_count();
   const unsigned grid = (unsigned)(tiles < slots ? tiles : slots);
-  kern<<<grid, kWsThreads, Cfg::kSmemBytes, s>>>(p, tb, tf, tp, tc);
+  kern<<<grid, Cfg::kThreads, Cfg::kSmemBytes, s>>>(p, tb, tf, tp, tc);
   ++g_launches;
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess || !REDUCE) return e;
@@ -1379,6 +1740,20 @@ static cudaError_t launch_tma(const FwdParams& p, const CUtensorMap& tb, const C
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr; cfg.numAttrs = 1;
   return cudaLaunchKernelEx(&cfg, fold_partials_kernel, p);
+}
+
+// Consumer warps per CTA.  The packed-arithmetic configuration on fp32 frames (computeTCL: both mask tests, C == 3) runs
+// best with 8 warps x 8 pixels per lane on large frames (Sintel shape: 130 vs 124 Gpix/s); small frames, where a larger
+// share of the tiles straddles a motion boundary and waits for global gathers (256 x 256 training crops: 87 vs 97), bf16
+// frames (98 vs 123) and every other configuration run best with 16 warps x 4 pixels.
+template <typename FrameT, int MASK, bool REDUCE, int CT, int LEAN>
+static cudaError_t launch_tma(const FwdParams& p, const CUtensorMap& tb, const CUtensorMap& tf, const CUtensorMap& tp, const CUtensorMap& tc,
+                              cudaStream_t s) {
+  constexpr bool packed8 = TCL_PACKED && (LEAN == 1 || LEAN == 2) && CT == 3 && MASK == MASK_COMPUTED && sizeof(FrameT) == 4;
+  if constexpr (packed8 && kCWarpsPacked != kCWarpsOther) {
+    if ((size_t)p.geo.H * p.geo.W >= (size_t)384 * 384) return launch_tma_cw<FrameT, MASK, REDUCE, CT, LEAN, kCWarpsPacked>(p, tb, tf, tp, tc, s);
+  }
+  return launch_tma_cw<FrameT, MASK, REDUCE, CT, LEAN, kCWarpsOther>(p, tb, tf, tp, tc, s);
 }
 
 template <typename FrameT, int MASK, bool REDUCE>
@@ -1493,13 +1868,15 @@ static int run_fused(const tclb200_tcl_args* a, cudaStream_t s) {
   const bool strides16 = bf_plane % 4 == 0 && bf_batch % 4 == 0 && ff_plane % 4 == 0 && ff_batch % 4 == 0;   // TMA: 16-byte strides
   // TMA needs 16-byte aligned bases and row strides; frames need C == 3 (the compiled box depth)
   bool tma = !g_force_generic && (a->W % 4 == 0) && ((a->W * esz) % 16 == 0) && aligned16(a->bf) && aligned16(a->ff) &&
-             aligned16(a->prev) && aligned16(a->cur) && (!a->prev || a->C == 3) && a->B <= 65535 * 16 && strides16;
+             aligned16(a->prev) && aligned16(a->cur) && (!a->prev || a->C == 3) && a->B <= 65535 * 16 && strides16 &&
+             a->H <= 16384 && a->W <= 16384;   // (box addresses are evaluated in fp32, see lean_tile)
   CUtensorMap tb, tf, tp, tc;
   memset(&tb, 0, sizeof(tb)); memset(&tf, 0, sizeof(tf)); memset(&tp, 0, sizeof(tp)); memset(&tc, 0, sizeof(tc));
   if (tma) {
+    const int bw = a->dtype == TCLB200_BF16 ? box_width<__nv_bfloat16>() : box_width<float>();
     tma = make_map(&tb, a->bf, 4, a->W, a->H, 2, a->B, kTW + 16, kTH + 2, 2, bf_plane, bf_batch);
-    if (tma && mask_kind == MASK_COMPUTED && (a->flags & TCLB200_OCC)) tma = make_map(&tf, a->ff, 4, a->W, a->H, 2, a->B, kBW, kBH, 2, ff_plane, ff_batch);
-    if (tma && a->prev) tma = make_map(&tp, a->prev, esz, a->W, a->H, 3, a->prev_index ? a->n_prev_frames : a->B, kBW, kBH, 3);
+    if (tma && mask_kind == MASK_COMPUTED && (a->flags & TCLB200_OCC)) tma = make_map(&tf, a->ff, 4, a->W, a->H, 2, a->B, bw, kBH, 2, ff_plane, ff_batch);
+    if (tma && a->prev) tma = make_map(&tp, a->prev, esz, a->W, a->H, 3, a->prev_index ? a->n_prev_frames : a->B, bw, kBH, 3);
     if (tma && a->prev && a->cur) tma = make_map(&tc, a->cur, esz, a->W, a->H, 3, a->cur_index ? a->n_cur_frames : a->B, kTW, kTH, 3);
   }
 

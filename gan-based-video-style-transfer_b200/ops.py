@@ -132,6 +132,7 @@ class _WarpFn(torch.autograd.Function):
         return _warp_forward(x, f, flags)
 
     @staticmethod
+    @torch.autograd.function.once_differentiable
     def backward(ctx, grad_out):
         x, f = ctx.saved_tensors
         if x.dtype != torch.float32:
@@ -378,7 +379,7 @@ def _host_tensor(t, name, dtype=None):
 
 
 def temporal_error_host(frames, ff, bf, prev_index=None, cur_index=None, mask=None, loss=L2, finalize=FIN_RMSE,
-                        flags=OCC | MOB, chunk_pairs=0, device=None, sync=True, return_sums=False):
+                        flags=OCC | MOB, chunk_pairs=0, device=None, sync=True, return_sums=False, max_device_frames=None):
     """The evaluation loop of utils/sintel_eval.py:206-222 (and solver.py:336-347) on HOST tensors.
 
     ``frames`` (F,C,H,W) fp32/bf16: the stylised frames of one or more clips, each stored once; ``ff`` / ``bf``
@@ -389,6 +390,10 @@ def temporal_error_host(frames, ff, bf, prev_index=None, cur_index=None, mask=No
     values per ``finalize``.  One C-ABI call (``tclb200_tcl_forward_host``) pipelines H2D copies and fused launches
     on ``device`` (default: the current CUDA device); there is no CPU arithmetic anywhere.
     ``return_sums=True`` returns ``(values, sums)`` with the per-pair float64 sums S_p as well (for pooled statistics).
+    ``max_device_frames``: device frame slots.  None = the whole frame bank stays resident when it takes at most a
+    quarter of the free device memory, else a ring of as many frames as that quarter holds (long or 4K clips: a slot is
+    reused once every chunk that reads its frame has completed; at least four chunks' worth of frames must fit).
+    A clip without pairs (P == 0) returns empty results.
     """
     if not torch.cuda.is_available():
         raise RuntimeError("tcl_b200: temporal_error_host needs a CUDA device; this path has no CPU implementation")
@@ -416,7 +421,18 @@ def temporal_error_host(frames, ff, bf, prev_index=None, cur_index=None, mask=No
         raise RuntimeError(f"tcl_b200: prev_index / cur_index must hold one frame index per pair ({P})")
     dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
     lib = _cabi.lib()
-    need = lib.tclb200_host_workspace_bytes(P, F_, C, H, W, dt, chunk_pairs, 1 if mask is not None else 0)
+    if P == 0:
+        out = torch.empty(0, dtype=torch.float32, pin_memory=True)
+        return (out, torch.empty(0, dtype=torch.float64, pin_memory=True)) if return_sums else out
+    slots = F_
+    if max_device_frames is not None:
+        slots = max(1, min(F_, int(max_device_frames)))
+    else:
+        frame_bytes = C * H * W * frames.element_size()
+        free_b = torch.cuda.mem_get_info(dev)[0] + (_host_ws_cache[dev.index].numel() if dev.index in _host_ws_cache else 0)
+        if F_ * frame_bytes > free_b // 4:
+            slots = max(1, min(F_, (free_b // 4) // frame_bytes))
+    need = lib.tclb200_host_workspace_bytes(P, slots, C, H, W, dt, chunk_pairs, 1 if mask is not None else 0)
     ws = _host_ws_cache.get(dev.index)
     if ws is None or ws.numel() < need:
         _host_ws_cache.pop(dev.index, None)
@@ -431,6 +447,7 @@ def temporal_error_host(frames, ff, bf, prev_index=None, cur_index=None, mask=No
     a.workspace, a.workspace_bytes = _ptr(ws), ws.numel()
     a.P, a.F, a.C, a.H, a.W = P, F_, C, H, W
     a.dtype, a.flags, a.loss, a.finalize, a.chunk_pairs = dt, flags, loss, finalize, chunk_pairs
+    a.frame_slots = 0 if slots >= F_ else slots
     with torch.cuda.device(dev):
         stream = torch.cuda.current_stream()
         check(lib.tclb200_tcl_forward_host(ctypes.byref(a), ctypes.c_void_p(stream.cuda_stream)))
@@ -452,6 +469,10 @@ def warp_blend(mask, prev, flow, img):
 
 
 class _TemporalLossFn(torch.autograd.Function):
+    """Gradients to ``prev`` and ``cur`` only (what the reference's trainers use: the flow and the mask come from the data
+    set or from a frozen flow network under no_grad).  ``temporal_loss`` refuses flows / masks that require grad instead of
+    silently returning no gradient for them; double backward is not defined (once_differentiable)."""
+
     @staticmethod
     def forward(ctx, prev, cur, flow, mask, loss, flags):
         res = fused_forward(flow, prev, cur, mask=mask, loss=loss, finalize=FIN_MEAN, flags=flags)
@@ -460,6 +481,7 @@ class _TemporalLossFn(torch.autograd.Function):
         return res.total_val.clone()
 
     @staticmethod
+    @torch.autograd.function.once_differentiable
     def backward(ctx, grad_out):
         prev, cur, flow, mask = ctx.saved_tensors
         if prev.dtype != torch.float32:
@@ -492,6 +514,9 @@ def temporal_loss(mask, cur, prev, flow, loss="l2", validity=False):
         mask = torch.ones((B, 1, H, W), dtype=torch.float32, device=flow.device)
     mask = mask.float().contiguous()
     flags = VALIDITY if validity else 0
+    if torch.is_grad_enabled() and (flow.requires_grad or mask.requires_grad):
+        raise RuntimeError("tcl_b200: temporal_loss differentiates w.r.t. cur and prev only; a flow or mask that requires grad would "
+                           "silently get none -- detach it, or compose the loss from tcl_b200.warp (differentiable w.r.t. its flow)")
     if torch.is_grad_enabled() and (prev.requires_grad or cur.requires_grad):
         return _TemporalLossFn.apply(prev, cur, flow, mask, code, flags)
     return fused_forward(flow, prev, cur, mask=mask, loss=code, finalize=FIN_MEAN, flags=flags).total_val

@@ -107,10 +107,12 @@ def unpack(packed: torch.Tensor, n_seq: int) -> dict:
 
 
 def evaluate_sharded(ff, bf, prev, cur, seq_of_pair: torch.Tensor, n_seq: int,
-                     group: Optional[dist.ProcessGroup] = None, chunk: Optional[int] = None) -> dict:
+                     group: Optional[dist.ProcessGroup] = None, chunk: Optional[int] = None, kernel_events=None) -> dict:
     """Temporal error of this rank's shard of pairs (already resident on its GPU) + the one all-reduce.
 
     ``chunk`` bounds the pairs per launch (None = one launch for the shard).  Returns ``unpack``'s dict.
+    ``kernel_events``: optional list; a (start, end) pair of CUDA timing events recorded around every fused launch is
+    appended to it (bench.py times the dominant kernel inside its timed region this way).
     """
     from . import ops
     n = bf.shape[0]
@@ -122,7 +124,13 @@ def evaluate_sharded(ff, bf, prev, cur, seq_of_pair: torch.Tensor, n_seq: int,
         packed = None
         for s in range(0, n, step):
             e = min(n, s + step)
+            if kernel_events is not None:
+                ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+                ev[0].record()
             res = ops.fused_forward(bf[s:e], prev[s:e], cur[s:e], ff=ff[s:e], finalize=ops.FIN_RMSE)
+            if kernel_events is not None:
+                ev[1].record()
+                kernel_events.append(ev)
             part = pack_local(res.pair_vals, res.total_sums[0], seq_of_pair[s:e], n_seq, C * H * W)
             packed = part if packed is None else packed + part
     return unpack(allreduce_sums(packed, group), n_seq)

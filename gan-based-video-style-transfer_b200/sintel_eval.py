@@ -14,14 +14,41 @@ import torch
 from . import ops
 
 
-def computeRAFT(model, img1, img2, it=20):
-    """Call the flow estimator like utils/sintel_eval.py:53-60 does and return the full-resolution flow."""
+class InputPadder:
+    """Pads images so that both dimensions are divisible by 8, like utils/raft/raft/utils/utils.py:7-24: replicate
+    padding; mode 'sintel' splits the rows top/bottom (pad_ht // 2 on top), any other mode pads at the bottom only."""
+
+    def __init__(self, dims, mode="sintel"):
+        self.ht, self.wd = dims[-2:]
+        pad_ht = (-self.ht) % 8
+        pad_wd = (-self.wd) % 8
+        left, top = pad_wd // 2, (pad_ht // 2 if mode == "sintel" else 0)
+        self._pad = [left, pad_wd - left, top, pad_ht - top]
+
+    def pad(self, *inputs):
+        return [torch.nn.functional.pad(x, self._pad, mode="replicate") for x in inputs]
+
+    def unpad(self, x):
+        ht, wd = x.shape[-2:]
+        return x[..., self._pad[2]:ht - self._pad[3], self._pad[0]:wd - self._pad[1]]
+
+
+def computeRAFT(model, img1, img2, it=20, crop=True):
+    """The reference's ``computeRAFT``: pad both images to multiples of 8 (``InputPadder(img1.shape)``, replicate mode,
+    sintel split), run the flow estimator, return the full-resolution flow.  ``crop=True`` is the
+    ConGAN/CycleGAN/MoGAN/StarGAN/fast_style_transfer/obst variant, ``flow_up[:, :, :H, :]`` (a view: rows from the TOP
+    of the padded flow, not ``unpad`` -- the reference's own choice, ConGAN/sintel_eval.py:54-61); ``crop=False`` the
+    StarGAN v2 one (utils/sintel_eval.py:53-60), which returns the padded flow as it is (its data set crops the frames to
+    432 rows, so nothing was padded).  With H % 8 == 0 the two are the same.  The fused kernel reads the cropped view in place."""
+    H = img1.shape[-2]
     with torch.no_grad():
+        image1, image2 = InputPadder(img1.shape).pad(img1, img2)
         try:
-            out = model(img1, img2, iters=it, test_mode=True)
+            out = model(image1, image2, iters=it, test_mode=True)
         except TypeError:
-            out = model(img1, img2)
-    return out[-1] if isinstance(out, (tuple, list)) else out
+            out = model(image1, image2)
+    flow_up = out[-1] if isinstance(out, (tuple, list)) else out
+    return flow_up[:, :, :H, :] if crop else flow_up
 
 
 def computeTCL_from_flows(ff, bf, styled_prev, img_fake):

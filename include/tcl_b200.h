@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define TCLB200_ABI_VERSION 4
+#define TCLB200_ABI_VERSION 5
 
 #define TCLB200_OK 0
 #define TCLB200_ERR_INVALID 1     /* bad argument (null pointer, non-positive size, unknown enum) */
@@ -59,6 +59,9 @@ typedef void* tclb200_stream_t; /* cudaStream_t */
 
 int tclb200_abi_version(void);
 const char* tclb200_last_error(void);
+/* the compile-time configuration of this build of the library ("abi=5 th=32 bh=40 ... hot_only=0 diag=0 trace=0"): the
+ * wrappers refuse a library built with tuning macros (tools/sweep_build.py) unless it was asked for by name   (ABI v5) */
+const char* tclb200_build_info(void);
 
 /* bytes of device scratch tclb200_tcl_forward needs for a (B,H,W) problem.  The scratch must be
  * zero-filled once when allocated; every call leaves it zeroed again. */
@@ -160,8 +163,12 @@ typedef struct tclb200_host_args {
   int P, F, C, H, W;
   int dtype, flags, loss, finalize; /* as in tclb200_tcl_args */
   int chunk_pairs;       /* pairs per launch, 0 = 32 */
+  int frame_slots;       /* device frame slots the workspace provides: 0 (or >= F) = the whole bank stays resident; fewer =
+                          * a ring -- a slot is reused once every chunk that reads its frame has completed; a window of
+                          * (3 + 1) chunks of pairs must fit (TCLB200_ERR_INVALID otherwise)          (ABI v5) */
 } tclb200_host_args;
 
+/* F here = the number of device frame slots to provision (tclb200_host_args.frame_slots, or the clip's F for a resident bank) */
 size_t tclb200_host_workspace_bytes(int P, int F, int C, int H, int W, int dtype, int chunk_pairs, int with_mask);
 int tclb200_tcl_forward_host(const tclb200_host_args* args, tclb200_stream_t stream);
 

@@ -249,10 +249,9 @@ def test_blend_and_computeTCL_dropins(tcl):
     class Net:            # utils/sintel_eval.py:104 arity (StarGAN v2)
         def generator(self, img, s):
             return img * s
-    flows = {id(cur): bf, id(prev): ff}
-
     def raft(a, b, iters=20, test_mode=True):   # computeRAFT(model, img2, img1) -> ff ; (img1, img2) -> bf
-        return None, flows[id(a)]
+        assert a.shape[-2] % 8 == 0 and a.shape[-1] % 8 == 0
+        return None, (bf if torch.equal(a, cur) else ff)
     img1, img2 = cur, prev
     s = torch.tensor(0.5, device=d)
     got = tcl.computeTCL(Net(), raft, s, cur, img1, img2)
@@ -265,6 +264,37 @@ def test_blend_and_computeTCL_dropins(tcl):
     got2 = tcl.computeTCL(Net2(), raft, cur, img1, img2)
     want2 = tp.temporal_error(ff, bf, prev, cur)
     assert abs(float(got2) - float(want2)) <= LOSS_RTOL * float(want2)
+
+
+def test_computeTCL_pads_like_the_reference_when_the_frame_height_is_not_a_multiple_of_8(tcl):
+    """Every reference computeRAFT pads with InputPadder(img1.shape) first (utils/sintel_eval.py:53-60); the ConGAN / CycleGAN /
+    MoGAN / StarGAN / fast_style_transfer / obst variants then hand on flow_up[:, :, :H, :] (ConGAN/sintel_eval.py:61).  Native
+    Sintel frames are 436 rows: the flow estimator must see 440, the fused kernel the 436-row view of its output, in place."""
+    d = dev()
+    H, W = 44, 64        # 44 % 8 == 4 -> 2 rows on top, 2 at the bottom (sintel mode)
+    ff, bf, prev, cur = (t.to(d) for t in case(tcl, 1, H, W, seed=9, max_shift=5.0))
+    padded = {}
+    for name, f in (("ff", ff), ("bf", bf)):   # what RAFT would return: a 48-row flow whose first 44 rows the variants keep
+        padded[name] = torch.cat([f, torch.full((1, 2, 4, W), 1e9, device=d)], dim=2)
+    seen = []
+
+    def raft(a, b, iters=20, test_mode=True):
+        assert a.shape[-2:] == (48, W) and b.shape[-2:] == (48, W), "computeRAFT must pad to a multiple of 8"
+        # replicate padding, 2 rows on top: rows 0..2 of the padded image are row 0 of the image
+        assert torch.equal(a[:, :, 0], a[:, :, 2]) and torch.equal(a[:, :, 1], a[:, :, 2])
+        seen.append(a)
+        return None, (padded["bf"] if torch.equal(a[:, :, 2:2 + H], cur) else padded["ff"])
+
+    class Net2:
+        def forward_eval(self, img):
+            return img
+    got = tcl.computeTCL(Net2(), raft, cur, cur, prev)
+    want = tp.temporal_error(ff, bf, prev, cur)
+    assert len(seen) == 2 and abs(float(got) - float(want)) <= LOSS_RTOL * float(want)
+    # the cropped flow is a view of RAFT's output (no copy), and the uncropped StarGAN v2 form returns it whole
+    v = tcl.sintel_eval.computeRAFT(raft, cur, prev)
+    assert v.shape == (1, 2, H, W) and v.data_ptr() == padded["bf"].data_ptr()
+    assert tcl.sintel_eval.computeRAFT(raft, cur, prev, crop=False).shape == (1, 2, 48, W)
 
 
 # ------------------------------------------------------------------ both forward kernels, every tile path
@@ -649,6 +679,52 @@ def test_host_entry_equals_device_path(tcl, oracle_mod, clips, H, W, chunk, dtyp
         tcl.temporal_error_host(frames.to(d), ff, bf, pi, ci)          # device tensor where host memory is expected
     with pytest.raises(RuntimeError):
         tcl.temporal_error_host(frames, ff, bf, pi, ci + T)            # index outside the frame bank
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("pairs_kind", ["consecutive", "long_term"])
+def test_host_entry_frame_ring_equals_resident_bank(tcl, pairs_kind):
+    """A device frame ring smaller than the clip (long / 4K clips that do not fit device memory): a slot is reused once every
+    chunk that reads its frame has completed.  Same bits as the resident bank; a ring too small for (3 + 1) chunks is refused
+    with an error, not wrong results.  Long-term pairs (t-5, t), utils/sintel_eval.py:84-86, keep frames alive for longer."""
+    H, W, T, chunk = 64, 128, 41, 2
+    if pairs_kind == "consecutive":
+        pi, ci = torch.arange(0, T - 1, dtype=torch.int32), torch.arange(1, T, dtype=torch.int32)
+    else:
+        pi = torch.cat([torch.arange(0, T - 1), torch.arange(0, T - 5)]).to(torch.int32)
+        ci = torch.cat([torch.arange(1, T), torch.arange(5, T)]).to(torch.int32)
+        order = torch.argsort(ci.long() * 2 + (ci - pi > 1).long(), stable=True)     # the evaluation loop's order: per target frame
+        pi, ci = pi[order].contiguous(), ci[order].contiguous()
+    P = pi.numel()
+    ff, bf = tcl.synth.make_flows(P, H, W, seed=77, max_shift=6.0)
+    frames, _ = tcl.synth.make_frames(T, 3, H, W, seed=78, kind="white")
+    want, want_s = tcl.temporal_error_host(frames, ff, bf, pi, ci, chunk_pairs=chunk, return_sums=True)       # resident bank
+    lo = 12 if pairs_kind == "consecutive" else 22
+    for slots in (lo, lo + 5, T - 1):
+        got, got_s = tcl.temporal_error_host(frames, ff, bf, pi, ci, chunk_pairs=chunk, return_sums=True, max_device_frames=slots)
+        assert torch.equal(got, want) and torch.equal(got_s, want_s), slots
+    with pytest.raises(RuntimeError, match="frame_slots too small"):
+        tcl.temporal_error_host(frames, ff, bf, pi, ci, chunk_pairs=chunk, max_device_frames=3)
+    # the failed call drained its streams and gave its pipe back: the next call works and is still right
+    assert torch.equal(tcl.temporal_error_host(frames, ff, bf, pi, ci, chunk_pairs=chunk, max_device_frames=lo), want)
+    # a clip of one frame has no pairs: empty results, no error
+    e, es = tcl.temporal_error_host(frames[:1], ff[:0], bf[:0], return_sums=True)
+    assert e.shape == (0,) and es.shape == (0,)
+
+
+def test_temporal_loss_refuses_gradients_it_does_not_compute(tcl):
+    d = dev()
+    ff, bf, prev, cur = (t.to(d) for t in case(tcl, 2, 32, 48, seed=5, max_shift=4.0))
+    mask = tcl.fbcCheckTorch(ff, bf)
+    cur.requires_grad_(True)
+    with pytest.raises(RuntimeError, match="cur and prev only"):
+        tcl.temporal_loss(mask, cur, prev, bf.clone().requires_grad_(True))
+    with pytest.raises(RuntimeError, match="cur and prev only"):
+        tcl.temporal_loss(mask.clone().requires_grad_(True), cur, prev, bf)
+    loss = tcl.temporal_loss(mask, cur, prev, bf)
+    (g,) = torch.autograd.grad(loss, cur, create_graph=True)
+    with pytest.raises(RuntimeError):      # once_differentiable: no silent wrong double backward
+        g.sum().backward()
 
 
 def test_aggregation_kernels_equal_the_host_logic(tcl):

@@ -106,3 +106,44 @@ def test_cpu_and_device_forms_of_the_aggregation_share_one_definition(tcl):
     assert u["per_sequence_mean"].tolist() == [2.0, 0.0, 6.0]
     assert float(u["mean_over_sequences"]) == 4.0 and float(u["mean_over_pairs"]) == 4.0       # the empty sequence does not count
     assert float(u["pooled_rmse"]) == 1.0 and float(u["n_pairs"]) == 4.0
+
+
+def test_input_padder_is_the_reference_one(tcl):
+    """sintel_eval.InputPadder against utils/raft/raft/utils/utils.py:7-24 (when the reference checkout is present) and against
+    its definition: replicate padding to multiples of 8, rows split top / bottom in 'sintel' mode."""
+    import importlib.util
+    import os
+    from conftest import REFERENCE_ROOT
+    ours = tcl.sintel_eval.InputPadder
+    ref_path = os.path.join(REFERENCE_ROOT, "utils", "raft", "raft", "utils", "utils.py")
+    theirs = None
+    if os.path.exists(ref_path):
+        spec = importlib.util.spec_from_file_location("raft_utils_ref", ref_path)
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        theirs = mod.InputPadder
+    g = torch.Generator().manual_seed(3)
+    for H, W in ((436, 1024), (432, 1024), (44, 61), (8, 8), (7, 9), (1080, 1920)):
+        x = torch.rand(1, 3, H, W, generator=g)
+        for mode in ("sintel", "kitti"):
+            p = ours(x.shape, mode)
+            (y,) = p.pad(x)
+            assert y.shape[-2] % 8 == 0 and y.shape[-1] % 8 == 0 and y.shape[-2] - H < 8 and y.shape[-1] - W < 8
+            assert torch.equal(p.unpad(y), x)
+            if theirs is not None:
+                q = theirs(x.shape, mode)
+                assert q._pad == p._pad and torch.equal(q.pad(x)[0], y) and torch.equal(q.unpad(y), x)
+    assert ours((436, 1024))._pad == [0, 0, 2, 2] and ours((436, 1024), "kitti")._pad == [0, 0, 0, 4]
+
+
+def test_computeRAFT_pads_then_crops_from_the_top(tcl):
+    seen = {}
+
+    def model(a, b, iters=20, test_mode=True):
+        seen["shape"], seen["iters"] = tuple(a.shape), iters
+        return None, torch.arange(a.shape[-2], dtype=torch.float32).view(1, 1, -1, 1).expand(1, 2, a.shape[-2], a.shape[-1])
+    img = torch.zeros(1, 3, 436, 64)
+    f = tcl.sintel_eval.computeRAFT(model, img, img, it=12)
+    assert seen == {"shape": (1, 3, 440, 64), "iters": 12}
+    assert f.shape == (1, 2, 436, 64) and float(f[0, 0, 0, 0]) == 0.0 and float(f[0, 0, -1, 0]) == 435.0   # flow_up[:, :, :H, :]
+    assert tcl.sintel_eval.computeRAFT(model, img, img, crop=False).shape == (1, 2, 440, 64)

@@ -1,4 +1,4 @@
-"""Turn the ncu --set full capture of `python bench.py --no-extras ...` into profiles/r01_bench_traffic.json
+"""Turn the ncu --set full capture of `python bench.py --no-extras ...` into profiles/r02_bench_traffic.json
 (the `roofline.traffic` figure bench.py reports).  usage: ncu_traffic.py rep.ncu-rep workload pairs_per_launch"""
 import csv
 import json
@@ -24,7 +24,10 @@ for vals in rows[2:]:
                gpu_time_us_under_ncu=float(m["gpu__time_duration.sum"][0].replace(",", "")),
                source=os.path.basename(rep))
     rec["dram_bytes_per_launch"] = rec["dram_bytes_read"] + rec["dram_bytes_write"]
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import bench
+    rec["kernel_source_hash"] = bench.kernel_source_hash()   # bench.py reports the figure only while the kernel sources are these
     best = rec
-out = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "profiles", "r01_bench_traffic.json")
+out = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "profiles", "r02_bench_traffic.json")
 json.dump(best, open(out, "w"), indent=1)
 print(best)
