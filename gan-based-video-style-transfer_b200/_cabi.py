@@ -22,7 +22,7 @@ FIN_MEAN, FIN_RMSE = 0, 1
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
-SOURCES = ["tcl_kernels.cu", "tcl_host.cu", "tcl_cv2.cu", "tcl_agg.cu"]
+SOURCES = ["tcl_kernels.cu", "tcl_host.cu", "tcl_cv2.cu", "tcl_agg.cu", "tcl_chain.cu"]
 HEADERS = ["tcl_math.cuh", "tcl_common.cuh"]
 
 
@@ -42,6 +42,8 @@ class TclArgs(ctypes.Structure):
         ("n_prev_frames", ctypes.c_int), ("n_cur_frames", ctypes.c_int),
         ("ff_plane_stride", ctypes.c_size_t), ("ff_batch_stride", ctypes.c_size_t),
         ("bf_plane_stride", ctypes.c_size_t), ("bf_batch_stride", ctypes.c_size_t),
+        ("bf_index", ctypes.c_void_p), ("ff_index", ctypes.c_void_p),
+        ("n_bf_fields", ctypes.c_int), ("n_ff_fields", ctypes.c_int), ("pair_group", ctypes.c_int),
     ]
 
 
@@ -124,6 +126,9 @@ _PROTOTYPES = {
     "tclb200_upsample_flow": (_c.c_int, [_vp, _vp, _vp, _i, _i, _i, _vp]),
     "tclb200_cv2_remap": (_c.c_int, [_vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "tclb200_cv2_fb_check": (_c.c_int, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp]),
+    "tclb200_reconet_scratch_bytes": (_c.c_size_t, [_i, _i, _i]),
+    "tclb200_reconet_loss": (_c.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _c.c_size_t, _i, _i, _i, _vp]),
+    "tclb200_ruder_input": (_c.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
     "tclb200_pack_sequence_sums": (_c.c_int, [_vp, _vp, _vp, _i, _i, _c.c_double, _vp, _vp]),
     "tclb200_unpack_sequence_means": (_c.c_int, [_vp, _i, _vp, _vp]),
     "tclb200_debug_force_generic": (None, [_i]),

@@ -78,6 +78,9 @@ struct FwdParams {
   size_t ff_plane, ff_batch, bf_plane, bf_batch;   // element strides between the two flow components / between pairs (rows are dense)
   const int* prev_index;   // clip mode: frame of `prev` / `cur` each pair reads (nullptr: its own)
   const int* cur_index;
+  const int* bf_index;     // flow field each pair reads as `bf` / `ff` (nullptr: its own)
+  const int* ff_index;
+  int pair_group;          // > 1: tiles of this many consecutive pairs are interleaved (window evaluations)
   void* warp_out;
   float* mask_out;
   void* blend_out;

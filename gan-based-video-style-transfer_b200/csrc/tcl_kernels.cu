@@ -183,6 +183,9 @@ __device__ __forceinline__ void finish_pixel(const FwdParams& p, const PixTaps& 
 // stored once can be the `cur` of pair t and the `prev` of pair t+1 (the second read then comes out of L2)
 __device__ __forceinline__ int prev_frame(const FwdParams& p, int pair) { return p.prev_index ? __ldg(p.prev_index + pair) : pair; }
 __device__ __forceinline__ int cur_frame(const FwdParams& p, int pair) { return p.cur_index ? __ldg(p.cur_index + pair) : pair; }
+// ... and the same for the flow fields: a window evaluation uses each field twice, as the `bf` of (s -> t) and the `ff` of (t -> s)
+__device__ __forceinline__ int bf_field(const FwdParams& p, int pair) { return p.bf_index ? __ldg(p.bf_index + pair) : pair; }
+__device__ __forceinline__ int ff_field(const FwdParams& p, int pair) { return p.ff_index ? __ldg(p.ff_index + pair) : pair; }
 
 template <typename FrameT>
 __device__ __forceinline__ PairPtrs<FrameT> pair_ptrs(const FwdParams& p, int pair, int cf, int C, size_t plane) {
@@ -212,7 +215,7 @@ __global__ void __launch_bounds__(kThreads) fused_forward_generic_kernel(const F
   unsigned near = 0;
   if (x < W && y < H) {
     const size_t o = (size_t)y * W + x;
-    const float* bu = p.bf + (size_t)pair * p.bf_batch;
+    const float* bu = p.bf + (size_t)bf_field(p, pair) * p.bf_batch;
     const float* bv = bu + p.bf_plane;
     const float u = __ldg(bu + o), v = __ldg(bv + o);
     float nb = sqnorm2(u, v, kV);
@@ -228,7 +231,7 @@ __global__ void __launch_bounds__(kThreads) fused_forward_generic_kernel(const F
       near += fabsf(margin) < kNearBand;
     }
     const PixTaps s = pix_taps(u, v, x, y, g);
-    GlobalSrc<float> fsrc{p.ff ? p.ff + (size_t)pair * p.ff_batch : nullptr, p.ff_plane, g};
+    GlobalSrc<float> fsrc{p.ff ? p.ff + (size_t)ff_field(p, pair) * p.ff_batch : nullptr, p.ff_plane, g};
     GlobalSrc<FrameT> psrc{p.prev ? reinterpret_cast<const FrameT*>(p.prev) + (size_t)prev_frame(p, pair) * C * plane : nullptr, plane, g};
     finish_pixel<FrameT, MASK, REDUCE, CT, false>(p, s, u, v, nb, keep, o, plane, pair, fsrc, psrc,
                                                   pair_ptrs<FrameT>(p, pair, cur_frame(p, pair), C, plane), nullptr, err, near);
@@ -307,7 +310,7 @@ __device__ __forceinline__ void lane_origin(int warp, int lane, int& lx0, int& l
   ly0 = Cfg::kRows * (warp >> 2) + (lane >> 4);
 }
 
-struct TileId { int pair, tile, x0, y0, edge, pf, cf, pad; };   // pf / cf: frame of `prev` / `cur` this pair reads
+struct TileId { int pair, tile, x0, y0, pf, cf, bfi, ffi; };   // pf / cf: frame of `prev` / `cur` this pair reads; bfi / ffi: its flow fields
 
 template <int NB, int NS, int CW>
 struct WsCtl {              // control block in shared memory
@@ -421,17 +424,29 @@ __global__ void __launch_bounds__(kThreads) fold_partials_kernel(const FwdParams
   }
 }
 
+// Global tile number -> pair and tile.  pair_group G > 1 interleaves the tiles of G consecutive pairs (tile 0 of pairs
+// g*G .. g*G+G-1, then their tiles 1, ...): the evaluations of one target frame's window read the same `cur` tile, the same
+// flow tiles and neighbouring boxes within microseconds of each other, so every re-read is an L2 hit.
 __device__ __forceinline__ TileId tile_id(const FwdParams& p, int tg, int TW, int TH) {
   TileId t;
-  t.pair = tg / p.tiles_per_pair;
-  t.tile = tg - t.pair * p.tiles_per_pair;
+  if (p.pair_group > 1) {
+    const int span = p.tiles_per_pair * p.pair_group;
+    const int grp = tg / span, r = tg - grp * span;
+    const int gsize = min(p.pair_group, p.B - grp * p.pair_group);
+    t.tile = r / gsize;
+    t.pair = grp * p.pair_group + (r - t.tile * gsize);
+  } else {
+    t.pair = tg / p.tiles_per_pair;
+    t.tile = tg - t.pair * p.tiles_per_pair;
+  }
   const int ty = t.tile / p.tiles_x, tx = t.tile - ty * p.tiles_x;
   t.x0 = tx * TW; t.y0 = ty * TH;
-  t.edge = ((t.x0 + TW > p.geo.W) || (t.y0 + TH > p.geo.H)) ? 1 : 0;
   t.pf = prev_frame(p, t.pair); t.cf = cur_frame(p, t.pair);
+  t.bfi = bf_field(p, t.pair); t.ffi = ff_field(p, t.pair);
   return t;
 }
-
+template <typename Cfg>
+__device__ __forceinline__ bool tile_edge(const TileId& t, const Geo& g) { return (t.x0 + Cfg::TW > g.W) || (t.y0 + Cfg::TH > g.H); }
 
 // ---- consumer: exact per-pixel path (all features; staged boxes, global gathers, or both in a mixed tile) -------
 template <typename FrameT, int MASK, bool REDUCE, int CT, int LEAN, typename Cfg, bool EDGE>
@@ -448,7 +463,7 @@ __device__ __forceinline__ float full_tile(const FwdParams& p, const float* s_bu
   const int ox = meta[0], oy = meta[1], mode = meta[2];   // mode 0: nothing staged, 1: every tap in the boxes, 2: mixed
   const SmemSrc<float, Cfg::BW, Cfg::BH * Cfg::BW> fs{s_ff, ox, oy};
   const SmemSrc<FrameT, Cfg::BW, Cfg::BH * Cfg::BW> ps{s_prev, ox, oy};
-  const GlobalSrc<float> fg{p.ff ? p.ff + (size_t)t.pair * p.ff_batch : nullptr, p.ff_plane, g};
+  const GlobalSrc<float> fg{p.ff ? p.ff + (size_t)t.ffi * p.ff_batch : nullptr, p.ff_plane, g};
   const GlobalSrc<FrameT> pg{p.prev ? reinterpret_cast<const FrameT*>(p.prev) + (size_t)t.pf * (CT > 0 ? CT : p.C) * plane : nullptr, plane, g};
   float err = 0.0f;
 #pragma unroll
@@ -612,7 +627,7 @@ __device__ __forceinline__ float lean_tile(const FwdParams& p, const float* s_bu
   const int box_x = meta[0], box_y = meta[1];
   const float box_xf = (float)box_x, box_yf = (float)box_y;
   const ptrdiff_t gplane = (ptrdiff_t)g.H * g.W;
-  const float* gff = (MIXED && MASK == MASK_COMPUTED) ? p.ff + (size_t)t.pair * p.ff_batch : nullptr;
+  const float* gff = (MIXED && MASK == MASK_COMPUTED) ? p.ff + (size_t)t.ffi * p.ff_batch : nullptr;
   const FrameT* gprev = (MIXED && CT == 3) ? reinterpret_cast<const FrameT*>(p.prev) + (size_t)t.pf * 3 * gplane : nullptr;
   LeanGeo lg;
   lg.i2x = __fmul_rn(2.0f, g.inv_dx); lg.i2y = __fmul_rn(2.0f, g.inv_dy);   // exact doubling: (2a)*r == a*(2r)
@@ -783,12 +798,12 @@ __device__ __forceinline__ float lean_tile(const FwdParams& p, const float* s_bu
     for (int k = 0; k < P; ++k)
       if ((outbits >> k) & 1u) {
         if (CT == 3) {
-          e[k] = pixel_global<FrameT, MASK, false, LOSS>(p.bf + (size_t)t.pair * p.bf_batch, p.bf_plane, p.ff + (size_t)t.pair * p.ff_batch, p.ff_plane,
+          e[k] = pixel_global<FrameT, MASK, false, LOSS>(p.bf + (size_t)t.bfi * p.bf_batch, p.bf_plane, p.ff + (size_t)t.ffi * p.ff_batch, p.ff_plane,
                                                    reinterpret_cast<const FrameT*>(p.prev) + (size_t)t.pf * 3 * plane, g, t.x0 + lx0,
                                                    t.y0 + ly0 + pix_dy(k), cur[k][0], cur[k][1], cur[k][2], mk[k]);
           keepbits |= 1u << k;   // the verdict is already applied
         } else {
-          const float kp = pixel_global<FrameT, MASK, true, LOSS>(p.bf + (size_t)t.pair * p.bf_batch, p.bf_plane, p.ff + (size_t)t.pair * p.ff_batch, p.ff_plane, nullptr, g,
+          const float kp = pixel_global<FrameT, MASK, true, LOSS>(p.bf + (size_t)t.bfi * p.bf_batch, p.bf_plane, p.ff + (size_t)t.ffi * p.ff_batch, p.ff_plane, nullptr, g,
                                                             t.x0 + lx0, t.y0 + ly0 + pix_dy(k), 0.0f, 0.0f, 0.0f, 0.0f);
           keepbits = (keepbits & ~(1u << k)) | ((kp != 0.0f ? 1u : 0u) << k);
         }
@@ -879,7 +894,7 @@ __device__ __forceinline__ float lean_tile_packed(const FwdParams& p, const floa
   const float xf = (float)(t.x0 + lx0), yf0 = (float)(t.y0 + ly0);
   const int c0 = (ly0 + 1) * BFW + lx0 + Cfg::kHaloL;
   const size_t gplane = (size_t)g.H * g.W;
-  const GlobalSrc<float> fg{(MIXED && MASK == MASK_COMPUTED) ? p.ff + (size_t)t.pair * p.ff_batch : nullptr, p.ff_plane, g};
+  const GlobalSrc<float> fg{(MIXED && MASK == MASK_COMPUTED) ? p.ff + (size_t)t.ffi * p.ff_batch : nullptr, p.ff_plane, g};
   const GlobalSrc<FrameT> pg{MIXED ? reinterpret_cast<const FrameT*>(p.prev) + (size_t)t.pf * 3 * gplane : nullptr, gplane, g};
   const bool xin = !EDGE || t.x0 + lx0 < g.W;
   const int rows_in = EDGE ? g.H - (t.y0 + ly0) : INT_MAX;   // pixel k is inside the image iff 2 * k < rows_in (and xin)
@@ -1016,7 +1031,7 @@ __device__ __forceinline__ float lean_tile_packed(const FwdParams& p, const floa
 #pragma unroll
     for (int k = 0; k < P; ++k)
       if ((outbits >> k) & 1u) {
-        e[k] = pixel_global<FrameT, MASK, false, LOSS>(p.bf + (size_t)t.pair * p.bf_batch, p.bf_plane, MASK == MASK_COMPUTED ? p.ff + (size_t)t.pair * p.ff_batch : nullptr, p.ff_plane,
+        e[k] = pixel_global<FrameT, MASK, false, LOSS>(p.bf + (size_t)t.bfi * p.bf_batch, p.bf_plane, MASK == MASK_COMPUTED ? p.ff + (size_t)t.ffi * p.ff_batch : nullptr, p.ff_plane,
                                                        reinterpret_cast<const FrameT*>(p.prev) + (size_t)t.pf * 3 * plane, g, t.x0 + lx0,
                                                        t.y0 + ly0 + pix_dy(k), cur[k][0], cur[k][1], cur[k][2], mk[k]);
         keepbits |= 1u << k;   // the verdict is already applied
@@ -1113,14 +1128,14 @@ __global__ void __launch_bounds__(Cfg::kThreads, 1) fused_forward_ws_kernel(cons
       const TileId t = tile_id(p, tg, Cfg::TW, Cfg::TH);
       ctl->tinfo[s] = t;
       mbar_expect_tx(&ctl->bf_full[s], Cfg::kBfLoad);
-      tma_load_4d(bf_stage(s), &tm_bf, &ctl->bf_full[s], t.x0 - Cfg::kHaloL, t.y0 - 1, 0, t.pair);
+      tma_load_4d(bf_stage(s), &tm_bf, &ctl->bf_full[s], t.x0 - Cfg::kHaloL, t.y0 - 1, 0, t.bfi);
       // the consumers read this tile's `cur` values straight from global memory NB tiles from now: have them in L2 by then
       if (LEAN && CT > 0 && p.cur != nullptr) tma_prefetch_l2_4d(&tm_cur, t.x0, t.y0, 0, t.cf);
     };
     // lane 0: the scanner has left the extent of x+u, y+v over local tile k in box[k % NB] -> origin of the source
     // boxes.  The coordinate map is monotone in x+u (every step is a correctly rounded monotone operation), so the
     // extreme taps come from the extreme sums.
-    struct Placement { int ox, oy, mode, pair, pf; };
+    struct Placement { int ox, oy, mode, ffi, pf; };
     auto place_src = [&](int k) -> Placement {
       const int sb = k % NB;
       const TileId t = ctl->tinfo[sb];
@@ -1155,7 +1170,7 @@ __global__ void __launch_bounds__(Cfg::kThreads, 1) fused_forward_ws_kernel(cons
         }
         if (mode != 1) atomicAdd(&g_tile_stats[mode == 2 ? 1 : 0], 1ull);
       }
-      return Placement{ox, oy, mode, t.pair, t.pf};
+      return Placement{ox, oy, mode, t.ffi, t.pf};
     };
     // ... and, once the source stage is free, the request itself (lane 0)
     auto issue_src = [&](int k, const Placement& pl) {
@@ -1168,7 +1183,7 @@ __global__ void __launch_bounds__(Cfg::kThreads, 1) fused_forward_ws_kernel(cons
 #endif
         TCL_STAMP(k, 0);
         mbar_expect_tx(&ctl->src_full[ss], (want_occ ? Cfg::kFfLoad : 0u) + (want_frames ? Cfg::kPrevLoad : 0u));
-        if (want_occ) tma_load_4d(ff_stage(ss), &tm_ff, &ctl->src_full[ss], pl.ox, pl.oy, 0, pl.pair);
+        if (want_occ) tma_load_4d(ff_stage(ss), &tm_ff, &ctl->src_full[ss], pl.ox, pl.oy, 0, pl.ffi);
         if (want_frames) tma_load_4d(prev_stage(ss), &tm_prev, &ctl->src_full[ss], pl.ox, pl.oy, 0, pl.pf);
       } else {
         mbar_arrive(&ctl->src_full[ss]);
@@ -1247,6 +1262,7 @@ __global__ void __launch_bounds__(Cfg::kThreads, 1) fused_forward_ws_kernel(cons
     mbar_wait_s(bf_full_s + 8u * sb, (k / NB) & 1);
     const TileId t = ctl->tinfo[sb];
     if (t.pair < 0) break;
+    const bool t_edge = tile_edge<Cfg>(t, g);
     // this tile's `cur` (and dataset mask) values: coalesced 64-byte row segments, streaming; requested before the wait
     // for the source boxes and first used at the very end of the per-pixel work
     float cur[P][Cfg::kC], mk[P];
@@ -1254,7 +1270,7 @@ __global__ void __launch_bounds__(Cfg::kThreads, 1) fused_forward_ws_kernel(cons
       const size_t pix = (size_t)(t.y0 * g.W + t.x0) + lane_off;
       const FrameT* cb = reinterpret_cast<const FrameT*>(p.cur) + (size_t)t.cf * Cfg::kC * plane + pix;
       const float* mb = MASK == MASK_GIVEN ? p.mask_in + (size_t)t.pair * plane + pix : nullptr;
-      if (!t.edge && p.cur_index != nullptr) {
+      if (!t_edge && p.cur_index != nullptr) {
         // clip mode: this frame is read again as the `prev` of the next pair -- do not mark its lines evict-first
 #pragma unroll
         for (int c = 0; c < Cfg::kC; ++c) {
@@ -1264,7 +1280,7 @@ __global__ void __launch_bounds__(Cfg::kThreads, 1) fused_forward_ws_kernel(cons
         }
 #pragma unroll
         for (int i = 0; i < P; ++i) mk[i] = MASK == MASK_GIVEN ? __ldcs(mb + (ptrdiff_t)pix_dy(i) * g.W) : 0.0f;
-      } else if (!t.edge) {
+      } else if (!t_edge) {
 #pragma unroll
         for (int c = 0; c < Cfg::kC; ++c) {
           const FrameT* pc = cb + (size_t)c * plane;
@@ -1293,14 +1309,14 @@ __global__ void __launch_bounds__(Cfg::kThreads, 1) fused_forward_ws_kernel(cons
     const int mode = ctl->meta[ss][2];
 #endif
     if (LEAN == 3) {   // nothing staged, nothing sampled: the flow tile alone decides
-      if (t.edge) lean_tile<FrameT, MASK, CT, TCLB200_L2, Cfg, true, false, false>(p, bf_stage(sb), ff_stage(ss), ctl->meta[ss], t, lx0, ly0, cur, mk);
+      if (t_edge) lean_tile<FrameT, MASK, CT, TCLB200_L2, Cfg, true, false, false>(p, bf_stage(sb), ff_stage(ss), ctl->meta[ss], t, lx0, ly0, cur, mk);
       else lean_tile<FrameT, MASK, CT, TCLB200_L2, Cfg, false, false, false>(p, bf_stage(sb), ff_stage(ss), ctl->meta[ss], t, lx0, ly0, cur, mk);
     } else if (LEAN && mode == 1) {
       if constexpr (kPacked) {
-        if (t.edge) err = lean_tile_packed<FrameT, MASK, kLoss, Cfg, true, false>(p, bf_stage(sb), ff_stage(ss), ctl->meta[ss], t, lx0, ly0, cur, mk);
+        if (t_edge) err = lean_tile_packed<FrameT, MASK, kLoss, Cfg, true, false>(p, bf_stage(sb), ff_stage(ss), ctl->meta[ss], t, lx0, ly0, cur, mk);
         else err = lean_tile_packed<FrameT, MASK, kLoss, Cfg, false, false>(p, bf_stage(sb), ff_stage(ss), ctl->meta[ss], t, lx0, ly0, cur, mk);
       } else {
-        if (t.edge) err = lean_tile<FrameT, MASK, CT, kLoss, Cfg, true, false, true, LEAN == 4>(p, bf_stage(sb), ff_stage(ss), ctl->meta[ss], t, lx0, ly0, cur, mk);
+        if (t_edge) err = lean_tile<FrameT, MASK, CT, kLoss, Cfg, true, false, true, LEAN == 4>(p, bf_stage(sb), ff_stage(ss), ctl->meta[ss], t, lx0, ly0, cur, mk);
         else err = lean_tile<FrameT, MASK, CT, kLoss, Cfg, false, false, true, LEAN == 4>(p, bf_stage(sb), ff_stage(ss), ctl->meta[ss], t, lx0, ly0, cur, mk);
       }
     } else if (LEAN == 4) {   // outputs wanted and the tile is mixed / unstaged: the feature-complete exact path
@@ -1308,7 +1324,7 @@ __global__ void __launch_bounds__(Cfg::kThreads, 1) fused_forward_ws_kernel(cons
     } else if (LEAN && mode == 2) {
       if constexpr (kPacked) err = lean_tile_packed<FrameT, MASK, kLoss, Cfg, true, true>(p, bf_stage(sb), ff_stage(ss), ctl->meta[ss], t, lx0, ly0, cur, mk);
       else err = lean_tile<FrameT, MASK, CT, kLoss, Cfg, true, true>(p, bf_stage(sb), ff_stage(ss), ctl->meta[ss], t, lx0, ly0, cur, mk);
-    } else if (LEAN || t.edge) {
+    } else if (LEAN || t_edge) {
       err = full_tile<FrameT, MASK, REDUCE, CT, LEAN, Cfg, true>(p, bf_stage(sb), ff_stage(ss), prev_stage(ss), ctl->meta[ss], t, lx0, ly0, cur, mk, have_cur, near);
     } else {
       err = full_tile<FrameT, MASK, REDUCE, CT, LEAN, Cfg, false>(p, bf_stage(sb), ff_stage(ss), prev_stage(ss), ctl->meta[ss], t, lx0, ly0, cur, mk, have_cur, near);
@@ -1850,6 +1866,9 @@ static int run_fused(const tclb200_tcl_args* a, cudaStream_t s) {
   if (a->blend_out && !a->cur) return fail(TCLB200_ERR_INVALID, "blend_out needs cur");
   if ((a->prev_index && a->n_prev_frames <= 0) || (a->cur_index && a->n_cur_frames <= 0))
     return fail(TCLB200_ERR_INVALID, "prev_index / cur_index need n_prev_frames / n_cur_frames");
+  if ((a->bf_index && a->n_bf_fields <= 0) || (a->ff && a->ff_index && a->n_ff_fields <= 0))
+    return fail(TCLB200_ERR_INVALID, "bf_index / ff_index need n_bf_fields / n_ff_fields");
+  if (a->pair_group < 0) return fail(TCLB200_ERR_INVALID, "pair_group must not be negative");
   if ((size_t)a->H * a->W >= (1u << 30)) return fail(TCLB200_ERR_UNSUPPORTED, "H*W must be below 2^30");
   const bool reduce = a->cur && (a->pair_sums || a->total_sums || a->pair_vals || a->total_val);
   const int mask_kind = a->ff ? MASK_COMPUTED : (a->mask_in ? MASK_GIVEN : MASK_NONE);
@@ -1874,8 +1893,9 @@ static int run_fused(const tclb200_tcl_args* a, cudaStream_t s) {
   memset(&tb, 0, sizeof(tb)); memset(&tf, 0, sizeof(tf)); memset(&tp, 0, sizeof(tp)); memset(&tc, 0, sizeof(tc));
   if (tma) {
     const int bw = a->dtype == TCLB200_BF16 ? box_width<__nv_bfloat16>() : box_width<float>();
-    tma = make_map(&tb, a->bf, 4, a->W, a->H, 2, a->B, kTW + 16, kTH + 2, 2, bf_plane, bf_batch);
-    if (tma && mask_kind == MASK_COMPUTED && (a->flags & TCLB200_OCC)) tma = make_map(&tf, a->ff, 4, a->W, a->H, 2, a->B, bw, kBH, 2, ff_plane, ff_batch);
+    tma = make_map(&tb, a->bf, 4, a->W, a->H, 2, a->bf_index ? a->n_bf_fields : a->B, kTW + 16, kTH + 2, 2, bf_plane, bf_batch);
+    if (tma && mask_kind == MASK_COMPUTED && (a->flags & TCLB200_OCC))
+      tma = make_map(&tf, a->ff, 4, a->W, a->H, 2, a->ff_index ? a->n_ff_fields : a->B, bw, kBH, 2, ff_plane, ff_batch);
     if (tma && a->prev) tma = make_map(&tp, a->prev, esz, a->W, a->H, 3, a->prev_index ? a->n_prev_frames : a->B, bw, kBH, 3);
     if (tma && a->prev && a->cur) tma = make_map(&tc, a->cur, esz, a->W, a->H, 3, a->cur_index ? a->n_cur_frames : a->B, kTW, kTH, 3);
   }
@@ -1885,6 +1905,8 @@ static int run_fused(const tclb200_tcl_args* a, cudaStream_t s) {
   p.ff = a->ff; p.bf = a->bf; p.mask_in = a->mask_in; p.prev = a->prev; p.cur = a->cur;
   p.ff_plane = ff_plane; p.ff_batch = ff_batch; p.bf_plane = bf_plane; p.bf_batch = bf_batch;
   p.prev_index = a->prev ? a->prev_index : nullptr; p.cur_index = a->cur ? a->cur_index : nullptr;
+  p.bf_index = a->bf_index; p.ff_index = a->ff ? a->ff_index : nullptr;
+  p.pair_group = a->pair_group > 1 ? a->pair_group : 1;
   p.warp_out = a->warp_out; p.mask_out = a->mask_out; p.blend_out = a->blend_out;
   p.pair_sums = a->pair_sums; p.total_sums = a->total_sums; p.pair_vals = a->pair_vals; p.total_val = a->total_val;
   p.near_threshold = a->near_threshold;

@@ -138,14 +138,19 @@ class _WarpFn(torch.autograd.Function):
         if x.dtype != torch.float32:
             raise RuntimeError("tcl_b200: warp backward is implemented for float32 frames")
         B, C, H, W = x.shape
-        need_x, need_f = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
-        gx = torch.empty_like(x) if need_x else None
-        gf = torch.empty_like(f) if need_f else None
-        go = grad_out.float().contiguous()
-        with torch.cuda.device(x.device):
-            check(_cabi.lib().tclb200_warp_backward(_ptr(go), _ptr(x), _ptr(f), _ptr(gx), _ptr(gf), B, C, H, W,
-                                                    ctx.flags, _stream_handle()))
+        gx, gf = _warp_backward_raw(grad_out, x, f, ctx.flags, ctx.needs_input_grad[0], ctx.needs_input_grad[1])
         return gx, gf, None
+
+
+def _warp_backward_raw(grad_out, x, f, flags, need_x=True, need_f=True):
+    """Autograd of ``warp`` / ``fs_lib.warp`` on raw tensors (``tclb200_warp_backward``): (grad_x, grad_f)."""
+    B, C, H, W = x.shape
+    gx = torch.empty_like(x) if need_x else None
+    gf = torch.empty_like(f) if need_f else None
+    go = grad_out.float().contiguous()
+    with torch.cuda.device(x.device):
+        check(_cabi.lib().tclb200_warp_backward(_ptr(go), _ptr(x), _ptr(f), _ptr(gx), _ptr(gf), B, C, H, W, flags, _stream_handle()))
+    return gx, gf
 
 
 def _warp(x, f, flags):
@@ -266,7 +271,7 @@ def _index(idx, B, n_frames, name, validate=True):
 
 def fused_forward(bf, prev, cur, ff=None, mask=None, loss=L2, finalize=FIN_RMSE, flags=OCC | MOB,
                   want_warp=False, want_mask=False, want_blend=False, want_near=False, want_sums=True,
-                  prev_index=None, cur_index=None, validate_index=True):
+                  prev_index=None, cur_index=None, validate_index=True, bf_index=None, ff_index=None, pair_group=0):
     """One launch: warp ``prev`` by ``bf``, build or read the mask, reduce the masked error against ``cur``.
 
     ``ff`` given -> the mask is computed (fbcCheckTorch semantics, tests per ``flags``);
@@ -275,11 +280,20 @@ def fused_forward(bf, prev, cur, ff=None, mask=None, loss=L2, finalize=FIN_RMSE,
     Clip mode: with ``prev_index`` / ``cur_index`` (int tensors, one entry per pair) ``prev`` / ``cur`` are banks of
     frames (F,C,H,W) and pair b reads frame ``prev_index[b]`` / ``cur_index[b]`` -- a video stored once serves as
     ``cur`` of pair t and ``prev`` of pair t+1 (see ``temporal_error_clip``).
+
+    Window mode: with ``bf_index`` / ``ff_index`` the flows are banks of fields as well and pair b reads field
+    ``bf_index[b]`` / ``ff_index[b]`` (a field is the ``bf`` of one evaluation and the ``ff`` of the opposite one);
+    ``pair_group`` interleaves the tiles of that many consecutive pairs (see ``temporal_error_window``).
     """
-    _require_cuda(bf, prev, cur, ff, mask)
+    _require_cuda(bf, prev, cur, ff, mask, bf_index, ff_index)
     bf, bf_plane, bf_batch = _flow_view(bf, "bf")
-    B, _, H, W = bf.shape
+    _, _, H, W = bf.shape
+    B = bf.shape[0] if bf_index is None else int(bf_index.numel())
     ff, ff_plane, ff_batch = _flow_view(ff, "ff") if ff is not None else (None, 0, 0)
+    bf_index = _index(bf_index, B, bf.shape[0], "bf_index", validate_index)
+    ff_index = _index(ff_index, B, ff.shape[0], "ff_index", validate_index) if ff is not None else None
+    if ff is not None and ff_index is None and ff.shape[0] != B:
+        raise RuntimeError(f"tcl_b200: ff holds {ff.shape[0]} fields for {B} pairs (pass ff_index for a bank of fields)")
     if prev.dim() != 4 or (prev_index is None and prev.shape[0] != B) or prev.shape[2:] != bf.shape[2:]:
         raise RuntimeError(f"tcl_b200: prev {tuple(prev.shape)} does not match flow {tuple(bf.shape)}")
     if cur.dim() != 4 or cur.shape[1:] != prev.shape[1:] or cur.dtype != prev.dtype or (cur_index is None and cur.shape[0] != B):
@@ -330,6 +344,9 @@ def fused_forward(bf, prev, cur, ff=None, mask=None, loss=L2, finalize=FIN_RMSE,
         a.prev_index, a.cur_index = _ptr(prev_index), _ptr(cur_index)
         a.n_prev_frames, a.n_cur_frames = prev.shape[0], cur.shape[0]
         a.ff_plane_stride, a.ff_batch_stride, a.bf_plane_stride, a.bf_batch_stride = ff_plane, ff_batch, bf_plane, bf_batch
+        a.bf_index, a.ff_index = _ptr(bf_index), _ptr(ff_index)
+        a.n_bf_fields, a.n_ff_fields = bf.shape[0], (ff.shape[0] if ff is not None else 0)
+        a.pair_group = int(pair_group)
         check(_cabi.lib().tclb200_tcl_forward(ctypes.byref(a), _stream_handle()))
     return res
 
@@ -355,6 +372,52 @@ def temporal_error_clip(frames, ff, bf):
     idx = torch.arange(T, dtype=torch.int32, device=frames.device)
     return fused_forward(bf, frames, frames, ff=ff, finalize=FIN_RMSE, prev_index=idx[:-1], cur_index=idx[1:],
                          validate_index=False).pair_vals
+
+
+def window_evaluations(n_frames, window=4):
+    """Index arrays of every directed evaluation of a clip's temporal windows (BASELINE config 4; the long-term pairs of
+    utils/sintel_eval.py:84-86,216-222 generalised to both directions): for every target frame t and every source
+    s = t-1 .. t-(window-1), "warp s into t" and "warp t into s".
+
+    Flow bank layout the indices refer to: for j enumerating (t, d = t-s) with t ascending, d = 1 .. window-1, field 2j is
+    flow(t -> s) (sampled on t's grid: the ``bf`` of warping s into t) and field 2j+1 is flow(s -> t).  Returns a dict of
+    int32 CPU tensors ``prev_index, cur_index, bf_index, ff_index`` (one entry per evaluation), ``target`` / ``source`` /
+    ``field_t`` / ``field_s`` (frames of field pair j) and ``group`` = 2 * (window-1), the evaluations per complete window;
+    complete windows come first, so that ``pair_group=group`` keeps every target frame's evaluations together."""
+    fields, full, part = [], [], []
+    for t in range(1, n_frames):
+        evs = []
+        for d in range(1, window):
+            s_ = t - d
+            if s_ < 0:
+                break
+            j = len(fields)
+            fields.append((t, s_))
+            evs.append((s_, t, 2 * j, 2 * j + 1))       # warp s into t: prev = s, cur = t, bf = flow(t -> s), ff = flow(s -> t)
+            evs.append((t, s_, 2 * j + 1, 2 * j))       # warp t into s
+        (full if len(evs) == 2 * (window - 1) else part).extend(evs)
+    evs = full + part
+    col = lambda k: torch.tensor([e[k] for e in evs], dtype=torch.int32)
+    return {"prev_index": col(0), "cur_index": col(1), "bf_index": col(2), "ff_index": col(3),
+            "field_t": torch.tensor([f[0] for f in fields], dtype=torch.int32), "field_s": torch.tensor([f[1] for f in fields], dtype=torch.int32),
+            "group": 2 * (window - 1), "n_complete": len(full)}
+
+
+def temporal_error_window(frames, flow_bank, window=4, index=None, finalize=FIN_RMSE):
+    """Temporal error of every directed evaluation of a clip's temporal windows in ONE launch, everything stored once:
+    ``frames`` (T,C,H,W) fp32/bf16, ``flow_bank`` (2*J,2,H,W) in the layout of ``window_evaluations`` (``index`` = its
+    result, computed when omitted).  Each frame is the ``cur`` of up to window-1 evaluations and the ``prev`` of as many,
+    each flow field the ``bf`` of one and the ``ff`` of the opposite one; the tiles of a target frame's evaluations are
+    interleaved (``pair_group``), so the re-reads are L2 hits: 4 frames + 6 fields per complete window of 6 evaluations
+    instead of 12 frames + 12 fields.  Returns the per-evaluation values (E,) in the order of ``index``."""
+    _require_cuda(frames, flow_bank)
+    if index is None:
+        index = window_evaluations(frames.shape[0], window)
+    dev = frames.device
+    to = lambda k: index[k].to(dev)
+    res = fused_forward(flow_bank, frames, frames, ff=flow_bank, finalize=finalize, prev_index=to("prev_index"), cur_index=to("cur_index"),
+                        bf_index=to("bf_index"), ff_index=to("ff_index"), pair_group=index["group"])
+    return res.pair_vals
 
 
 _host_ws_cache = {}

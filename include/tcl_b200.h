@@ -136,6 +136,17 @@ typedef struct tclb200_tcl_args {
    * the /8-padded image cropped by InputPadder.unpad (utils/raft/raft/utils/utils.py:21-24) or flow_up[:,:,:H,:]
    * (methods/GAN-based/ConGAN/sintel_eval.py:61) is such a view -- it is read in place, no gather copy. */
   size_t ff_plane_stride, ff_batch_stride, bf_plane_stride, bf_batch_stride;
+  /* window mode (optional, NULL / 0 = off; ABI v5): `bf` / `ff` hold n_bf_fields / n_ff_fields flow fields and pair b reads
+   * field bf_index[b] / ff_index[b] (device int32 arrays of B entries).  The evaluations of a temporal window use every
+   * field twice -- flow(t -> s) is the `bf` of "warp frame s into t" and the `ff` of "warp frame t into s"
+   * (utils/sintel_eval.py:84-86,216-222: long-term pairs of a target frame; BASELINE config 4: 3 source frames x both
+   * directions) -- so with clip mode on top a window of 4 frames and 3 flow pairs is stored once and serves 6 evaluations.
+   * pair_group > 1 interleaves the tiles of that many consecutive pairs (the evaluations of one target frame), so that
+   * their shared `cur` tile, flow tiles and neighbouring source boxes are re-read within microseconds: L2 hits, not HBM. */
+  const int* bf_index;
+  const int* ff_index;
+  int n_bf_fields, n_ff_fields;
+  int pair_group;
 } tclb200_tcl_args;
 
 int tclb200_tcl_forward(const tclb200_tcl_args* args, tclb200_stream_t stream);
@@ -212,6 +223,24 @@ int tclb200_upsample_flow(const float* flow, const float* mask, float* out, int 
 int tclb200_cv2_remap(const float* src, const float* flow, float* out, int N, int H, int W, int C, tclb200_stream_t stream);
 int tclb200_cv2_fb_check(const float* ff, const float* bf, float* mask, int N, int H, int W, int flags, int prewarped,
                          unsigned long long* near_threshold, tclb200_stream_t stream);
+
+/* Warp chains of the learning-based trainers ("next" row of the scope table, rank 2), fp32 NCHW, C = 3, device pointers.
+ *   tclb200_reconet_loss   ReCoNet's output-level temporal loss, methods/learning-based/fs_reconet.py:63-69:
+ *                            mean((mask * ((styled2 - warp(styled1,flow)) - luminance(img2 - warp(img1,flow))))**2)
+ *                          with warp = fs_lib.warp (fs_lib.py:5-39); the two warps share the sampling position, weights and
+ *                          validity factor of the pixel.  mask (B,1,H,W) or NULL (= ones).  Outputs: loss_out [1] fp32 (the
+ *                          mean) and / or sum_out [1] fp64 (the sum of squares); lum_out (B,1,H,W) or NULL receives the
+ *                          luminance term (the backward is tclb200_tcl_backward with cur = styled2 - lum, TCLB200_VALIDITY).
+ *                          scratch: device memory >= tclb200_reconet_scratch_bytes(B,H,W), contents irrelevant.
+ *   tclb200_ruder_input    one step of Ruder's recurrent chain, fs_ruder.py:50-75: cat_out (B,7,H,W) =
+ *                          cat((img, mask, warp(styled_prev, flow)), 1) in one pass; warp_out (B,3,H,W) or NULL also receives
+ *                          the warped frame (`loss_warped`, fs_ruder.py:97).  mask NULL = ones.                      (ABI v5) */
+size_t tclb200_reconet_scratch_bytes(int B, int H, int W);
+int tclb200_reconet_loss(const float* flow, const float* mask, const float* styled1, const float* styled2, const float* img1,
+                         const float* img2, float* lum_out, float* loss_out, double* sum_out, void* scratch, size_t scratch_bytes,
+                         int B, int H, int W, tclb200_stream_t stream);
+int tclb200_ruder_input(const float* img, const float* mask, const float* styled_prev, const float* flow, float* cat_out,
+                        float* warp_out, int B, int H, int W, tclb200_stream_t stream);
 
 /* Aggregation of the evaluation loop (per-video mean of the per-pair RMSE, StarGANv2AdvCon/core/solver.py:352-354; mean over
  * videos, utils/sintel_eval.py:112-126) around the one all-reduce of the sharded evaluation.  All pointers are device pointers.

@@ -25,6 +25,8 @@ Reference lines followed (paths relative to the upstream repository root):
 * ``tcl_l2``             -> ``methods/GAN-based/StarGANv2AdvCon/core/solver.py:444``
 * ``tcl_l1``             -> ``methods/GAN-based/MoGAN/models/cycle_gan_model.py:280-281``
 * ``blend``              -> ``methods/optimization-based/obst_eval.py:500``
+* ``reconet_output_loss``-> ``methods/learning-based/fs_reconet.py:63-69``  (``o_temporal_loss`` / ``gamma_o``)
+* ``ruder_input``        -> ``methods/learning-based/fs_ruder.py:47-50``    (``warp`` + ``torch.cat`` of one chain step)
 """
 import torch
 import torch.nn.functional as F
@@ -134,6 +136,20 @@ def tcl_l1(mask, cur, warped):
 
 def blend(mask, warped, img):
     return mask * warped + (1 - mask) * img
+
+
+def reconet_output_loss(mask, styled2, styled1, img2, img1, flow):
+    """ReCoNet's output-level temporal loss without its weight (fs_reconet.py:63-69); ``warp`` there is fs_lib.warp."""
+    output_term = styled2 - validity_warp(styled1, flow)
+    input_term = img2 - validity_warp(img1, flow)
+    input_term = (0.2126 * input_term[:, 0, :, :] + 0.7152 * input_term[:, 1, :, :] + 0.0722 * input_term[:, 2, :, :]).unsqueeze(1)
+    return ((mask * (output_term - input_term)) ** 2).mean()
+
+
+def ruder_input(img, mask, styled_prev, flow):
+    """One step of Ruder's chain (fs_ruder.py:47-50): the network input and the warped frame."""
+    warped = validity_warp(styled_prev, flow)
+    return torch.cat((img, mask, warped), 1), warped
 
 
 def temporal_error(ff, bf, prev, cur):

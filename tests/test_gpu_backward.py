@@ -88,3 +88,51 @@ def test_congan_soft_mask_and_scalar_masked_l1(tcl):
     torch.exp(-50 * torch.abs(c_ref - tp.backward_warp(prev, bf)).mean()).backward()
     got.backward()
     assert float((c.grad - c_ref.grad).abs().max()) <= 1e-5 * float(c_ref.grad.abs().max())
+
+
+# ------------------------------------------------------------------ warp chains of the learning-based trainers
+@pytest.mark.gpu
+@pytest.mark.parametrize("B,H,W,shift", [(2, 64, 96, 5.0), (1, 37, 53, 30.0), (4, 256, 256, 12.0)])
+def test_reconet_output_temporal_loss_matches_the_reference_expression(tcl, B, H, W, shift):
+    """fs_reconet.py:63-69 in one fused pass: value within 1e-5 relative, gradients to both stylised frames within 1e-5 of
+    autograd through the reference's op sequence (oracle/torch_port.py on the same GPU)."""
+    d = torch.device("cuda")
+    ff, bf, s1, s2 = _inputs(tcl, B, H, W, 21, shift)
+    i1, i2 = (t.to(d) for t in tcl.synth.make_frames(B, 3, H, W, seed=22, kind="smooth"))
+    mask = tcl.fbcCheckTorch(ff, bf)
+    a1, a2 = s1.clone().requires_grad_(True), s2.clone().requires_grad_(True)
+    want = tp.reconet_output_loss(mask, a2, a1, i2, i1, bf)
+    gw1, gw2 = torch.autograd.grad(want * 100.0, (a1, a2))
+    b1, b2 = s1.clone().requires_grad_(True), s2.clone().requires_grad_(True)
+    got = tcl.reconet_output_temporal_loss(mask, b2, b1, i2, i1, bf)
+    assert got.dim() == 0 and abs(float(got) - float(want)) <= 1e-5 * abs(float(want))
+    gg1, gg2 = torch.autograd.grad(got * 100.0, (b1, b2))
+    scale = float(gw2.abs().max())
+    assert float((gg2 - gw2).abs().max()) <= 1e-5 * max(scale, 1e-12)
+    assert float((gg1 - gw1).abs().max()) <= 1e-5 * max(float(gw1.abs().max()), scale, 1e-12)
+    # no mask = a mask of ones
+    ones = torch.ones_like(mask)
+    want1 = float(tp.reconet_output_loss(ones, s2, s1, i2, i1, bf))
+    assert abs(float(tcl.reconet_output_temporal_loss(None, s2, s1, i2, i1, bf)) - want1) <= 1e-5 * want1
+    with pytest.raises(RuntimeError):
+        tcl.reconet_output_temporal_loss(mask, b2, b1, i2, i1, bf.clone().requires_grad_(True))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("B,H,W,shift", [(2, 64, 96, 5.0), (1, 37, 53, 30.0)])
+def test_ruder_network_input_is_warp_plus_cat(tcl, B, H, W, shift):
+    """fs_ruder.py:47-50: cat((img, mask, warp(styled_prev, flow)), 1) bit for bit, the warped frame as well, and the gradient
+    the chain sends back to the previous stylised frame through both uses of the warp."""
+    d = torch.device("cuda")
+    ff, bf, sp, img = _inputs(tcl, B, H, W, 33, shift)
+    mask = tcl.fbcCheckTorch(ff, bf)
+    want_cat, want_w = tp.ruder_input(img, mask, sp, bf)
+    cat, warped = tcl.ruder_network_input(img, mask, sp, bf)
+    assert cat.shape == (B, 7, H, W) and torch.equal(cat, want_cat) and torch.equal(warped, want_w)
+    a, b = sp.clone().requires_grad_(True), sp.clone().requires_grad_(True)
+    wc, ww = tp.ruder_input(img, mask, a, bf)
+    gc, gw = tcl.ruder_network_input(img, mask, b, bf)
+    w1 = torch.randn_like(wc)
+    ga = torch.autograd.grad((wc * w1).sum() + 0.5 * ((mask * (ww - img)) ** 2).mean(), a)[0]
+    gb = torch.autograd.grad((gc * w1).sum() + 0.5 * ((mask * (gw - img)) ** 2).mean(), b)[0]
+    assert float((ga - gb).abs().max()) <= 1e-5 * max(float(ga.abs().max()), 1e-12)

@@ -712,6 +712,35 @@ def test_host_entry_frame_ring_equals_resident_bank(tcl, pairs_kind):
     assert e.shape == (0,) and es.shape == (0,)
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("dtype,H,W", [(torch.float32, 96, 128), (torch.bfloat16, 128, 192), (torch.float32, 436, 1024)])
+def test_window_mode_equals_independent_pairs(tcl, dtype, H, W):
+    """BASELINE config 4 (per target frame a 4-frame window, both directions): frames and flow fields stored once, every
+    evaluation reaches them through index arrays, the tiles of a target's six evaluations interleaved -- one launch, the
+    bits of the same evaluations run as independent pairs on materialised tensors, and the oracle's value for two of them."""
+    d = dev()
+    T, window = 7, 4
+    idx = tcl.window_evaluations(T, window)
+    J = idx["field_t"].numel()
+    assert J == 15 and idx["prev_index"].numel() == 30 and idx["n_complete"] == 24 and idx["group"] == 6
+    ff, bf = tcl.synth.make_flows(J, H, W, seed=91, max_shift=8.0, device=d)
+    bank = torch.stack([bf, ff], dim=1).reshape(2 * J, 2, H, W).contiguous()      # field 2j = flow(t -> s), 2j+1 = flow(s -> t)
+    frames, _ = tcl.synth.make_frames(T, 3, H, W, seed=92, kind="white", device=d, dtype=dtype)
+    got = tcl.temporal_error_window(frames, bank, window, idx)
+    li = lambda k: idx[k].long().to(d)
+    want = tcl.temporal_error_per_pair(bank[li("ff_index")].contiguous(), bank[li("bf_index")].contiguous(),
+                                       frames[li("prev_index")].contiguous(), frames[li("cur_index")].contiguous())
+    assert got.shape == (30,) and torch.equal(got, want)
+    for e in (0, 1, 29):     # "warp s into t", "warp t into s", an evaluation of an incomplete window
+        o = tp.temporal_error(bank[li("ff_index")[e:e + 1]], bank[li("bf_index")[e:e + 1]], frames[li("prev_index")[e:e + 1]].float(),
+                              frames[li("cur_index")[e:e + 1]].float())
+        assert abs(float(got[e]) - float(o)) <= LOSS_RTOL * float(o)
+    # without the interleaved schedule: same bits
+    res = tcl.fused_forward(bank, frames, frames, ff=bank, prev_index=li("prev_index").int(), cur_index=li("cur_index").int(),
+                            bf_index=li("bf_index").int(), ff_index=li("ff_index").int())
+    assert torch.equal(res.pair_vals, want)
+
+
 def test_temporal_loss_refuses_gradients_it_does_not_compute(tcl):
     d = dev()
     ff, bf, prev, cur = (t.to(d) for t in case(tcl, 2, 32, 48, seed=5, max_shift=4.0))

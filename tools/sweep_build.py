@@ -33,7 +33,7 @@ VARIANTS = {
     "trace": {"TCL_TRACE": 1, "TCL_HOT_ONLY": 1},
 }
 # the rest of the library (host entry, cv2 flavour, aggregation) is linked in from the regular build's objects
-OTHER_OBJS = [os.path.join(CSRC, o) for o in ("tcl_host.o", "tcl_cv2.o", "tcl_agg.o")]
+OTHER_OBJS = [os.path.join(CSRC, o) for o in ("tcl_host.o", "tcl_cv2.o", "tcl_agg.o", "tcl_chain.o")]
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     names = sys.argv[1:] or list(VARIANTS)
