@@ -347,6 +347,50 @@ def strong_scaling_leg(tcl, args, dist, device, rank, world, pairs_in_seq, seed,
     return res
 
 
+def band_split_leg(tcl, args, dist, device, rank, world, seed, steps):
+    """Fewer pairs than GPUs (BASELINE config 5: one 4K pair on eight GPUs): the same pair on every rank, one
+    horizontal band of target rows each, the bands' sums added by the path's one all-reduce (sharding.evaluate_banded)."""
+    cfg = tcl.synth.CONFIGS[args.workload]
+    H, W, C = cfg["H"], cfg["W"], cfg["C"]
+    d = make_shard(tcl, args.workload, 1, seed, device, args.frames, chunk=1)
+    out = {}
+
+    def step():
+        out["r"] = tcl.evaluate_banded(d["ff"], d["bf"], d["prev"], d["cur"])
+    for _ in range(10):
+        step()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(20):
+        step()
+    torch.cuda.synchronize()
+    t = torch.tensor([(time.perf_counter() - t0) / 20 * 1e3], device=device, dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    pre = int(1000.0 / max(float(t[0]), 1e-3)) + 1
+    for _ in range(pre):
+        step()
+    torch.cuda.synchronize()
+    dist.barrier()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(steps):
+        step()
+    b.record()
+    torch.cuda.synchronize()
+    dist.barrier()
+    t = torch.tensor([a.elapsed_time(b) / steps], device=device, dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t[0])
+    whole = tcl.fused_forward(d["bf"], d["prev"], d["cur"], ff=d["ff"])
+    _, per = time_kernel(lambda: tcl.fused_forward(d["bf"], d["prev"], d["cur"], ff=d["ff"]), 20, 5)
+    rel = abs(float(out["r"]["pair_sums"][0]) - float(whole.pair_sums[0])) / float(whole.pair_sums[0])
+    return dict(pairs=1, shape=f"{W}x{H}", bands=[list(tcl.band_rows(H, world, q)) for q in range(world)], ms_per_evaluation=ms,
+                gpix_per_s=H * W / ms / 1e6, single_gpu_ms_per_evaluation=sorted(per)[len(per) // 2],
+                rmse=float(out["r"]["pair_rmse"][0]), single_gpu_rmse=float(whole.pair_vals[0]), sum_rel_diff_vs_single_gpu=rel,
+                note="eager calls: one banded launch + fold + one all-reduce of the pair's fp64 sum per evaluation, max over ranks")
+
+
 def h2d_ceiling(device, src, dist=None, reps=3):
     """Concurrent pinned-host -> device copy rate of this box, measured in the same run: every rank copies up to 2 GiB of its
     pinned staging buffer with ONE cudaMemcpyAsync at the same time (barrier-aligned); GB/s of this rank, best of `reps`."""
@@ -743,6 +787,11 @@ def main():
                 line["strong_scaling"] = strong_scaling_leg(tcl, args, dist, device, rank, world, pairs_in_seq, GLOBAL_SEED, max(args.steps, 20))
             except Exception as ex:
                 line["strong_scaling"] = {"error": repr(ex)}
+        if world > 1 and args.workload == "uhd4k_stress":
+            try:
+                line["band_split"] = band_split_leg(tcl, args, dist, device, rank, world, GLOBAL_SEED, max(args.steps, 20))
+            except Exception as ex:
+                line["band_split"] = {"error": repr(ex)}
         if world == 1:
             try:
                 line["cuda_eager_baseline"] = cuda_eager_rate(tcl, args.workload, args.frames, device)

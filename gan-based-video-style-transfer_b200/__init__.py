@@ -10,7 +10,7 @@ from .ops import (FusedResult, free_workspaces, generateMask, fbcCheckTorch, fbc
                   fused_forward, gradient, temporal_error, temporal_error_clip, temporal_error_host, temporal_error_per_pair, temporal_loss,
                   temporal_rmse_per_sample, upsample_flow, warp, warp_blend, window_evaluations, temporal_error_window)
 from .sintel_eval import (aggregate_means, computeTCL, computeTCL_from_flows, save_dict_as_json)  # noqa: F401
-from .sharding import (ShardPlan, plan_shards, evaluate_sharded, evaluate_sharded_host, allreduce_sums)  # noqa: F401
+from .sharding import (ShardPlan, plan_shards, evaluate_sharded, evaluate_sharded_host, evaluate_banded, band_rows, allreduce_sums)  # noqa: F401
 from .chains import reconet_output_temporal_loss, ruder_network_input  # noqa: F401
 from . import synth  # noqa: F401
 from . import ingest  # noqa: F401

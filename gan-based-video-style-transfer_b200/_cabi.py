@@ -44,6 +44,7 @@ class TclArgs(ctypes.Structure):
         ("bf_plane_stride", ctypes.c_size_t), ("bf_batch_stride", ctypes.c_size_t),
         ("bf_index", ctypes.c_void_p), ("ff_index", ctypes.c_void_p),
         ("n_bf_fields", ctypes.c_int), ("n_ff_fields", ctypes.c_int), ("pair_group", ctypes.c_int),
+        ("row_begin", ctypes.c_int), ("row_end", ctypes.c_int),
     ]
 
 

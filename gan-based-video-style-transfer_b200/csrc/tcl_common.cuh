@@ -81,6 +81,7 @@ struct FwdParams {
   const int* bf_index;     // flow field each pair reads as `bf` / `ff` (nullptr: its own)
   const int* ff_index;
   int pair_group;          // > 1: tiles of this many consecutive pairs are interleaved (window evaluations)
+  int row_begin, row_end;  // rows of every pair this launch covers ([0, H) unless the frame is split into bands over several GPUs)
   void* warp_out;
   float* mask_out;
   void* blend_out;

@@ -209,11 +209,11 @@ __global__ void __launch_bounds__(kThreads) fused_forward_generic_kernel(const F
   const int pair = blockIdx.x / p.tiles_per_pair;
   const int tile = blockIdx.x - pair * p.tiles_per_pair;
   const int ty = tile / p.tiles_x, tx = tile - ty * p.tiles_x;
-  const int x = tx * 32 + lane, y = ty * kWarps + wrp;
+  const int x = tx * 32 + lane, y = p.row_begin + ty * kWarps + wrp;   // (band mode: rows [row_begin, row_end) only)
   const int C = CT > 0 ? CT : p.C;
   float err = 0.0f;
   unsigned near = 0;
-  if (x < W && y < H) {
+  if (x < W && y < p.row_end) {
     const size_t o = (size_t)y * W + x;
     const float* bu = p.bf + (size_t)bf_field(p, pair) * p.bf_batch;
     const float* bv = bu + p.bf_plane;
@@ -332,7 +332,7 @@ __device__ __forceinline__ float fmax_nan(float a, float b) { float r; asm("max.
 // inside the image -> box[4].  Non-finite flow propagates (min/max.NaN; a NaN wins the min or the max of the ordered
 // encoding, depending on its sign) and is rejected by the placement.  One LDS.128 per component and four pixels.
 template <typename Cfg>
-__device__ __forceinline__ void scan_flow_tile(const float* s_bu, const TileId& t, const Geo& g, int* box, int lane) {
+__device__ __forceinline__ void scan_flow_tile(const float* s_bu, const TileId& t, const Geo& g, int row_end, int* box, int lane) {
   const float* s_bv = s_bu + Cfg::kBfH * Cfg::kBfW;
   const int c4 = 4 * (lane & 15), rh = lane >> 4;
   // W % 4 == 0: a lane's four columns are all inside the image or all outside
@@ -340,7 +340,7 @@ __device__ __forceinline__ void scan_flow_tile(const float* s_bu, const TileId& 
   const float xf = (float)(t.x0 + c4);
   const float inf = __int_as_float(0x7f800000);
   float xmin = inf, ymin = inf, xmax = -inf, ymax = -inf;
-  const int rows = min(Cfg::TH, g.H - t.y0);
+  const int rows = min(Cfg::TH, row_end - t.y0);
   if (colok) {
 #pragma unroll 4
     for (int r = rh; r < rows; r += 2) {
@@ -440,13 +440,13 @@ __device__ __forceinline__ TileId tile_id(const FwdParams& p, int tg, int TW, in
     t.tile = tg - t.pair * p.tiles_per_pair;
   }
   const int ty = t.tile / p.tiles_x, tx = t.tile - ty * p.tiles_x;
-  t.x0 = tx * TW; t.y0 = ty * TH;
+  t.x0 = tx * TW; t.y0 = p.row_begin + ty * TH;
   t.pf = prev_frame(p, t.pair); t.cf = cur_frame(p, t.pair);
   t.bfi = bf_field(p, t.pair); t.ffi = ff_field(p, t.pair);
   return t;
 }
 template <typename Cfg>
-__device__ __forceinline__ bool tile_edge(const TileId& t, const Geo& g) { return (t.x0 + Cfg::TW > g.W) || (t.y0 + Cfg::TH > g.H); }
+__device__ __forceinline__ bool tile_edge(const TileId& t, const Geo& g, int row_end) { return (t.x0 + Cfg::TW > g.W) || (t.y0 + Cfg::TH > row_end); }
 
 // ---- consumer: exact per-pixel path (all features; staged boxes, global gathers, or both in a mixed tile) -------
 template <typename FrameT, int MASK, bool REDUCE, int CT, int LEAN, typename Cfg, bool EDGE>
@@ -470,7 +470,7 @@ __device__ __forceinline__ float full_tile(const FwdParams& p, const float* s_bu
   for (int k = 0; k < Cfg::kPPL; ++k) {   // fully unrolled: cur[k] / mk[k] must stay in registers
     const int lx = lx0, ly = ly0 + pix_dy(k);
     const int x = t.x0 + lx, y = t.y0 + ly;
-    if (EDGE && (x >= W || y >= H)) continue;
+    if (EDGE && (x >= W || y >= p.row_end)) continue;
     const int c = (ly + 1) * Cfg::kBfW + lx + Cfg::kHaloL;
     const float u = s_bu[c], v = s_bv[c];
     float nb, keep = 1.0f;
@@ -663,7 +663,7 @@ __device__ __forceinline__ float lean_tile(const FwdParams& p, const float* s_bu
 #pragma unroll
     for (int j = 0; j < P; ++j) {
       const int k = j, dyk = 2 * j;
-      const bool inside = !EDGE || (xin && t.y0 + ly0 + dyk < g.H);
+      const bool inside = !EDGE || (xin && t.y0 + ly0 + dyk < p.row_end);
       const float u = uc[2 * j + 1], v = vc[2 * j + 1];
       const float s0 = __fmaf_rn(u, u, __fmul_rn(v, v));
       bool keep = inside, amb = false;
@@ -816,7 +816,7 @@ __device__ __forceinline__ float lean_tile(const FwdParams& p, const float* s_bu
     float* mo = (MASK == MASK_COMPUTED && p.mask_out) ? p.mask_out + (size_t)t.pair * gplane + pix0 : nullptr;
 #pragma unroll
     for (int k = 0; k < P; ++k) {
-      const bool inside = !EDGE || (xin && t.y0 + ly0 + pix_dy(k) < g.H);
+      const bool inside = !EDGE || (xin && t.y0 + ly0 + pix_dy(k) < p.row_end);
       if (!inside) continue;
       const ptrdiff_t off = (ptrdiff_t)pix_dy(k) * g.W;
       const float keepf = MASK == MASK_GIVEN ? mk[k] : (((keepbits >> k) & 1u) ? 1.0f : 0.0f);
@@ -833,7 +833,7 @@ __device__ __forceinline__ float lean_tile(const FwdParams& p, const float* s_bu
     float* mo = p.mask_out + (size_t)t.pair * gplane + (size_t)(t.y0 + ly0) * g.W + (t.x0 + lx0);
 #pragma unroll
     for (int k = 0; k < P; ++k) {
-      const bool inside = !EDGE || (xin && t.y0 + ly0 + pix_dy(k) < g.H);
+      const bool inside = !EDGE || (xin && t.y0 + ly0 + pix_dy(k) < p.row_end);
       if (inside) __stcs(mo + (ptrdiff_t)pix_dy(k) * g.W, ((keepbits >> k) & 1u) ? 1.0f : 0.0f);
     }
     return 0.0f;
@@ -897,7 +897,7 @@ __device__ __forceinline__ float lean_tile_packed(const FwdParams& p, const floa
   const GlobalSrc<float> fg{(MIXED && MASK == MASK_COMPUTED) ? p.ff + (size_t)t.ffi * p.ff_batch : nullptr, p.ff_plane, g};
   const GlobalSrc<FrameT> pg{MIXED ? reinterpret_cast<const FrameT*>(p.prev) + (size_t)t.pf * 3 * gplane : nullptr, gplane, g};
   const bool xin = !EDGE || t.x0 + lx0 < g.W;
-  const int rows_in = EDGE ? g.H - (t.y0 + ly0) : INT_MAX;   // pixel k is inside the image iff 2 * k < rows_in (and xin)
+  const int rows_in = EDGE ? p.row_end - (t.y0 + ly0) : INT_MAX;   // pixel k is inside the image iff 2 * k < rows_in (and xin)
   const float bx_hi = box_xf + (float)(BW - 2), by_hi = box_yf + (float)(Cfg::BH - 2);   // top-left taps inside the boxes: [box, box + size - 2]
   // byte address of a pixel's top-left tap, in floating point (see lean_tile)
   const uint32_t ff_base = smem_u32(s_ff), prev_base = smem_u32(s_prev);
@@ -1238,7 +1238,7 @@ __global__ void __launch_bounds__(Cfg::kThreads, 1) fused_forward_ws_kernel(cons
       const int sb = k % NB;
       mbar_wait_idle(&ctl->bf_full[sb], (k / NB) & 1);
       if (ctl->tinfo[sb].pair < 0) return;
-      scan_flow_tile<Cfg>(bf_stage(sb), ctl->tinfo[sb], g, ctl->box[sb], lane);
+      scan_flow_tile<Cfg>(bf_stage(sb), ctl->tinfo[sb], g, p.row_end, ctl->box[sb], lane);
       __syncwarp();
       if (lane == 0) mbar_arrive(&ctl->scanned[sb]);
     }
@@ -1260,9 +1260,11 @@ __global__ void __launch_bounds__(Cfg::kThreads, 1) fused_forward_ws_kernel(cons
     float err = 0.0f;
     const int sb = k % NB, ss = k % NS;   // stage indices of this tile
     mbar_wait_s(bf_full_s + 8u * sb, (k / NB) & 1);
-    const TileId t = ctl->tinfo[sb];
+    // (a reference into shared memory, not a register copy: the fields only the rare paths need -- pf, bfi, ffi -- are read
+    // there; the slot is rewritten only after this warp has arrived on done[] for the tile)
+    const TileId& t = ctl->tinfo[sb];
     if (t.pair < 0) break;
-    const bool t_edge = tile_edge<Cfg>(t, g);
+    const bool t_edge = tile_edge<Cfg>(t, g, p.row_end);
     // this tile's `cur` (and dataset mask) values: coalesced 64-byte row segments, streaming; requested before the wait
     // for the source boxes and first used at the very end of the per-pixel work
     float cur[P][Cfg::kC], mk[P];
@@ -1292,7 +1294,7 @@ __global__ void __launch_bounds__(Cfg::kThreads, 1) fused_forward_ws_kernel(cons
       } else {
 #pragma unroll
         for (int i = 0; i < P; ++i) {
-          const bool inside = t.x0 + lx0 < g.W && t.y0 + ly0 + pix_dy(i) < g.H;
+          const bool inside = t.x0 + lx0 < g.W && t.y0 + ly0 + pix_dy(i) < p.row_end;
           const ptrdiff_t off = (ptrdiff_t)pix_dy(i) * g.W;
 #pragma unroll
           for (int c = 0; c < Cfg::kC; ++c) cur[i][c] = (have_cur && inside) ? ld_stream(cb + off + (size_t)c * plane) : 0.0f;
@@ -1869,6 +1871,10 @@ static int run_fused(const tclb200_tcl_args* a, cudaStream_t s) {
   if ((a->bf_index && a->n_bf_fields <= 0) || (a->ff && a->ff_index && a->n_ff_fields <= 0))
     return fail(TCLB200_ERR_INVALID, "bf_index / ff_index need n_bf_fields / n_ff_fields");
   if (a->pair_group < 0) return fail(TCLB200_ERR_INVALID, "pair_group must not be negative");
+  const bool band = a->row_begin != 0 || a->row_end != 0;
+  if (band && (a->row_begin < 0 || a->row_end <= a->row_begin || a->row_end > a->H))
+    return fail(TCLB200_ERR_INVALID, "band mode needs 0 <= row_begin < row_end <= H");
+  if (band && (a->pair_vals || a->total_val)) return fail(TCLB200_ERR_INVALID, "band mode returns sums only (pair_sums / total_sums): a band's mean is not the frame's");
   if ((size_t)a->H * a->W >= (1u << 30)) return fail(TCLB200_ERR_UNSUPPORTED, "H*W must be below 2^30");
   const bool reduce = a->cur && (a->pair_sums || a->total_sums || a->pair_vals || a->total_val);
   const int mask_kind = a->ff ? MASK_COMPUTED : (a->mask_in ? MASK_GIVEN : MASK_NONE);
@@ -1912,8 +1918,10 @@ static int run_fused(const tclb200_tcl_args* a, cudaStream_t s) {
   p.near_threshold = a->near_threshold;
   p.geo = make_geo(a->H, a->W);
   p.B = a->B; p.C = a->prev ? a->C : 0;
+  p.row_begin = band ? a->row_begin : 0;
+  p.row_end = band ? a->row_end : a->H;
   p.tiles_x = tma ? cdiv(a->W, kTW) : cdiv(a->W, 32);
-  p.tiles_per_pair = p.tiles_x * (tma ? cdiv(a->H, kTH) : cdiv(a->H, kWarps));
+  p.tiles_per_pair = p.tiles_x * (tma ? cdiv(p.row_end - p.row_begin, kTH) : cdiv(p.row_end - p.row_begin, kWarps));
   p.flags = a->flags; p.loss = a->loss; p.finalize = a->finalize;
   p.inv_count = a->prev ? 1.0 / ((double)a->C * a->H * a->W) : 0.0;
   if ((size_t)p.B * p.tiles_per_pair >= 0x7fffffffu) return fail(TCLB200_ERR_UNSUPPORTED, "too many tiles for one launch");

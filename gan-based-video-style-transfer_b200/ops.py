@@ -271,7 +271,7 @@ def _index(idx, B, n_frames, name, validate=True):
 
 def fused_forward(bf, prev, cur, ff=None, mask=None, loss=L2, finalize=FIN_RMSE, flags=OCC | MOB,
                   want_warp=False, want_mask=False, want_blend=False, want_near=False, want_sums=True,
-                  prev_index=None, cur_index=None, validate_index=True, bf_index=None, ff_index=None, pair_group=0):
+                  prev_index=None, cur_index=None, validate_index=True, bf_index=None, ff_index=None, pair_group=0, rows=None):
     """One launch: warp ``prev`` by ``bf``, build or read the mask, reduce the masked error against ``cur``.
 
     ``ff`` given -> the mask is computed (fbcCheckTorch semantics, tests per ``flags``);
@@ -284,6 +284,9 @@ def fused_forward(bf, prev, cur, ff=None, mask=None, loss=L2, finalize=FIN_RMSE,
     Window mode: with ``bf_index`` / ``ff_index`` the flows are banks of fields as well and pair b reads field
     ``bf_index[b]`` / ``ff_index[b]`` (a field is the ``bf`` of one evaluation and the ``ff`` of the opposite one);
     ``pair_group`` interleaves the tiles of that many consecutive pairs (see ``temporal_error_window``).
+
+    Band mode: ``rows=(r0, r1)`` evaluates target rows [r0, r1) of every pair only (inputs stay whole frames); the result
+    carries ``pair_sums`` / ``total_sums`` but no means (see ``sharding.evaluate_banded``).
     """
     _require_cuda(bf, prev, cur, ff, mask, bf_index, ff_index)
     bf, bf_plane, bf_batch = _flow_view(bf, "bf")
@@ -316,11 +319,16 @@ def fused_forward(bf, prev, cur, ff=None, mask=None, loss=L2, finalize=FIN_RMSE,
     else:
         mask = None
     res = FusedResult()
+    if rows is not None:
+        r0, r1 = int(rows[0]), int(rows[1])
+        if not (0 <= r0 < r1 <= H):
+            raise RuntimeError(f"tcl_b200: rows must satisfy 0 <= r0 < r1 <= H = {H}, got {rows}")
     if want_sums:
-        f32 = torch.empty(B + 1, dtype=torch.float32, device=dev)
         f64 = torch.empty(B + 2, dtype=torch.float64, device=dev)
-        res.pair_vals, res.total_val = f32[:B], f32[B]
         res.pair_sums, res.total_sums = f64[:B], f64[B:]
+        if rows is None:
+            f32 = torch.empty(B + 1, dtype=torch.float32, device=dev)
+            res.pair_vals, res.total_val = f32[:B], f32[B]
     if want_warp:
         res.warp = torch.empty_like(prev) if out_like is None else torch.empty_like(out_like)
     if want_mask:
@@ -347,6 +355,8 @@ def fused_forward(bf, prev, cur, ff=None, mask=None, loss=L2, finalize=FIN_RMSE,
         a.bf_index, a.ff_index = _ptr(bf_index), _ptr(ff_index)
         a.n_bf_fields, a.n_ff_fields = bf.shape[0], (ff.shape[0] if ff is not None else 0)
         a.pair_group = int(pair_group)
+        if rows is not None:
+            a.row_begin, a.row_end = r0, r1
         check(_cabi.lib().tclb200_tcl_forward(ctypes.byref(a), _stream_handle()))
     return res
 
@@ -429,6 +439,7 @@ def free_workspaces():
     long clip.  The caches are plain dicts: like the reference's loops, the wrappers assume one Python thread per device."""
     _scratch_cache.clear()
     _host_ws_cache.clear()
+    _loss_plans.clear()
 
 
 def _host_tensor(t, name, dtype=None):
@@ -531,6 +542,61 @@ def warp_blend(mask, prev, flow, img):
     return fused_forward(flow, prev, img, mask=mask, want_blend=True, want_sums=False).blend
 
 
+# The training loss is a ~30 us job called every iteration (solver.py:427-446, twice per step): its wrapper avoids every
+# avoidable Python / dispatcher cost -- one argument struct per (device, stream) filled in place, the scratch looked up once,
+# a single 4-byte result tensor, no device-context switch when the tensors' device is already current, one scalar op in backward.
+_loss_plans = {}
+
+
+class _LossPlan:
+    __slots__ = ("args", "scratch", "scratch_bytes", "stream", "lib", "fwd", "bwd")
+
+    def __init__(self, device, stream_handle):
+        self.args = TclArgs()
+        self.stream = ctypes.c_void_p(stream_handle)
+        self.lib = _cabi.lib()
+        self.fwd, self.bwd = self.lib.tclb200_tcl_forward, self.lib.tclb200_tcl_backward
+        self.scratch, self.scratch_bytes = None, 0
+
+
+def _loss_plan(device, B, H, W):
+    handle = torch.cuda.current_stream(device).cuda_stream
+    key = (device.index, handle)
+    plan = _loss_plans.get(key)
+    if plan is None:
+        plan = _loss_plans[key] = _LossPlan(device, handle)
+    need = plan.lib.tclb200_scratch_bytes(B, H, W)
+    if plan.scratch is None or plan.scratch_bytes < need:
+        plan.scratch = _scratch(B, H, W, device)
+        plan.scratch_bytes = plan.scratch.numel()
+        plan.args.scratch, plan.args.scratch_bytes = plan.scratch.data_ptr(), plan.scratch_bytes
+    return plan
+
+
+def _loss_forward(prev, cur, flow, mask, loss, flags):
+    """mean masked error of the training loss: one launch pair, total only (no per-pair outputs)."""
+    B, C, H, W = prev.shape
+    dev = prev.device
+    out = torch.empty((), dtype=torch.float32, device=dev)
+    switch = torch.cuda.current_device() != dev.index
+    if switch:
+        ctx = torch.cuda.device(dev)
+        ctx.__enter__()
+    try:
+        plan = _loss_plan(dev, B, H, W)
+        a = plan.args
+        a.bf, a.mask_in, a.prev, a.cur, a.total_val = flow.data_ptr(), mask.data_ptr(), prev.data_ptr(), cur.data_ptr(), out.data_ptr()
+        a.B, a.C, a.H, a.W = B, C, H, W
+        a.dtype, a.flags, a.loss, a.finalize = (F32 if prev.dtype == torch.float32 else BF16), flags, loss, FIN_MEAN
+        rc = plan.fwd(ctypes.byref(a), plan.stream)
+        if rc != 0:
+            check(rc)
+    finally:
+        if switch:
+            ctx.__exit__(None, None, None)
+    return out
+
+
 class _TemporalLossFn(torch.autograd.Function):
     """Gradients to ``prev`` and ``cur`` only (what the reference's trainers use: the flow and the mask come from the data
     set or from a frozen flow network under no_grad).  ``temporal_loss`` refuses flows / masks that require grad instead of
@@ -538,10 +604,9 @@ class _TemporalLossFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, prev, cur, flow, mask, loss, flags):
-        res = fused_forward(flow, prev, cur, mask=mask, loss=loss, finalize=FIN_MEAN, flags=flags)
         ctx.save_for_backward(prev, cur, flow, mask)
         ctx.loss, ctx.flags = loss, flags
-        return res.total_val.clone()
+        return _loss_forward(prev, cur, flow, mask, loss, flags)
 
     @staticmethod
     @torch.autograd.function.once_differentiable
@@ -553,11 +618,22 @@ class _TemporalLossFn(torch.autograd.Function):
         need_prev, need_cur = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
         gp = torch.empty_like(prev) if need_prev else None
         gc = torch.empty_like(cur) if need_cur else None
-        scale = (grad_out.float() / float(B * C * H * W)).reshape(1).contiguous()
-        with torch.cuda.device(prev.device):
-            check(_cabi.lib().tclb200_tcl_backward(_ptr(flow), _ptr(mask), _ptr(prev), _ptr(cur), _ptr(scale),
-                                                   _ptr(gp), _ptr(gc), B, C, H, W, ctx.flags, ctx.loss,
-                                                   _stream_handle()))
+        scale = grad_out.to(torch.float32).reshape(1) * (1.0 / float(B * C * H * W))
+        dev = prev.device
+        switch = torch.cuda.current_device() != dev.index
+        if switch:
+            dctx = torch.cuda.device(dev)
+            dctx.__enter__()
+        try:
+            plan = _loss_plan(dev, B, H, W)
+            rc = plan.bwd(flow.data_ptr(), mask.data_ptr(), prev.data_ptr(), cur.data_ptr(), scale.data_ptr(),
+                          gp.data_ptr() if gp is not None else None, gc.data_ptr() if gc is not None else None,
+                          B, C, H, W, ctx.flags, ctx.loss, plan.stream)
+            if rc != 0:
+                check(rc)
+        finally:
+            if switch:
+                dctx.__exit__(None, None, None)
         return gp, gc, None, None, None, None
 
 
@@ -568,21 +644,35 @@ def temporal_loss(mask, cur, prev, flow, loss="l2", validity=False):
     ``loss='l1'``: (mask*abs(warp(prev,flow) - cur)).mean()         (MoGAN cycle_gan_model.py:280-281)
     ``validity`` selects fs_lib.warp for the learning-based trainers.
     """
-    _require_cuda(mask, cur, prev, flow)
-    code = {"l2": L2, "l1": L1}[loss]
-    flow = _flow(flow)
-    prev, cur = prev.contiguous(), cur.contiguous()
+    if not (cur.is_cuda and prev.is_cuda and flow.is_cuda and (mask is None or mask.is_cuda)):
+        _require_cuda(mask, cur, prev, flow)
+    code = L2 if loss == "l2" else {"l1": L1}[loss]
+    if flow.dim() != 4 or flow.shape[1] != 2:
+        raise RuntimeError(f"tcl_b200: flow must be (B,2,H,W), got {tuple(flow.shape)}")
     B, _, H, W = flow.shape
+    if flow.dtype != torch.float32 or not flow.is_contiguous():
+        flow = flow.float().contiguous()
+    if not prev.is_contiguous():
+        prev = prev.contiguous()
+    if not cur.is_contiguous():
+        cur = cur.contiguous()
+    if prev.dim() != 4 or prev.shape[0] != B or prev.shape[2] != H or prev.shape[3] != W or cur.shape != prev.shape or cur.dtype != prev.dtype:
+        raise RuntimeError(f"tcl_b200: prev {tuple(prev.shape)} / cur {tuple(cur.shape)} must be (B,C,H,W) frames matching the flow {tuple(flow.shape)}")
+    _frame_dtype(prev)
     if mask is None:
         mask = torch.ones((B, 1, H, W), dtype=torch.float32, device=flow.device)
-    mask = mask.float().contiguous()
+    elif mask.dtype != torch.float32 or not mask.is_contiguous():
+        mask = mask.float().contiguous()
+    if mask.shape != (B, 1, H, W):
+        raise RuntimeError(f"tcl_b200: mask must be (B,1,H,W), got {tuple(mask.shape)}")
     flags = VALIDITY if validity else 0
-    if torch.is_grad_enabled() and (flow.requires_grad or mask.requires_grad):
-        raise RuntimeError("tcl_b200: temporal_loss differentiates w.r.t. cur and prev only; a flow or mask that requires grad would "
-                           "silently get none -- detach it, or compose the loss from tcl_b200.warp (differentiable w.r.t. its flow)")
-    if torch.is_grad_enabled() and (prev.requires_grad or cur.requires_grad):
-        return _TemporalLossFn.apply(prev, cur, flow, mask, code, flags)
-    return fused_forward(flow, prev, cur, mask=mask, loss=code, finalize=FIN_MEAN, flags=flags).total_val
+    if torch.is_grad_enabled():
+        if flow.requires_grad or mask.requires_grad:
+            raise RuntimeError("tcl_b200: temporal_loss differentiates w.r.t. cur and prev only; a flow or mask that requires grad would "
+                               "silently get none -- detach it, or compose the loss from tcl_b200.warp (differentiable w.r.t. its flow)")
+        if prev.requires_grad or cur.requires_grad:
+            return _TemporalLossFn.apply(prev, cur, flow, mask, code, flags)
+    return _loss_forward(prev, cur, flow, mask, code, flags)
 
 
 def generateMask(simg, prev, flow):

@@ -136,6 +136,38 @@ def evaluate_sharded(ff, bf, prev, cur, seq_of_pair: torch.Tensor, n_seq: int,
     return unpack(allreduce_sums(packed, group), n_seq)
 
 
+def band_rows(H: int, world: int, rank: int, align: int = 32):
+    """Rows [r0, r1) of an H-row frame that ``rank`` of ``world`` evaluates: contiguous bands of whole 32-row tile rows,
+    balanced to within one tile row (the last band takes the frame's ragged end; a band may be empty when world > H/32)."""
+    blocks = (H + align - 1) // align
+    base, rem = divmod(blocks, world)
+    b0 = rank * base + min(rank, rem)
+    b1 = b0 + base + (1 if rank < rem else 0)
+    return min(H, b0 * align), min(H, b1 * align)
+
+
+def evaluate_banded(ff, bf, prev, cur, group: Optional[dist.ProcessGroup] = None, rank: Optional[int] = None,
+                    world: Optional[int] = None) -> dict:
+    """Fewer pairs than GPUs (one 4K pair on eight GPUs, BASELINE config 5): every rank holds the same
+    whole pairs, evaluates one horizontal band of target rows of each (the flow gradient and the bilinear taps read beyond
+    the band: the inputs are replicated, nothing is exchanged), and the bands' fp64 sums of squares are added with the path's
+    one all-reduce.  Returns ``pair_sums`` (B,) fp64 and ``pair_rmse`` (B,) fp32, identical on every rank."""
+    from . import ops
+    if world is None:
+        world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+    if rank is None:
+        rank = dist.get_rank(group) if dist.is_available() and dist.is_initialized() else 0
+    B, _, H, W = bf.shape
+    C = prev.shape[1]
+    r0, r1 = band_rows(H, world, rank)
+    if r1 > r0:
+        sums = ops.fused_forward(bf, prev, cur, ff=ff, rows=(r0, r1)).pair_sums.clone()
+    else:
+        sums = torch.zeros(B, dtype=torch.float64, device=bf.device)
+    sums = allreduce_sums(sums, group)
+    return {"pair_sums": sums, "pair_rmse": (sums / float(C * H * W)).sqrt().float(), "rows": (r0, r1)}
+
+
 def evaluate_sharded_host(frames, ff, bf, prev_index, cur_index, seq_of_pair, n_seq: int,
                           group: Optional[dist.ProcessGroup] = None, device=None, chunk_pairs: int = 0) -> dict:
     """The same evaluation with this rank's shard in HOST memory (``ops.temporal_error_host``: frames of the rank's clips

@@ -147,6 +147,12 @@ typedef struct tclb200_tcl_args {
   const int* ff_index;
   int n_bf_fields, n_ff_fields;
   int pair_group;
+  /* band mode (optional, 0 / 0 = whole frames; ABI v5): only target rows [row_begin, row_end) of every pair are evaluated
+   * (sums, mask_out / warp_out / blend_out rows); the inputs are still whole frames -- the flow gradient reads the rows next
+   * to the band and the taps land wherever the flow points.  A job with fewer pairs than GPUs (one 4K pair on eight GPUs,
+   * BASELINE config 5) splits every frame into horizontal bands, one per GPU, and adds the bands' pair_sums with the path's
+   * one all-reduce.  pair_vals / total_val are refused in this mode (a band's mean is not the frame's). */
+  int row_begin, row_end;
 } tclb200_tcl_args;
 
 int tclb200_tcl_forward(const tclb200_tcl_args* args, tclb200_stream_t stream);

@@ -33,6 +33,9 @@ def _worker(rank, world, port, out_dir):
     seq = torch.tensor(plan.seq_of_pair, dtype=torch.long, device=device)
     out = tcl.evaluate_sharded(ff[sl].contiguous(), bf[sl].contiguous(), prev[sl].contiguous(), cur[sl].contiguous(), seq, len(pairs))
     torch.cuda.synchronize()
+    # fewer pairs than GPUs: the same two pairs on both ranks, one horizontal band each
+    banded = tcl.evaluate_banded(ff[:2].contiguous(), bf[:2].contiguous(), prev[:2].contiguous(), cur[:2].contiguous())
+    out = dict(out, band_sums=banded["pair_sums"], band_rmse=banded["pair_rmse"])
     torch.save({k: v.detach().cpu() for k, v in out.items()}, os.path.join(out_dir, f"r{rank}.pt"))
     dist.barrier()
     dist.destroy_process_group()
@@ -53,4 +56,9 @@ def test_two_rank_sharded_evaluation_equals_single_gpu(tcl, tmp_path):
         for key in ("per_sequence_mean", "mean_over_sequences", "mean_over_pairs", "n_pairs"):
             assert torch.equal(got[key], one[key]), (r, key)
         assert torch.allclose(got["pooled_rmse"], one["pooled_rmse"], rtol=1e-12, atol=0.0)
+    whole = tcl.fused_forward(bf[:2].contiguous(), prev[:2].contiguous(), cur[:2].contiguous(), ff=ff[:2].contiguous())
+    for r in range(2):
+        got = torch.load(os.path.join(tmp_path, f"r{r}.pt"))
+        assert torch.allclose(got["band_sums"], whole.pair_sums.cpu(), rtol=1e-12, atol=0.0)   # (bands of whole 32-row tile rows)
+        assert torch.allclose(got["band_rmse"], whole.pair_vals.cpu(), rtol=1e-6, atol=0.0)
     assert int(one["n_pairs"]) == sum(pairs) and float(one["per_sequence_mean"][2]) == 0.0   # the sequence without pairs

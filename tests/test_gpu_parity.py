@@ -741,6 +741,41 @@ def test_window_mode_equals_independent_pairs(tcl, dtype, H, W):
     assert torch.equal(res.pair_vals, want)
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("H,W,force", [(436, 1024, False), (100, 96, False), (77, 53, True)])
+def test_band_mode_adds_up_to_the_whole_frame(tcl, force_generic, H, W, force):
+    """Fewer pairs than GPUs: a frame is split into horizontal bands of target rows.  The bands' sums add up to
+    the whole frame's, the per-pixel outputs of a band are the whole-frame outputs on its rows, whatever the band edges
+    (unaligned to the 32-row tiles, one-row bands, TMA and generic kernels).  Bands made of whole tile rows (what
+    sharding.band_rows hands out) group the pixels into lanes and tiles exactly like the whole frame: their fp64 sums agree
+    to 1e-12; other band edges regroup the fp32 per-lane partial sums (1e-6, far inside the path's 1e-5)."""
+    d = dev()
+    force_generic(force)
+    try:
+        ff, bf, prev, cur = (t.to(d) for t in case(tcl, 2, H, W, seed=13, max_shift=9.0))
+        whole = tcl.fused_forward(bf, prev, cur, ff=ff, want_mask=True, want_warp=True)
+        whole_sums = tcl.fused_forward(bf, prev, cur, ff=ff).pair_sums     # (the reduction-only configuration, like the bands)
+        for edges, rtol in (([0, 1, 33, H // 2 + 3, H - 1, H], 1e-6), ([0, 32, 64, H], 1e-12 if not force else 1e-6)):
+            total = torch.zeros(2, dtype=torch.float64, device=d)
+            for r0, r1 in zip(edges, edges[1:]):
+                part = tcl.fused_forward(bf, prev, cur, ff=ff, rows=(r0, r1))
+                assert part.pair_vals is None and part.total_val is None
+                total += part.pair_sums
+                o = tcl.fused_forward(bf, prev, cur, ff=ff, rows=(r0, r1), want_mask=True, want_warp=True, want_sums=False)
+                assert torch.equal(o.mask[:, :, r0:r1], whole.mask[:, :, r0:r1]) and torch.equal(o.warp[:, :, r0:r1], whole.warp[:, :, r0:r1])
+            assert torch.allclose(total, whole_sums, rtol=rtol, atol=0.0), (edges, total, whole_sums)
+        # sharding.band_rows covers every row once for any world size; evaluate_banded at world 1 = the whole frame
+        for world in (1, 2, 3, 8, 16):
+            bands = [tcl.band_rows(H, world, r) for r in range(world)]
+            assert bands[0][0] == 0 and bands[-1][1] == H and all(a[1] == b[0] for a, b in zip(bands, bands[1:]))
+        one = tcl.evaluate_banded(ff, bf, prev, cur)
+        assert torch.equal(one["pair_sums"], whole_sums) and torch.allclose(one["pair_rmse"], whole.pair_vals, rtol=1e-6, atol=0.0)
+        with pytest.raises(RuntimeError):
+            tcl.fused_forward(bf, prev, cur, ff=ff, rows=(5, 5))
+    finally:
+        force_generic(False)
+
+
 def test_temporal_loss_refuses_gradients_it_does_not_compute(tcl):
     d = dev()
     ff, bf, prev, cur = (t.to(d) for t in case(tcl, 2, 32, 48, seed=5, max_shift=4.0))
