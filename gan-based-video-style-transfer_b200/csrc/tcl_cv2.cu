@@ -98,27 +98,19 @@ __global__ void __launch_bounds__(256) cv2_remap_kernel(const float* __restrict_
 }
 
 // fb_check(warp_flow(ff, bf), bf)  (prewarped: fb_check(ff, bf) with ff already warped by the caller)
+// Measured and dropped (round 2): staging the CTA's 34 x 10 `bf` tile in shared memory so that the centre value and the four
+// np.gradient neighbours become shared-memory reads -- 111 Gpix/s against 124 with the five L1-served gathers below (the
+// barrier and the clamped ring loads cost more than the L1 hits they replace; the four 8-byte `ff` taps are what is left).
 __global__ void __launch_bounds__(256) cv2_fb_check_kernel(const float2* __restrict__ ff, const float2* __restrict__ bf,
                                                            float* __restrict__ mask, int H, int W, int flags, int prewarped,
                                                            unsigned long long* near_threshold) {
-  // the CTA's 32 x 8 pixels of `bf` plus a one-pixel ring, staged once with coalesced 8-byte loads: the centre value and the
-  // four np.gradient neighbours of every pixel are then shared-memory reads (they were five gathers through L1).  Ring
-  // positions outside the image hold the clamped neighbour -- exactly what np.gradient's one-sided border difference reads.
-  __shared__ float2 s_bf[10][34];
-  const int lx = threadIdx.x & 31, ly = threadIdx.x >> 5;
-  const int x = blockIdx.x * 32 + lx, y = blockIdx.y * 8 + ly, n = blockIdx.z;
-  const size_t img = (size_t)n * H * W;
-  const float2* b = bf + img;
-  for (int i = threadIdx.x; i < 340; i += 256) {
-    const int ry = i / 34, rx = i - ry * 34;
-    const int gx = min(max((int)blockIdx.x * 32 + rx - 1, 0), W - 1), gy = min(max((int)blockIdx.y * 8 + ry - 1, 0), H - 1);
-    s_bf[ry][rx] = __ldg(b + (size_t)gy * W + gx);
-  }
-  __syncthreads();
+  const int x = blockIdx.x * 32 + (threadIdx.x & 31), y = blockIdx.y * 8 + (threadIdx.x >> 5), n = blockIdx.z;
   unsigned near = 0;
   if (x < W && y < H) {
+    const size_t img = (size_t)n * H * W;
+    const float2* b = bf + img;
     const size_t o = (size_t)y * W + x;
-    const float2 c = s_bf[ly + 1][lx + 1];
+    const float2 c = __ldg(b + o);
     float2 wf;
     if (prewarped) {
       wf = __ldcs(ff + img + o);
@@ -152,8 +144,8 @@ __global__ void __launch_bounds__(256) cv2_fb_check_kernel(const float2* __restr
     }
     if (flags & TCLB200_MOB) {
       // np.gradient: one-sided on the border, halved central difference inside (H, W >= 2 checked by the host)
-      const float2 l = s_bf[ly + 1][lx], r = s_bf[ly + 1][lx + 2];
-      const float2 up = s_bf[ly][lx + 1], dn = s_bf[ly + 2][lx + 1];
+      const float2 l = __ldg(b + o - (x > 0 ? 1 : 0)), r = __ldg(b + o + (x + 1 < W ? 1 : 0));
+      const float2 up = __ldg(b + o - (y > 0 ? (size_t)W : 0)), dn = __ldg(b + o + (y + 1 < H ? (size_t)W : 0));
       const bool xe = x == 0 || x + 1 == W, ye = y == 0 || y + 1 == H;
       float ux = __fsub_rn(r.x, l.x), vx = __fsub_rn(r.y, l.y), uy = __fsub_rn(dn.x, up.x), vy = __fsub_rn(dn.y, up.y);
       if (!xe) { ux = __fmul_rn(ux, 0.5f); vx = __fmul_rn(vx, 0.5f); }

@@ -6,8 +6,10 @@
 // the frame bank of the clip(s), which frame each pair warps / compares with -- as HOST pointers and runs it as a
 // software pipeline:
 //
-//   copy stream     chunk k: the frames its pairs need that are not on the device yet (each frame crosses PCIe ONCE:
-//                   28 B/px per pair instead of 40 for a clip), then the two flows of its pairs into ring slot k % 3
+//   copy streams    chunk k (on copy stream k % 2: two streams keep the link busy across the gaps between one stream's
+//                   copies -- with eight ranks sharing one host memory system those gaps are bandwidth nobody else can use):
+//                   the frames its pairs need that are not on the device yet (each frame crosses PCIe ONCE: 28 B/px per
+//                   pair instead of 40 for a clip), then the two flows of its pairs into ring slot k % 3
 //   caller's stream chunk k: one fused launch (tclb200_tcl_forward in clip mode) on that slot, results into the
 //                   device result array; after the last chunk one D2H copy of the per-pair results
 //
@@ -38,7 +40,8 @@ namespace tcl { void set_last_error(const char* msg); }   // tcl_kernels.cu: the
 namespace {
 
 constexpr int kRing = 3;
-constexpr int kDefaultChunk = 32;
+constexpr size_t kDefaultChunkBytes = (size_t)256 << 20;   // default chunk: as many pairs as make one flow copy about this large
+constexpr int kMaxDefaultChunk = 128;
 
 inline size_t up256(size_t v) { return (v + 255) & ~(size_t)255; }
 
@@ -52,9 +55,16 @@ struct Layout {
 Layout make_layout(int P, int F, int C, int H, int W, int dtype, int chunk_pairs, bool with_mask) {
   Layout L;
   memset(&L, 0, sizeof(L));
-  L.chunk = chunk_pairs > 0 ? chunk_pairs : kDefaultChunk;
-  if (L.chunk > P) L.chunk = P;
   const size_t px = (size_t)H * W;
+  // few, large copies keep the link busy (measured, Sintel shape, one GPU: chunks of 16 / 32 / 64 / 128 pairs reach 0.82 /
+  // 0.93 / 0.98 / 0.99 of the link's rate); the default is sized in bytes so that 4K pairs do not need a 25 GB ring
+  if (chunk_pairs > 0) {
+    L.chunk = chunk_pairs;
+  } else {
+    const size_t by_bytes = kDefaultChunkBytes / (px * 2 * sizeof(float));
+    L.chunk = by_bytes < 1 ? 1 : (by_bytes > (size_t)kMaxDefaultChunk ? kMaxDefaultChunk : (int)by_bytes);
+  }
+  if (L.chunk > P) L.chunk = P;
   L.frame_bytes = px * C * (dtype == TCLB200_BF16 ? 2 : 4);
   L.flow_bytes = px * 2 * sizeof(float);
   L.mask_bytes = px * sizeof(float);
@@ -83,12 +93,13 @@ int hfail(int code, const char* what, const char* detail = "") {
 
 // copy stream + ring events of one call in flight; pooled per device and reused (never destroyed: process lifetime)
 struct Pipe {
-  cudaStream_t copy = nullptr;
+  cudaStream_t copy[2] = {nullptr, nullptr};
   cudaEvent_t ready[kRing] = {}, done[kRing] = {}, fork = nullptr;
   int device = -1;
   cudaError_t init() {
-    cudaError_t e = cudaStreamCreateWithFlags(&copy, cudaStreamNonBlocking);
-    if (e != cudaSuccess) return e;
+    cudaError_t e;
+    for (int i = 0; i < 2; ++i)
+      if ((e = cudaStreamCreateWithFlags(&copy[i], cudaStreamNonBlocking)) != cudaSuccess) return e;
     for (int i = 0; i < kRing; ++i) {
       if ((e = cudaEventCreateWithFlags(&ready[i], cudaEventDisableTiming)) != cudaSuccess) return e;
       if ((e = cudaEventCreateWithFlags(&done[i], cudaEventDisableTiming)) != cudaSuccess) return e;
@@ -101,7 +112,8 @@ struct Pipe {
       if (done[i]) cudaEventDestroy(done[i]);
     }
     if (fork) cudaEventDestroy(fork);
-    if (copy) cudaStreamDestroy(copy);
+    for (int i = 0; i < 2; ++i)
+      if (copy[i]) cudaStreamDestroy(copy[i]);
   }
 };
 
@@ -169,61 +181,80 @@ extern "C" int tclb200_tcl_forward_host(const tclb200_host_args* a, tclb200_stre
   Pipe* pipe = acquire_pipe(&perr);
   if (!pipe) return hfail(TCLB200_ERR_CUDA, "copy stream / events: ", cudaGetErrorString(perr));
   auto bail = [&](int rc) {
-    cudaStreamSynchronize(pipe->copy);
+    cudaStreamSynchronize(pipe->copy[0]);
+    cudaStreamSynchronize(pipe->copy[1]);
     cudaStreamSynchronize(comp);
     release_pipe(pipe);
     return rc;
   };
-  // the workspace may still be in use by earlier work on the caller's stream
-  HOST_TRY(cudaEventRecord(pipe->fork, comp));
-  HOST_TRY(cudaStreamWaitEvent(pipe->copy, pipe->fork, 0));
-  HOST_TRY(cudaMemsetAsync(ws + L.scratch, 0, tclb200_scratch_bytes(L.chunk, a->H, a->W), comp));
-
-  // frame -> device slot; a slot is free again once the last chunk that reads its frame has completed
+  // frame -> device slot; a slot is free again once the last chunk that reads its frame has completed.  The whole schedule
+  // (which frames every chunk uploads into which slots, every pair's slot indices) depends on the pair order alone, so it is
+  // worked out on the host first and the index arrays go up in ONE copy before the pipeline starts: an asynchronous copy from
+  // pageable memory synchronises its stream first, and one such copy per chunk would drain the copy stream at every chunk
+  // boundary (measured with eight ranks: 185 of the 232 GB/s the box's host side can feed).
   const int n_chunks = (a->P + L.chunk - 1) / L.chunk;
-  std::vector<int> slot_of((size_t)a->F, -1), last_use((size_t)a->F, -1), free_slots, h_prev((size_t)a->P), h_cur((size_t)a->P);
+  std::vector<int> slot_of((size_t)a->F, -1), last_use((size_t)a->F, -1), free_slots, h_idx(2 * (size_t)a->P);
+  int* h_prev = h_idx.data();
+  int* h_cur = h_idx.data() + a->P;
   std::vector<std::vector<int>> dies((size_t)n_chunks);   // frames whose last reader is chunk k
+  struct Run { int frame, slot, count; };
+  std::vector<std::vector<Run>> uploads((size_t)n_chunks);
   for (int p = 0; p < a->P; ++p) { last_use[(size_t)a->prev_index[p]] = p / L.chunk; last_use[(size_t)a->cur_index[p]] = p / L.chunk; }
   for (int f = 0; f < a->F; ++f) if (last_use[(size_t)f] >= 0) dies[(size_t)last_use[(size_t)f]].push_back(f);
   free_slots.reserve((size_t)S);
   for (int i = S - 1; i >= 0; --i) free_slots.push_back(i);   // handed out in increasing order: consecutive frames, consecutive slots
-  int released = 0;   // chunks whose frames have been released
-  std::vector<int> want;
+  {
+    int released = 0;   // chunks whose frames have been released
+    std::vector<int> want;
+    for (int s = 0, k = 0; s < a->P; s += L.chunk, ++k) {
+      const int n = a->P - s < L.chunk ? a->P - s : L.chunk;
+      if (k >= kRing)     // when chunk k is staged, chunk k - kRing has been consumed: the frames nobody reads after it are free
+        for (; released <= k - kRing; ++released)
+          for (int f : dies[(size_t)released]) { free_slots.push_back(slot_of[(size_t)f]); slot_of[(size_t)f] = -1; }
+      want.clear();
+      for (int p = s; p < s + n; ++p) {
+        const int f2[2] = {a->prev_index[p], a->cur_index[p]};
+        for (int j = 0; j < 2; ++j)
+          if (slot_of[(size_t)f2[j]] < 0) {
+            if (free_slots.empty()) {
+              release_pipe(pipe);
+              return hfail(TCLB200_ERR_INVALID, "frame_slots too small: a window of (3 + 1) chunks of pairs must fit the device frame ring");
+            }
+            slot_of[(size_t)f2[j]] = free_slots.back(); free_slots.pop_back();
+            want.push_back(f2[j]);
+          }
+        h_prev[p] = slot_of[(size_t)f2[0]]; h_cur[p] = slot_of[(size_t)f2[1]];
+      }
+      // runs of consecutive frames in consecutive slots go as one copy
+      for (size_t i = 0; i < want.size();) {
+        size_t j = i + 1;
+        while (j < want.size() && want[j] == want[j - 1] + 1 && slot_of[(size_t)want[j]] == slot_of[(size_t)want[j - 1]] + 1) ++j;
+        uploads[(size_t)k].push_back(Run{want[i], slot_of[(size_t)want[i]], (int)(j - i)});
+        i = j;
+      }
+    }
+  }
+  // the workspace may still be in use by earlier work on the caller's stream
+  HOST_TRY(cudaEventRecord(pipe->fork, comp));
+  HOST_TRY(cudaStreamWaitEvent(pipe->copy[0], pipe->fork, 0));
+  HOST_TRY(cudaStreamWaitEvent(pipe->copy[1], pipe->fork, 0));
+  HOST_TRY(cudaMemsetAsync(ws + L.scratch, 0, tclb200_scratch_bytes(L.chunk, a->H, a->W), comp));
+  HOST_TRY(cudaMemcpyAsync(ws + L.prev_idx, h_prev, sizeof(int) * (size_t)a->P, cudaMemcpyHostToDevice, comp));
+  HOST_TRY(cudaMemcpyAsync(ws + L.cur_idx, h_cur, sizeof(int) * (size_t)a->P, cudaMemcpyHostToDevice, comp));
+
   const char* h_frames = reinterpret_cast<const char*>(a->frames);
   for (int s = 0, k = 0; s < a->P; s += L.chunk, ++k) {
     const int n = a->P - s < L.chunk ? a->P - s : L.chunk;
     const int slot = k % kRing;
-    if (k >= kRing) {
-      HOST_TRY(cudaStreamWaitEvent(pipe->copy, pipe->done[slot], 0));   // chunk k - kRing has been consumed: its flow slot is free ...
-      for (; released <= k - kRing; ++released)                           // ... and so are the frames nobody reads after it
-        for (int f : dies[(size_t)released]) { free_slots.push_back(slot_of[(size_t)f]); slot_of[(size_t)f] = -1; }
-    }
-    // frames this chunk needs and the device does not hold yet; runs of consecutive frames / slots go as one copy
-    want.clear();
-    for (int p = s; p < s + n; ++p) {
-      const int f2[2] = {a->prev_index[p], a->cur_index[p]};
-      for (int j = 0; j < 2; ++j)
-        if (slot_of[(size_t)f2[j]] < 0) {
-          if (free_slots.empty()) return bail(hfail(TCLB200_ERR_INVALID, "frame_slots too small: a window of (3 + 1) chunks of pairs must fit the device frame ring"));
-          slot_of[(size_t)f2[j]] = free_slots.back(); free_slots.pop_back();
-          want.push_back(f2[j]);
-        }
-      h_prev[(size_t)p] = slot_of[(size_t)f2[0]]; h_cur[(size_t)p] = slot_of[(size_t)f2[1]];
-    }
-    for (size_t i = 0; i < want.size();) {
-      size_t j = i + 1;
-      while (j < want.size() && want[j] == want[j - 1] + 1 && slot_of[(size_t)want[j]] == slot_of[(size_t)want[j - 1]] + 1) ++j;
-      HOST_TRY(cudaMemcpyAsync(ws + L.frames + (size_t)slot_of[(size_t)want[i]] * L.frame_bytes, h_frames + (size_t)want[i] * L.frame_bytes,
-                               (j - i) * L.frame_bytes, cudaMemcpyHostToDevice, pipe->copy));
-      i = j;
-    }
-    // (pageable host vectors: the runtime stages these small copies before the call returns)
-    HOST_TRY(cudaMemcpyAsync(ws + L.prev_idx + sizeof(int) * (size_t)s, h_prev.data() + s, sizeof(int) * (size_t)n, cudaMemcpyHostToDevice, pipe->copy));
-    HOST_TRY(cudaMemcpyAsync(ws + L.cur_idx + sizeof(int) * (size_t)s, h_cur.data() + s, sizeof(int) * (size_t)n, cudaMemcpyHostToDevice, pipe->copy));
-    if (a->ff) HOST_TRY(cudaMemcpyAsync(ws + L.flows[slot][0], a->ff + (size_t)s * 2 * a->H * a->W, (size_t)n * L.flow_bytes, cudaMemcpyHostToDevice, pipe->copy));
-    HOST_TRY(cudaMemcpyAsync(ws + L.flows[slot][1], a->bf + (size_t)s * 2 * a->H * a->W, (size_t)n * L.flow_bytes, cudaMemcpyHostToDevice, pipe->copy));
-    if (with_mask) HOST_TRY(cudaMemcpyAsync(ws + L.mask[slot], a->mask_in + (size_t)s * a->H * a->W, (size_t)n * L.mask_bytes, cudaMemcpyHostToDevice, pipe->copy));
-    HOST_TRY(cudaEventRecord(pipe->ready[slot], pipe->copy));
+    cudaStream_t cs = pipe->copy[k & 1];
+    if (k >= kRing) HOST_TRY(cudaStreamWaitEvent(cs, pipe->done[slot], 0));   // chunk k - kRing has been consumed: its flow slot and the frame slots released with it are free
+    for (const Run& r : uploads[(size_t)k])
+      HOST_TRY(cudaMemcpyAsync(ws + L.frames + (size_t)r.slot * L.frame_bytes, h_frames + (size_t)r.frame * L.frame_bytes,
+                               (size_t)r.count * L.frame_bytes, cudaMemcpyHostToDevice, cs));
+    if (a->ff) HOST_TRY(cudaMemcpyAsync(ws + L.flows[slot][0], a->ff + (size_t)s * 2 * a->H * a->W, (size_t)n * L.flow_bytes, cudaMemcpyHostToDevice, cs));
+    HOST_TRY(cudaMemcpyAsync(ws + L.flows[slot][1], a->bf + (size_t)s * 2 * a->H * a->W, (size_t)n * L.flow_bytes, cudaMemcpyHostToDevice, cs));
+    if (with_mask) HOST_TRY(cudaMemcpyAsync(ws + L.mask[slot], a->mask_in + (size_t)s * a->H * a->W, (size_t)n * L.mask_bytes, cudaMemcpyHostToDevice, cs));
+    HOST_TRY(cudaEventRecord(pipe->ready[slot], cs));
     HOST_TRY(cudaStreamWaitEvent(comp, pipe->ready[slot], 0));
 
     tclb200_tcl_args t;

@@ -179,7 +179,7 @@ typedef struct tclb200_host_args {
   size_t workspace_bytes;
   int P, F, C, H, W;
   int dtype, flags, loss, finalize; /* as in tclb200_tcl_args */
-  int chunk_pairs;       /* pairs per launch, 0 = 32 */
+  int chunk_pairs;       /* pairs per launch, 0 = as many as make a flow copy of about 256 MB (at most 128) */
   int frame_slots;       /* device frame slots the workspace provides: 0 (or >= F) = the whole bank stays resident; fewer =
                           * a ring -- a slot is reused once every chunk that reads its frame has completed; a window of
                           * (3 + 1) chunks of pairs must fit (TCLB200_ERR_INVALID otherwise)          (ABI v5) */
