@@ -81,6 +81,7 @@ struct FwdParams {
   const int* bf_index;     // flow field each pair reads as `bf` / `ff` (nullptr: its own)
   const int* ff_index;
   int pair_group;          // > 1: tiles of this many consecutive pairs are interleaved (window evaluations)
+  int cw_packed;           // host side only: launch the 8-consumer-warp variant (the tensor maps' boxes are sized for it)
   int row_begin, row_end;  // rows of every pair this launch covers ([0, H) unless the frame is split into bands over several GPUs)
   void* warp_out;
   float* mask_out;
@@ -175,6 +176,9 @@ __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, unsigned bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
+#ifndef TCL_IDLE_SLEEP_NS
+#define TCL_IDLE_SLEEP_NS 40   // back-off of the helper warps' waits (producer, scanners)
+#endif
 #ifndef TCL_WAIT_HINT_NS
 #define TCL_WAIT_HINT_NS 0   // > 0: let the hardware park a waiting warp for up to this many ns per poll
 #endif
@@ -220,7 +224,7 @@ __device__ __forceinline__ void mbar_wait_idle(uint64_t* bar, unsigned parity) {
         : "r"(smem_u32(bar)), "r"(parity)
         : "memory");
     if (done) return;
-    __nanosleep(40);
+    __nanosleep(TCL_IDLE_SLEEP_NS);
   }
 }
 // TMA prefetch of a 4-D tile into L2 (no shared-memory destination, nothing to wait for)

@@ -43,8 +43,11 @@
 #define TCL_TH 32     // tile height (the width is 64)
 #endif
 #ifndef TCL_BH
-#define TCL_BH 40     // source-box height
+#define TCL_BH 42     // source-box height with 16 consumer warps (32 rows + 1 + 9 rows of slack for the flow's local spread) ...
 #endif
+#ifndef TCL_BH8
+#define TCL_BH8 44    // ... and with 8 (their control block is smaller): as tall as 227 KB of shared memory allow -- measured on the
+#endif                // Sintel shape, sustained: 40 / 42 / 44 rows = 115.7 / 118.2 / 120.2 Gpix/s (fewer tiles straddle a motion boundary)
 #ifndef TCL_BW
 #define TCL_BW 80     // source-box width for fp32 frames: 16 (mod 32), see WsCfg
 #endif
@@ -299,7 +302,8 @@ struct WsCfg {
   static_assert(kBfW % 32 == 16, "flow-tile pitch must be 16 (mod 32) words: adjacent rows fall into disjoint bank halves");
   static_assert((BW * (int)sizeof(FrameT)) % 16 == 0 && BW % 4 == 0, "TMA: box rows are multiples of 16 bytes");
 #if TCL_DIAG != 3
-  static_assert(NB >= NS + 2, "the flow tile of a tile is scanned NS tiles ahead: it must have been requested a tile before that");
+  static_assert(NB >= NS + 1, "the flow tile of a tile is scanned NS tiles ahead of its use");
+  static_assert(kSmemBytes <= 232448, "a CTA has at most 227 KB of shared memory");
 #endif
 };
 // row of pixel k of a lane, relative to the lane's first row
@@ -366,7 +370,23 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 __device__ __forceinline__ void mbar_arrive_s(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
+#ifndef TCL_CONS_HINT_NS
+#define TCL_CONS_HINT_NS 0   // > 0: the consumers' waits let the hardware park the warp for up to this many ns per poll
+#endif
 __device__ __forceinline__ void mbar_wait_s(uint32_t bar, unsigned parity) {
+#if TCL_CONS_HINT_NS > 0
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(bar),
+      "r"(parity), "r"((unsigned)TCL_CONS_HINT_NS)
+      : "memory");
+#else
   asm volatile(
       "{\n"
       ".reg .pred p;\n"
@@ -378,6 +398,7 @@ __device__ __forceinline__ void mbar_wait_s(uint32_t bar, unsigned parity) {
       "}\n" ::"r"(bar),
       "r"(parity)
       : "memory");
+#endif
 }
 
 // Fold kernel of the warp-specialised path: the hot kernel only stores one fp64 partial per tile (no fences, no
@@ -1666,7 +1687,7 @@ extern "C" const char* tclb200_last_error(void) { return g_err; }
 #define TCL_CWARPS_S "8/16"
 #endif
 extern "C" const char* tclb200_build_info(void) {
-  return "abi=" TCL_STR(TCLB200_ABI_VERSION) " th=" TCL_STR(TCL_TH) " bh=" TCL_STR(TCL_BH) " bw=" TCL_STR(TCL_BW) " bw16=" TCL_STR(TCL_BW16)
+  return "abi=" TCL_STR(TCLB200_ABI_VERSION) " th=" TCL_STR(TCL_TH) " bh=" TCL_STR(TCL_BH) "/" TCL_STR(TCL_BH8) " bw=" TCL_STR(TCL_BW) " bw16=" TCL_STR(TCL_BW16)
          " ns=" TCL_STR(TCL_NS) " nb=" TCL_STR(TCL_NB) " cwarps=" TCL_CWARPS_S " scanners=" TCL_STR(TCL_SCANNERS) " packed=" TCL_STR(TCL_PACKED)
          " packed_given=" TCL_STR(TCL_PACKED_GIVEN) " hot_only=" TCL_STR(TCL_HOT_ONLY_V) " diag=" TCL_STR(TCL_DIAG) " trace=" TCL_STR(TCL_TRACE_V);
 }
@@ -1674,7 +1695,8 @@ extern "C" const char* tclb200_build_info(void) {
 // tile shape of the TMA kernel: 64 x TH pixels per tile, 80 x BH source boxes: after rounding the box origin down
 // to a 16-byte boundary the taps may still spread >= 8 px in x and BH-TH-1 px in y beyond the tile's own extent
 // before the tile falls back to global gathers
-constexpr int kTW = 64, kTH = TCL_TH, kBH = TCL_BH;
+constexpr int kTW = 64, kTH = TCL_TH;
+constexpr int box_height(int cw) { return cw == 8 ? TCL_BH8 : TCL_BH; }
 template <typename FrameT> constexpr int box_width() { return sizeof(FrameT) == 4 ? TCL_BW : TCL_BW16; }
 
 static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
@@ -1731,7 +1753,7 @@ static int sm_count() {   // of the current device, cached per device index (a p
 template <typename FrameT, int MASK, bool REDUCE, int CT, int LEAN, int CW>
 static cudaError_t launch_tma_cw(const FwdParams& p, const CUtensorMap& tb, const CUtensorMap& tf, const CUtensorMap& tp, const CUtensorMap& tc,
                                  cudaStream_t s) {
-  using Cfg = WsCfg<FrameT, CT, kTW, kTH, box_width<FrameT>(), kBH, TCL_NB, TCL_NS, CW>;
+  using Cfg = WsCfg<FrameT, CT, kTW, kTH, box_width<FrameT>(), box_height(CW), TCL_NB, TCL_NS, CW>;
   auto kern = fused_forward_ws_kernel<FrameT, MASK, REDUCE, CT, LEAN, Cfg>;
   static bool configured[64] = {};  // per instantiation and device (the attribute is a per-device property of the function)
   int dev = 0;
@@ -1767,10 +1789,12 @@ static cudaError_t launch_tma_cw(const FwdParams& p, const CUtensorMap& tb, cons
 template <typename FrameT, int MASK, bool REDUCE, int CT, int LEAN>
 static cudaError_t launch_tma(const FwdParams& p, const CUtensorMap& tb, const CUtensorMap& tf, const CUtensorMap& tp, const CUtensorMap& tc,
                               cudaStream_t s) {
+  // (decided by run_fused, which sized the tensor maps' boxes for it: wants_packed8)
   constexpr bool packed8 = TCL_PACKED && (LEAN == 1 || LEAN == 2) && CT == 3 && MASK == MASK_COMPUTED && sizeof(FrameT) == 4;
   if constexpr (packed8 && kCWarpsPacked != kCWarpsOther) {
-    if ((size_t)p.geo.H * p.geo.W >= (size_t)384 * 384) return launch_tma_cw<FrameT, MASK, REDUCE, CT, LEAN, kCWarpsPacked>(p, tb, tf, tp, tc, s);
+    if (p.cw_packed) return launch_tma_cw<FrameT, MASK, REDUCE, CT, LEAN, kCWarpsPacked>(p, tb, tf, tp, tc, s);
   }
+  if (p.cw_packed && kCWarpsPacked != kCWarpsOther) return cudaErrorInvalidConfiguration;   // (tensor maps sized for the other variant)
   return launch_tma_cw<FrameT, MASK, REDUCE, CT, LEAN, kCWarpsOther>(p, tb, tf, tp, tc, s);
 }
 
@@ -1895,10 +1919,17 @@ static int run_fused(const tclb200_tcl_args* a, cudaStream_t s) {
   bool tma = !g_force_generic && (a->W % 4 == 0) && ((a->W * esz) % 16 == 0) && aligned16(a->bf) && aligned16(a->ff) &&
              aligned16(a->prev) && aligned16(a->cur) && (!a->prev || a->C == 3) && a->B <= 65535 * 16 && strides16 &&
              a->H <= 16384 && a->W <= 16384;   // (box addresses are evaluated in fp32, see lean_tile)
+  // the packed-arithmetic configuration on large fp32 frames runs with 8 consumer warps and taller boxes (launch_tma): the
+  // same conditions as dispatch()'s `lean` for the computed-mask reductions
+  const bool cw_packed = TCL_PACKED && kCWarpsPacked != kCWarpsOther && tma && a->dtype == TCLB200_F32 && mask_kind == MASK_COMPUTED && reduce &&
+                         a->prev && a->cur && a->C == 3 && !a->warp_out && !a->mask_out && !a->blend_out && !a->near_threshold &&
+                         !(a->flags & TCLB200_VALIDITY) && (a->flags & (TCLB200_OCC | TCLB200_MOB)) == (TCLB200_OCC | TCLB200_MOB) &&
+                         (size_t)a->H * a->W >= (size_t)384 * 384;
   CUtensorMap tb, tf, tp, tc;
   memset(&tb, 0, sizeof(tb)); memset(&tf, 0, sizeof(tf)); memset(&tp, 0, sizeof(tp)); memset(&tc, 0, sizeof(tc));
   if (tma) {
     const int bw = a->dtype == TCLB200_BF16 ? box_width<__nv_bfloat16>() : box_width<float>();
+    const int kBH = box_height(cw_packed ? kCWarpsPacked : kCWarpsOther);
     tma = make_map(&tb, a->bf, 4, a->W, a->H, 2, a->bf_index ? a->n_bf_fields : a->B, kTW + 16, kTH + 2, 2, bf_plane, bf_batch);
     if (tma && mask_kind == MASK_COMPUTED && (a->flags & TCLB200_OCC))
       tma = make_map(&tf, a->ff, 4, a->W, a->H, 2, a->ff_index ? a->n_ff_fields : a->B, bw, kBH, 2, ff_plane, ff_batch);
@@ -1913,6 +1944,7 @@ static int run_fused(const tclb200_tcl_args* a, cudaStream_t s) {
   p.prev_index = a->prev ? a->prev_index : nullptr; p.cur_index = a->cur ? a->cur_index : nullptr;
   p.bf_index = a->bf_index; p.ff_index = a->ff ? a->ff_index : nullptr;
   p.pair_group = a->pair_group > 1 ? a->pair_group : 1;
+  p.cw_packed = cw_packed ? 1 : 0;
   p.warp_out = a->warp_out; p.mask_out = a->mask_out; p.blend_out = a->blend_out;
   p.pair_sums = a->pair_sums; p.total_sums = a->total_sums; p.pair_vals = a->pair_vals; p.total_val = a->total_val;
   p.near_threshold = a->near_threshold;

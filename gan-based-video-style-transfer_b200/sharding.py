@@ -1,5 +1,9 @@
 """Sharding of frame pairs over the GPUs of one box + the single sum all-reduce.
 
+``pack_local`` / ``unpack`` also accept CPU tensors and then do the same fp64 arithmetic with torch ops: that branch is host
+logic of the aggregation (a few dozen numbers), exercised by the world-size-2 gloo tests on the GPU-less build box; it is not
+a CPU path of the warp / mask / error computation -- there is none.
+
 Pairs are independent (each reads only its own two flows and two frames), so the path shards by
 pair with no data-path collective.  The only cross-GPU step is the final aggregation of the
 reference's evaluation loop (per-video mean of per-pair RMSE, then the mean over videos:
@@ -57,9 +61,16 @@ def pack_local(pair_vals: torch.Tensor, sum_sq: torch.Tensor, seq_of_pair: torch
         import ctypes
         from . import _cabi
         packed = torch.empty(2 * n_seq + 2, dtype=torch.float64, device=pair_vals.device)
-        vals = pair_vals.float().contiguous()
-        seq = seq_of_pair.to(device=pair_vals.device, dtype=torch.long).contiguous()
-        ssq = sum_sq.double().reshape(1).contiguous() if n else None
+        # (the evaluation calls this every step with tensors that already have the right form: no copies, no dispatcher calls then)
+        vals = pair_vals if (pair_vals.dtype == torch.float32 and pair_vals.is_contiguous()) else pair_vals.float().contiguous()
+        seq = seq_of_pair if (seq_of_pair.dtype == torch.long and seq_of_pair.device == pair_vals.device and seq_of_pair.is_contiguous()) \
+            else seq_of_pair.to(device=pair_vals.device, dtype=torch.long).contiguous()
+        if not n:
+            ssq = None
+        elif sum_sq.dtype == torch.float64 and sum_sq.is_contiguous():
+            ssq = sum_sq          # (one element: a 0-dim tensor or a view of the launch's total_sums)
+        else:
+            ssq = sum_sq.double().reshape(1).contiguous()
         ptr = lambda t: ctypes.c_void_p(t.data_ptr()) if t is not None else None
         with torch.cuda.device(pair_vals.device):
             _cabi.check(_cabi.lib().tclb200_pack_sequence_sums(ptr(vals), ptr(ssq), ptr(seq), n, n_seq, float(elems_per_pair), ptr(packed),

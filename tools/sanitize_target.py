@@ -46,5 +46,11 @@ tcl.split_fc2_block(torch.randn(2, 32, 48, 9, device=d))
 cc = tcl.cv2compat
 hw_ff, hw_bf = ff[0].permute(1, 2, 0).contiguous(), bf[0].permute(1, 2, 0).contiguous()
 cc.fb_check_flows(hw_ff, hw_bf); cc.warp_image(prev[0].permute(1, 2, 0).contiguous(), hw_bf)
+idx = tcl.window_evaluations(3, 3)                                                   # window mode (flow / frame banks, interleaved tiles)
+bank = torch.cat([bf, ff, bf[:1], ff[:1]], 0)[: 2 * idx["field_t"].numel()].contiguous()
+tcl.temporal_error_window(torch.cat([prev, cur[:1]], 0), bank, 3, idx)
+tcl.fused_forward(bf, prev, cur, ff=ff, rows=(17, 71))                               # band mode
+tcl.reconet_output_temporal_loss(m, cur, prev, cur * 0.5, prev * 0.5, bf)            # learning-based chains
+tcl.ruder_network_input(cur, m, prev, bf)
 torch.cuda.synchronize()
 print("sanitize_target ok", float(r.total_val), float(r2.total_val), float(r3.total_val))

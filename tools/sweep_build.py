@@ -30,6 +30,23 @@ VARIANTS = {
     "full_pg0": {"TCL_PACKED_GIVEN": 0},
     "full_w16": {"TCL_CWARPS": 16},
     "full_w8": {"TCL_CWARPS": 8},
+    "hot_s1": {"TCL_HOT_ONLY": 1, "TCL_SCANNERS": 1},
+    "hot_sleep200": {"TCL_HOT_ONLY": 1, "TCL_IDLE_SLEEP_NS": 200},
+    "hot_hint1000": {"TCL_HOT_ONLY": 1, "TCL_CONS_HINT_NS": 1000},
+    "hot_hint1000_sleep200": {"TCL_HOT_ONLY": 1, "TCL_CONS_HINT_NS": 1000, "TCL_IDLE_SLEEP_NS": 200},
+    "hot_s3x": {"TCL_HOT_ONLY": 1, "TCL_SCANNERS": 3},
+    "hot_s4x": {"TCL_HOT_ONLY": 1, "TCL_SCANNERS": 4},
+    "hot_bh42": {"TCL_HOT_ONLY": 1, "TCL_BH": 42},
+    "hot_bh44": {"TCL_HOT_ONLY": 1, "TCL_BH": 44},
+    "hot_nb3_bh44": {"TCL_HOT_ONLY": 1, "TCL_BH": 44, "TCL_NB": 3},
+    "hot_nb3_bh48": {"TCL_HOT_ONLY": 1, "TCL_BH": 48, "TCL_NB": 3},
+    "hot_nb3_bh49_s3": {"TCL_HOT_ONLY": 1, "TCL_BH": 49, "TCL_NB": 3, "TCL_SCANNERS": 3},
+    "hot_s3_bh44": {"TCL_HOT_ONLY": 1, "TCL_SCANNERS": 3, "TCL_BH": 44},
+    "hot_w16_bh42": {"TCL_HOT_ONLY": 1, "TCL_CWARPS": 16, "TCL_BH": 42},
+    "hot_w16": {"TCL_HOT_ONLY": 1, "TCL_CWARPS": 16},
+    "hot_s3_bh42": {"TCL_HOT_ONLY": 1, "TCL_SCANNERS": 3, "TCL_BH": 42},
+    "hot_bh38": {"TCL_HOT_ONLY": 1, "TCL_BH": 38},
+    "hot_bh36": {"TCL_HOT_ONLY": 1, "TCL_BH": 36},
     "trace": {"TCL_TRACE": 1, "TCL_HOT_ONLY": 1},
 }
 # the rest of the library (host entry, cv2 flavour, aggregation) is linked in from the regular build's objects
