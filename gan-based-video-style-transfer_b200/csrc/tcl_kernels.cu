@@ -60,6 +60,15 @@
 #ifndef TCL_NB
 #define TCL_NB (TCL_NS + 2)   // flow-tile stages in flight
 #endif
+// Configurations without a computed mask (dataset mask: the training loss; no mask: warp on its own, blend) stage no `ff`
+// planes: their source stage is 3/5 of the size and a THIRD one fits, which takes the wait for the source boxes off their
+// (shorter) per-tile critical path.
+#ifndef TCL_NS_NOFF
+#define TCL_NS_NOFF 3
+#endif
+#ifndef TCL_BH_NOFF
+#define TCL_BH_NOFF 40
+#endif
 #ifndef TCL_SCANNERS
 #define TCL_SCANNERS 2   // scanner warps (one warp needs about a tile period per tile and would pace the pipeline)
 #endif
@@ -272,7 +281,7 @@ constexpr int kCWarpsPacked = 8, kCWarpsOther = 16;
 // adjacent pixels per lane -- lose more to the shear of real flows, 1.5 wavefronts per tap read, than their register
 // reuse saves).  A lane's rows interleave with its partner's, so the column's flow values are still shared between a
 // lane's pixels: 2 * P + 1 + 2 * P shared-memory reads per flow component and P pixels instead of 5 * P.
-template <typename FrameT, int CT, int TW_, int TH_, int BW_, int BH_, int NB_, int NS_, int CW_>
+template <typename FrameT, int CT, int TW_, int TH_, int BW_, int BH_, int NB_, int NS_, int CW_, bool FF_ = true>
 struct WsCfg {
   static constexpr int TW = TW_, TH = TH_, BW = BW_, BH = BH_, NB = NB_, NS = NS_;
   static constexpr int CW = CW_;                 // consumer warps; then the producer warp (TMA requests, box placement, per-tile
@@ -291,7 +300,7 @@ struct WsCfg {
   static constexpr unsigned kFfLoad = 2u * BH * BW * 4u;
   static constexpr unsigned kPrevLoad = (unsigned)(CT > 0 ? CT : 0) * BH * BW * (unsigned)sizeof(FrameT);
   static constexpr size_t kBfStage = align_up(kBfLoad, 128);
-  static constexpr size_t kFfStage = align_up(kFfLoad, 128);
+  static constexpr size_t kFfStage = FF_ ? align_up(kFfLoad, 128) : 0;   // (configurations without a computed mask stage no `ff` planes)
   static constexpr size_t kSrcStage = kFfStage + align_up(kPrevLoad, 128);
   static constexpr size_t kBfOff = 0;
   static constexpr size_t kSrcOff = kBfOff + NB * kBfStage;
@@ -1688,7 +1697,7 @@ extern "C" const char* tclb200_last_error(void) { return g_err; }
 #endif
 extern "C" const char* tclb200_build_info(void) {
   return "abi=" TCL_STR(TCLB200_ABI_VERSION) " th=" TCL_STR(TCL_TH) " bh=" TCL_STR(TCL_BH) "/" TCL_STR(TCL_BH8) " bw=" TCL_STR(TCL_BW) " bw16=" TCL_STR(TCL_BW16)
-         " ns=" TCL_STR(TCL_NS) " nb=" TCL_STR(TCL_NB) " cwarps=" TCL_CWARPS_S " scanners=" TCL_STR(TCL_SCANNERS) " packed=" TCL_STR(TCL_PACKED)
+         " ns=" TCL_STR(TCL_NS) "/" TCL_STR(TCL_NS_NOFF) " nb=" TCL_STR(TCL_NB) " cwarps=" TCL_CWARPS_S " scanners=" TCL_STR(TCL_SCANNERS) " packed=" TCL_STR(TCL_PACKED)
          " packed_given=" TCL_STR(TCL_PACKED_GIVEN) " hot_only=" TCL_STR(TCL_HOT_ONLY_V) " diag=" TCL_STR(TCL_DIAG) " trace=" TCL_STR(TCL_TRACE_V);
 }
 
@@ -1753,7 +1762,9 @@ static int sm_count() {   // of the current device, cached per device index (a p
 template <typename FrameT, int MASK, bool REDUCE, int CT, int LEAN, int CW>
 static cudaError_t launch_tma_cw(const FwdParams& p, const CUtensorMap& tb, const CUtensorMap& tf, const CUtensorMap& tp, const CUtensorMap& tc,
                                  cudaStream_t s) {
-  using Cfg = WsCfg<FrameT, CT, kTW, kTH, box_width<FrameT>(), box_height(CW), TCL_NB, TCL_NS, CW>;
+  constexpr bool has_ff = MASK == MASK_COMPUTED;
+  constexpr int NS = has_ff ? TCL_NS : TCL_NS_NOFF, NB = has_ff ? TCL_NB : TCL_NS_NOFF + 2;
+  using Cfg = WsCfg<FrameT, CT, kTW, kTH, box_width<FrameT>(), (has_ff ? box_height(CW) : TCL_BH_NOFF), NB, NS, CW, has_ff>;
   auto kern = fused_forward_ws_kernel<FrameT, MASK, REDUCE, CT, LEAN, Cfg>;
   static bool configured[64] = {};  // per instantiation and device (the attribute is a per-device property of the function)
   int dev = 0;
@@ -1929,7 +1940,7 @@ static int run_fused(const tclb200_tcl_args* a, cudaStream_t s) {
   memset(&tb, 0, sizeof(tb)); memset(&tf, 0, sizeof(tf)); memset(&tp, 0, sizeof(tp)); memset(&tc, 0, sizeof(tc));
   if (tma) {
     const int bw = a->dtype == TCLB200_BF16 ? box_width<__nv_bfloat16>() : box_width<float>();
-    const int kBH = box_height(cw_packed ? kCWarpsPacked : kCWarpsOther);
+    const int kBH = mask_kind == MASK_COMPUTED ? box_height(cw_packed ? kCWarpsPacked : kCWarpsOther) : TCL_BH_NOFF;
     tma = make_map(&tb, a->bf, 4, a->W, a->H, 2, a->bf_index ? a->n_bf_fields : a->B, kTW + 16, kTH + 2, 2, bf_plane, bf_batch);
     if (tma && mask_kind == MASK_COMPUTED && (a->flags & TCLB200_OCC))
       tma = make_map(&tf, a->ff, 4, a->W, a->H, 2, a->ff_index ? a->n_ff_fields : a->B, bw, kBH, 2, ff_plane, ff_batch);
