@@ -270,7 +270,7 @@ extern "C" int tclb200_tcl_forward_host(const tclb200_host_args* a, tclb200_stre
     t.pair_sums = reinterpret_cast<double*>(ws + L.sums) + s;
     t.scratch = ws + L.scratch; t.scratch_bytes = tclb200_scratch_bytes(L.chunk, a->H, a->W);
     t.B = n; t.C = a->C; t.H = a->H; t.W = a->W;
-    t.dtype = a->dtype; t.flags = a->flags; t.loss = a->loss; t.finalize = a->finalize;
+    t.dtype = a->dtype; t.flags = a->flags | TCLB200_THROUGHPUT; t.loss = a->loss; t.finalize = a->finalize;
     const int rc = tclb200_tcl_forward(&t, stream);
     if (rc != TCLB200_OK) return bail(rc);   // tclb200_last_error() already holds the message
     HOST_TRY(cudaEventRecord(pipe->done[slot], comp));

@@ -33,6 +33,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <string.h>
+#include <type_traits>
 
 #include "../../include/tcl_b200.h"
 #include "tcl_common.cuh"
@@ -48,6 +49,9 @@
 #ifndef TCL_BH8
 #define TCL_BH8 44    // ... and with 8 (their control block is smaller): as tall as 227 KB of shared memory allow -- measured on the
 #endif                // Sintel shape, sustained: 40 / 42 / 44 rows = 115.7 / 118.2 / 120.2 Gpix/s (fewer tiles straddle a motion boundary)
+#ifndef TCL_BH16
+#define TCL_BH16 TCL_BH   // ... with bf16 frames (their boxes are smaller: room for more rows)
+#endif
 #ifndef TCL_BW
 #define TCL_BW 80     // source-box width for fp32 frames: 16 (mod 32), see WsCfg
 #endif
@@ -253,6 +257,122 @@ __global__ void __launch_bounds__(kThreads) fused_forward_generic_kernel(const F
 }
 
 // ---------------------------------------------------------------------------------------------
+// direct forward kernel: short launches of the training loss (dataset mask, C == 3, reduction only)
+// ---------------------------------------------------------------------------------------------
+// The persistent TMA pipeline below needs ~7 us to fill and drain and works a tile at a time; a training batch
+// (16 x 256 x 256, solver.py:427-446) is only 3.5 tile rounds long.  This kernel puts the launch in flight at once instead:
+// one CTA of 256 threads per 512 consecutive pixels of a pair (two pixels per thread, one step), 12 KB of shared memory,
+// four or more CTAs resident per SM.  Thread 0 requests the chunk's flow, mask and `cur` values with six bulk copies
+// (cp.async.bulk: no registers tied up while they fly) and prefetches the chunk's own stretch of `prev` into L2; the taps
+// of `prev` are exact predicated gathers from global memory (grid_sample's zero padding), consecutive lanes on
+// consecutive pixels.  One fp64 partial per chunk, then the fold kernel behind it (programmatic dependent launch) exactly
+// as for the TMA kernel.  Measured (tools/small_launch.py, CUDA-graph replay over L2-rotating buffers): 4 / 16 / 32 pairs of
+// 256 x 256: 7.2 / 17.9 / 29.6 us against 10.2 / 21.7 / 34 us on the pipeline; from 64 pairs on the pipeline wins.
+// Variants measured and dropped: 128 threads x 8 pixels (19.4 us at 16 pairs), 512 threads x 2 pixels (18.1), 256 x 4 (18.5),
+// six resident CTAs at 42 registers (18.0), no L2 prefetch (+0.4 us, +1.9 us at 4 pairs).
+constexpr int kDirectThreads = 256, kDirectChunk = 512, kDirectResident = 4;
+
+__device__ __forceinline__ void bulk_load_1d(void* dst, const void* src, unsigned bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+template <typename FrameT, int LOSS>
+__global__ void __launch_bounds__(kDirectThreads, kDirectResident) fused_forward_direct_kernel(const FwdParams p) {
+  constexpr int CH = kDirectChunk, PPT = CH / kDirectThreads;
+  __shared__ __align__(128) float s_f[3][CH];      // u, v, mask of the chunk
+  __shared__ __align__(128) FrameT s_c[3][CH];     // cur
+  __shared__ __align__(8) uint64_t s_bar[2];       // [0] flow landed, [1] mask and cur landed
+  __shared__ double s_red[kDirectThreads / 32];
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // let the fold kernel get resident early
+  const Geo& g = p.geo;
+  const int W = g.W;
+  const size_t plane = (size_t)g.H * W;
+  const int pair = blockIdx.x / p.tiles_per_pair, chunk = blockIdx.x - pair * p.tiles_per_pair;
+  const int i0 = p.row_begin * W + chunk * CH;               // (band mode: rows [row_begin, row_end) only)
+  const int n = min(CH, p.row_end * W - i0);                 // a multiple of 4 (8 with bf16 frames): the host checks W
+  const FrameT* prev = reinterpret_cast<const FrameT*>(p.prev) + (size_t)prev_frame(p, pair) * 3 * plane;
+  if (threadIdx.x == 0) {
+    const float* bu = p.bf + (size_t)bf_field(p, pair) * p.bf_batch + i0;
+    const FrameT* cur = reinterpret_cast<const FrameT*>(p.cur) + (size_t)cur_frame(p, pair) * 3 * plane + i0;
+    const unsigned fb = (unsigned)n * 4u, cb = (unsigned)n * (unsigned)sizeof(FrameT);
+    mbar_init(&s_bar[0], 1);
+    mbar_init(&s_bar[1], 1);
+    fence_barrier_init();
+    mbar_expect_tx(&s_bar[0], 2u * fb);
+    bulk_load_1d(s_f[0], bu, fb, &s_bar[0]);
+    bulk_load_1d(s_f[1], bu + p.bf_plane, fb, &s_bar[0]);
+    // this chunk's own stretch of the three `prev` planes into L2: the taps of a chunk land elsewhere (where the flow
+    // points), but all chunks together cover the frames, so the whole launch's DRAM reads are requested in its first
+    // microsecond and the gathers below mostly hit L2
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+      asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(prev + (size_t)c * plane + i0), "r"(cb) : "memory");
+    mbar_expect_tx(&s_bar[1], fb + 3u * cb);
+    bulk_load_1d(s_f[2], p.mask_in + (size_t)pair * plane + i0, fb, &s_bar[1]);
+    bulk_load_1d(s_c[0], cur, cb, &s_bar[1]);
+    bulk_load_1d(s_c[1], cur + plane, cb, &s_bar[1]);
+    bulk_load_1d(s_c[2], cur + 2 * plane, cb, &s_bar[1]);
+  }
+  int i = threadIdx.x;
+  int y = (int)((unsigned)(i0 + i) / (unsigned)W), x = i0 + i - y * W;
+  const int step_y = kDirectThreads / W, step_x = kDirectThreads - step_y * W;   // pixel i + 256 is that far from pixel i
+  __syncthreads();               // the barriers are initialised
+  mbar_wait(&s_bar[0], 0);
+  float err = 0.0f;
+  // two pixels per step, branch-free (a lane beyond the chunk's end recomputes pixel 0 and drops it): the 24 gathers of
+  // a step are independent and in flight together
+#pragma unroll 1
+  for (int j = 0; j < PPT; j += 2) {
+    Taps t[2];
+    float keep[2];
+    int ii[2];
+    bool ok[2];
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      ok[q] = i < n;
+      ii[q] = ok[q] ? i : 0;
+      t[q] = full_taps(pix_taps(s_f[0][ii[q]], s_f[1][ii[q]], x, y, g), g);
+      i += kDirectThreads;
+      x += step_x; y += step_y;
+      if (x >= W) { x -= W; ++y; }
+    }
+    float w[2][3];
+#pragma unroll
+    for (int q = 0; q < 2; ++q)
+#pragma unroll
+      for (int c = 0; c < 3; ++c) w[q][c] = sample_global(prev + (size_t)c * plane, t[q], W, kV);
+    if (j == 0) mbar_wait(&s_bar[1], 0);   // (the first gathers are under way before mask and cur are needed)
+    keep[0] = s_f[2][ii[0]]; keep[1] = s_f[2][ii[1]];
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      float e = err;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const float xc = to_f32(s_c[c][ii[q]]);
+        if (LOSS == TCLB200_L2) {
+          const float md = __fmul_rn(keep[q], __fsub_rn(xc, w[q][c]));   // mask*(cur - warp)   solver.py:444
+          e = __fmaf_rn(md, md, e);
+        } else {
+          e = __fadd_rn(e, __fmul_rn(keep[q], fabsf(__fsub_rn(w[q][c], xc))));   // mask*|warp - cur|   MoGAN cycle_gan_model.py:281
+        }
+      }
+      err = ok[q] ? e : err;
+    }
+  }
+  double s = warp_sum((double)err);
+  if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    s = 0.0;
+#pragma unroll
+    for (int k = 0; k < kDirectThreads / 32; ++k) s += s_red[k];
+    __stcg(&p.scratch.partials[(size_t)pair * p.tiles_per_pair + chunk], s);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // pieces of the TMA-staged, persistent, warp-specialised forward kernel (the hot kernel, described at its definition)
 // ---------------------------------------------------------------------------------------------
 __device__ unsigned long long g_tile_stats[2];   // debug statistics: tiles taken from global memory entirely / mixed tiles
@@ -451,6 +571,58 @@ __global__ void __launch_bounds__(kThreads) fold_partials_kernel(const FwdParams
     if (p.total_sums) { p.total_sums[0] = A; p.total_sums[1] = Bv; }
     if (p.total_val) *p.total_val = finalise_value(A * p.inv_count / (double)p.B, p.finalize);
     *p.scratch.batch_ticket = 0;
+  }
+}
+
+// The same for short launches (<= kFoldSmallPairs pairs, a few thousand partials): ONE CTA, 256 threads per pair and four
+// pairs at a time, no tickets and no second trip through L2 -- about half the latency of the two-level fold above, which
+// matters when the whole launch is 10-20 us.  Same summation order as fold_partials_kernel, so a pair's value does not
+// depend on which of the two folded it.
+constexpr int kFoldSmallPairs = 64, kFoldSmallPartials = 16384, kFoldSmallGroups = 1024 / kThreads;
+__global__ void __launch_bounds__(1024) fold_partials_small_kernel(const FwdParams p) {
+  __shared__ double s_S[kFoldSmallPairs];
+  __shared__ double s_red[kFoldSmallGroups][kWarps];
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  const int grp = threadIdx.x / kThreads, t = threadIdx.x - grp * kThreads, lane = t & 31, w = t >> 5;
+  const unsigned tpp = p.tiles_per_pair;
+  for (int base = 0; base < p.B; base += kFoldSmallGroups) {
+    const int pair = base + grp;
+    double s = 0.0;
+    if (pair < p.B) {
+      double* pp = p.scratch.partials + (size_t)pair * tpp;
+      for (unsigned i = t; i < tpp; i += kThreads) {
+        s += __ldcg(pp + i);
+        __stcg(pp + i, 0.0);
+      }
+    }
+    s = warp_sum(s);
+    if (lane == 0) s_red[grp][w] = s;
+    __syncthreads();
+    if (t == 0 && pair < p.B) {
+      double S = 0.0;
+#pragma unroll
+      for (int i = 0; i < kWarps; ++i) S += s_red[grp][i];
+      if (p.pair_sums) p.pair_sums[pair] = S;
+      if (p.pair_vals) p.pair_vals[pair] = finalise_value(S * p.inv_count, p.finalize);
+      s_S[pair] = S;
+    }
+    __syncthreads();
+  }
+  if (grp != 0) return;
+  double a = 0.0, b = 0.0;
+  for (int i = t; i < p.B; i += kThreads) {
+    a += s_S[i];
+    b += (double)finalise_value(s_S[i] * p.inv_count, p.finalize);
+  }
+  a = warp_sum(a); b = warp_sum(b);
+  if (lane == 0) { s_red[0][w] = a; s_red[1][w] = b; }
+  asm volatile("bar.sync 1, 256;" ::: "memory");   // (the first group's 256 threads only)
+  if (t == 0) {
+    double A = 0.0, Bv = 0.0;
+#pragma unroll
+    for (int i = 0; i < kWarps; ++i) { A += s_red[0][i]; Bv += s_red[1][i]; }
+    if (p.total_sums) { p.total_sums[0] = A; p.total_sums[1] = Bv; }
+    if (p.total_val) *p.total_val = finalise_value(A * p.inv_count / (double)p.B, p.finalize);
   }
 }
 
@@ -968,7 +1140,11 @@ __device__ __forceinline__ float lean_tile_packed(const FwdParams& p, const floa
     }
     // sampling position: the reference's [-1,1] round trip (flowtools.py:28-29 + grid_sampler's unnormalise), see lean_taps
     const float2 ax = add2(f2(xf), u), ay = add2(f2(yf0 + (float)(2 * j0), yf0 + (float)(2 * j1)), v);
-    const float2 tx = add2(add2(mul2(ax, f2(lg.i2x)), f2(-1.0f)), f2(1.0f)), ty = add2(add2(mul2(ay, f2(lg.i2y)), f2(-1.0f)), f2(1.0f));
+    // (the products are SCALAR multiplies on purpose: ptxas 12.9 contracts mul.rn.f32x2 + add.rn.f32x2 into one FFMA2 -- one
+    // rounding instead of the reference's two -- although both carry .rn; it leaves scalar mul.rn / add.rn alone.  Seen as a
+    // floor() one below the scanner's on a coordinate 5e-6 ulp from a rounding boundary: taps outside the staged box.)
+    const float2 qx = f2(__fmul_rn(ax.x, lg.i2x), __fmul_rn(ax.y, lg.i2x)), qy = f2(__fmul_rn(ay.x, lg.i2y), __fmul_rn(ay.y, lg.i2y));
+    const float2 tx = add2(add2(qx, f2(-1.0f)), f2(1.0f)), ty = add2(add2(qy, f2(-1.0f)), f2(1.0f));
     const float2 ix = mul2(fma2(tx, f2(lg.Wf), f2(-1.0f)), f2(0.5f)), iy = mul2(fma2(ty, f2(lg.Hf), f2(-1.0f)), f2(0.5f));
     const float2 fxf = f2(floorf(ix.x), floorf(ix.y)), fyf = f2(floorf(iy.x), floorf(iy.y));
     const float2 fx1 = sub2(add2(fxf, f2(1.0f)), ix), fx0 = sub2(ix, fxf);
@@ -1705,7 +1881,7 @@ extern "C" const char* tclb200_build_info(void) {
 // to a 16-byte boundary the taps may still spread >= 8 px in x and BH-TH-1 px in y beyond the tile's own extent
 // before the tile falls back to global gathers
 constexpr int kTW = 64, kTH = TCL_TH;
-constexpr int box_height(int cw) { return cw == 8 ? TCL_BH8 : TCL_BH; }
+constexpr int box_height(int cw, int esize) { return esize == 2 ? TCL_BH16 : (cw == 8 ? TCL_BH8 : TCL_BH); }
 template <typename FrameT> constexpr int box_width() { return sizeof(FrameT) == 4 ? TCL_BW : TCL_BW16; }
 
 static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
@@ -1759,12 +1935,14 @@ static int sm_count() {   // of the current device, cached per device index (a p
   return v;
 }
 
+static cudaError_t launch_fold(const FwdParams& p, cudaStream_t s);
+
 template <typename FrameT, int MASK, bool REDUCE, int CT, int LEAN, int CW>
 static cudaError_t launch_tma_cw(const FwdParams& p, const CUtensorMap& tb, const CUtensorMap& tf, const CUtensorMap& tp, const CUtensorMap& tc,
                                  cudaStream_t s) {
   constexpr bool has_ff = MASK == MASK_COMPUTED;
   constexpr int NS = has_ff ? TCL_NS : TCL_NS_NOFF, NB = has_ff ? TCL_NB : TCL_NS_NOFF + 2;
-  using Cfg = WsCfg<FrameT, CT, kTW, kTH, box_width<FrameT>(), (has_ff ? box_height(CW) : TCL_BH_NOFF), NB, NS, CW, has_ff>;
+  using Cfg = WsCfg<FrameT, CT, kTW, kTH, box_width<FrameT>(), (has_ff ? box_height(CW, (int)sizeof(FrameT)) : TCL_BH_NOFF), NB, NS, CW, has_ff>;
   auto kern = fused_forward_ws_kernel<FrameT, MASK, REDUCE, CT, LEAN, Cfg>;
   static bool configured[64] = {};  // per instantiation and device (the attribute is a per-device property of the function)
   int dev = 0;
@@ -1782,15 +1960,7 @@ static cudaError_t launch_tma_cw(const FwdParams& p, const CUtensorMap& tb, cons
   ++g_launches;
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess || !REDUCE) return e;
-  ++g_launches;
-  cudaLaunchConfig_t cfg;
-  memset(&cfg, 0, sizeof(cfg));
-  cfg.gridDim = dim3((unsigned)p.B); cfg.blockDim = dim3(kThreads); cfg.stream = s;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
-  cfg.attrs = attr; cfg.numAttrs = 1;
-  return cudaLaunchKernelEx(&cfg, fold_partials_kernel, p);
+  return launch_fold(p, s);
 }
 
 // Consumer warps per CTA.  The packed-arithmetic configuration on fp32 frames (computeTCL: both mask tests, C == 3) runs
@@ -1809,6 +1979,29 @@ static cudaError_t launch_tma(const FwdParams& p, const CUtensorMap& tb, const C
   return launch_tma_cw<FrameT, MASK, REDUCE, CT, LEAN, kCWarpsOther>(p, tb, tf, tp, tc, s);
 }
 
+static cudaError_t launch_fold(const FwdParams& p, cudaStream_t s) {   // behind a kernel that stored one fp64 partial per tile
+  ++g_launches;
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  const bool small = p.B <= kFoldSmallPairs && (size_t)p.B * p.tiles_per_pair <= (size_t)kFoldSmallPartials;
+  cfg.gridDim = dim3(small ? 1u : (unsigned)p.B); cfg.blockDim = dim3(small ? 1024 : kThreads); cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  return small ? cudaLaunchKernelEx(&cfg, fold_partials_small_kernel, p) : cudaLaunchKernelEx(&cfg, fold_partials_kernel, p);
+}
+
+template <typename FrameT>
+static cudaError_t launch_direct(const FwdParams& p, cudaStream_t s) {
+  auto kern = p.loss == TCLB200_L1 ? fused_forward_direct_kernel<FrameT, TCLB200_L1> : fused_forward_direct_kernel<FrameT, TCLB200_L2>;
+  kern<<<(unsigned)((size_t)p.B * p.tiles_per_pair), kDirectThreads, 0, s>>>(p);
+  ++g_launches;
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  return launch_fold(p, s);
+}
+
 template <typename FrameT, int MASK, bool REDUCE>
 static cudaError_t launch_generic(const FwdParams& p, cudaStream_t s) {
   const unsigned grid = (unsigned)((size_t)p.B * p.tiles_per_pair);
@@ -1821,10 +2014,10 @@ static cudaError_t launch_generic(const FwdParams& p, cudaStream_t s) {
 template <typename FrameT>
 static cudaError_t dispatch(const FwdParams& p, int mask_kind, bool reduce, bool tma, const CUtensorMap& tb, const CUtensorMap& tf,
                             const CUtensorMap& tp, const CUtensorMap& tc, cudaStream_t s) {
-#ifdef TCL_HOT_ONLY   // tuning builds (tools/sweep_build.py): only the fp32 computeTCL configuration, compiles in seconds
-  if (sizeof(FrameT) == 4 && mask_kind == MASK_COMPUTED && reduce && tma && p.C == 3 && p.prev && p.cur && !p.warp_out && !p.mask_out &&
+#ifdef TCL_HOT_ONLY   // tuning builds (tools/sweep_build.py): only the fp32 (1) or bf16 (2) computeTCL configuration, compiles in seconds
+  if (sizeof(FrameT) == (TCL_HOT_ONLY == 2 ? 2 : 4) && mask_kind == MASK_COMPUTED && reduce && tma && p.C == 3 && p.prev && p.cur && !p.warp_out && !p.mask_out &&
       !p.blend_out && !p.near_threshold && p.loss == TCLB200_L2)
-    return launch_tma<float, MASK_COMPUTED, true, 3, 1>(p, tb, tf, tp, tc, s);
+    return launch_tma<typename std::conditional<TCL_HOT_ONLY == 2, __nv_bfloat16, float>::type, MASK_COMPUTED, true, 3, 1>(p, tb, tf, tp, tc, s);
   if (mask_kind == MASK_COMPUTED && !reduce && !p.prev) return launch_generic<float, MASK_COMPUTED, false>(p, s);
   return cudaErrorNotSupported;
 #else
@@ -1888,8 +2081,14 @@ extern "C" int tclb200_debug_trace(unsigned long long* out, size_t bytes) {
 }
 #endif
 
-static int g_force_generic = 0;  // test hook: exercise the generic kernel on TMA-capable shapes
+// test / tuning hook: 1 = the generic kernel on TMA-capable shapes, 2 = never the direct kernel, 3 = the direct kernel whatever the size
+static int g_force_generic = 0;
 extern "C" void tclb200_debug_force_generic(int on) { g_force_generic = on; }
+// launches up to this many pixels go to the direct kernel when their configuration allows (training loss with a dataset
+// mask); beyond it the persistent pipeline's steady state wins (measured, tools/small_launch.py)
+#ifndef TCL_DIRECT_MAX_PX
+#define TCL_DIRECT_MAX_PX (2u << 20)
+#endif
 
 static int run_fused(const tclb200_tcl_args* a, cudaStream_t s) {
   if (!a) return fail(TCLB200_ERR_INVALID, "args is NULL");
@@ -1927,7 +2126,7 @@ static int run_fused(const tclb200_tcl_args* a, cudaStream_t s) {
     return fail(TCLB200_ERR_INVALID, "flow plane / pair strides must be at least H*W");
   const bool strides16 = bf_plane % 4 == 0 && bf_batch % 4 == 0 && ff_plane % 4 == 0 && ff_batch % 4 == 0;   // TMA: 16-byte strides
   // TMA needs 16-byte aligned bases and row strides; frames need C == 3 (the compiled box depth)
-  bool tma = !g_force_generic && (a->W % 4 == 0) && ((a->W * esz) % 16 == 0) && aligned16(a->bf) && aligned16(a->ff) &&
+  bool tma = g_force_generic != 1 && (a->W % 4 == 0) && ((a->W * esz) % 16 == 0) && aligned16(a->bf) && aligned16(a->ff) &&
              aligned16(a->prev) && aligned16(a->cur) && (!a->prev || a->C == 3) && a->B <= 65535 * 16 && strides16 &&
              a->H <= 16384 && a->W <= 16384;   // (box addresses are evaluated in fp32, see lean_tile)
   // the packed-arithmetic configuration on large fp32 frames runs with 8 consumer warps and taller boxes (launch_tma): the
@@ -1936,11 +2135,16 @@ static int run_fused(const tclb200_tcl_args* a, cudaStream_t s) {
                          a->prev && a->cur && a->C == 3 && !a->warp_out && !a->mask_out && !a->blend_out && !a->near_threshold &&
                          !(a->flags & TCLB200_VALIDITY) && (a->flags & (TCLB200_OCC | TCLB200_MOB)) == (TCLB200_OCC | TCLB200_MOB) &&
                          (size_t)a->H * a->W >= (size_t)384 * 384;
+  // short launches of the training loss (dataset mask, reduction only): the direct kernel, no tensor maps needed
+  const size_t launch_px = (size_t)a->B * (size_t)((band ? a->row_end - a->row_begin : a->H)) * a->W;
+  const bool direct = tma && g_force_generic != 2 && mask_kind == MASK_GIVEN && reduce && a->C == 3 && !a->warp_out && !a->mask_out &&
+                      !a->blend_out && !a->near_threshold && !(a->flags & (TCLB200_VALIDITY | TCLB200_THROUGHPUT)) && aligned16(a->mask_in) &&
+                      (launch_px <= TCL_DIRECT_MAX_PX || g_force_generic == 3);
   CUtensorMap tb, tf, tp, tc;
   memset(&tb, 0, sizeof(tb)); memset(&tf, 0, sizeof(tf)); memset(&tp, 0, sizeof(tp)); memset(&tc, 0, sizeof(tc));
-  if (tma) {
+  if (tma && !direct) {
     const int bw = a->dtype == TCLB200_BF16 ? box_width<__nv_bfloat16>() : box_width<float>();
-    const int kBH = mask_kind == MASK_COMPUTED ? box_height(cw_packed ? kCWarpsPacked : kCWarpsOther) : TCL_BH_NOFF;
+    const int kBH = mask_kind == MASK_COMPUTED ? box_height(cw_packed ? kCWarpsPacked : kCWarpsOther, esz) : TCL_BH_NOFF;
     tma = make_map(&tb, a->bf, 4, a->W, a->H, 2, a->bf_index ? a->n_bf_fields : a->B, kTW + 16, kTH + 2, 2, bf_plane, bf_batch);
     if (tma && mask_kind == MASK_COMPUTED && (a->flags & TCLB200_OCC))
       tma = make_map(&tf, a->ff, 4, a->W, a->H, 2, a->ff_index ? a->n_ff_fields : a->B, bw, kBH, 2, ff_plane, ff_batch);
@@ -1965,6 +2169,7 @@ static int run_fused(const tclb200_tcl_args* a, cudaStream_t s) {
   p.row_end = band ? a->row_end : a->H;
   p.tiles_x = tma ? cdiv(a->W, kTW) : cdiv(a->W, 32);
   p.tiles_per_pair = p.tiles_x * (tma ? cdiv(p.row_end - p.row_begin, kTH) : cdiv(p.row_end - p.row_begin, kWarps));
+  if (direct) { p.tiles_x = 0; p.tiles_per_pair = (int)(((size_t)(p.row_end - p.row_begin) * a->W + kDirectChunk - 1) / kDirectChunk); }
   p.flags = a->flags; p.loss = a->loss; p.finalize = a->finalize;
   p.inv_count = a->prev ? 1.0 / ((double)a->C * a->H * a->W) : 0.0;
   if ((size_t)p.B * p.tiles_per_pair >= 0x7fffffffu) return fail(TCLB200_ERR_UNSUPPORTED, "too many tiles for one launch");
@@ -1978,7 +2183,12 @@ static int run_fused(const tclb200_tcl_args* a, cudaStream_t s) {
     p.scratch.batch_ticket = p.scratch.pair_ticket + a->B;
     // long launches of the TMA kernel hand out tiles through a counter (two words behind the tickets)
     const size_t tiles = (size_t)p.B * p.tiles_per_pair;
-    p.scratch.tile_ctr = (tma && tiles > 16 * (size_t)sm_count()) ? p.scratch.batch_ticket + 1 : nullptr;
+    p.scratch.tile_ctr = (tma && !direct && tiles > 16 * (size_t)sm_count()) ? p.scratch.batch_ticket + 1 : nullptr;
+  }
+  if (direct) {
+    const cudaError_t e = a->dtype == TCLB200_BF16 ? launch_direct<__nv_bfloat16>(p, s) : launch_direct<float>(p, s);
+    if (e != cudaSuccess) return fail(TCLB200_ERR_CUDA, "fused forward (direct) launch: %s", cudaGetErrorString(e));
+    return TCLB200_OK;
   }
   const cudaError_t e = a->dtype == TCLB200_BF16 ? dispatch<__nv_bfloat16>(p, mask_kind, reduce, tma, tb, tf, tp, tc, s)
                                                  : dispatch<float>(p, mask_kind, reduce, tma, tb, tf, tp, tc, s);

@@ -46,6 +46,10 @@ extern "C" {
 #define TCLB200_MOB 2
 /* fs_lib.warp validity mask (methods/learning-based/fs_lib.py:29-39) */
 #define TCLB200_VALIDITY 4
+/* this launch is one chunk of a longer evaluation: always the persistent pipeline (short launches of the training loss
+ * otherwise take a latency-optimised kernel with another, equally fixed, summation tree), so that per-pair values do not
+ * depend on how the caller chunked the pairs; set by tclb200_tcl_forward_host for its own launches */
+#define TCLB200_THROUGHPUT 8
 
 /* masked error */
 #define TCLB200_L2 0 /* sum (m*(cur-warp))^2   solver.py:444, sintel_eval.py:110, metrics/eval.py:138 */
@@ -258,8 +262,9 @@ int tclb200_pack_sequence_sums(const float* pair_vals, const double* sum_sq, con
                                double elems_per_pair, double* packed, tclb200_stream_t stream);
 int tclb200_unpack_sequence_means(const double* packed, int n_seq, double* out, tclb200_stream_t stream);
 
-/* Test hook (process-global, not for production use): route TMA-capable shapes through the generic
- * global-memory kernel so that both kernels are exercised on the same inputs.  0 = off (default). */
+/* Test hook (process-global, not for production use): pin the forward kernel so that all of them are exercised on the
+ * same inputs.  0 = off (default); 1 = the generic global-memory kernel also for TMA-capable shapes; 2 = never the direct
+ * kernel of short training-loss launches (always the persistent TMA pipeline); 3 = the direct kernel whatever the size. */
 void tclb200_debug_force_generic(int on);
 
 /* Diagnostics (process-global device counters, not for production use): out2[0] = tiles of the TMA kernel that

@@ -126,3 +126,24 @@ def test_product_package_never_touches_the_oracle():
             assert "import oracle" not in src and "from oracle" not in src and "tcl_oracle" not in src, path
             if path.endswith(".py"):
                 assert "grid_sample(" not in src, f"{path}: the product path must not fall back to F.grid_sample"
+
+
+def test_packed_products_are_not_contracted_in_the_shipped_library():
+    """ptxas 12.9 fuses mul.rn.f32x2 + add.rn.f32x2 into one FFMA2 (one rounding where the reference has two).  The hot kernel
+    therefore multiplies its coordinate products as scalars; in its SASS every `... * W - 1` FFMA2 (flowtools.py:28-29 + the
+    sampler's unnormalise) must be matched by a separate packed `- 1` add -- a contracted product would show up as extra FFMA2s
+    with a -1 addend and no FADD2."""
+    import shutil
+    import subprocess
+    import tcl_b200
+    if shutil.which("cuobjdump") is None:
+        pytest.skip("cuobjdump not available")
+    lib = tcl_b200._cabi.build()
+    names = subprocess.run(["cuobjdump", "-elf", lib], capture_output=True, text=True).stdout
+    hot = sorted({w for line in names.splitlines() for w in line.split()
+                  if w.startswith("_ZN3tcl23fused_forward_ws_kernelIfLi2ELb1ELi3ELi1E") and "Li8ELb1E" in w and not w.startswith(".")})
+    assert hot, "hot kernel not found in the library"
+    sass = subprocess.run(["cuobjdump", "-sass", "-fun", hot[0], lib], capture_output=True, text=True).stdout
+    fma_m1 = sum(1 for l in sass.splitlines() if "FFMA2" in l and ", -1 ;" in l)
+    add_m1 = sum(1 for l in sass.splitlines() if "FADD2" in l and ", -1 ;" in l)
+    assert fma_m1 > 0 and fma_m1 == add_m1, (fma_m1, add_m1)

@@ -673,8 +673,16 @@ def test_host_entry_equals_device_path(tcl, oracle_mod, clips, H, W, chunk, dtyp
     # dataset-mask variant (utils/metrics/eval.py:137-138) through the same entry
     mask = tcl.fbcCheckTorch(ff.to(d), bf.to(d)).cpu()
     got_m = tcl.temporal_error_host(frames, None, bf, pi, ci, mask=mask, chunk_pairs=chunk)
-    want_m = tcl.temporal_rmse_per_sample(mask.to(d), fd[ci.long()].contiguous(), fd[pi.long()].contiguous(), bf.to(d)).cpu()
+    # (the host entry always launches the persistent pipeline, TCLB200_THROUGHPUT; a short device-resident launch of this
+    # configuration would take the direct kernel, whose sums agree to 1e-6 but follow another tree)
+    tcl._cabi.lib().tclb200_debug_force_generic(2)
+    try:
+        want_m = tcl.temporal_rmse_per_sample(mask.to(d), fd[ci.long()].contiguous(), fd[pi.long()].contiguous(), bf.to(d)).cpu()
+    finally:
+        tcl._cabi.lib().tclb200_debug_force_generic(0)
     assert torch.equal(got_m, want_m)
+    auto_m = tcl.temporal_rmse_per_sample(mask.to(d), fd[ci.long()].contiguous(), fd[pi.long()].contiguous(), bf.to(d)).cpu()
+    assert torch.allclose(got_m, auto_m, rtol=1e-6, atol=0.0)
     with pytest.raises(RuntimeError):
         tcl.temporal_error_host(frames.to(d), ff, bf, pi, ci)          # device tensor where host memory is expected
     with pytest.raises(RuntimeError):
@@ -774,6 +782,75 @@ def test_band_mode_adds_up_to_the_whole_frame(tcl, force_generic, H, W, force):
             tcl.fused_forward(bf, prev, cur, ff=ff, rows=(5, 5))
     finally:
         force_generic(False)
+
+
+@pytest.mark.gpu
+def test_packed_coordinate_products_round_twice_like_the_reference(tcl, force_generic):
+    """Regression: ptxas 12.9 contracts mul.rn.f32x2 + add.rn.f32x2 into one FFMA2, so the packed hot path once computed
+    g = 2(y+v)/(H-1) - 1 (flowtools.py:29) with ONE rounding.  On this pair (the 1080p bf16 window workload, weak shard of
+    rank 7) pixel (1216, 544) has (y+v)*i2y - 1 a 0.04 ulp from a rounding boundary: floor(iy) came out 594 where the
+    reference's two roundings -- and the scanner that placed the source box -- give 595, the taps left the staged box and
+    the pair's error was inf.  The products are scalar multiplies now; both frame types are checked against the exact path."""
+    d = dev()
+    H, W, seed = 1080, 1920, 1234 + 2000 + 100000 * 7
+    ff, bf = tcl.synth.make_flows(6, H, W, seed=seed, max_shift=56.0, max_rot_deg=2.0, device=d)
+    prev, cur = tcl.synth.make_frames(6, 3, H, W, seed=seed, kind="smooth", device=d, dtype=torch.bfloat16)
+    assert abs(float(bf[2, 1, 544, 1216]) - 50.94862747192383) < 1e-6      # (the data set still holds the borderline pixel)
+    for frames in ((prev, cur), (prev.float(), cur.float())):
+        hot = tcl.fused_forward(bf, frames[0], frames[1], ff=ff)
+        force_generic(1)
+        exact = tcl.fused_forward(bf, frames[0], frames[1], ff=ff)
+        force_generic(0)
+        assert bool(torch.isfinite(hot.pair_sums).all())
+        assert torch.allclose(hot.pair_sums, exact.pair_sums, rtol=1e-6, atol=0.0), (hot.pair_sums, exact.pair_sums)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("B,H,W,shift", [(16, 256, 256, 24.0), (3, 100, 96, 9.0), (2, 436, 1024, 32.0), (5, 36, 8, 3.0), (1, 1080, 1920, 60.0)])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_direct_kernel_equals_the_other_forward_kernels(tcl, force_generic, B, H, W, shift, dtype):
+    """Short launches of the training loss (dataset mask, solver.py:427-446) run on the direct kernel (one CTA per 1024
+    consecutive pixels, bulk-copied flow / mask / cur, gathers from global memory).  Same per-pixel arithmetic as the TMA
+    pipeline and the generic kernel, another summation tree: per-pair sums agree to 1e-6 with both and with the fp64 sum
+    over the bit-exact warp output; L2 and L1, {0,1} and soft masks, bands of rows, frames reached through index arrays."""
+    d = dev()
+    ff, bf = tcl.synth.make_flows(B, H, W, seed=77 + W, max_shift=shift, max_rot_deg=3.0, n_rects=6, rect_shift=20.0, device=d)
+    prev, cur = tcl.synth.make_frames(B, 3, H, W, seed=77 + W, kind="white", device=d, dtype=dtype)
+    hard = tcl.fbcCheckTorch(ff, bf)
+    soft = torch.rand(B, 1, H, W, device=d, generator=torch.Generator(device=d).manual_seed(5))
+    warp = tcl.warp(prev, bf).double() if dtype == torch.float32 else tp.backward_warp(prev.float(), bf).double()
+    rtol = 1e-6 if dtype == torch.float32 else 1e-5
+    lib = tcl._cabi.lib()
+    try:
+        for mask in (hard, soft):
+            for loss in (tcl.ops.L2, tcl.ops.L1):
+                diff = cur.double() - warp
+                want = ((mask.double() * diff) ** 2 if loss == tcl.ops.L2 else mask.double() * diff.abs()).sum(dim=(1, 2, 3))
+                got = {}
+                for force in (3, 2, 1):       # direct, TMA pipeline, generic
+                    force_generic(force)
+                    r = tcl.fused_forward(bf, prev, cur, mask=mask, loss=loss, finalize=tcl.ops.FIN_MEAN)
+                    got[force] = r
+                    assert torch.allclose(r.pair_sums, want, rtol=rtol, atol=1e-30), (force, loss, r.pair_sums, want)
+                assert torch.allclose(got[3].pair_sums, got[2].pair_sums, rtol=2e-6, atol=0.0)
+                assert torch.allclose(got[3].pair_sums, got[1].pair_sums, rtol=1e-6, atol=0.0)
+                assert torch.allclose(got[3].pair_vals, got[1].pair_vals, rtol=1e-6, atol=0.0)
+                assert torch.allclose(got[3].total_val, got[1].total_val, rtol=1e-6, atol=0.0)
+        force_generic(3)
+        whole = tcl.fused_forward(bf, prev, cur, mask=hard).pair_sums
+        again = tcl.fused_forward(bf, prev, cur, mask=hard).pair_sums
+        assert torch.equal(whole, again)                       # deterministic
+        if H >= 36:                                            # bands of rows add up to the frame
+            total = torch.zeros(B, dtype=torch.float64, device=d)
+            for r0, r1 in ((0, 1), (1, 33), (33, H)):
+                total += tcl.fused_forward(bf, prev, cur, mask=hard, rows=(r0, r1)).pair_sums
+            assert torch.allclose(total, whole, rtol=1e-6, atol=0.0)   # (bands regroup the fp32 per-thread sums)
+        if B >= 2:                                             # clip mode: frames and flows through index arrays
+            idx = torch.arange(B - 1, -1, -1, device=d, dtype=torch.int32)
+            r = tcl.fused_forward(bf, prev, cur, mask=hard.flip(0).contiguous(), prev_index=idx, cur_index=idx, bf_index=idx)
+            assert torch.equal(r.pair_sums, whole.flip(0))
+    finally:
+        force_generic(0)
 
 
 def test_temporal_loss_refuses_gradients_it_does_not_compute(tcl):

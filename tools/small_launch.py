@@ -1,4 +1,4 @@
-"""Small-launch latency: TMA kernel vs generic kernel at training-batch sizes (CUDA-graph replay, L2-rotating buffers)."""
+"""Small-launch latency: direct kernel vs TMA pipeline vs generic kernel at training-batch sizes (CUDA-graph replay, L2-rotating buffers)."""
 import os, sys
 import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -40,10 +40,24 @@ def bench(B, H, W, generic, mode, nbuf=12):
     torch.cuda.synchronize()
     lib.tclb200_debug_force_generic(0)
     us = a.elapsed_time(b) / 20 / nbuf * 1e3
-    print(f"B={B:3d} {H}x{W} mode={mode:4s} {'generic' if generic else 'tma    '}  {us:7.1f} us/launch  {B*H*W/us/1e3:6.1f} Gpix/s", flush=True)
+    name = {0: "auto   ", 1: "generic", 2: "tma    ", 3: "direct "}[int(generic)]
+    print(f"B={B:3d} {H}x{W} mode={mode:4s} {name}  {us:7.1f} us/launch  {B*H*W/us/1e3:6.1f} Gpix/s", flush=True)
 
-for B in (4, 16, 64):
+if len(sys.argv) > 1 and sys.argv[1] == "one":     # for ncu: a few plain launches of the training shape on the direct kernel
+    ff, bf = tcl.synth.make_flows(16, 256, 256, seed=100, max_shift=24.0, max_rot_deg=6.0, device=dev)
+    prev, cur = tcl.synth.make_frames(16, 3, 256, 256, seed=100, device=dev)
+    m = tcl.fbcCheckTorch(ff, bf)
+    for _ in range(3):
+        tcl.fused_forward(bf, prev, cur, mask=m, finalize=tcl.ops.FIN_MEAN)
+    torch.cuda.synchronize()
+    sys.exit(0)
+for B in (4, 16, 64, 128):
     for mode in ("mask", "ff"):
-        for generic in (False, True):
-            bench(B, 256, 256, generic, mode)
-bench(1, 436, 1024, False, "ff"); bench(1, 436, 1024, True, "ff")
+        for force in ((3, 2, 1) if mode == "mask" else (2, 1)):
+            if B == 128 and force == 1:
+                continue
+            bench(B, 256, 256, force, mode, nbuf=12 if B <= 16 else 4)
+for B in (1, 8, 24):
+    for force in (3, 2):
+        bench(B, 436, 1024, force, "mask", nbuf=8 if B == 1 else 3)
+bench(1, 436, 1024, 2, "ff"); bench(1, 436, 1024, 1, "ff")

@@ -48,6 +48,10 @@ VARIANTS = {
     "hot_bh38": {"TCL_HOT_ONLY": 1, "TCL_BH": 38},
     "hot_bh36": {"TCL_HOT_ONLY": 1, "TCL_BH": 36},
     "trace": {"TCL_TRACE": 1, "TCL_HOT_ONLY": 1},
+    "bf16_bh42": {"TCL_HOT_ONLY": 2, "TCL_BH16": 42},
+    "bf16_bh48": {"TCL_HOT_ONLY": 2, "TCL_BH16": 48},
+    "bf16_bh54": {"TCL_HOT_ONLY": 2, "TCL_BH16": 54},
+    "bf16_bh60": {"TCL_HOT_ONLY": 2, "TCL_BH16": 60},
 }
 # the rest of the library (host entry, cv2 flavour, aggregation) is linked in from the regular build's objects
 OTHER_OBJS = [os.path.join(CSRC, o) for o in ("tcl_host.o", "tcl_cv2.o", "tcl_agg.o", "tcl_chain.o")]
@@ -63,6 +67,6 @@ if __name__ == "__main__":
     for n, pr in procs:
         out = pr.communicate()[0]
         lines = out.splitlines()
-        hot = [i for i, l in enumerate(lines) if "ws_kernelIfLi2ELb1ELi3ELb1" in l and "Compiling" in l]
+        hot = [i for i, l in enumerate(lines) if ("ws_kernelIfLi2ELb1ELi3ELb1" in l or "ws_kernelI13__nv_bfloat16Li2ELb1ELi3" in l) and "Compiling" in l]
         info = " | ".join(l.strip() for l in lines[hot[0] + 1:hot[0] + 4]) if hot else "?"
         print(n, "rc", pr.returncode, info[:230])
