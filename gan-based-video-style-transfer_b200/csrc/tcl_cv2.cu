@@ -178,10 +178,17 @@ __global__ void __launch_bounds__(256) occlusion_u8_kernel(const uint8_t* __rest
   __shared__ float lut[256];   // (a warp's 128 lookups hit arbitrary entries: shared memory, not the constant cache)
   lut[threadIdx.x] = c_occ_lut[threadIdx.x];
   __syncthreads();
-  // four pixels per lane and step: one 32-bit load, one 128-bit store
-  for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n4; i += (size_t)gridDim.x * 256) {
-    const uchar4 v = __ldcs(reinterpret_cast<const uchar4*>(src) + i);
-    __stcs(reinterpret_cast<float4*>(dst) + i, make_float4(lut[v.x], lut[v.y], lut[v.z], lut[v.w]));
+  // four pixels per lane and step (one 32-bit load, one 128-bit store, both fully coalesced), four independent steps in flight
+  constexpr int K = 4;
+  for (size_t i0 = (size_t)blockIdx.x * (256 * K) + threadIdx.x; i0 < n4; i0 += (size_t)gridDim.x * (256 * K)) {
+    uchar4 v[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k)
+      if (i0 + k * 256 < n4) v[k] = __ldcs(reinterpret_cast<const uchar4*>(src) + i0 + k * 256);
+#pragma unroll
+    for (int k = 0; k < K; ++k)
+      if (i0 + k * 256 < n4)
+        __stcs(reinterpret_cast<float4*>(dst) + i0 + k * 256, make_float4(lut[v[k].x], lut[v[k].y], lut[v[k].z], lut[v[k].w]));
   }
   if (blockIdx.x == 0 && threadIdx.x < (unsigned)(n - 4 * n4)) {   // the 0..3 trailing pixels (or a tiny unaligned buffer)
     const size_t j = 4 * n4 + threadIdx.x;
@@ -253,7 +260,7 @@ extern "C" int tclb200_occlusion_u8_to_mask(const uint8_t* src, float* dst, size
   const size_t n4 = vec ? n / 4 : 0;
   if (n - 4 * n4 > 256)   // (the scalar tail covers at most one CTA's worth of pixels)
     return cfail(TCLB200_ERR_UNSUPPORTED, "src must be 4-byte and dst 16-byte aligned (or n <= 256)");
-  const size_t want = n4 ? (n4 + 255) / 256 : 1, cap = 148 * 8 * 4;   // grid-stride beyond a few waves
+  const size_t want = n4 ? (n4 + 1023) / 1024 : 1, cap = 148 * 8 * 4;   // (a CTA covers 256 x 4 steps x 4 pixels per pass) grid-stride beyond a few waves
   const unsigned grid = (unsigned)(want < cap ? want : cap);
   occlusion_u8_kernel<<<grid, 256, 0, s>>>(src, dst, n4, n);
   tcl::count_launch();

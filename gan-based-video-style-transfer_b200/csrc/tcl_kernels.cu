@@ -1773,6 +1773,34 @@ __global__ void __launch_bounds__(kSplitPx) hwc_split_kernel(const SplitParams p
   }
 }
 
+// Two interleaved channels (the .flo payload, utils/flowlib.py:33-48: u0 v0 u1 v1 ...): no staging needed.  A lane loads one
+// float4 = two pixels (a warp: 512 contiguous bytes) and stores one float2 per plane (256 contiguous bytes each); four
+// independent loads per lane are in flight before the first store.  8 B/px read, 8 B/px written.
+struct Split2Params {
+  const float* src;
+  float* dst[2];            // plane of channel 0 / 1 of sample 0 (nullptr: channel not requested)
+  long long dstride[2];     // elements between consecutive samples of that destination
+  long long plane;          // H * W, even
+  long long pairs;          // N * plane / 2 pixel pairs in all
+};
+__global__ void __launch_bounds__(256) hwc2_split_kernel(const Split2Params p) {
+  constexpr int K = 4;
+  const long long half = p.plane / 2;
+  long long i = ((long long)blockIdx.x * K) * 256 + threadIdx.x;
+  float4 v[K];
+#pragma unroll
+  for (int k = 0; k < K; ++k)
+    if (i + k * 256 < p.pairs) v[k] = __ldcs(reinterpret_cast<const float4*>(p.src) + i + k * 256);
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    const long long j = i + k * 256;
+    if (j >= p.pairs) break;
+    const long long n = j / half, q = j - n * half;   // sample, pixel pair within its plane
+    if (p.dst[0]) __stcs(reinterpret_cast<float2*>(p.dst[0] + n * p.dstride[0]) + q, make_float2(v[k].x, v[k].z));
+    if (p.dst[1]) __stcs(reinterpret_cast<float2*>(p.dst[1] + n * p.dstride[1]) + q, make_float2(v[k].y, v[k].w));
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // RAFT's convex 8x flow upsampling (utils/raft/raft/raft.py:72-83), the step right before the path: the flows the
 // kernels above consume are produced by it.  softmax over the 9 mask logits, convex combination of the 3x3 coarse
@@ -2303,6 +2331,26 @@ extern "C" int tclb200_hwc_split(const float* src, int N, int H, int W, int Cs, 
   for (int i = 0; i < n_out; ++i) {
     if (!dst[i] || c0[i] < 0 || cd[i] <= 0 || c0[i] + cd[i] > Cs) return fail(TCLB200_ERR_INVALID, "bad output channel range");
     p.dst[i] = dst[i]; p.c0[i] = c0[i]; p.cd[i] = cd[i];
+  }
+  if (Cs == 2 && p.plane % 2 == 0 && aligned16(src)) {   // the .flo layout: vector kernel when every plane start is 8-byte aligned
+    Split2Params q;
+    memset(&q, 0, sizeof(q));
+    q.src = src; q.plane = p.plane; q.pairs = (long long)N * p.plane / 2;
+    bool ok = true;
+    for (int i = 0; i < n_out; ++i)
+      for (int c = c0[i]; c < c0[i] + cd[i]; ++c) {
+        if (q.dst[c]) ok = false;   // (a channel requested twice: the general kernel handles it)
+        q.dst[c] = dst[i] + (long long)(c - c0[i]) * p.plane;
+        q.dstride[c] = (long long)cd[i] * p.plane;
+        ok = ok && (reinterpret_cast<uintptr_t>(q.dst[c]) & 7u) == 0;
+      }
+    const long long blocks = (q.pairs + 4 * 256 - 1) / (4 * 256);
+    if (ok && blocks < 0x7fffffffLL) {
+      hwc2_split_kernel<<<(unsigned)blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(q);
+      ++g_launches;
+      CUDA_TRY(cudaGetLastError());
+      return TCLB200_OK;
+    }
   }
   const long long chunks = (p.plane + kSplitPx - 1) / kSplitPx;
   if (chunks * N >= 0x7fffffffLL) return fail(TCLB200_ERR_UNSUPPORTED, "too many chunks for one launch");

@@ -440,7 +440,19 @@ def test_hwc_split_matches_moveaxis(tcl, tmp_path, N, H, W, Cs):
             assert np.array_equal(o[name].cpu().numpy(), block[..., c0:c0 + cd].permute(0, 3, 1, 2).numpy())
 
 
-@pytest.mark.parametrize("shape", [(436, 1024), (2, 37, 53), (1, 1), (3, 5, 7)])
+@pytest.mark.parametrize("N,H,W", [(3, 436, 1024), (2, 7, 6), (2, 7, 5), (1, 1, 2), (5, 64, 130)])
+def test_two_channel_split_vector_kernel(tcl, N, H, W):
+    """Two interleaved channels (.flo payloads, utils/flowlib.py:33-48) take a vector kernel when the plane size is even;
+    any selection of the two channels, several samples; odd planes fall back to the general kernel.  Bit-exact."""
+    d = dev()
+    block = torch.randn(N, H, W, 2, generator=torch.Generator().manual_seed(H * W)).to(d)
+    for parts in ([("flow", 0, 2)], [("u", 0, 1), ("v", 1, 1)], [("v", 1, 1)], [("v", 1, 1), ("u", 0, 1)]):
+        o = tcl.hwc_split(block, parts)
+        for name, c0, cd in parts:
+            assert torch.equal(o[name], block[..., c0:c0 + cd].permute(0, 3, 1, 2)), (parts, name)
+
+
+@pytest.mark.parametrize("shape", [(436, 1024), (2, 37, 53), (1, 1), (3, 5, 7), (40, 1080, 1920)])
 def test_sintel_occlusion_png_to_mask_exact(tcl, shape):
     """utils/sintel_dataset.py:64-65: mask = io.imread(png)/255.0 ; mask = 1.0 - mask (float64) ; torch .float()"""
     d = dev()
