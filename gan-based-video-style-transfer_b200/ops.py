@@ -555,7 +555,7 @@ class _LossPlan:
         self.args = TclArgs()
         self.stream = ctypes.c_void_p(stream_handle)
         self.lib = _cabi.lib()
-        self.fwd, self.bwd = self.lib.tclb200_tcl_forward, self.lib.tclb200_tcl_backward
+        self.fwd, self.bwd = self.lib.tclb200_tcl_forward, self.lib.tclb200_tcl_backward_scaled
         self.scratch, self.scratch_bytes = None, 0
 
 
@@ -618,7 +618,8 @@ class _TemporalLossFn(torch.autograd.Function):
         need_prev, need_cur = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
         gp = torch.empty_like(prev) if need_prev else None
         gc = torch.empty_like(cur) if need_cur else None
-        scale = grad_out.to(torch.float32).reshape(1) * (1.0 / float(B * C * H * W))
+        # the upstream gradient as it is; the kernel multiplies it by 1/N (one rounded fp32 product, like `grad_out * (1.0 / N)`)
+        scale = grad_out if (grad_out.dtype == torch.float32 and grad_out.is_cuda) else grad_out.to(device=prev.device, dtype=torch.float32)
         dev = prev.device
         switch = torch.cuda.current_device() != dev.index
         if switch:
@@ -626,7 +627,7 @@ class _TemporalLossFn(torch.autograd.Function):
             dctx.__enter__()
         try:
             plan = _loss_plan(dev, B, H, W)
-            rc = plan.bwd(flow.data_ptr(), mask.data_ptr(), prev.data_ptr(), cur.data_ptr(), scale.data_ptr(),
+            rc = plan.bwd(flow.data_ptr(), mask.data_ptr(), prev.data_ptr(), cur.data_ptr(), scale.data_ptr(), 1.0 / float(B * C * H * W),
                           gp.data_ptr() if gp is not None else None, gc.data_ptr() if gc is not None else None,
                           B, C, H, W, ctx.flags, ctx.loss, plan.stream)
             if rc != 0:

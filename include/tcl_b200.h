@@ -201,6 +201,12 @@ int tclb200_tcl_forward_host(const tclb200_host_args* args, tclb200_stream_t str
 int tclb200_tcl_backward(const float* bf, const float* mask, const float* prev, const float* cur,
                          const float* grad_scale, float* grad_prev, float* grad_cur, int B, int C, int H, int W,
                          int flags, int loss, tclb200_stream_t stream);
+/* The same with a host factor applied to the device scalar inside the kernel (one rounded fp32 product, exactly what
+ * `grad_out * (1.0 / N)` gives in torch): the autograd wrapper passes the upstream gradient itself and 1/(B*C*H*W), which
+ * saves the one-element multiply launch a mean loss otherwise needs in front of every backward. */
+int tclb200_tcl_backward_scaled(const float* bf, const float* mask, const float* prev, const float* cur,
+                                const float* grad_scale, float scale_mul, float* grad_prev, float* grad_cur, int B, int C,
+                                int H, int W, int flags, int loss, tclb200_stream_t stream);
 
 /* Dataset ingest ("next" row of the scope table): HWC -> planar NCHW de-interleave on the GPU.
  *   - the 9-channel FlyingChairs2 / Hollywood2 blocks [img1 3 | img2 3 | mask 1 | flow 2]

@@ -797,6 +797,25 @@ def test_band_mode_adds_up_to_the_whole_frame(tcl, force_generic, H, W, force):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_hot_path_equals_generic_kernel_on_a_large_sample(tcl, force_generic, dtype):
+    """Rare events (a coordinate on a rounding boundary, a test too close to call, a tile that barely fits its box) need many
+    pixels to show: 4 x 96 Sintel-shape pairs (171 Mpx) through the hot path and through the generic exact kernel, per-pair sums
+    to 1e-6 (a single wrong mask verdict or tap moves a pair's sum by more than that only if it matters; a tap outside its
+    box shows as a gross error)."""
+    d = dev()
+    for rep in range(4):
+        ff, bf = tcl.synth.make_flows(96, 436, 1024, seed=9000 + 131 * rep, max_shift=40.0, max_rot_deg=4.0, n_rects=8, rect_shift=25.0, device=d)
+        prev, cur = tcl.synth.make_frames(96, 3, 436, 1024, seed=9000 + 131 * rep, kind="smooth" if rep % 2 else "white", device=d, dtype=dtype)
+        hot = tcl.fused_forward(bf, prev, cur, ff=ff)
+        force_generic(1)
+        exact = tcl.fused_forward(bf, prev, cur, ff=ff)
+        force_generic(0)
+        assert bool(torch.isfinite(hot.pair_sums).all())
+        assert torch.allclose(hot.pair_sums, exact.pair_sums, rtol=1e-6 if dtype == torch.float32 else 1e-5, atol=0.0), rep
+
+
+@pytest.mark.gpu
 def test_packed_coordinate_products_round_twice_like_the_reference(tcl, force_generic):
     """Regression: ptxas 12.9 contracts mul.rn.f32x2 + add.rn.f32x2 into one FFMA2, so the packed hot path once computed
     g = 2(y+v)/(H-1) - 1 (flowtools.py:29) with ONE rounding.  On this pair (the 1080p bf16 window workload, weak shard of
