@@ -575,7 +575,9 @@ def other_workloads(tcl, device, frames, peak):
             out.append(dict(workload=name, pairs=n, shape=f'{cfg["W"]}x{cfg["H"]}', dtype=cfg["dtype"], mask=mode,
                             ms_per_launch_median=ms, timing="CUDA graph of one launch per rotating buffer, median of 20 replays", gpix_per_s=px / ms / 1e6, bytes_per_px=bpp,
                             achieved_gbs=px * bpp / ms / 1e6, frac_of_measured_peak=px * bpp / ms / 1e6 / peak,
-                            rotating_buffers=nbuf, working_set_mb=px * bpp * nbuf / 1e6))
+                            rotating_buffers=nbuf, working_set_mb=px * bpp * nbuf / 1e6,
+                            kernel=("fused_forward_direct_kernel (dataset mask, launch <= 2 Mpx) + fold_partials_small_kernel" if mode == "mask_in" and px <= (2 << 20)
+                                    else "fused_forward_ws_kernel + fold kernel")))
             del bufs, masks
             torch.cuda.empty_cache()
         except Exception as ex:  # report, never hide

@@ -79,6 +79,12 @@
 #ifndef TCL_PACKED
 #define TCL_PACKED 1  // interior staged tiles of the reducing hot configurations use packed fp32 arithmetic (lean_tile_packed)
 #endif
+#ifndef TCL_NS_MASK
+#define TCL_NS_MASK 3   // source-box stages of fbcCheckTorch on its own (two `ff` planes per stage)
+#endif
+#ifndef TCL_PACKED_MASK
+#define TCL_PACKED_MASK 1    // ... and for fbcCheckTorch on its own (mask_out only)
+#endif
 #ifndef TCL_PACKED_GIVEN
 #define TCL_PACKED_GIVEN 1   // ... also with a dataset mask (the training loss)
 #endif
@@ -1078,13 +1084,14 @@ __device__ __forceinline__ float2 staged_tap4x2(uint32_t a0, uint32_t a1, float2
 // EDGE: the tile overhangs the image (pixels outside are computed on a safe address and dropped); MIXED: a motion boundary
 // runs through the tile and the taps of some pixels lie outside the staged boxes -- those pixels are redone one by one
 // from global memory after the loop (pixel_global, exact), every other pixel of the tile keeps the fast path.
-template <typename FrameT, int MASK, int LOSS, typename Cfg, bool EDGE = false, bool MIXED = false>
+template <typename FrameT, int MASK, int LOSS, typename Cfg, bool EDGE = false, bool MIXED = false, int CT = 3>
 __device__ __forceinline__ float lean_tile_packed(const FwdParams& p, const float* s_bu, const float* s_ff, const int* meta, const TileId& t,
                                                   int lx0, int ly0, const float (&cur)[Cfg::kPPL][Cfg::kC], const float (&mk)[Cfg::kPPL]) {
   constexpr int P = Cfg::kPPL, BW = Cfg::BW, BFW = Cfg::kBfW, PL = Cfg::BH * Cfg::BW;
   constexpr float kHi = 1.0f + kFilterEps, kLo = 1.0f - kFilterEps;
   constexpr int FE = (int)sizeof(FrameT);
-  static_assert(P % 2 == 0 && Cfg::kC == 3 && MASK != MASK_NONE, "pixel pairs, three channels, a reducing configuration");
+  // CT == 3: the reducing configurations (computeTCL, training loss); CT == 0: fbcCheckTorch on its own (mask_out only, no frames)
+  static_assert(P % 2 == 0 && MASK != MASK_NONE && ((CT == 3 && Cfg::kC == 3) || (CT == 0 && MASK == MASK_COMPUTED)), "pixel pairs; three channels or mask-only");
   // mixed tiles, pixels whose taps left the boxes: computed masks fetch those taps from global memory inside the loop (a
   // warp-uniform branch); with a dataset mask the pixel is so cheap that waiting for global loads inside the loop costs
   // more than redoing the few pixels after it (measured: 131 vs 149 Gpix/s on the Sintel shape)
@@ -1100,7 +1107,7 @@ __device__ __forceinline__ float lean_tile_packed(const FwdParams& p, const floa
   const int c0 = (ly0 + 1) * BFW + lx0 + Cfg::kHaloL;
   const size_t gplane = (size_t)g.H * g.W;
   const GlobalSrc<float> fg{(MIXED && MASK == MASK_COMPUTED) ? p.ff + (size_t)t.ffi * p.ff_batch : nullptr, p.ff_plane, g};
-  const GlobalSrc<FrameT> pg{MIXED ? reinterpret_cast<const FrameT*>(p.prev) + (size_t)t.pf * 3 * gplane : nullptr, gplane, g};
+  const GlobalSrc<FrameT> pg{(MIXED && CT == 3) ? reinterpret_cast<const FrameT*>(p.prev) + (size_t)t.pf * 3 * gplane : nullptr, gplane, g};
   const bool xin = !EDGE || t.x0 + lx0 < g.W;
   const int rows_in = EDGE ? p.row_end - (t.y0 + ly0) : INT_MAX;   // pixel k is inside the image iff 2 * k < rows_in (and xin)
   const float bx_hi = box_xf + (float)(BW - 2), by_hi = box_yf + (float)(Cfg::BH - 2);   // top-left taps inside the boxes: [box, box + size - 2]
@@ -1168,7 +1175,9 @@ __device__ __forceinline__ float lean_tile_packed(const FwdParams& p, const floa
       a = staged_tap4x2<float, 0, BW>(fa0, fa1, nw, ne, sw, se);
       b = staged_tap4x2<float, PL * 4, BW>(fa0, fa1, nw, ne, sw, se);
     }
-    if (FE == 4) {   // fp32 frames: the prev planes sit behind the ff planes, the same address registers serve them
+    if (CT == 0) {
+      w3[0] = w3[1] = w3[2] = f2(0.0f);
+    } else if (FE == 4) {   // fp32 frames: the prev planes sit behind the ff planes, the same address registers serve them
       w3[0] = staged_tap4x2<FrameT, (int)Cfg::kFfStage, BW>(fa0, fa1, nw, ne, sw, se);
       w3[1] = staged_tap4x2<FrameT, (int)Cfg::kFfStage + PL * FE, BW>(fa0, fa1, nw, ne, sw, se);
       w3[2] = staged_tap4x2<FrameT, (int)Cfg::kFfStage + 2 * PL * FE, BW>(fa0, fa1, nw, ne, sw, se);
@@ -1188,12 +1197,12 @@ __device__ __forceinline__ float lean_tile_packed(const FwdParams& p, const floa
         if (o0) {
           const PixTaps st{(int)fxf.x, (int)fyf.x, nw.x, ne.x, sw.x, se.x};
           if (MASK == MASK_COMPUTED) { a.x = fg.sample(0, st); b.x = fg.sample(1, st); }
-          w3[0].x = pg.sample(0, st); w3[1].x = pg.sample(1, st); w3[2].x = pg.sample(2, st);
+          if (CT == 3) { w3[0].x = pg.sample(0, st); w3[1].x = pg.sample(1, st); w3[2].x = pg.sample(2, st); }
         }
         if (o1) {
           const PixTaps st{(int)fxf.y, (int)fyf.y, nw.y, ne.y, sw.y, se.y};
           if (MASK == MASK_COMPUTED) { a.y = fg.sample(0, st); b.y = fg.sample(1, st); }
-          w3[0].y = pg.sample(0, st); w3[1].y = pg.sample(1, st); w3[2].y = pg.sample(2, st);
+          if (CT == 3) { w3[0].y = pg.sample(0, st); w3[1].y = pg.sample(1, st); w3[2].y = pg.sample(2, st); }
         }
       }
     }
@@ -1209,7 +1218,7 @@ __device__ __forceinline__ float lean_tile_packed(const FwdParams& p, const floa
     }
     float2 acc = f2(0.0f);
 #pragma unroll
-    for (int ch = 0; ch < 3; ++ch) {
+    for (int ch = 0; ch < (CT == 3 ? 3 : 0); ++ch) {
       const float2 d = sub2(f2(cur[j0][ch], cur[j1][ch]), w3[ch]);
       // mask*|warp - cur| (MoGAN :281) / (mask*(cur - warp))^2
       acc = LOSS == TCLB200_L1 ? add2(acc, f2(fabsf(d.x), fabsf(d.y))) : fma2(d, d, acc);
@@ -1240,11 +1249,24 @@ __device__ __forceinline__ float lean_tile_packed(const FwdParams& p, const floa
 #pragma unroll
     for (int k = 0; k < P; ++k)
       if ((outbits >> k) & 1u) {
-        e[k] = pixel_global<FrameT, MASK, false, LOSS>(p.bf + (size_t)t.bfi * p.bf_batch, p.bf_plane, MASK == MASK_COMPUTED ? p.ff + (size_t)t.ffi * p.ff_batch : nullptr, p.ff_plane,
-                                                       reinterpret_cast<const FrameT*>(p.prev) + (size_t)t.pf * 3 * plane, g, t.x0 + lx0,
-                                                       t.y0 + ly0 + pix_dy(k), cur[k][0], cur[k][1], cur[k][2], mk[k]);
-        keepbits |= 1u << k;   // the verdict is already applied
+        if (CT == 3) {
+          e[k] = pixel_global<FrameT, MASK, false, LOSS>(p.bf + (size_t)t.bfi * p.bf_batch, p.bf_plane, MASK == MASK_COMPUTED ? p.ff + (size_t)t.ffi * p.ff_batch : nullptr, p.ff_plane,
+                                                         reinterpret_cast<const FrameT*>(p.prev) + (size_t)t.pf * 3 * plane, g, t.x0 + lx0,
+                                                         t.y0 + ly0 + pix_dy(k), cur[k][0], cur[k][CT == 3 ? 1 : 0], cur[k][CT == 3 ? 2 : 0], mk[k]);
+          keepbits |= 1u << k;   // the verdict is already applied
+        } else {
+          const float kp = pixel_global<FrameT, MASK, true, LOSS>(p.bf + (size_t)t.bfi * p.bf_batch, p.bf_plane, p.ff + (size_t)t.ffi * p.ff_batch, p.ff_plane, nullptr, g,
+                                                                  t.x0 + lx0, t.y0 + ly0 + pix_dy(k), 0.0f, 0.0f, 0.0f, 0.0f);
+          keepbits = (keepbits & ~(1u << k)) | ((kp != 0.0f ? 1u : 0u) << k);
+        }
       }
+  }
+  if (CT == 0) {   // mask-only: store the verdicts (two coalesced 64-byte row segments per warp instruction)
+    float* mo = p.mask_out + (size_t)t.pair * gplane + (size_t)(t.y0 + ly0) * g.W + (t.x0 + lx0);
+#pragma unroll
+    for (int k = 0; k < P; ++k)
+      if (!EDGE || (xin && 2 * k < rows_in)) __stcs(mo + (ptrdiff_t)pix_dy(k) * g.W, ((keepbits >> k) & 1u) ? 1.0f : 0.0f);
+    return 0.0f;
   }
   float err = 0.0f;
 #pragma unroll
@@ -1281,7 +1303,9 @@ __global__ void __launch_bounds__(Cfg::kThreads, 1) fused_forward_ws_kernel(cons
   constexpr int kCWarps = Cfg::CW;
   constexpr int kLoss = LEAN == 2 ? TCLB200_L1 : TCLB200_L2;
   // interior / edge / mixed staged tiles of the reducing hot configurations: packed fp32 arithmetic (lean_tile_packed)
-  constexpr bool kPacked = TCL_PACKED && (LEAN == 1 || LEAN == 2) && CT == 3 && (MASK == MASK_COMPUTED || (MASK == MASK_GIVEN && TCL_PACKED_GIVEN));
+  // ... and fbcCheckTorch on its own (mask_out only)
+  constexpr bool kPacked = TCL_PACKED && (((LEAN == 1 || LEAN == 2) && CT == 3 && (MASK == MASK_COMPUTED || (MASK == MASK_GIVEN && TCL_PACKED_GIVEN))) ||
+                                          (TCL_PACKED_MASK && LEAN == 1 && CT == 0 && MASK == MASK_COMPUTED && !REDUCE));
   using Ctl = WsCtl<NB, NS, kCWarps>;
   static_assert(sizeof(Ctl) <= Cfg::kCtlBytes, "control block too large");
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -1524,8 +1548,8 @@ __global__ void __launch_bounds__(Cfg::kThreads, 1) fused_forward_ws_kernel(cons
       else lean_tile<FrameT, MASK, CT, TCLB200_L2, Cfg, false, false, false>(p, bf_stage(sb), ff_stage(ss), ctl->meta[ss], t, lx0, ly0, cur, mk);
     } else if (LEAN && mode == 1) {
       if constexpr (kPacked) {
-        if (t_edge) err = lean_tile_packed<FrameT, MASK, kLoss, Cfg, true, false>(p, bf_stage(sb), ff_stage(ss), ctl->meta[ss], t, lx0, ly0, cur, mk);
-        else err = lean_tile_packed<FrameT, MASK, kLoss, Cfg, false, false>(p, bf_stage(sb), ff_stage(ss), ctl->meta[ss], t, lx0, ly0, cur, mk);
+        if (t_edge) err = lean_tile_packed<FrameT, MASK, kLoss, Cfg, true, false, CT>(p, bf_stage(sb), ff_stage(ss), ctl->meta[ss], t, lx0, ly0, cur, mk);
+        else err = lean_tile_packed<FrameT, MASK, kLoss, Cfg, false, false, CT>(p, bf_stage(sb), ff_stage(ss), ctl->meta[ss], t, lx0, ly0, cur, mk);
       } else {
         if (t_edge) err = lean_tile<FrameT, MASK, CT, kLoss, Cfg, true, false, true, LEAN == 4>(p, bf_stage(sb), ff_stage(ss), ctl->meta[ss], t, lx0, ly0, cur, mk);
         else err = lean_tile<FrameT, MASK, CT, kLoss, Cfg, false, false, true, LEAN == 4>(p, bf_stage(sb), ff_stage(ss), ctl->meta[ss], t, lx0, ly0, cur, mk);
@@ -1533,7 +1557,7 @@ __global__ void __launch_bounds__(Cfg::kThreads, 1) fused_forward_ws_kernel(cons
     } else if (LEAN == 4) {   // outputs wanted and the tile is mixed / unstaged: the feature-complete exact path
       err = full_tile<FrameT, MASK, REDUCE, CT, 0, Cfg, true>(p, bf_stage(sb), ff_stage(ss), prev_stage(ss), ctl->meta[ss], t, lx0, ly0, cur, mk, have_cur, near);
     } else if (LEAN && mode == 2) {
-      if constexpr (kPacked) err = lean_tile_packed<FrameT, MASK, kLoss, Cfg, true, true>(p, bf_stage(sb), ff_stage(ss), ctl->meta[ss], t, lx0, ly0, cur, mk);
+      if constexpr (kPacked) err = lean_tile_packed<FrameT, MASK, kLoss, Cfg, true, true, CT>(p, bf_stage(sb), ff_stage(ss), ctl->meta[ss], t, lx0, ly0, cur, mk);
       else err = lean_tile<FrameT, MASK, CT, kLoss, Cfg, true, true>(p, bf_stage(sb), ff_stage(ss), ctl->meta[ss], t, lx0, ly0, cur, mk);
     } else if (LEAN || t_edge) {
       err = full_tile<FrameT, MASK, REDUCE, CT, LEAN, Cfg, true>(p, bf_stage(sb), ff_stage(ss), prev_stage(ss), ctl->meta[ss], t, lx0, ly0, cur, mk, have_cur, near);
@@ -1973,7 +1997,8 @@ template <typename FrameT, int MASK, bool REDUCE, int CT, int LEAN, int CW>
 static cudaError_t launch_tma_cw(const FwdParams& p, const CUtensorMap& tb, const CUtensorMap& tf, const CUtensorMap& tp, const CUtensorMap& tc,
                                  cudaStream_t s) {
   constexpr bool has_ff = MASK == MASK_COMPUTED;
-  constexpr int NS = has_ff ? TCL_NS : TCL_NS_NOFF, NB = has_ff ? TCL_NB : TCL_NS_NOFF + 2;
+  // (mask-only launches stage no frame planes: a third source stage fits beside the flow ring)
+  constexpr int NS = has_ff ? (CT == 0 && LEAN == 1 ? TCL_NS_MASK : TCL_NS) : TCL_NS_NOFF, NB = has_ff ? (CT == 0 && LEAN == 1 ? TCL_NS_MASK + 2 : TCL_NB) : TCL_NS_NOFF + 2;
   using Cfg = WsCfg<FrameT, CT, kTW, kTH, box_width<FrameT>(), (has_ff ? box_height(CW, (int)sizeof(FrameT)) : TCL_BH_NOFF), NB, NS, CW, has_ff>;
   auto kern = fused_forward_ws_kernel<FrameT, MASK, REDUCE, CT, LEAN, Cfg>;
   static bool configured[64] = {};  // per instantiation and device (the attribute is a per-device property of the function)
@@ -2003,7 +2028,8 @@ template <typename FrameT, int MASK, bool REDUCE, int CT, int LEAN>
 static cudaError_t launch_tma(const FwdParams& p, const CUtensorMap& tb, const CUtensorMap& tf, const CUtensorMap& tp, const CUtensorMap& tc,
                               cudaStream_t s) {
   // (decided by run_fused, which sized the tensor maps' boxes for it: wants_packed8)
-  constexpr bool packed8 = TCL_PACKED && (LEAN == 1 || LEAN == 2) && CT == 3 && MASK == MASK_COMPUTED && sizeof(FrameT) == 4;
+  constexpr bool packed8 = TCL_PACKED && MASK == MASK_COMPUTED && sizeof(FrameT) == 4 &&
+                           (((LEAN == 1 || LEAN == 2) && CT == 3) || (TCL_PACKED_MASK && LEAN == 1 && CT == 0 && !REDUCE));
   if constexpr (packed8 && kCWarpsPacked != kCWarpsOther) {
     if (p.cw_packed) return launch_tma_cw<FrameT, MASK, REDUCE, CT, LEAN, kCWarpsPacked>(p, tb, tf, tp, tc, s);
   }
@@ -2163,8 +2189,10 @@ static int run_fused(const tclb200_tcl_args* a, cudaStream_t s) {
              a->H <= 16384 && a->W <= 16384;   // (box addresses are evaluated in fp32, see lean_tile)
   // the packed-arithmetic configuration on large fp32 frames runs with 8 consumer warps and taller boxes (launch_tma): the
   // same conditions as dispatch()'s `lean` for the computed-mask reductions
-  const bool cw_packed = TCL_PACKED && kCWarpsPacked != kCWarpsOther && tma && a->dtype == TCLB200_F32 && mask_kind == MASK_COMPUTED && reduce &&
-                         a->prev && a->cur && a->C == 3 && !a->warp_out && !a->mask_out && !a->blend_out && !a->near_threshold &&
+  const bool cw_hot = reduce && a->prev && a->cur && a->C == 3 && !a->warp_out && !a->mask_out && !a->blend_out;
+  const bool cw_mask = TCL_PACKED_MASK && !reduce && !a->prev && a->mask_out;   // (dispatch()'s `lean_mask`: fbcCheckTorch on its own)
+  const bool cw_packed = TCL_PACKED && kCWarpsPacked != kCWarpsOther && tma && a->dtype == TCLB200_F32 && mask_kind == MASK_COMPUTED &&
+                         (cw_hot || cw_mask) && !a->near_threshold &&
                          !(a->flags & TCLB200_VALIDITY) && (a->flags & (TCLB200_OCC | TCLB200_MOB)) == (TCLB200_OCC | TCLB200_MOB) &&
                          (size_t)a->H * a->W >= (size_t)384 * 384;
   // short launches of the training loss (dataset mask, reduction only): the direct kernel, no tensor maps needed

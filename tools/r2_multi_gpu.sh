@@ -1,5 +1,5 @@
 #!/bin/bash
-# usage: r2_call20.sh N
+# usage: r2_multi_gpu.sh N
 N=$1
 mkdir -p gpurun_out
 if [ "$N" = "2" ]; then
