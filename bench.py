@@ -488,7 +488,7 @@ def e2e_rate(tcl, shard, pairs_in_seq, steps, warmup, device, chunk=0):
         seqs = seqs[:int(t[0])]
         P, F = sum(seqs), sum(seqs) + len(seqs)
     saved_affinity = os.sched_getaffinity(0)
-    if world > 1:   # (N = 1 measured 55 GB/s unbound; the cpu_baseline leg that follows must see every host core)
+    if world > 1 and not os.environ.get("TCL_BENCH_NO_BIND"):   # (N = 1 measured 55 GB/s unbound; the cpu_baseline leg that follows must see every host core)
         bind_to_gpu_numa_node(device.index)
     setup_error = None
     try:
@@ -520,21 +520,34 @@ def e2e_rate(tcl, shard, pairs_in_seq, steps, warmup, device, chunk=0):
         res = tcl.evaluate_sharded_host(frames_h, ff_h, bf_h, prev_i, cur_i, seq_ids, len(pairs_in_seq), chunk_pairs=chunk)
         return float(res["mean_over_pairs"])
 
+    # short steps (config 4: 286 MB, ~6 ms per rank) are timed over ~2 s worth of them: measured on 2 GPUs, single steps of such a
+    # run take 9-99 ms instead of 6 (host-side stalls of lock-stepped ranks), and ten steps would report whichever outliers they caught.
+    # Every rank derives the same count from the step's bytes (the step contains a collective).
+    h2d = F * frame_b + 2 * P * flow_b + 2 * 4 * P
+    steps = max(steps, min(400, int(2.0 / (h2d / 50e9))))
+    import gc
     for _ in range(warmup):
         step()
     torch.cuda.synchronize()
     lib.tclb200_debug_launch_count(1)
+    gc.collect()
+    gc.disable()           # (no collector pauses inside the timed region; nothing here creates reference cycles)
     t0 = time.perf_counter()
+    step_ms = []
     for _ in range(steps):
+        ts = time.perf_counter()
         mean_rmse = step()
+        step_ms.append((time.perf_counter() - ts) * 1e3)
     torch.cuda.synchronize()
     el = time.perf_counter() - t0
+    gc.enable()
+    step_ms.sort()
     launches = int(lib.tclb200_debug_launch_count(0))
     os.sched_setaffinity(0, saved_affinity)
-    h2d = F * frame_b + 2 * P * flow_b + 2 * 4 * P
     return dict(value=steps * P / el, unit="pairs/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=12 * P + 8,
                 ms_per_step=el / steps * 1e3, h2d_gb_per_s=h2d * steps / el / 1e9, pairs_per_step=P, frames_per_step=F,
-                sequences_per_step=len(seqs), gpu_launches_per_step=launches // max(steps, 1), mean_rmse=mean_rmse,
+                sequences_per_step=len(seqs), gpu_launches_per_step=launches // max(steps, 1), mean_rmse=mean_rmse, steps=steps,
+                step_ms_rank0=dict(median=round(step_ms[len(step_ms) // 2], 3), p90=round(step_ms[int(len(step_ms) * 0.9)], 3), max=round(step_ms[-1], 3)),
                 h2d_ceiling_gb_per_s=ceiling, h2d_first_2gib_gb_per_s=ceiling_2g, h2d_pattern_gb_per_s=pattern,
                 note=f"tcl_b200.evaluate_sharded_host = temporal_error_host (C ABI tclb200_tcl_forward_host) + packed sums + one all-reduce when N > 1: pinned host clips -> chunks of pairs ({chunk or 'library default: ~256 MB per flow copy'}), "
                      "3-slot device ring, two internal copy streams; every frame crosses PCIe once per step (28.3 B/px per pair "

@@ -499,15 +499,18 @@ def temporal_error_host(frames, ff, bf, prev_index=None, cur_index=None, mask=No
         out = torch.empty(0, dtype=torch.float32, pin_memory=True)
         return (out, torch.empty(0, dtype=torch.float64, pin_memory=True)) if return_sums else out
     slots = F_
+    ws = _host_ws_cache.get(dev.index)
+    with_mask = 1 if mask is not None else 0
     if max_device_frames is not None:
         slots = max(1, min(F_, int(max_device_frames)))
-    else:
+    elif ws is None or ws.numel() < lib.tclb200_host_workspace_bytes(P, F_, C, H, W, dt, chunk_pairs, with_mask):
+        # only when a workspace has to be allocated: cudaMemGetInfo costs 1.5 ms at the median and 20-90 ms in one call of ten
+        # (measured, tools/e2e_stall_probe.py) -- per step it was the whole difference between a 6 ms step and a 12 ms one
         frame_bytes = C * H * W * frames.element_size()
-        free_b = torch.cuda.mem_get_info(dev)[0] + (_host_ws_cache[dev.index].numel() if dev.index in _host_ws_cache else 0)
+        free_b = torch.cuda.mem_get_info(dev)[0] + (ws.numel() if ws is not None else 0)
         if F_ * frame_bytes > free_b // 4:
             slots = max(1, min(F_, (free_b // 4) // frame_bytes))
-    need = lib.tclb200_host_workspace_bytes(P, slots, C, H, W, dt, chunk_pairs, 1 if mask is not None else 0)
-    ws = _host_ws_cache.get(dev.index)
+    need = lib.tclb200_host_workspace_bytes(P, slots, C, H, W, dt, chunk_pairs, with_mask)
     if ws is None or ws.numel() < need:
         _host_ws_cache.pop(dev.index, None)
         ws = torch.empty(need, dtype=torch.uint8, device=dev)
