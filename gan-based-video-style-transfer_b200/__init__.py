@@ -11,7 +11,7 @@ from .ops import (FusedResult, free_workspaces, generateMask, fbcCheckTorch, fbc
                   temporal_rmse_per_sample, upsample_flow, warp, warp_blend, window_evaluations, temporal_error_window)
 from .sintel_eval import (aggregate_means, computeTCL, computeTCL_from_flows, save_dict_as_json)  # noqa: F401
 from .sharding import (ShardPlan, plan_shards, evaluate_sharded, evaluate_sharded_host, evaluate_banded, band_rows, allreduce_sums)  # noqa: F401
-from .chains import reconet_output_temporal_loss, ruder_network_input  # noqa: F401
+from .chains import reconet_output_temporal_loss, ruder_network_input, long_term_blend_step  # noqa: F401
 from . import synth  # noqa: F401
 from . import ingest  # noqa: F401
 from . import cv2compat  # noqa: F401
@@ -21,4 +21,4 @@ __all__ = ["gradient", "warp", "fbcCheckTorch", "fbcCheckTorch_mob", "fs_warp", 
            "temporal_error", "temporal_error_per_pair", "temporal_error_clip", "temporal_error_host", "generateMask", "temporal_loss", "temporal_rmse_per_sample",
            "warp_blend", "computeTCL", "computeTCL_from_flows", "save_dict_as_json", "aggregate_means",
            "plan_shards", "evaluate_sharded", "evaluate_sharded_host", "allreduce_sums", "synth",
-           "reconet_output_temporal_loss", "ruder_network_input", "window_evaluations", "temporal_error_window"]
+           "reconet_output_temporal_loss", "ruder_network_input", "long_term_blend_step", "window_evaluations", "temporal_error_window"]

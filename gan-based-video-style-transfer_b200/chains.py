@@ -4,6 +4,8 @@
   (``o_temporal_loss`` without its ``gamma_o`` weight)
 * ``ruder_network_input``          -- one step of Ruder's recurrent chain, methods/learning-based/fs_ruder.py:50-75:
   ``torch.cat((img, mask, warp(styled_prev, flow)), 1)`` plus the warped frame for the loss of ``:97``
+* ``long_term_blend_step``         -- one step of the optimisation-based method's cumulative long-term initialisation,
+  methods/optimization-based/obst_eval.py:512-518 (disabled upstream: the lines sit inside a string literal)
 
 Both use ``fs_lib.warp`` (methods/learning-based/fs_lib.py:5-39: bilinear taps times the binarised warp of an all-ones
 image) as the reference trainers do (``from fs_lib import warp``).  CUDA fp32 tensors only; no CPU implementation.
@@ -127,3 +129,23 @@ def ruder_network_input(img, mask, styled_prev, flow):
     if torch.is_grad_enabled() and (flow.requires_grad or img.requires_grad or (m is not None and m.requires_grad)):
         raise RuntimeError("tcl_b200: ruder_network_input differentiates w.r.t. styled_prev only (images, masks and flows are data)")
     return _RuderInputFn.apply(sp, img, m, flow)
+
+
+def long_term_blend_step(mask_last, ff_last, bf_last, styled_past, pre):
+    """One step of the cumulative long-term initialisation of methods/optimization-based/obst_eval.py:515-516 (the block is
+    disabled upstream -- it sits inside a string literal -- and kept here for whoever switches it back on):
+
+        mask_last = torch.clamp(mask_last - fbcCheckTorch(ff_last, bf_last), 0.0, 1.0)
+        pre       = mask_last * warp(styled_past, bf_last) + (1 - mask_last) * pre
+
+    Two launches of the library (the consistency mask; warp + blend in one pass, ``obst_eval.py:500``'s form) around the one
+    elementwise clamp; no gradients, like the reference's initialisation.  Returns ``(mask_last, pre)``.  ``fbcCheckTorch`` is the
+    two-test mask of utils/flowtools.py:34-58 as imported by the evaluation scripts; pass ``ops.fbcCheckTorch_mob`` results through
+    ``mask_last`` yourself for the motion-boundary-only copy."""
+    from .ops import fbcCheckTorch, warp_blend
+    _require_cuda(mask_last, ff_last, bf_last, styled_past, pre)
+    B, _, H, W = bf_last.shape
+    mask_last = _mask1(mask_last, B, H, W)
+    with torch.no_grad():
+        mask_last = torch.clamp(mask_last - fbcCheckTorch(ff_last, bf_last), 0.0, 1.0)
+        return mask_last, warp_blend(mask_last, styled_past, bf_last, pre)

@@ -152,6 +152,12 @@ def ruder_input(img, mask, styled_prev, flow):
     return torch.cat((img, mask, warped), 1), warped
 
 
+def long_term_step(mask_last, ff_last, bf_last, styled_past, pre):
+    """One step of the cumulative long-term initialisation (obst_eval.py:515-516, disabled upstream)."""
+    mask_last = torch.clamp(mask_last - fb_consistency(ff_last, bf_last), 0.0, 1.0)
+    return mask_last, mask_last * backward_warp(styled_past, bf_last) + (1 - mask_last) * pre
+
+
 def temporal_error(ff, bf, prev, cur):
     """computeTCL minus RAFT and the generator (utils/sintel_eval.py:104-110)."""
     m = fb_consistency(ff, bf)

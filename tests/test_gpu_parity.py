@@ -266,6 +266,19 @@ def test_blend_and_computeTCL_dropins(tcl):
     assert abs(float(got2) - float(want2)) <= LOSS_RTOL * float(want2)
 
 
+def test_cumulative_long_term_mask_step(tcl):
+    """obst_eval.py:515-516 (disabled upstream): mask_last = clamp(mask_last - fbc, 0, 1); pre = mask_last*warp + (1-mask_last)*pre.
+    Mask and blended frame carry the bits of the op sequence."""
+    d = dev()
+    for B, H, W, seed in ((1, 64, 96, 21), (2, 436, 1024, 22)):
+        ff, bf, styled, pre = (t.to(d) for t in case(tcl, B, H, W, seed=seed, kind="smooth", max_shift=8.0))
+        for mask_last in (torch.ones(B, 1, H, W, device=d), (torch.rand(B, 1, H, W, device=d) > 0.3).float()):
+            got_m, got_pre = tcl.long_term_blend_step(mask_last, ff, bf, styled, pre)
+            want_m, want_pre = tp.long_term_step(mask_last, ff, bf, styled, pre)
+            assert torch.equal(got_m, want_m) and 0 < float(got_m.mean()) < 1
+            assert torch.equal(got_pre, want_pre)
+
+
 def test_computeTCL_pads_like_the_reference_when_the_frame_height_is_not_a_multiple_of_8(tcl):
     """Every reference computeRAFT pads with InputPadder(img1.shape) first (utils/sintel_eval.py:53-60); the ConGAN / CycleGAN /
     MoGAN / StarGAN / fast_style_transfer / obst variants then hand on flow_up[:, :, :H, :] (ConGAN/sintel_eval.py:61).  Native

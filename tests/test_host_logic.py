@@ -24,7 +24,8 @@ def test_wrappers_refuse_cpu_tensors_instead_of_falling_back(tcl):
     for call in (lambda: tcl.warp(x, f), lambda: tcl.fs_warp(x, f), lambda: tcl.fbcCheckTorch(f, f),
                  lambda: tcl.gradient(f[:, 0]), lambda: tcl.temporal_error(f, f, x, x),
                  lambda: tcl.temporal_loss(torch.ones(1, 1, 8, 8), x, x, f), lambda: tcl.hwc_split(torch.zeros(1, 8, 8, 9), tcl.ingest.FC2_LAYOUT),
-                 lambda: tcl.upsample_flow(f, torch.zeros(1, 576, 8, 8)), lambda: tcl.temporal_error_clip(x.repeat(2, 1, 1, 1), f, f)):
+                 lambda: tcl.upsample_flow(f, torch.zeros(1, 576, 8, 8)), lambda: tcl.temporal_error_clip(x.repeat(2, 1, 1, 1), f, f),
+                 lambda: tcl.long_term_blend_step(torch.ones(1, 1, 8, 8), f, f, x, x)):
         with pytest.raises(RuntimeError):
             call()
 

@@ -72,6 +72,17 @@ def test_torch_port_bit_identical_to_reference(reference, tcl, shape):
     assert torch.equal(((m * (cur - w)) ** 2).mean() ** 0.5, tp.temporal_error(ff, bf, prev, cur))
 
 
+def test_long_term_step_is_the_upstream_lines(reference, tcl):
+    """obst_eval.py:515-516 (inside a string literal upstream), executed with the imported flowtools functions."""
+    flowtools, _ = reference
+    ff, bf, styled, pre = _synth_case(tcl, 1, 64, 96, seed=5, kind="smooth", max_shift=6.0)
+    mask_last = (torch.rand(1, 1, 64, 96, generator=torch.Generator().manual_seed(1)) > 0.3).float()
+    m = torch.clamp(mask_last - flowtools.fbcCheckTorch(ff, bf, device="cpu"), 0.0, 1.0)
+    want = m * flowtools.warp(styled, bf) + (1 - m) * pre
+    got_m, got = tp.long_term_step(mask_last, ff, bf, styled, pre)
+    assert torch.equal(got_m, m) and torch.equal(got, want) and 0 < float(m.mean()) < 1
+
+
 def test_reference_autograd_matches_port(reference, tcl):
     flowtools, _ = reference
     ff, bf, prev, cur = _synth_case(tcl, 1, 20, 28, seed=3, max_shift=3.0)
