@@ -90,6 +90,32 @@ def test_congan_soft_mask_and_scalar_masked_l1(tcl):
     assert float((c.grad - c_ref.grad).abs().max()) <= 1e-5 * float(c_ref.grad.abs().max())
 
 
+@pytest.mark.parametrize("B,C,H,W,shift,soft", [(4, 3, 64, 96, 8.0, False), (2, 3, 256, 256, 24.0, False), (2, 32, 64, 64, 6.0, True), (1, 5, 37, 53, 20.0, True)])
+def test_learning_based_temporal_loss_uses_fs_lib_warp(tcl, B, C, H, W, shift, soft):
+    """fs_ruder.py:97 / fs_huang.py:55-56: ((mask*(warp(prev, flow) - cur))**2).mean() with ``from fs_lib import warp`` (the
+    validity-masked warp), and ReCoNet's feature-level term fs_reconet.py:56-61 (the same on C-channel feature maps under a
+    bilinearly resized, i.e. soft, mask): value within 1e-5 relative, gradients to both frames within 1e-5."""
+    d = torch.device("cuda:0")
+    ff, bf = tcl.synth.make_flows(B, H, W, seed=71, max_shift=shift, device=d)
+    prev, cur = (t.to(d) for t in tcl.synth.make_frames(B, C, H, W, seed=71, kind="smooth"))
+    mask = tcl.fbcCheckTorch(ff, bf)
+    if soft:   # fs_reconet.py:59: the mask goes through a bilinear resize first
+        mask = torch.nn.functional.interpolate(torch.nn.functional.avg_pool2d(mask, 2), size=(H, W), mode="bilinear")
+        assert 0 < int(((mask > 0) & (mask < 1)).sum())
+    p, c = prev.clone().requires_grad_(True), cur.clone().requires_grad_(True)
+    want = tp.tcl_l2(mask, c, tp.validity_warp(p, bf))
+    (want * 10.0).backward()
+    p2, c2 = prev.clone().requires_grad_(True), cur.clone().requires_grad_(True)
+    got = tcl.temporal_loss(mask, c2, p2, bf, validity=True)
+    (got * 10.0).backward()
+    assert abs(float(got) - float(want)) <= 1e-5 * float(want)
+    assert float((c2.grad - c.grad).abs().max()) <= 1e-5 * float(c.grad.abs().max())
+    assert float((p2.grad - p.grad).abs().max()) <= 1e-5 * float(p.grad.abs().max())
+    # the validity factor matters on these inputs (the flow leaves the frame somewhere): not the plain warp's loss
+    plain = tp.tcl_l2(mask, cur, tp.backward_warp(prev, bf))
+    assert float(plain) != float(want)
+
+
 # ------------------------------------------------------------------ warp chains of the learning-based trainers
 @pytest.mark.gpu
 @pytest.mark.parametrize("B,H,W,shift", [(2, 64, 96, 5.0), (1, 37, 53, 30.0), (4, 256, 256, 12.0)])
