@@ -602,8 +602,8 @@ def _loss_forward(prev, cur, flow, mask, loss, flags):
 
 class _TemporalLossFn(torch.autograd.Function):
     """Gradients to ``prev`` and ``cur`` only (what the reference's trainers use: the flow and the mask come from the data
-    set or from a frozen flow network under no_grad).  ``temporal_loss`` refuses flows / masks that require grad instead of
-    silently returning no gradient for them; double backward is not defined (once_differentiable)."""
+    set or from a frozen flow network under no_grad).  ``temporal_loss`` routes flows / masks that require grad through the
+    differentiable ``warp`` instead (never a silently missing gradient); double backward is not defined (once_differentiable)."""
 
     @staticmethod
     def forward(ctx, prev, cur, flow, mask, loss, flags):
@@ -642,7 +642,8 @@ class _TemporalLossFn(torch.autograd.Function):
 
 
 def temporal_loss(mask, cur, prev, flow, loss="l2", validity=False):
-    """Training temporal loss, differentiable w.r.t. ``cur`` and ``prev``.
+    """Training temporal loss, differentiable w.r.t. ``cur`` and ``prev`` in one fused launch each way; a ``flow`` or ``mask``
+    that requires grad gets its gradient too (composed from the differentiable ``warp``, like the reference expression).
 
     ``loss='l2'``: ((mask*(cur - warp(prev,flow)))**2).mean()      (solver.py:444, fs_ruder.py:97)
     ``loss='l1'``: (mask*abs(warp(prev,flow) - cur)).mean()         (MoGAN cycle_gan_model.py:280-281)
@@ -672,8 +673,11 @@ def temporal_loss(mask, cur, prev, flow, loss="l2", validity=False):
     flags = VALIDITY if validity else 0
     if torch.is_grad_enabled():
         if flow.requires_grad or mask.requires_grad:
-            raise RuntimeError("tcl_b200: temporal_loss differentiates w.r.t. cur and prev only; a flow or mask that requires grad would "
-                               "silently get none -- detach it, or compose the loss from tcl_b200.warp (differentiable w.r.t. its flow)")
+            # a learnable flow (MoGAN's motion network: warp(fake_B, netM_A(bf)), cycle_gan_model.py:177-178,280) or a soft mask that
+            # is being trained: the fused backward has no gradient for them, so the loss is composed like the reference expression
+            # from the differentiable warp (gradients to the frame and the flow, tclb200_warp_backward) and autograd's elementwise ops
+            w = _warp(prev, flow, flags)
+            return ((mask * (cur - w)) ** 2).mean() if code == L2 else (mask * torch.abs(w - cur)).mean()
         if prev.requires_grad or cur.requires_grad:
             return _TemporalLossFn.apply(prev, cur, flow, mask, code, flags)
     return _loss_forward(prev, cur, flow, mask, code, flags)

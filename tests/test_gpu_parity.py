@@ -897,15 +897,32 @@ def test_direct_kernel_equals_the_other_forward_kernels(tcl, force_generic, B, H
         force_generic(0)
 
 
-def test_temporal_loss_refuses_gradients_it_does_not_compute(tcl):
+@pytest.mark.parametrize("loss", ["l2", "l1"])
+def test_temporal_loss_with_a_learnable_flow_or_mask_gets_every_gradient(tcl, loss):
+    """MoGAN warps with the output of its motion network (cycle_gan_model.py:177-178: warp(fake_B, netM_A(bf_real_A)); loss at
+    :280): the flow requires grad.  The fused backward has no gradient for flow / mask, so such calls are composed from the
+    differentiable warp -- same value, gradients to frames, flow and mask within 1e-5 / 1e-4 of the reference expression's."""
+    d = dev()
+    ff, bf, prev, cur = (t.to(d) for t in case(tcl, 2, 32, 48, seed=5, kind="smooth", max_shift=4.0))
+    mask = tcl.fbcCheckTorch(ff, bf) * 0.75 + 0.125          # a soft mask
+    ref_fn = tp.tcl_l2 if loss == "l2" else tp.tcl_l1
+    grads = []
+    for mine in (False, True):
+        p, c, f, m = (t.clone().requires_grad_(True) for t in (prev, cur, bf, mask))
+        val = tcl.temporal_loss(m, c, p, f, loss=loss) if mine else ref_fn(m, c, tp.backward_warp(p, f))
+        (val * 100.0).backward()
+        grads.append((float(val), p.grad, c.grad, f.grad, m.grad))
+    (rv, *rg), (kv, *kg) = grads
+    assert abs(kv - rv) <= LOSS_RTOL * abs(rv)
+    for r, k, tol in zip(rg, kg, (1e-5, 1e-5, 1e-4, 1e-5)):
+        assert k is not None and float((k - r).abs().max()) <= tol * max(float(r.abs().max()), 1e-12)
+
+
+def test_temporal_loss_is_once_differentiable(tcl):
     d = dev()
     ff, bf, prev, cur = (t.to(d) for t in case(tcl, 2, 32, 48, seed=5, max_shift=4.0))
     mask = tcl.fbcCheckTorch(ff, bf)
     cur.requires_grad_(True)
-    with pytest.raises(RuntimeError, match="cur and prev only"):
-        tcl.temporal_loss(mask, cur, prev, bf.clone().requires_grad_(True))
-    with pytest.raises(RuntimeError, match="cur and prev only"):
-        tcl.temporal_loss(mask.clone().requires_grad_(True), cur, prev, bf)
     loss = tcl.temporal_loss(mask, cur, prev, bf)
     (g,) = torch.autograd.grad(loss, cur, create_graph=True)
     with pytest.raises(RuntimeError):      # once_differentiable: no silent wrong double backward
