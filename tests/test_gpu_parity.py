@@ -176,9 +176,25 @@ def test_ragged_and_tiny_shapes(tcl, oracle_mod, B, C, H, W):
     v = oracle_mod.ATEN_CUDA
     assert np.array_equal(tcl.warp(prev.to(d), bf.to(d)).cpu().numpy(), oracle_mod.warp(prev.numpy(), bf.numpy(), v))
     assert np.array_equal(tcl.fbcCheckTorch(ff.to(d), bf.to(d)).cpu().numpy(), oracle_mod.fbcheck(ff.numpy(), bf.numpy(), variant=v))
+    assert np.array_equal(tcl.fs_warp(prev.to(d), bf.to(d)).cpu().numpy(), oracle_mod.validity_warp(prev.numpy(), bf.numpy(), v))
     res = tcl.fused_forward(bf.to(d), prev.to(d), cur.to(d), ff=ff.to(d))
     o = oracle_mod.temporal_error_sums(ff.numpy(), bf.numpy(), prev.numpy(), cur.numpy(), variant=v)
     assert np.allclose(res.pair_sums.cpu().numpy(), o, rtol=LOSS_RTOL, atol=1e-30)
+
+
+def test_reconet_feature_level_warp(tcl):
+    """fs_reconet.py:56-61: the flow is resized to the feature map (bilinear) and rescaled, then ``fs_lib.warp`` moves a
+    many-channel feature map at a quarter of the frame size -- bits of the op sequence."""
+    d = dev()
+    B, C, H, W = 2, 48, 256, 256
+    ff, bf = tcl.synth.make_flows(B, H, W, seed=91, max_shift=24.0, device=d)
+    fmap = torch.randn(B, C, H // 4, W // 4, device=d)
+    fflow = torch.nn.functional.interpolate(bf, size=fmap.shape[2:], mode="bilinear")
+    fflow[:, 0, :, :] *= float(fmap.shape[2]) / bf.shape[2]
+    fflow[:, 1, :, :] *= float(fmap.shape[3]) / bf.shape[3]
+    want = tp.validity_warp(fmap, fflow)
+    got = tcl.fs_warp(fmap, fflow)
+    assert torch.equal(got, want) and 0 < int((want == 0).all(dim=1).sum()) < B * (H // 4) * (W // 4)
 
 
 def test_out_of_frame_and_extreme_flows(tcl, oracle_mod):
